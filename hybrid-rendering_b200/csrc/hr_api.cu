@@ -1,0 +1,716 @@
+// hr_api.cu — implementation of the C ABI declared in include/hr_api.h.
+// Host sequencing mirrors the reference's pass classes:
+//   RayTracedShadows::render  src/ray_traced_shadows.cpp:100-116 (+ stages :938-1255)
+//   RayTracedAO::render       src/ray_traced_ao.cpp:98-112      (+ stages :829-1137)
+#include "hr_internal.h"
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+static std::string g_last_error;
+static std::mutex  g_err_mutex;
+extern int         g_hr_atrous_impl;
+
+void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
+{
+    char    buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_last_error = buf;
+    if (ctx) ctx->last_error = buf;
+}
+
+static FrameConsts make_consts(const hr_frame* f)
+{
+    FrameConsts c;
+    memcpy(c.view_proj_inverse, f->ubo.view_proj_inverse, 64);
+    memcpy(c.prev_view_proj, f->ubo.prev_view_proj, 64);
+    memcpy(c.cam_pos, f->ubo.cam_pos, 16);
+    c.light = f->ubo.light;
+    memcpy(c.z_buffer_params, f->z_buffer_params, 16);
+    memcpy(c.camera_delta, f->camera_delta, 12);
+    c.num_frames = f->num_frames;
+    return c;
+}
+
+static GBufLevelDev level_view(const hr_ctx* ctx, int slot, int mip)
+{
+    GBufLevelDev l;
+    int          w = ctx->gb_w, h = ctx->gb_h;
+    for (int m = 0; m < mip; m++) { w = w / 2 > 0 ? w / 2 : 1; h = h / 2 > 0 ? h / 2 : 1; }
+    l.W     = w;
+    l.H     = h;
+    l.gb1   = (const uint32_t*)ctx->slot[slot].gb1[mip];
+    l.gb2   = (const uint2*)ctx->slot[slot].gb2[mip];
+    l.gb3   = (const uint2*)ctx->slot[slot].gb3[mip];
+    l.depth = ctx->slot[slot].depth[mip];
+    return l;
+}
+
+// ---- stage timing (DW_SCOPED_SAMPLE equivalent) ---------------------------------------------------------------
+static void timer_begin(hr_pass* p, cudaStream_t st)
+{
+    if (!p->ctx->profiling) return;
+    p->timer.names.clear();
+    p->timer.used = 0;
+    if (p->timer.ev.empty())
+    {
+        p->timer.ev.resize(32);
+        for (auto& e : p->timer.ev) cudaEventCreate(&e);
+    }
+    cudaEventRecord(p->timer.ev[p->timer.used++], st);
+}
+static void timer_mark(hr_pass* p, const char* name, cudaStream_t st)
+{
+    if (!p->ctx->profiling || p->timer.used >= (int)p->timer.ev.size()) return;
+    p->timer.names.push_back(name);
+    cudaEventRecord(p->timer.ev[p->timer.used++], st);
+}
+
+extern "C" {
+
+int hr_version(void) { return HR_VERSION; }
+
+int hr_init(int device, hr_ctx** out)
+{
+    if (!out) return HR_ERR_INVALID_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    {
+        hr_set_error(nullptr, "hr_init: no CUDA device available (this library has no CPU fallback)");
+        return HR_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { hr_set_error(nullptr, "hr_init: device %d out of range (%d devices)", device, n); return HR_ERR_INVALID_ARG; }
+    hr_ctx* ctx = new hr_ctx();
+    ctx->device = device;
+    HR_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HR_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    HR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->build_stream, cudaStreamNonBlocking));
+    *out = ctx;
+    return HR_OK;
+}
+
+int hr_shutdown(hr_ctx* ctx)
+{
+    if (!ctx) return HR_ERR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; s++)
+    {
+        for (int m = 1; m < HR_MAX_MIPS; m++)
+        {
+            cudaFree(ctx->slot[s].gb1[m]); cudaFree(ctx->slot[s].gb2[m]); cudaFree(ctx->slot[s].gb3[m]); cudaFree(ctx->slot[s].depth[m]);
+        }
+        for (int k = 0; k < 4; k++) cudaFree(ctx->owned_mip0[s][k]);
+    }
+    cudaFree(ctx->d_sobol);
+    cudaFree(ctx->d_scr_rank);
+    if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
+    delete ctx;
+    return HR_OK;
+}
+
+const char* hr_last_error(hr_ctx* ctx)
+{
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    return ctx ? ctx->last_error.c_str() : g_last_error.c_str();
+}
+
+int hr_debug_set(int key, int value)
+{
+    if (key == 1) { g_hr_atrous_impl = value; return HR_OK; }
+    return HR_ERR_INVALID_ARG;
+}
+
+int      hr_ctx_set_profiling(hr_ctx* ctx, int enabled) { if (!ctx) return HR_ERR_INVALID_ARG; ctx->profiling = enabled != 0; return HR_OK; }
+uint64_t hr_ctx_launch_count(hr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hr_bluenoise_set(hr_ctx* ctx, const uint8_t* sobol, const uint8_t* sr)
+{
+    HR_REQUIRE(ctx, ctx && sobol && sr, HR_ERR_INVALID_ARG, "hr_bluenoise_set: null argument");
+    if (!ctx->d_sobol) HR_CUDA(ctx, cudaMalloc(&ctx->d_sobol, 256 * 4));
+    if (!ctx->d_scr_rank) HR_CUDA(ctx, cudaMalloc(&ctx->d_scr_rank, 128 * 128 * 4));
+    HR_CUDA(ctx, cudaMemcpy(ctx->d_sobol, sobol, 256 * 4, cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(ctx->d_scr_rank, sr, 128 * 128 * 4, cudaMemcpyHostToDevice));
+    ctx->bn_set = true;
+    return HR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scene
+// ---------------------------------------------------------------------------------------------------------------
+int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, const uint32_t* indices, size_t n_indices, const hr_instance* instances,
+                   size_t n_instances, const hr_material* materials, size_t n_materials, hr_scene** out)
+{
+    HR_REQUIRE(ctx, ctx && vertices && indices && instances && out, HR_ERR_INVALID_ARG, "hr_scene_build: null argument");
+    // flatten instances to a world-space triangle soup in primitive order (instances in order, triangles in index order);
+    // same arithmetic as transform_vertex (scene_descriptor_set.glsl:147-156): mat4 * vec4 position, normalize(mat3 * normal).
+    std::vector<float>    soup;
+    std::vector<float>    vnorm;
+    std::vector<uint32_t> prim_inst, prim_mat;
+    for (size_t ii = 0; ii < n_instances; ii++)
+    {
+        const hr_instance& in = instances[ii];
+        const float*       M  = in.model;
+        if ((size_t)in.first_index + in.index_count > n_indices) { hr_set_error(ctx, "hr_scene_build: instance %zu index range out of bounds", ii); return HR_ERR_INVALID_ARG; }
+        for (uint32_t k = 0; k + 2 < in.index_count; k += 3)
+        {
+            for (int j = 0; j < 3; j++)
+            {
+                const size_t vi = (size_t)in.base_vertex + indices[in.first_index + k + j];
+                if (vi >= n_vertices) { hr_set_error(ctx, "hr_scene_build: vertex index out of bounds"); return HR_ERR_INVALID_ARG; }
+                const hr_vertex& v = vertices[vi];
+                const float      x = v.position[0], y = v.position[1], z = v.position[2];
+                soup.push_back(((M[0] * x + M[4] * y) + M[8] * z) + M[12]);
+                soup.push_back(((M[1] * x + M[5] * y) + M[9] * z) + M[13]);
+                soup.push_back(((M[2] * x + M[6] * y) + M[10] * z) + M[14]);
+                const float nx = v.normal[0], ny = v.normal[1], nz = v.normal[2];
+                float       wx = (M[0] * nx + M[4] * ny) + M[8] * nz, wy = (M[1] * nx + M[5] * ny) + M[9] * nz, wz = (M[2] * nx + M[6] * ny) + M[10] * nz;
+                const float l = sqrtf((wx * wx + wy * wy) + wz * wz);
+                const float il = l > 0.0f ? 1.0f / l : 0.0f;
+                vnorm.push_back(wx * il); vnorm.push_back(wy * il); vnorm.push_back(wz * il); vnorm.push_back(0.0f);
+            }
+            prim_inst.push_back((uint32_t)ii);
+            prim_mat.push_back(in.material_idx);
+        }
+    }
+    const size_t n = prim_inst.size();
+    HR_REQUIRE(ctx, n > 0, HR_ERR_INVALID_ARG, "hr_scene_build: scene has no triangles");
+    HR_REQUIRE(ctx, n < (1u << 28), HR_ERR_UNSUPPORTED, "hr_scene_build: more than 2^28 triangles");
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    hr_scene* sc = new hr_scene();
+    sc->ctx      = ctx;
+    sc->n_tris   = (uint32_t)n;
+    const size_t ni = n > 1 ? n - 1 : 1;
+#define ALLOC(ptr, bytes) HR_CUDA(ctx, cudaMalloc((void**)&(ptr), (bytes)))
+    ALLOC(sc->d_tri_verts, n * 9 * sizeof(float));
+    ALLOC(sc->d_prim_inst, n * sizeof(uint32_t));
+    ALLOC(sc->d_prim_mat, n * sizeof(uint32_t));
+    ALLOC(sc->d_vnormals, n * 3 * sizeof(float4));
+    ALLOC(sc->d_keys, n * sizeof(uint64_t));
+    ALLOC(sc->d_keys_sorted, n * sizeof(uint64_t));
+    ALLOC(sc->d_vals, n * sizeof(uint32_t));
+    ALLOC(sc->d_vals_sorted, n * sizeof(uint32_t));
+    ALLOC(sc->d_tri_aabb, n * 6 * sizeof(float));
+    ALLOC(sc->d_bounds_i, 6 * sizeof(int));
+    ALLOC(sc->d_children, ni * sizeof(int2));
+    ALLOC(sc->d_ranges, ni * sizeof(int2));
+    ALLOC(sc->d_parent, (2 * n) * sizeof(int));
+    ALLOC(sc->d_node_aabb, ni * 6 * sizeof(float));
+    ALLOC(sc->d_flags, ni * sizeof(int));
+    ALLOC(sc->d_nodes, ni * 4 * sizeof(float4));
+    ALLOC(sc->d_tris, n * 3 * sizeof(float4));
+    if (n_materials && materials)
+    {
+        ALLOC(sc->d_materials, n_materials * sizeof(hr_material));
+        HR_CUDA(ctx, cudaMemcpy(sc->d_materials, materials, n_materials * sizeof(hr_material), cudaMemcpyHostToDevice));
+        sc->n_materials = (uint32_t)n_materials;
+    }
+#undef ALLOC
+    HR_CUDA(ctx, cudaMemcpy(sc->d_tri_verts, soup.data(), n * 9 * sizeof(float), cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_prim_inst, prim_inst.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_prim_mat, prim_mat.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_vnormals, vnorm.data(), n * 3 * sizeof(float4), cudaMemcpyHostToDevice));
+    int rc = hr_scene_rebuild(sc, ctx->build_stream);
+    if (rc != HR_OK) { hr_scene_destroy(sc); return rc; }
+    HR_CUDA(ctx, cudaStreamSynchronize(ctx->build_stream));
+    // bounds for info
+    int bi[6];
+    HR_CUDA(ctx, cudaMemcpy(bi, sc->d_bounds_i, sizeof(bi), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < 6; a++)
+    {
+        int   i = bi[a] >= 0 ? bi[a] : bi[a] ^ 0x7FFFFFFF;
+        float f;
+        memcpy(&f, &i, 4);
+        (a < 3 ? sc->info.bounds_min[a] : sc->info.bounds_max[a - 3]) = f;
+    }
+    *out = sc;
+    if (!ctx->scene) ctx->scene = sc;
+    return HR_OK;
+}
+
+int hr_scene_rebuild(hr_scene* sc, void* stream)
+{
+    if (!sc) return HR_ERR_INVALID_ARG;
+    hr_ctx*      ctx = sc->ctx;
+    cudaStream_t st  = (cudaStream_t)stream;
+    cudaEvent_t  e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+    int rc = hr_bvh_build(sc, st);
+    if (rc != HR_OK) return rc;
+    if (ctx->profiling)
+    {
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&sc->info.build_ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    sc->info.n_triangles = sc->n_tris;
+    sc->info.n_nodes     = sc->n_nodes;
+    return HR_OK;
+}
+
+int hr_scene_destroy(hr_scene* sc)
+{
+    if (!sc) return HR_ERR_INVALID_ARG;
+    if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
+    void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
+                     sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_tris,
+                     sc->d_materials, sc->d_sort_tmp };
+    for (void* p : ptrs) cudaFree(p);
+    delete sc;
+    return HR_OK;
+}
+
+int hr_scene_set_current(hr_ctx* ctx, hr_scene* scene) { if (!ctx) return HR_ERR_INVALID_ARG; ctx->scene = scene; return HR_OK; }
+int hr_scene_get_info(hr_scene* sc, hr_scene_info* out) { if (!sc || !out) return HR_ERR_INVALID_ARG; *out = sc->info; return HR_OK; }
+
+int hr_trace_any(hr_ctx* ctx, const float* d_rays, size_t n, uint32_t* d_out, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && ctx->scene, HR_ERR_NOT_READY, "hr_trace_any: no current scene");
+    launch_trace_any(hr_bvh_view(ctx->scene), d_rays, n, d_out, (cudaStream_t)stream);
+    ctx->launches++;
+    HR_CHECK_LAUNCH(ctx);
+    return HR_OK;
+}
+int hr_trace_closest(hr_ctx* ctx, const float* d_rays, size_t n, float* d_t, uint32_t* d_prim, float* d_uv, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && ctx->scene, HR_ERR_NOT_READY, "hr_trace_closest: no current scene");
+    launch_trace_closest(hr_bvh_view(ctx->scene), d_rays, n, d_t, d_prim, d_uv, (cudaStream_t)stream);
+    ctx->launches++;
+    HR_CHECK_LAUNCH(ctx);
+    return HR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// G-buffer
+// ---------------------------------------------------------------------------------------------------------------
+int hr_gbuffer_create(hr_ctx* ctx, int width, int height)
+{
+    HR_REQUIRE(ctx, ctx && width > 0 && height > 0, HR_ERR_INVALID_ARG, "hr_gbuffer_create: bad size");
+    HR_REQUIRE(ctx, ctx->gb_w == 0, HR_ERR_INVALID_ARG, "hr_gbuffer_create: already created");
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->gb_w = width;
+    ctx->gb_h = height;
+    for (int s = 0; s < 2; s++)
+    {
+        int w = width, h = height;
+        for (int m = 0; m < HR_MAX_MIPS; m++)
+        {
+            const size_t px = (size_t)w * h;
+            HR_CUDA(ctx, cudaMalloc(&ctx->slot[s].gb1[m], px * 4));
+            HR_CUDA(ctx, cudaMalloc(&ctx->slot[s].gb2[m], px * 8));
+            HR_CUDA(ctx, cudaMalloc(&ctx->slot[s].gb3[m], px * 8));
+            HR_CUDA(ctx, cudaMalloc((void**)&ctx->slot[s].depth[m], px * 4));
+            HR_CUDA(ctx, cudaMemset(ctx->slot[s].gb1[m], 0, px * 4));
+            HR_CUDA(ctx, cudaMemset(ctx->slot[s].gb2[m], 0, px * 8));
+            HR_CUDA(ctx, cudaMemset(ctx->slot[s].gb3[m], 0, px * 8));
+            HR_CUDA(ctx, cudaMemset(ctx->slot[s].depth[m], 0, px * 4));
+            w = w / 2 > 0 ? w / 2 : 1;
+            h = h / 2 > 0 ? h / 2 : 1;
+        }
+        ctx->owned_mip0[s][0] = ctx->slot[s].gb1[0];
+        ctx->owned_mip0[s][1] = ctx->slot[s].gb2[0];
+        ctx->owned_mip0[s][2] = ctx->slot[s].gb3[0];
+        ctx->owned_mip0[s][3] = ctx->slot[s].depth[0];
+        ctx->slot[s].valid    = true; // zero-initialised history is a valid (empty) frame
+    }
+    return HR_OK;
+}
+
+static int gbuffer_copy_in(hr_ctx* ctx, int slot, const hr_gbuffer_desc* src, cudaMemcpyKind kind, cudaStream_t st)
+{
+    HR_REQUIRE(ctx, ctx && src && (slot == 0 || slot == 1), HR_ERR_INVALID_ARG, "hr_gbuffer_upload: bad argument");
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_upload: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, src->width == ctx->gb_w && src->height == ctx->gb_h, HR_ERR_INVALID_ARG, "hr_gbuffer_upload: size mismatch");
+    HR_REQUIRE(ctx, src->gb2 && src->gb3 && src->depth, HR_ERR_INVALID_ARG, "hr_gbuffer_upload: gb2/gb3/depth are required");
+    GBufSlot& s = ctx->slot[slot];
+    // restore library-owned mip0 storage if the slot was bound zero-copy before
+    s.gb1[0]   = ctx->owned_mip0[slot][0];
+    s.gb2[0]   = ctx->owned_mip0[slot][1];
+    s.gb3[0]   = ctx->owned_mip0[slot][2];
+    s.depth[0] = (float*)ctx->owned_mip0[slot][3];
+    const size_t px = (size_t)ctx->gb_w * ctx->gb_h;
+    if (src->gb1) HR_CUDA(ctx, cudaMemcpyAsync(s.gb1[0], src->gb1, px * 4, kind, st));
+    HR_CUDA(ctx, cudaMemcpyAsync(s.gb2[0], src->gb2, px * 8, kind, st));
+    HR_CUDA(ctx, cudaMemcpyAsync(s.gb3[0], src->gb3, px * 8, kind, st));
+    HR_CUDA(ctx, cudaMemcpyAsync(s.depth[0], src->depth, px * 4, kind, st));
+    return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, st);
+}
+
+int hr_gbuffer_upload(hr_ctx* ctx, int slot, const hr_gbuffer_desc* host, void* stream) { return gbuffer_copy_in(ctx, slot, host, cudaMemcpyHostToDevice, (cudaStream_t)stream); }
+int hr_gbuffer_copy_from_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev, void* stream) { return gbuffer_copy_in(ctx, slot, dev, cudaMemcpyDeviceToDevice, (cudaStream_t)stream); }
+
+int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && dev && (slot == 0 || slot == 1), HR_ERR_INVALID_ARG, "hr_gbuffer_bind_device: bad argument");
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_bind_device: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, dev->width == ctx->gb_w && dev->height == ctx->gb_h, HR_ERR_INVALID_ARG, "hr_gbuffer_bind_device: size mismatch");
+    HR_REQUIRE(ctx, dev->gb2 && dev->gb3 && dev->depth, HR_ERR_INVALID_ARG, "hr_gbuffer_bind_device: gb2/gb3/depth are required");
+    GBufSlot& s = ctx->slot[slot];
+    s.gb1[0]    = const_cast<void*>(dev->gb1);
+    s.gb2[0]    = const_cast<void*>(dev->gb2);
+    s.gb3[0]    = const_cast<void*>(dev->gb3);
+    s.depth[0]  = (float*)const_cast<void*>(dev->depth);
+    return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, (cudaStream_t)stream);
+}
+
+int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* dst, size_t bytes)
+{
+    HR_REQUIRE(ctx, ctx && dst && (slot == 0 || slot == 1) && mip >= 0 && mip < HR_MAX_MIPS && which >= 0 && which <= 3, HR_ERR_INVALID_ARG,
+               "hr_gbuffer_download: bad argument");
+    GBufLevelDev l  = level_view(ctx, slot, mip);
+    const size_t px = (size_t)l.W * l.H;
+    const void*  src = which == 0 ? (const void*)l.depth : which == 1 ? (const void*)l.gb1 : which == 2 ? (const void*)l.gb2 : (const void*)l.gb3;
+    const size_t need = px * (which == 0 || which == 1 ? 4 : 8);
+    HR_REQUIRE(ctx, bytes == need, HR_ERR_INVALID_ARG, "hr_gbuffer_download: byte count mismatch");
+    HR_CUDA(ctx, cudaDeviceSynchronize());
+    HR_CUDA(ctx, cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+    return HR_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Pass helpers
+// ---------------------------------------------------------------------------------------------------------------
+static int texel_size(int fmt)
+{
+    switch (fmt)
+    {
+        case HR_FMT_R32_UINT: return 4;
+        case HR_FMT_R16F: return 2;
+        case HR_FMT_RG16F: return 4;
+        case HR_FMT_RGBA16F: return 8;
+        case HR_FMT_R8_UINT: return 1;
+    }
+    return 0;
+}
+
+template <typename T>
+static int pass_alloc(hr_pass* p, T*& ptr, size_t count, int fill_byte = 0)
+{
+    HR_CUDA(p->ctx, cudaMalloc((void**)&ptr, count * sizeof(T)));
+    HR_CUDA(p->ctx, cudaMemset(ptr, fill_byte, count * sizeof(T)));
+    p->allocs.push_back(ptr);
+    return HR_OK;
+}
+
+static void set_view(hr_pass* p, int which, void* ptr, int w, int h, int fmt)
+{
+    p->out_view[which].p   = ptr;
+    p->out_view[which].w   = w;
+    p->out_view[which].h   = h;
+    p->out_view[which].fmt = fmt;
+}
+
+static int pass_common_create(hr_ctx* ctx, int width, int height, int scale, int kind, hr_pass** out)
+{
+    HR_REQUIRE(ctx, ctx && out && width > 0 && height > 0 && scale >= 0 && scale < HR_MAX_MIPS, HR_ERR_INVALID_ARG, "pass create: bad argument");
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    hr_pass* p = new hr_pass();
+    p->ctx     = ctx;
+    p->kind    = kind;
+    p->W0      = width;
+    p->H0      = height;
+    p->scale   = scale;
+    int w = width, h = height;
+    for (int m = 0; m < scale; m++) { w = w / 2 > 0 ? w / 2 : 1; h = h / 2 > 0 ? h / 2 : 1; } // = swapchain / 2^scale, ray_traced_shadows.cpp:78-83
+    p->W = w;
+    p->H = h;
+    *out = p;
+    return HR_OK;
+}
+
+static int check_render_ready(hr_pass* p, const hr_frame* f, const void* params, bool needs_scene)
+{
+    hr_ctx* ctx = p ? p->ctx : nullptr;
+    HR_REQUIRE(ctx, p && f && params, HR_ERR_INVALID_ARG, "render: null argument");
+    HR_REQUIRE(ctx, ctx->gb_w == p->W0 && ctx->gb_h == p->H0, HR_ERR_NOT_READY, "render: G-buffer not created or size differs from the pass");
+    HR_REQUIRE(ctx, !needs_scene || ctx->scene, HR_ERR_NOT_READY, "render: no scene set (hr_scene_build / hr_scene_set_current)");
+    HR_REQUIRE(ctx, ctx->bn_set, HR_ERR_NOT_READY, "render: blue-noise tables not set (hr_bluenoise_set)");
+    HR_REQUIRE(ctx, f->ping_pong == 0 || f->ping_pong == 1, HR_ERR_INVALID_ARG, "render: ping_pong must be 0 or 1");
+    return HR_OK;
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shadows
+// ---------------------------------------------------------------------------------------------------------------
+void hr_shadows_default_params(hr_shadows_params* p)
+{
+    p->bias = 0.5f; p->alpha = 0.01f; p->moments_alpha = 0.2f; p->phi_visibility = 10.0f; p->phi_normal = 32.0f; p->sigma_depth = 1.0f;
+    p->power = 1.2f; p->radius = 1; p->filter_iterations = 4; p->feedback_iteration = 1; p->denoise = 1;
+}
+
+int hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
+{
+    int rc = pass_common_create(ctx, width, height, scale, PASS_SHADOWS, out);
+    if (rc != HR_OK) return rc;
+    hr_pass*     p  = *out;
+    const size_t px = (size_t)p->W * p->H, mw = (p->W + 7) / 8, mh = (p->H + 3) / 4, tw = (p->W + 7) / 8, th = (p->H + 7) / 8;
+#define A(call) do { rc = (call); if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; } } while (0)
+    A(pass_alloc(p, p->mask, mw * mh));
+    A(pass_alloc(p, p->temporal_out, px));
+    A(pass_alloc(p, p->moments[0], px));
+    A(pass_alloc(p, p->moments[1], px));
+    A(pass_alloc(p, p->prev_image, px));
+    A(pass_alloc(p, p->atrous[0], px));
+    A(pass_alloc(p, p->atrous[1], px));
+    A(pass_alloc(p, p->tile_flags, tw * th));
+    if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
+#undef A
+    return HR_OK;
+}
+
+int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* prm, void* stream)
+{
+    int rc = check_render_ready(p, f, prm, true);
+    if (rc != HR_OK) return rc;
+    hr_ctx* ctx = p->ctx;
+    HR_REQUIRE(ctx, p->kind == PASS_SHADOWS, HR_ERR_INVALID_ARG, "hr_shadows_render: not a shadows pass");
+    HR_REQUIRE(ctx, prm->filter_iterations >= 0 && prm->filter_iterations <= 8 && prm->radius >= 1 && prm->radius <= 2, HR_ERR_INVALID_ARG,
+               "hr_shadows_render: filter_iterations must be 0..8 and radius 1..2");
+    cudaStream_t       st  = (cudaStream_t)stream;
+    const int          pp  = f->ping_pong;
+    const FrameConsts  fc  = make_consts(f);
+    const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
+    const int          row0 = 0, row1 = p->H;
+    const size_t       px = (size_t)p->W * p->H;
+    timer_begin(p, st);
+
+    // clear_images (ray_traced_shadows.cpp:938-968): first frame => history image and moments[!pp] = 0
+    if (p->first)
+    {
+        HR_CUDA(ctx, cudaMemsetAsync(p->prev_image, 0, px * sizeof(__half2), st));
+        HR_CUDA(ctx, cudaMemsetAsync(p->moments[!pp], 0, px * sizeof(uint2), st));
+        p->first = false;
+    }
+    // ray_trace (:972-1011)
+    launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, row0, row1, st);
+    ctx->launches++;
+    timer_mark(p, "Ray Trace", st);
+    set_view(p, HR_SHADOWS_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = p->mask;
+    int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
+    if (prm->denoise)
+    {
+        // temporal_accumulation (:1041-1090); reset_args (:1015-1037) is subsumed by the per-tile flag image
+        launch_shadows_temporal(cur, prev, p->mask, p->prev_image, p->moments[!pp], fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp],
+                                p->tile_flags, row0, row1, st);
+        ctx->launches++;
+        timer_mark(p, "Temporal Accumulation", st);
+        // a_trous_filter (:1094-1215).  The reference ping-pongs image[0]/image[1] and copies the output of
+        // feedback_iteration into prev_image; here that iteration writes prev_image directly and the next one reads it.
+        const __half2* in      = p->temporal_out;
+        __half2*       last    = p->temporal_out;
+        int            toggle  = 1; // reference: first write_idx = 1
+        for (int i = 0; i < prm->filter_iterations; i++)
+        {
+            __half2* dst = (i == prm->feedback_iteration) ? p->prev_image : p->atrous[toggle];
+            if (i == prm->filter_iterations - 1 && dst == p->prev_image)
+            { // final output must not alias the history image: filter into atrous[], then copy (reference semantics)
+                dst = p->atrous[toggle];
+            }
+            const float power = (i == prm->filter_iterations - 1) ? prm->power : 0.0f;
+            launch_shadows_atrous(cur, in, p->tile_flags, prm->radius, 1 << i, prm->phi_visibility, prm->phi_normal, prm->sigma_depth, power, dst, row0, row1, st);
+            ctx->launches++;
+            if (i == prm->feedback_iteration && dst != p->prev_image)
+                HR_CUDA(ctx, cudaMemcpyAsync(p->prev_image, dst, px * sizeof(__half2), cudaMemcpyDeviceToDevice, st));
+            in     = dst;
+            last   = dst;
+            toggle = !toggle;
+            static const char* names[8] = { "A-Trous 0", "A-Trous 1", "A-Trous 2", "A-Trous 3", "A-Trous 4", "A-Trous 5", "A-Trous 6", "A-Trous 7" };
+            timer_mark(p, names[i], st);
+        }
+        if (prm->feedback_iteration < 0 || prm->feedback_iteration >= prm->filter_iterations)
+        { /* no feedback: prev_image keeps its previous contents, like the reference */ }
+        set_view(p, HR_SHADOWS_OUT_TEMPORAL_ACCUMULATION, p->temporal_out, p->W, p->H, HR_FMT_RG16F);
+        set_view(p, HR_SHADOWS_OUT_ATROUS, last, p->W, p->H, HR_FMT_RG16F);
+        set_view(p, HR_SHADOWS_OUT_MOMENTS, p->moments[pp], p->W, p->H, HR_FMT_RGBA16F);
+        set_view(p, HR_SHADOWS_OUT_PREV_IMAGE, p->prev_image, p->W, p->H, HR_FMT_RG16F);
+        set_view(p, HR_SHADOWS_OUT_TILE_FLAGS, p->tile_flags, (p->W + 7) / 8, (p->H + 7) / 8, HR_FMT_R8_UINT);
+        final_ptr = last; final_w = p->W; final_h = p->H; final_fmt = HR_FMT_RG16F;
+        if (p->scale != HR_SCALE_FULL)
+        { // upsample (:1219-1255)
+            const GBufLevelDev g0 = level_view(ctx, pp, 0);
+            launch_upsample_scalar(g0, cur, last, 2, 0.0f, 0.0f, p->upsample_out, 0, p->H0, st);
+            ctx->launches++;
+            timer_mark(p, "Upsample", st);
+            set_view(p, HR_SHADOWS_OUT_UPSAMPLE, p->upsample_out, p->W0, p->H0, HR_FMT_R16F);
+            final_ptr = p->upsample_out; final_w = p->W0; final_h = p->H0; final_fmt = HR_FMT_R16F;
+        }
+    }
+    set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
+    HR_CHECK_LAUNCH(ctx);
+    return HR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ambient occlusion
+// ---------------------------------------------------------------------------------------------------------------
+void hr_ao_default_params(hr_ao_params* p)
+{
+    p->ray_length = 7.0f; p->bias = 0.3f; p->alpha = 0.01f; p->power = 1.2f; p->blur_radius = 4; p->denoise = 1;
+}
+
+int hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
+{
+    int rc = pass_common_create(ctx, width, height, scale, PASS_AO, out);
+    if (rc != HR_OK) return rc;
+    hr_pass*     p  = *out;
+    const size_t px = (size_t)p->W * p->H, mw = (p->W + 7) / 8, mh = (p->H + 3) / 4, tw = (p->W + 7) / 8, th = (p->H + 7) / 8;
+#define A(call) do { rc = (call); if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; } } while (0)
+    A(pass_alloc(p, p->mask, mw * mh));
+    for (int i = 0; i < 2; i++)
+    {
+        A(pass_alloc(p, p->ao_color[i], px));
+        A(pass_alloc(p, p->ao_len[i], px));
+        A(pass_alloc(p, p->ao_blur[i], px));
+    }
+    A(pass_alloc(p, p->tile_flags, tw * th));
+    if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
+#undef A
+    return HR_OK;
+}
+
+int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* stream)
+{
+    int rc = check_render_ready(p, f, prm, true);
+    if (rc != HR_OK) return rc;
+    hr_ctx* ctx = p->ctx;
+    HR_REQUIRE(ctx, p->kind == PASS_AO, HR_ERR_INVALID_ARG, "hr_ao_render: not an AO pass");
+    HR_REQUIRE(ctx, prm->blur_radius >= 1 && prm->blur_radius <= 16, HR_ERR_INVALID_ARG, "hr_ao_render: blur_radius must be 1..16");
+    cudaStream_t       st  = (cudaStream_t)stream;
+    const int          pp  = f->ping_pong;
+    const FrameConsts  fc  = make_consts(f);
+    const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
+    const int          row0 = 0, row1 = p->H;
+    const size_t       px = (size_t)p->W * p->H;
+    timer_begin(p, st);
+    if (p->first)
+    { // clear_images, ray_traced_ao.cpp:829-860
+        HR_CUDA(ctx, cudaMemsetAsync(p->ao_len[!pp], 0, px * sizeof(__half), st));
+        HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
+        p->first = false;
+    }
+    launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, row0, row1, st);
+    ctx->launches++;
+    timer_mark(p, "Ray Trace", st);
+    set_view(p, HR_AO_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = p->mask;
+    int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
+    if (prm->denoise)
+    {
+        launch_ao_temporal(cur, prev, p->mask, p->ao_color[!pp], p->ao_len[!pp], fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
+        ctx->launches++;
+        timer_mark(p, "Temporal Accumulation", st);
+        // bilateral_blur (:1032-1137): pass labelled "Vertical" uses direction (1,0), then (0,1)
+        launch_ao_blur(cur, p->ao_color[pp], p->tile_flags, f->z_buffer_params, 1, 0, prm->blur_radius, p->ao_blur[0], row0, row1, st);
+        launch_ao_blur(cur, p->ao_blur[0], p->tile_flags, f->z_buffer_params, 0, 1, prm->blur_radius, p->ao_blur[1], row0, row1, st);
+        ctx->launches += 2;
+        timer_mark(p, "Bilateral Blur", st);
+        set_view(p, HR_AO_OUT_TEMPORAL_ACCUMULATION, p->ao_color[pp], p->W, p->H, HR_FMT_R16F);
+        set_view(p, HR_AO_OUT_HISTORY_LENGTH, p->ao_len[pp], p->W, p->H, HR_FMT_R16F);
+        set_view(p, HR_AO_OUT_BILATERAL_BLUR, p->ao_blur[1], p->W, p->H, HR_FMT_R16F);
+        set_view(p, HR_AO_OUT_TILE_FLAGS, p->tile_flags, (p->W + 7) / 8, (p->H + 7) / 8, HR_FMT_R8_UINT);
+        final_ptr = p->ao_blur[1]; final_w = p->W; final_h = p->H; final_fmt = HR_FMT_R16F;
+        if (p->scale != HR_SCALE_FULL)
+        { // upsample (:918-957)
+            const GBufLevelDev g0 = level_view(ctx, pp, 0);
+            launch_upsample_scalar(g0, cur, p->ao_blur[1], 1, 1.0f, prm->power, p->upsample_out, 0, p->H0, st);
+            ctx->launches++;
+            timer_mark(p, "Upsample", st);
+            set_view(p, HR_AO_OUT_UPSAMPLE, p->upsample_out, p->W0, p->H0, HR_FMT_R16F);
+            final_ptr = p->upsample_out; final_w = p->W0; final_h = p->H0; final_fmt = HR_FMT_R16F;
+        }
+    }
+    set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
+    HR_CHECK_LAUNCH(ctx);
+    return HR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Common pass functions
+// ---------------------------------------------------------------------------------------------------------------
+int hr_pass_output(hr_pass* p, int which, hr_image* out)
+{
+    hr_ctx* ctx = p ? p->ctx : nullptr;
+    HR_REQUIRE(ctx, p && out && which >= 0 && which < 128, HR_ERR_INVALID_ARG, "hr_pass_output: bad argument");
+    const hr_pass::Img& v = p->out_view[which];
+    HR_REQUIRE(ctx, v.p != nullptr, HR_ERR_NOT_READY, "hr_pass_output: output not produced by the last render");
+    out->data = v.p; out->width = v.w; out->height = v.h; out->format = v.fmt;
+    return HR_OK;
+}
+
+int hr_pass_download(hr_pass* p, int which, void* dst, size_t bytes, void* stream)
+{
+    hr_image img;
+    int      rc = hr_pass_output(p, which, &img);
+    if (rc != HR_OK) return rc;
+    hr_ctx*      ctx  = p->ctx;
+    const size_t need = (size_t)img.width * img.height * texel_size(img.format);
+    HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download: byte count mismatch");
+    HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return HR_OK;
+}
+
+int hr_pass_reset_history(hr_pass* p) { if (!p) return HR_ERR_INVALID_ARG; p->first = true; return HR_OK; }
+
+int hr_pass_destroy(hr_pass* p)
+{
+    if (!p) return HR_ERR_INVALID_ARG;
+    cudaSetDevice(p->ctx->device);
+    cudaDeviceSynchronize();
+    for (void* a : p->allocs) cudaFree(a);
+    for (auto& e : p->timer.ev) cudaEventDestroy(e);
+    delete p;
+    return HR_OK;
+}
+
+int hr_pass_stage_times(hr_pass* p, const char** names, float* ms, int cap, int* n)
+{
+    if (!p || !n) return HR_ERR_INVALID_ARG;
+    *n = 0;
+    if (!p->ctx->profiling || p->timer.used < 2) return HR_OK;
+    cudaEventSynchronize(p->timer.ev[p->timer.used - 1]);
+    const int cnt = (int)p->timer.names.size();
+    for (int i = 0; i < cnt && i < cap; i++)
+    {
+        float t = 0.0f;
+        cudaEventElapsedTime(&t, p->timer.ev[i], p->timer.ev[i + 1]);
+        if (names) names[i] = p->timer.names[i].c_str();
+        if (ms) ms[i] = t;
+        (*n)++;
+    }
+    return HR_OK;
+}
+
+int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end)
+{
+    if (height <= 0 || world <= 0 || rank < 0 || rank >= world || !row_begin || !row_end) return HR_ERR_INVALID_ARG;
+    const int tiles = (height + 7) / 8;
+    const int base = tiles / world, rem = tiles % world;
+    const int t0 = rank * base + (rank < rem ? rank : rem), t1 = t0 + base + (rank < rem ? 1 : 0);
+    *row_begin = t0 * 8 < height ? t0 * 8 : height;
+    *row_end   = t1 * 8 < height ? t1 * 8 : height;
+    return HR_OK;
+}
+
+int hr_shard_config(hr_ctx* ctx, int rank, int world)
+{
+    HR_REQUIRE(ctx, ctx && world >= 1 && rank >= 0 && rank < world, HR_ERR_INVALID_ARG, "hr_shard_config: bad rank/world");
+    ctx->rank  = rank;
+    ctx->world = world;
+    return HR_OK;
+}
+
+} // extern "C"

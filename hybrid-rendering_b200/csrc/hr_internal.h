@@ -1,0 +1,173 @@
+// hr_internal.h — internal types of libhr_b200 (not part of the ABI).
+#pragma once
+#include "../../include/hr_api.h"
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#define HR_VERSION 100
+
+// ---- error plumbing -------------------------------------------------------------------------------
+void        hr_set_error(hr_ctx* ctx, const char* fmt, ...);
+#define HR_CUDA(ctx, expr)                                                                                         \
+    do {                                                                                                           \
+        cudaError_t _e = (expr);                                                                                   \
+        if (_e != cudaSuccess) {                                                                                   \
+            hr_set_error((ctx), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);       \
+            return _e == cudaErrorMemoryAllocation ? HR_ERR_OUT_OF_MEMORY : HR_ERR_CUDA;                           \
+        }                                                                                                          \
+    } while (0)
+#define HR_CHECK_LAUNCH(ctx) HR_CUDA(ctx, cudaGetLastError())
+#define HR_REQUIRE(ctx, cond, code, msg)                                   \
+    do {                                                                   \
+        if (!(cond)) { hr_set_error((ctx), "%s", (msg)); return (code); } \
+    } while (0)
+
+// ---- device-side views ----------------------------------------------------------------------------
+struct GBufLevelDev {          // one mip of one G-buffer slot
+    int            W, H;
+    const uint2*   gb2;        // RGBA16F as 4 halves = uint2
+    const uint2*   gb3;        // RGBA16F
+    const float*   depth;      // D32
+    const uint32_t* gb1;       // RGBA8 (may be null)
+};
+
+struct BvhDev {                // traversal view of hr_scene
+    const float4* nodes;       // 4 x float4 per node (see bvh_build.cu)
+    const float4* tris;        // 3 x float4 per triangle in leaf order: (v0,prim) (e1,0) (e2,0)
+    int           root_is_valid;
+};
+
+struct FrameConsts {           // what kernels need from hr_frame (passed by value as a kernel param)
+    float    view_proj_inverse[16];
+    float    prev_view_proj[16];
+    float    cam_pos[4];
+    hr_light light;
+    float    z_buffer_params[4];
+    float    camera_delta[3];
+    uint32_t num_frames;
+};
+
+// ---- objects ----------------------------------------------------------------------------------------
+struct GBufSlot {
+    void*  gb1[HR_MAX_MIPS]   = {};
+    void*  gb2[HR_MAX_MIPS]   = {};
+    void*  gb3[HR_MAX_MIPS]   = {};
+    float* depth[HR_MAX_MIPS] = {};
+    bool   owns_mip0          = true; // false when bound zero-copy
+    bool   valid              = false;
+};
+
+struct hr_ctx {
+    int          device = 0;
+    std::string  last_error;
+    // blue noise (device)
+    uint8_t*     d_sobol    = nullptr; // 256*4
+    uint8_t*     d_scr_rank = nullptr; // 128*128*4
+    bool         bn_set     = false;
+    // g-buffer
+    int          gb_w = 0, gb_h = 0;
+    GBufSlot     slot[2];
+    void*        owned_mip0[2][4] = {}; // library-owned mip0 storage (gb1,gb2,gb3,depth) kept when a slot is bound zero-copy
+    // scene
+    hr_scene*    scene = nullptr;
+    // sharding
+    int          rank = 0, world = 1;
+    // profiling
+    bool         profiling = false;
+    uint64_t     launches  = 0;
+    int          sm_count  = 148;
+    cudaStream_t build_stream = nullptr;
+};
+
+struct hr_scene {
+    hr_ctx*  ctx     = nullptr;
+    uint32_t n_tris  = 0;
+    uint32_t n_nodes = 0;
+    // inputs kept on device for rebuilds
+    float*    d_tri_verts = nullptr; // n*9 world-space
+    uint32_t* d_prim_inst = nullptr; // instance (= mesh id) per primitive
+    // build scratch
+    uint64_t* d_keys = nullptr, *d_keys_sorted = nullptr;
+    uint32_t* d_vals = nullptr, *d_vals_sorted = nullptr;
+    float*    d_tri_aabb = nullptr;  // n*6
+    int*      d_bounds_i = nullptr;  // 6 ordered-int min/max
+    int2*     d_children = nullptr;  // n-1
+    int2*     d_ranges   = nullptr;  // n-1 (first,last)
+    int*      d_parent   = nullptr;  // 2n-1
+    float*    d_node_aabb = nullptr; // (n-1)*6
+    int*      d_flags    = nullptr;  // n-1
+    void*     d_sort_tmp = nullptr;
+    size_t    sort_tmp_bytes = 0;
+    // outputs
+    float4*   d_nodes = nullptr;     // n_nodes*4
+    float4*   d_tris  = nullptr;     // n*3
+    // shading data (reflections / ddgi hit shading)
+    float4*   d_vnormals = nullptr;  // n*3 world-space vertex normals in primitive order
+    uint32_t* d_prim_mat = nullptr;  // material index per primitive
+    hr_material* d_materials = nullptr;
+    uint32_t  n_materials = 0;
+    hr_scene_info info {};
+};
+
+enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4 };
+
+struct StageTimer {
+    std::vector<std::string> names;
+    std::vector<cudaEvent_t> ev; // names.size()+1 events
+    int                      used = 0;
+};
+
+struct hr_pass {
+    hr_ctx* ctx  = nullptr;
+    int     kind = 0;
+    int     W = 0, H = 0;      // pass resolution
+    int     W0 = 0, H0 = 0;    // full resolution
+    int     scale = 0;         // = g_buffer_mip
+    bool    first = true;      // own m_first_frame (ray_traced_ao.cpp:829)
+    int     final_which = 0;
+    // generic image table: which -> (ptr, w, h, format)
+    struct Img { void* p = nullptr; int w = 0, h = 0, fmt = 0; };
+    Img     img[16];
+    Img     out_view[128];     // indexed by `which` (filled per render)
+    // shadows
+    uint32_t* mask = nullptr;
+    __half2*  temporal_out = nullptr;
+    uint2*    moments[2] = { nullptr, nullptr };
+    __half2*  prev_image = nullptr;
+    __half2*  atrous[2] = { nullptr, nullptr };
+    uint8_t*  tile_flags = nullptr;
+    __half*   upsample_out = nullptr;
+    // ao
+    __half*   ao_color[2] = { nullptr, nullptr };
+    __half*   ao_len[2] = { nullptr, nullptr };
+    __half*   ao_blur[2] = { nullptr, nullptr };
+    StageTimer timer;
+    std::vector<void*> allocs;
+};
+
+// ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
+int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st);
+int hr_bvh_build(hr_scene* sc, cudaStream_t st);
+BvhDev hr_bvh_view(const hr_scene* sc);
+
+void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
+                              uint32_t* mask, int row0, int row1, cudaStream_t st);
+void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
+                         const uint8_t* sr, uint32_t* mask, int row0, int row1, cudaStream_t st);
+void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st);
+void launch_trace_closest(const BvhDev& bvh, const float* rays, size_t n, float* out_t, uint32_t* out_prim, float* out_uv, cudaStream_t st);
+
+void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half2* prev_image, const uint2* prev_moments,
+                             const FrameConsts& fc, float alpha, float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags,
+                             int row0, int row1, cudaStream_t st);
+void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n,
+                           float sigma_z, float power, __half2* out, int row0, int row1, cudaStream_t st);
+void launch_upsample_scalar(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, int in_channels, float sky_value, float power,
+                            __half* out, int row0, int row1, cudaStream_t st);
+void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half* prev_ao, const __half* prev_len,
+                        const FrameConsts& fc, float alpha, __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
+void launch_ao_blur(const GBufLevelDev& g, const __half* in, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, __half* out,
+                    int row0, int row1, cudaStream_t st);

@@ -1,0 +1,255 @@
+// svgf_temporal.cu — temporal reprojection + accumulation for the bit-mask effects.
+//   K3  shadows/shadows_denoise_reprojection.comp:196-293  (+ reprojection.glsl:115-328, REPROJECTION_MOMENTS)
+//   K9  ao/ao_denoise_reprojection.comp:191-260            (history length in its own R16F image)
+// K2/K8 (reset_args) and the tile *lists* are replaced by a per-8x8-tile flag byte (1 = denoise list): the lists' order
+// is non-deterministic in the reference (atomicAdd) and only membership matters.
+//
+// One CTA = 32x8 pixels (4 reference tiles), one warp per pixel row => every G-buffer / history row access is a
+// contiguous 32-pixel span.  The 17x17 box mean of the packed ray mask is computed from 24 64-bit row bitmaps held in
+// shared memory: count = sum_rows popcll(row & window) — exact (integers <= 289), like the reference's float sums.
+#include "glsl_fast.cuh"
+#include "hr_internal.h"
+
+namespace {
+
+using namespace gf;
+
+struct Tap { float3 n; float mesh_id; float depth; };
+
+__device__ __forceinline__ bool inside(int x, int y, int W, int H) { return x >= 0 && y >= 0 && x < W && y < H; }
+
+__device__ __forceinline__ Tap fetch_prev(const GBufLevelDev& p, int x, int y)
+{
+    Tap t;
+    if (inside(x, y, p.W, p.H))
+    {
+        const size_t i  = (size_t)y * p.W + x;
+        const float2 e  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(p.gb2 + i)));
+        const float2 g3 = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(p.gb3 + i) + 1)); // (mesh id, linear z)
+        t.n       = octohedral_to_direction(e.x, e.y);
+        t.mesh_id = g3.x;
+        t.depth   = __ldg(p.depth + i);
+    }
+    else
+    { // texelFetch out of bounds => zeros
+        t.n       = octohedral_to_direction(0.0f, 0.0f);
+        t.mesh_id = 0.0f;
+        t.depth   = 0.0f;
+    }
+    return t;
+}
+
+// is_reprojection_valid, reprojection.glsl:52-67 (frame test hoisted by the caller)
+__device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 cur_n, float cur_mesh, float hu, float hv, const float* vpi)
+{
+    if (!(cur_mesh == t.mesh_id)) return false;
+    const float3 hp = world_position_from_depth(hu, hv, t.depth, vpi);
+    const float3 d  = make_float3(cur_pos.x - hp.x, cur_pos.y - hp.y, cur_pos.z - hp.z);
+    if (fabsf(dot3(d, cur_n)) > 5.0f) return false; // PLANE_DISTANCE
+    const float nd = fabsf(dot3(cur_n, t.n));
+    if (!(nd * nd > 0.1f)) return false; // NORMAL_DISTANCE
+    return true;
+}
+
+// MODE 0: shadows (history RG16F .r, moments RGBA16F (m1,m2,N,0)); MODE 1: AO (history R16F, length R16F)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const void* __restrict__ hist_img,
+                                                   const void* __restrict__ hist_aux, FrameConsts fc, float alpha_p, float moments_alpha_p,
+                                                   void* __restrict__ out_img, void* __restrict__ out_aux, uint8_t* __restrict__ tile_flags, int row0, int row1)
+{
+    __shared__ unsigned long long s_rows[24];
+    __shared__ uint32_t           s_flags;
+    const int W = cur.W, H = cur.H, MW = (W + 7) >> 3, MH = (H + 3) >> 2;
+    const int x0 = blockIdx.x * 32, y0 = row0 + blockIdx.y * 8;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const uint32_t oob_word = MODE == 0 ? 0u : 0xFFFFFFFFu; // ao_denoise_reprojection.comp:111-112
+
+    if (threadIdx.x == 0) s_flags = 0;
+    if (threadIdx.x < 24)
+    {
+        const int          r  = threadIdx.x;              // region row, pixel y = y0 - 8 + r
+        const int          my = (y0 >> 2) - 2 + (r >> 2); // mask row
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int c = 0; c < 6; c++)
+        {
+            const int      mx = (x0 >> 3) - 1 + c;
+            const uint32_t w  = (mx < 0 || my < 0 || mx >= MW || my >= MH) ? oob_word : __ldg(mask + (size_t)my * MW + mx);
+            bits |= (unsigned long long)((w >> ((r & 3) * 8)) & 0xFFu) << (c * 8);
+        }
+        s_rows[r] = bits;
+    }
+    __syncthreads();
+
+    const int x = x0 + lx, y = y0 + ly;
+    bool      flag = false;
+    if (x < W && y < H && y < row1)
+    {
+        // neighborhood_mean: window columns lx .. lx+16 of the 48-wide region, rows ly .. ly+16
+        const unsigned long long win = 0x1FFFFull << lx;
+        int cnt = 0;
+#pragma unroll
+        for (int r = 0; r < 17; r++) cnt += __popcll(s_rows[ly + r] & win);
+        const float mean = (float)cnt / 289.0f;
+
+        const size_t idx   = (size_t)y * W + x;
+        const float  depth = __ldg(cur.depth + idx);
+        float        o0 = 0.0f, o1 = 0.0f, m0 = 0.0f, m1 = 0.0f, hlen = 0.0f;
+        if (MODE == 1) o0 = 1.0f;
+        if (depth != 1.0f)
+        {
+            const float vis = (float)((s_rows[ly + 8] >> (lx + 8)) & 1ull);
+            // ---- reproject(), reprojection.glsl:115-328 ----
+            const float  fw = (float)W, fh = (float)H;
+            const float  tu = ((float)x + 0.5f) / fw, tv = ((float)y + 0.5f) / fh;
+            const float4 g2 = h4_to_f4(__ldg(cur.gb2 + idx));
+            const float2 g3 = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(cur.gb3 + idx) + 1));
+            const float3 cn = octohedral_to_direction(g2.x, g2.y);
+            const float  cmesh = g3.x;
+            const float3 cpos  = world_position_from_depth(tu, tv, depth, fc.view_proj_inverse);
+            const float  hfx = (float)x + g2.z * fw, hfy = (float)y + g2.w * fh;   // history_coord_floor (:176)
+            const int    hcx = (int)(hfx + 0.5f), hcy = (int)(hfy + 0.5f);         // history_coord (:175)
+            const float  hu = tu + g2.z, hv = tv + g2.w;                           // history_tex_coord (:177)
+            const bool   in_frame = inside(hcx, hcy, W, H);                        // out_of_frame_disocclusion_check on history_coord
+            const int    bx = (int)hfx, by = (int)hfy;                             // ivec2(history_coord_floor) truncates
+
+            float hcol = 0.0f, hm0 = 0.0f, hm1 = 0.0f;
+            bool  valid = false;
+            if (in_frame)
+            {
+                const float fx = hfx - floorf(hfx), fy = hfy - floorf(hfy);
+                const float w4[4] = { (1 - fx) * (1 - fy), fx * (1 - fy), (1 - fx) * fy, fx * fy };
+                float sumw = 0.0f;
+                bool  any  = false;
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                {
+                    const int px = bx + (s & 1), py = by + (s >> 1);
+                    const Tap t  = fetch_prev(prev, px, py);
+                    if (tap_valid(t, cpos, cn, cmesh, hu, hv, fc.view_proj_inverse))
+                    {
+                        any = true;
+                        float hv0 = 0.0f, a0 = 0.0f, a1 = 0.0f;
+                        if (inside(px, py, W, H))
+                        {
+                            const size_t pi = (size_t)py * W + px;
+                            if (MODE == 0)
+                            {
+                                hv0 = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi)).x;
+                                const float2 mm = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi)));
+                                a0 = mm.x;
+                                a1 = mm.y;
+                            }
+                            else hv0 = __half2float(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
+                        }
+                        hcol += w4[s] * hv0;
+                        hm0 += w4[s] * a0;
+                        hm1 += w4[s] * a1;
+                        sumw += w4[s];
+                    }
+                }
+                if (any)
+                {
+                    valid = sumw >= 0.01f;
+                    if (valid) { hcol /= sumw; hm0 /= sumw; hm1 /= sumw; }
+                    else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
+                }
+                if (!valid)
+                {
+                    float cntv = 0.0f;
+                    for (int yy = -1; yy <= 1; yy++)
+                        for (int xx = -1; xx <= 1; xx++)
+                        {
+                            const int px = hcx + xx, py = hcy + yy;
+                            const Tap t  = fetch_prev(prev, px, py);
+                            if (tap_valid(t, cpos, cn, cmesh, hu, hv, fc.view_proj_inverse))
+                            {
+                                if (inside(px, py, W, H))
+                                {
+                                    const size_t pi = (size_t)py * W + px;
+                                    if (MODE == 0)
+                                    {
+                                        hcol += h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi)).x;
+                                        const float2 mm = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi)));
+                                        hm0 += mm.x;
+                                        hm1 += mm.y;
+                                    }
+                                    else hcol += __half2float(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
+                                }
+                                cntv += 1.0f;
+                            }
+                        }
+                    if (cntv > 0.0f) { valid = true; hcol /= cntv; hm0 /= cntv; hm1 /= cntv; }
+                }
+            }
+            float hist_len = 0.0f;
+            if (valid)
+            { // history_coord is inside the frame here
+                const size_t hi = (size_t)hcy * W + hcx;
+                if (MODE == 0) hist_len = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + hi) + 1)).x;
+                else hist_len = __half2float(__ldg(reinterpret_cast<const __half*>(hist_aux) + hi));
+            }
+            else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
+            // ---- accumulate ----
+            hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
+            if (valid)
+            {
+                const float sd = sqrtf(fmaxf(mean - mean * mean, 0.0f));
+                hcol           = fminf(fmaxf(hcol, mean - 0.5f * sd), mean + 0.5f * sd);
+            }
+            const float alpha = valid ? fmaxf(alpha_p, 1.0f / hlen) : 1.0f;
+            if (MODE == 0)
+            {
+                const float am = valid ? fmaxf(moments_alpha_p, 1.0f / hlen) : 1.0f;
+                m0 = hm0 * (1.0f - am) + vis * am;
+                m1 = hm1 * (1.0f - am) + (vis * vis) * am;
+                o1 = fmaxf(0.0f, m1 - m0 * m0);
+            }
+            o0 = hcol * (1.0f - alpha) + vis * alpha;
+        }
+        if (MODE == 0)
+        {
+            reinterpret_cast<uint32_t*>(out_img)[idx] = f2_to_h2(o0, o1);
+            reinterpret_cast<uint2*>(out_aux)[idx]    = make_uint2(f2_to_h2(m0, m1), f2_to_h2(hlen, 0.0f));
+            flag = depth != 1.0f && o0 > 0.0f;
+        }
+        else
+        {
+            reinterpret_cast<__half*>(out_img)[idx] = __float2half_rn(o0);
+            reinterpret_cast<__half*>(out_aux)[idx] = __float2half_rn(hlen);
+            flag = o0 < 1.0f;
+        }
+    }
+    // tile classification: 4 tiles of 8 columns per CTA
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, flag);
+    if (lx == 0 && b)
+    {
+        uint32_t t = ((b & 0xFFu) ? 1u : 0u) | ((b & 0xFF00u) ? 2u : 0u) | ((b & 0xFF0000u) ? 4u : 0u) | ((b & 0xFF000000u) ? 8u : 0u);
+        atomicOr(&s_flags, t);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4)
+    {
+        const int tx = (x0 >> 3) + threadIdx.x, ty = y0 >> 3, TW = (W + 7) >> 3;
+        if (tx < TW && y0 < H && y0 < row1) tile_flags[(size_t)ty * TW + tx] = (s_flags >> threadIdx.x) & 1u;
+    }
+}
+
+} // namespace
+
+void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half2* prev_image, const uint2* prev_moments,
+                             const FrameConsts& fc, float alpha, float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags,
+                             int row0, int row1, cudaStream_t st)
+{
+    if (row1 <= row0) return;
+    dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
+    k_temporal<0><<<grid, 256, 0, st>>>(cur, prev, mask, prev_image, prev_moments, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
+}
+
+void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half* prev_ao, const __half* prev_len,
+                        const FrameConsts& fc, float alpha, __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
+{
+    if (row1 <= row0) return;
+    dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
+    k_temporal<1><<<grid, 256, 0, st>>>(cur, prev, mask, prev_ao, prev_len, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
+}

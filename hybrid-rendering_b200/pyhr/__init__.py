@@ -1,0 +1,357 @@
+"""pyhr — thin ctypes binding over the C ABI (include/hr_api.h) and the synthetic-input library (host/synth.h).
+
+Used by tests/ and bench.py only; the product is the C ABI + CUDA kernels.  PyTorch appears solely as a provider of
+device memory / streams where a caller wants to hand device pointers to the ABI.  There is no CPU fallback: loading
+or initialising fails loudly when the CUDA library or a GPU is missing.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.dirname(_HERE)
+BUILD_DIR = os.path.join(PKG_ROOT, "build")
+LIB_PRODUCT = os.path.join(BUILD_DIR, "libhr_b200.so")
+LIB_SYNTH = os.path.join(BUILD_DIR, "libhr_synth.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_u8_p = C.POINTER(C.c_uint8)
+c_u16_p = C.POINTER(C.c_uint16)
+c_u32_p = C.POINTER(C.c_uint32)
+
+
+# ---------------------------------------------------------------------------------------------- ABI structs
+class hr_light(C.Structure):
+    _fields_ = [("data0", C.c_float * 4), ("data1", C.c_float * 4), ("data2", C.c_float * 4), ("data3", C.c_float * 4)]
+
+
+class hr_ubo(C.Structure):
+    _fields_ = [("view_inverse", C.c_float * 16), ("proj_inverse", C.c_float * 16), ("view_proj_inverse", C.c_float * 16),
+                ("prev_view_proj", C.c_float * 16), ("view_proj", C.c_float * 16), ("cam_pos", C.c_float * 4),
+                ("current_prev_jitter", C.c_float * 4), ("light", hr_light)]
+
+
+class hr_frame(C.Structure):
+    _fields_ = [("ubo", hr_ubo), ("num_frames", C.c_uint32), ("ping_pong", C.c_int32), ("first_frame", C.c_int32),
+                ("z_buffer_params", C.c_float * 4), ("camera_delta", C.c_float * 3), ("frame_time", C.c_float)]
+
+
+class hr_vertex(C.Structure):
+    _fields_ = [("position", C.c_float * 4), ("tex_coord", C.c_float * 4), ("normal", C.c_float * 4), ("tangent", C.c_float * 4),
+                ("bitangent", C.c_float * 4)]
+
+
+class hr_material(C.Structure):
+    _fields_ = [("albedo", C.c_float * 4), ("emissive", C.c_float * 4), ("roughness", C.c_float), ("metallic", C.c_float), ("_pad", C.c_float * 2)]
+
+
+class hr_instance(C.Structure):
+    _fields_ = [("model", C.c_float * 16), ("first_index", C.c_uint32), ("index_count", C.c_uint32), ("base_vertex", C.c_uint32),
+                ("material_idx", C.c_uint32)]
+
+
+class hr_scene_info(C.Structure):
+    _fields_ = [("n_triangles", C.c_uint64), ("n_nodes", C.c_uint64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
+                ("build_ms", C.c_float)]
+
+
+class hr_gbuffer_desc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("gb1", C.c_void_p), ("gb2", C.c_void_p), ("gb3", C.c_void_p), ("depth", C.c_void_p)]
+
+
+class hr_image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("format", C.c_int32)]
+
+
+class hr_shadows_params(C.Structure):
+    _fields_ = [("bias", C.c_float), ("alpha", C.c_float), ("moments_alpha", C.c_float), ("phi_visibility", C.c_float), ("phi_normal", C.c_float),
+                ("sigma_depth", C.c_float), ("power", C.c_float), ("radius", C.c_int32), ("filter_iterations", C.c_int32),
+                ("feedback_iteration", C.c_int32), ("denoise", C.c_int32)]
+
+
+class hr_ao_params(C.Structure):
+    _fields_ = [("ray_length", C.c_float), ("bias", C.c_float), ("alpha", C.c_float), ("power", C.c_float), ("blur_radius", C.c_int32),
+                ("denoise", C.c_int32)]
+
+
+class hrs_light_desc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("rot_y_deg", C.c_float), ("rot_x_deg", C.c_float), ("position", C.c_float * 3), ("radius", C.c_float),
+                ("intensity", C.c_float), ("color", C.c_float * 3), ("cone_inner_deg", C.c_float), ("cone_outer_deg", C.c_float)]
+
+
+HR_FMT = {1: ("<u4", 1), 2: ("<f2", 1), 3: ("<f2", 2), 4: ("<f2", 4), 5: ("u1", 1)}  # hr_format -> (dtype, channels)
+
+# every symbol include/hr_api.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "hr_init", "hr_shutdown", "hr_last_error", "hr_version", "hr_bluenoise_set", "hr_scene_build", "hr_scene_destroy", "hr_scene_set_current",
+    "hr_scene_get_info", "hr_scene_rebuild", "hr_trace_any", "hr_trace_closest", "hr_gbuffer_create", "hr_gbuffer_upload",
+    "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
+    "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
+    "hr_pass_destroy", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows",
+]
+
+_product = None
+_synth = None
+
+
+def load_product():
+    """dlopen the CUDA library.  Raises (never falls back) if it has not been built."""
+    global _product
+    if _product is None:
+        if not os.path.exists(LIB_PRODUCT):
+            raise RuntimeError(f"{LIB_PRODUCT} not found: build it with `make -C {PKG_ROOT}` (no CPU fallback exists)")
+        lib = C.CDLL(LIB_PRODUCT)
+        lib.hr_last_error.restype = C.c_char_p
+        lib.hr_last_error.argtypes = [C.c_void_p]
+        lib.hr_ctx_launch_count.restype = C.c_uint64
+        lib.hr_ctx_launch_count.argtypes = [C.c_void_p]
+        _product = lib
+    return _product
+
+
+def load_synth():
+    global _synth
+    if _synth is None:
+        if not os.path.exists(LIB_SYNTH):
+            raise RuntimeError(f"{LIB_SYNTH} not found: build it with `make -C {PKG_ROOT}`")
+        lib = C.CDLL(LIB_SYNTH)
+        lib.hrs_scene_create.restype = C.c_void_p
+        lib.hrs_scene_create.argtypes = [C.c_int, C.c_int, C.c_uint32]
+        lib.hrs_scene_destroy.argtypes = [C.c_void_p]
+        lib.hrs_scene_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+        for n in ("hrs_scene_vertices", "hrs_scene_indices", "hrs_scene_instances", "hrs_scene_materials"):
+            getattr(lib, n).restype = C.c_void_p
+            getattr(lib, n).argtypes = [C.c_void_p]
+        lib.hrs_scene_bounds.argtypes = [C.c_void_p, c_float_p, c_float_p]
+        lib.hrs_scene_world_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hrs_default_light.argtypes = [C.POINTER(hrs_light_desc)]
+        lib.hrs_make_frame.argtypes = [C.POINTER(hr_frame), c_float_p, c_float_p, C.c_int, C.c_int, C.POINTER(hrs_light_desc), C.POINTER(hr_frame), C.c_uint32]
+        lib.hrs_write_gbuffer.argtypes = [C.c_void_p, C.POINTER(hr_frame), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hrs_blue_noise.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p]
+        _synth = lib
+    return _synth
+
+
+class HrError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------------------------------------- synthetic inputs
+SCENE_SINGLE_TRIANGLE, SCENE_GROUND_PLANE, SCENE_SHADOWS_TEST, SCENE_ARCADE = 0, 1, 2, 3
+
+
+class SynthScene:
+    def __init__(self, kind, target_tris=0, seed=7):
+        self.lib = load_synth()
+        self.h = self.lib.hrs_scene_create(kind, target_tris, seed)
+        if not self.h:
+            raise HrError("hrs_scene_create failed")
+        c = [C.c_uint64() for _ in range(4)]
+        self.lib.hrs_scene_counts(self.h, *[C.byref(x) for x in c])
+        self.n_vertices, self.n_indices, self.n_instances, self.n_materials = [int(x.value) for x in c]
+        self.n_tris = self.n_indices // 3
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.hrs_scene_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def raw(self):
+        """(vertices_ptr, indices_ptr, instances_ptr, materials_ptr) host pointers valid while self lives."""
+        L = self.lib
+        return (L.hrs_scene_vertices(self.h), L.hrs_scene_indices(self.h), L.hrs_scene_instances(self.h), L.hrs_scene_materials(self.h))
+
+    def world_triangles(self):
+        tri = np.empty((self.n_tris, 9), np.float32)
+        inst = np.empty(self.n_tris, np.uint32)
+        self.lib.hrs_scene_world_triangles(self.h, _ptr(tri), _ptr(inst))
+        return tri, inst
+
+    def bounds(self):
+        mn = (C.c_float * 3)()
+        mx = (C.c_float * 3)()
+        self.lib.hrs_scene_bounds(self.h, mn, mx)
+        return np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+
+def default_light(**kw):
+    l = hrs_light_desc()
+    load_synth().hrs_default_light(C.byref(l))
+    for k, v in kw.items():
+        if isinstance(v, (tuple, list)):
+            for i, x in enumerate(v):
+                getattr(l, k)[i] = x
+        else:
+            setattr(l, k, v)
+    return l
+
+
+def make_frame(cam_pos, cam_target, W, H, prev=None, num_frames=0, light=None):
+    f = hr_frame()
+    p = (C.c_float * 3)(*cam_pos)
+    t = (C.c_float * 3)(*cam_target)
+    load_synth().hrs_make_frame(C.byref(f), p, t, W, H, C.byref(light) if light is not None else None, C.byref(prev) if prev is not None else None,
+                                num_frames)
+    return f
+
+
+class GBufferHost:
+    """mip-0 G-buffer in host memory in the reference's formats."""
+
+    def __init__(self, W, H, pinned=False):
+        self.W, self.H = W, H
+        if pinned:
+            import torch
+            self._t = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory(), torch.empty((H, W, 4), dtype=torch.int16).pin_memory(),
+                       torch.empty((H, W, 4), dtype=torch.int16).pin_memory(), torch.empty((H, W), dtype=torch.float32).pin_memory()]
+            self.gb1 = self._t[0].numpy()
+            self.gb2 = self._t[1].numpy().view(np.uint16)
+            self.gb3 = self._t[2].numpy().view(np.uint16)
+            self.depth = self._t[3].numpy()
+        else:
+            self.gb1 = np.zeros((H, W, 4), np.uint8)
+            self.gb2 = np.zeros((H, W, 4), np.uint16)
+            self.gb3 = np.zeros((H, W, 4), np.uint16)
+            self.depth = np.zeros((H, W), np.float32)
+
+    def desc(self):
+        return hr_gbuffer_desc(self.W, self.H, _ptr(self.gb1), _ptr(self.gb2), _ptr(self.gb3), _ptr(self.depth))
+
+    def nbytes(self):
+        return self.gb1.nbytes + self.gb2.nbytes + self.gb3.nbytes + self.depth.nbytes
+
+
+def write_gbuffer(scene: SynthScene, frame: hr_frame, W, H, out: GBufferHost = None, pinned=False):
+    g = out if out is not None else GBufferHost(W, H, pinned)
+    load_synth().hrs_write_gbuffer(scene.h, C.byref(frame), W, H, _ptr(g.gb1), _ptr(g.gb2), _ptr(g.gb3), _ptr(g.depth))
+    return g
+
+
+def blue_noise(seed=1234):
+    sobol = np.empty((256, 4), np.uint8)
+    sr = np.empty((128, 128, 4), np.uint8)
+    load_synth().hrs_blue_noise(seed, _ptr(sobol), _ptr(sr))
+    return sobol, sr
+
+
+# ---------------------------------------------------------------------------------------------- product wrappers
+class Context:
+    def __init__(self, device=0):
+        self.lib = load_product()
+        h = C.c_void_p()
+        rc = self.lib.hr_init(device, C.byref(h))
+        if rc != 0:
+            raise HrError(f"hr_init failed ({rc}): {self.lib.hr_last_error(None).decode()}")
+        self.h = h
+        self._keep = []
+
+    def check(self, rc, what=""):
+        if rc != 0:
+            raise HrError(f"{what} failed ({rc}): {self.lib.hr_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.hr_shutdown(self.h)
+            self.h = None
+
+    def set_bluenoise(self, sobol, sr):
+        self.check(self.lib.hr_bluenoise_set(self.h, _ptr(np.ascontiguousarray(sobol)), _ptr(np.ascontiguousarray(sr))), "hr_bluenoise_set")
+
+    def build_scene(self, s: SynthScene):
+        v, i, inst, m = s.raw()
+        out = C.c_void_p()
+        self.check(self.lib.hr_scene_build(self.h, C.c_void_p(v), C.c_size_t(s.n_vertices), C.c_void_p(i), C.c_size_t(s.n_indices), C.c_void_p(inst),
+                                           C.c_size_t(s.n_instances), C.c_void_p(m), C.c_size_t(s.n_materials), C.byref(out)), "hr_scene_build")
+        self.check(self.lib.hr_scene_set_current(self.h, out), "hr_scene_set_current")
+        return out
+
+    def scene_info(self, scene):
+        info = hr_scene_info()
+        self.check(self.lib.hr_scene_get_info(scene, C.byref(info)), "hr_scene_get_info")
+        return info
+
+    def gbuffer_create(self, W, H):
+        self.check(self.lib.hr_gbuffer_create(self.h, W, H), "hr_gbuffer_create")
+
+    def gbuffer_upload(self, slot, g: GBufferHost, stream=0):
+        d = g.desc()
+        self.check(self.lib.hr_gbuffer_upload(self.h, slot, C.byref(d), C.c_void_p(stream)), "hr_gbuffer_upload")
+
+    def gbuffer_copy_from_device(self, slot, desc: hr_gbuffer_desc, stream=0):
+        self.check(self.lib.hr_gbuffer_copy_from_device(self.h, slot, C.byref(desc), C.c_void_p(stream)), "hr_gbuffer_copy_from_device")
+
+    def gbuffer_bind_device(self, slot, desc: hr_gbuffer_desc, stream=0):
+        self.check(self.lib.hr_gbuffer_bind_device(self.h, slot, C.byref(desc), C.c_void_p(stream)), "hr_gbuffer_bind_device")
+
+    def gbuffer_download(self, slot, mip, which, W, H):
+        w, h = W, H
+        for _ in range(mip):
+            w, h = max(w // 2, 1), max(h // 2, 1)
+        if which == 0:
+            a = np.empty((h, w), np.float32)
+        elif which == 1:
+            a = np.empty((h, w, 4), np.uint8)
+        else:
+            a = np.empty((h, w, 4), np.uint16)
+        self.check(self.lib.hr_gbuffer_download(self.h, slot, mip, which, _ptr(a), C.c_size_t(a.nbytes)), "hr_gbuffer_download")
+        return a
+
+    def launch_count(self):
+        return int(self.lib.hr_ctx_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self.lib.hr_ctx_set_profiling(self.h, int(on))
+
+
+class Pass:
+    def __init__(self, ctx: Context, kind, W, H, scale):
+        self.ctx, self.kind, self.lib = ctx, kind, ctx.lib
+        h = C.c_void_p()
+        create = {"shadows": self.lib.hr_shadows_create, "ao": self.lib.hr_ao_create}[kind]
+        ctx.check(create(ctx.h, W, H, scale, C.byref(h)), f"hr_{kind}_create")
+        self.h = h
+        if kind == "shadows":
+            self.params = hr_shadows_params()
+            self.lib.hr_shadows_default_params(C.byref(self.params))
+        else:
+            self.params = hr_ao_params()
+            self.lib.hr_ao_default_params(C.byref(self.params))
+
+    def render(self, frame: hr_frame, stream=0):
+        fn = {"shadows": self.lib.hr_shadows_render, "ao": self.lib.hr_ao_render}[self.kind]
+        self.ctx.check(fn(self.h, C.byref(frame), C.byref(self.params), C.c_void_p(stream)), f"hr_{self.kind}_render")
+
+    def output(self, which):
+        img = hr_image()
+        self.ctx.check(self.lib.hr_pass_output(self.h, which, C.byref(img)), "hr_pass_output")
+        return img
+
+    def download(self, which, stream=0, out=None):
+        img = self.output(which)
+        dt, ch = HR_FMT[img.format]
+        shape = (img.height, img.width) if ch == 1 else (img.height, img.width, ch)
+        a = out if out is not None else np.empty(shape, np.dtype(dt))
+        self.ctx.check(self.lib.hr_pass_download(self.h, which, _ptr(a), C.c_size_t(a.nbytes), C.c_void_p(stream)), "hr_pass_download")
+        return a
+
+    def stage_times(self):
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = C.c_int()
+        self.ctx.check(self.lib.hr_pass_stage_times(self.h, names, ms, 32, C.byref(n)), "hr_pass_stage_times")
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    def reset_history(self):
+        self.lib.hr_pass_reset_history(self.h)
+
+    def destroy(self):
+        if self.h:
+            self.lib.hr_pass_destroy(self.h)
+            self.h = None

@@ -1,0 +1,287 @@
+/*
+ * hr_api.h — C ABI of the B200-native ray-trace + SVGF hot path.
+ *
+ * This is the drop-in boundary for the four render passes of diharaw/hybrid-rendering
+ * (RayTracedShadows, RayTracedAO, RayTracedReflections, DDGI).  The reference has no
+ * FFI of its own; its seam is the C++ pass-class interface
+ *     Pass(backend, CommonResources*, GBuffer*, RayTraceScale)   src/ray_traced_shadows.h:23
+ *     void render(cmd_buf)                                       src/ray_traced_shadows.h:26
+ *     DescriptorSet::Ptr output_ds()                             src/ray_traced_shadows.h:28
+ * and each entry point below cites the reference interface it replaces.
+ *
+ * Conventions: every function returns 0 (HR_OK) or a negative hr_status; the message
+ * is available from hr_last_error().  All pointers are plain; "device" pointers are CUDA
+ * device addresses on the context's GPU.  All work is enqueued on the caller's stream
+ * (a cudaStream_t passed as void*); no hidden synchronisation except where documented
+ * (hr_*_download, hr_scene_build).  One hr_ctx per GPU; a ctx is not thread-safe.
+ * No torch / C++ types cross this boundary.
+ */
+#ifndef HR_API_H
+#define HR_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HR_API __attribute__((visibility("default")))
+
+typedef enum hr_status {
+    HR_OK                = 0,
+    HR_ERR_INVALID_ARG   = -1,
+    HR_ERR_CUDA          = -2,
+    HR_ERR_OUT_OF_MEMORY = -3,
+    HR_ERR_NOT_READY     = -4, /* e.g. render before scene / g-buffer / blue-noise were set */
+    HR_ERR_UNSUPPORTED   = -5,
+    HR_ERR_NCCL          = -6
+} hr_status;
+
+typedef struct hr_ctx   hr_ctx;   /* CommonResources + Backend equivalent, one per GPU (src/common.h:181-243) */
+typedef struct hr_scene hr_scene; /* RayTracedScene equivalent: device LBVH instead of BLAS/TLAS            */
+typedef struct hr_pass  hr_pass;  /* one of the four pass objects                                           */
+
+/* ------------------------------------------------------------------------------------------------
+ * Plain-data mirrors of the reference's per-frame constants
+ * ---------------------------------------------------------------------------------------------- */
+
+/* struct Light, src/common.h:106-158: data0 = dir.xyz|intensity, data1 = pos.xyz|radius,
+ * data2 = color.rgb, data3 = type|cos_outer|cos_inner.  data0.xyz points TOWARDS the light
+ * (src/main.cpp:963). */
+typedef struct hr_light {
+    float data0[4];
+    float data1[4];
+    float data2[4];
+    float data3[4];
+} hr_light;
+
+enum { HR_LIGHT_DIRECTIONAL = 0, HR_LIGHT_POINT = 1, HR_LIGHT_SPOT = 2 }; /* src/shaders/common.glsl:23-25 */
+
+/* struct UBO, src/common.h:161-179 (416 bytes).  Matrices are column-major like glm. */
+typedef struct hr_ubo {
+    float    view_inverse[16];
+    float    proj_inverse[16];
+    float    view_proj_inverse[16];
+    float    prev_view_proj[16];
+    float    view_proj[16];
+    float    cam_pos[4];
+    float    current_prev_jitter[4];
+    hr_light light;
+} hr_ubo;
+
+/* The CommonResources fields a pass pulls every frame (src/common.h:186-191). */
+typedef struct hr_frame {
+    hr_ubo   ubo;
+    uint32_t num_frames;         /* CommonResources::num_frames; blue-noise sample index            */
+    int32_t  ping_pong;          /* CommonResources::ping_pong; selects current/history G-buffer    */
+    int32_t  first_frame;        /* CommonResources::first_frame                                    */
+    float    z_buffer_params[4]; /* src/main.cpp:253-254                                            */
+    float    camera_delta[3];    /* CommonResources::camera_delta (reflections temporal)            */
+    float    frame_time;         /* CommonResources::frame_time                                     */
+} hr_frame;
+
+/* RayTraceScale, src/common.h:39-44 */
+enum { HR_SCALE_FULL = 0, HR_SCALE_HALF = 1, HR_SCALE_QUARTER = 2 };
+
+/* ------------------------------------------------------------------------------------------------
+ * Context  (replaces dw::vk::Backend + CommonResources construction, src/common.cpp:302-322)
+ * ---------------------------------------------------------------------------------------------- */
+HR_API int         hr_init(int device, hr_ctx** out);
+HR_API int         hr_shutdown(hr_ctx* ctx);
+HR_API const char* hr_last_error(hr_ctx* ctx); /* ctx may be NULL: returns the last global error */
+HR_API int         hr_version(void);
+
+/* Blue-noise tables (src/blue_noise.cpp:5-33, sampled by src/shaders/bnd_sampler.glsl:4-24).
+ * sobol: 256 x RGBA8 (sobol_256_4d.png); scrambling_ranking: 128 x 128 x RGBA8 (…_1spp.png). Host pointers. */
+HR_API int hr_bluenoise_set(hr_ctx* ctx, const uint8_t* sobol_256x4, const uint8_t* scrambling_ranking_128x128x4);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scene  (replaces dw::RayTracedScene + driver BLAS/TLAS build,
+ *         external/dwSampleFramework/extras/ray_traced_scene.cpp:196-248, src/mesh.cpp:169-231)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* dw::Vertex, external/dwSampleFramework/include/mesh.h:16-23 (80 bytes) */
+typedef struct hr_vertex {
+    float position[4];
+    float tex_coord[4];
+    float normal[4];
+    float tangent[4];
+    float bitangent[4];
+} hr_vertex;
+
+/* Material constants used when no textures are bound (src/shaders/scene_descriptor_set.glsl:180-229). */
+typedef struct hr_material {
+    float albedo[4];   /* linear rgb, a */
+    float emissive[4];
+    float roughness;
+    float metallic;
+    float _pad[2];
+} hr_material;
+
+/* One (instance, sub-mesh) draw range: model matrix + index range + material.
+ * ray_traced_scene.cpp:573-613 (instance data), mesh.h SubMesh. */
+typedef struct hr_instance {
+    float    model[16]; /* column-major */
+    uint32_t first_index;
+    uint32_t index_count;
+    uint32_t base_vertex;
+    uint32_t material_idx;
+} hr_instance;
+
+/* Builds the device LBVH (Morton sort + Karras hierarchy + bottom-up fit) over all instances'
+ * world-space triangles.  Host pointers in; synchronises the context's build stream before returning. */
+HR_API int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, const uint32_t* indices, size_t n_indices,
+                          const hr_instance* instances, size_t n_instances, const hr_material* materials, size_t n_materials,
+                          hr_scene** out);
+HR_API int hr_scene_destroy(hr_scene* scene);
+HR_API int hr_scene_set_current(hr_ctx* ctx, hr_scene* scene); /* CommonResources::current_scene() */
+/* Build statistics / debug: n_tris, n_nodes, build time of the last build in ms. */
+typedef struct hr_scene_info {
+    uint64_t n_triangles;
+    uint64_t n_nodes;
+    float    bounds_min[3];
+    float    bounds_max[3];
+    float    build_ms;
+} hr_scene_info;
+HR_API int hr_scene_get_info(hr_scene* scene, hr_scene_info* out);
+/* Re-run only the device build (the reference rebuilds its TLAS every frame, src/main.cpp:74). */
+HR_API int hr_scene_rebuild(hr_scene* scene, void* stream);
+
+/* Generic ray query against the current scene, for tests of the traversal kernel.
+ * rays: n x 8 floats {ox,oy,oz,tmin, dx,dy,dz,tmax} (device).  any-hit: out_hit[n] uint32 (1 = hit).
+ * closest: out_t[n] float (tmax if miss), out_prim[n] uint32 (0xFFFFFFFF if miss), out_uv[n*2]. */
+HR_API int hr_trace_any(hr_ctx* ctx, const float* d_rays, size_t n, uint32_t* d_out_hit, void* stream);
+HR_API int hr_trace_closest(hr_ctx* ctx, const float* d_rays, size_t n, float* d_out_t, uint32_t* d_out_prim, float* d_out_uv, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * G-buffer  (replaces GBuffer::output_ds()/history_ds(), src/g_buffer.cpp:201-211; formats :254-263)
+ *   gb1   RGBA8   albedo.rgb | metallic
+ *   gb2   RGBA16F oct normal.xy | motion.xy (prev_uv - cur_uv)
+ *   gb3   RGBA16F roughness | curvature | mesh id | linear z (view-space w; -1 = sky)
+ *   depth D32     z_clip / w_clip, 1.0 = sky
+ * Two slots mirror the reference's double buffering: slot[frame.ping_pong] is "current",
+ * slot[!frame.ping_pong] is "history".
+ * ---------------------------------------------------------------------------------------------- */
+#define HR_MAX_MIPS 3
+
+typedef struct hr_gbuffer_desc {
+    int32_t     width, height; /* mip 0 */
+    const void* gb1;           /* may be NULL (not read on the hot path) */
+    const void* gb2;
+    const void* gb3;
+    const void* depth;
+} hr_gbuffer_desc;
+
+/* Allocate library-owned device storage for both slots (mips 0..HR_MAX_MIPS-1). */
+HR_API int hr_gbuffer_create(hr_ctx* ctx, int width, int height);
+/* Host -> device copy of mip 0 into slot, then NEAREST mip chain on device (g_buffer.cpp:236-244). Async on stream. */
+HR_API int hr_gbuffer_upload(hr_ctx* ctx, int slot, const hr_gbuffer_desc* host_mip0, void* stream);
+/* Device -> device variant (inputs already resident in HBM). */
+HR_API int hr_gbuffer_copy_from_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev_mip0, void* stream);
+/* Zero-copy: bind caller-owned device mip-0 images as slot; the library only builds mips 1.. from them. */
+HR_API int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev_mip0, void* stream);
+/* Read back one mip of a slot (tests). which: 1,2,3 = gb1..3, 0 = depth. Synchronous. */
+HR_API int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* host_dst, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pass outputs
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum hr_format { HR_FMT_R32_UINT = 1, HR_FMT_R16F = 2, HR_FMT_RG16F = 3, HR_FMT_RGBA16F = 4, HR_FMT_R8_UINT = 5 } hr_format;
+
+typedef struct hr_image {
+    void*   data; /* device pointer, dense rows (pitch = width * texel size) */
+    int32_t width, height;
+    int32_t format; /* hr_format */
+} hr_image;
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray-traced shadows  (src/ray_traced_shadows.{h,cpp}; shaders/shadows/ *)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_shadows_params { /* defaults: src/ray_traced_shadows.h:50-115 */
+    float   bias;               /* 0.5  */
+    float   alpha;              /* 0.01 */
+    float   moments_alpha;      /* 0.2  */
+    float   phi_visibility;     /* 10   */
+    float   phi_normal;         /* 32   */
+    float   sigma_depth;        /* 1    */
+    float   power;              /* 1.2  */
+    int32_t radius;             /* 1    */
+    int32_t filter_iterations;  /* 4    */
+    int32_t feedback_iteration; /* 1    */
+    int32_t denoise;            /* 1    */
+} hr_shadows_params;
+
+/* OutputType, src/ray_traced_shadows.h:10-16 (+ internals for tests) */
+enum {
+    HR_SHADOWS_OUT_RAY_TRACE             = 0, /* R32_UINT mask ceil(W/8) x ceil(H/4) */
+    HR_SHADOWS_OUT_TEMPORAL_ACCUMULATION = 1, /* RG16F (visibility, variance) */
+    HR_SHADOWS_OUT_ATROUS                = 2, /* RG16F */
+    HR_SHADOWS_OUT_UPSAMPLE              = 3, /* R16F full-res (scale != FULL) */
+    HR_SHADOWS_OUT_MOMENTS               = 4, /* RGBA16F (m1, m2, history length, 0) of this frame */
+    HR_SHADOWS_OUT_PREV_IMAGE            = 5, /* RG16F history image (a-trous output after feedback_iteration) */
+    HR_SHADOWS_OUT_TILE_FLAGS            = 6, /* R8_UINT per 8x8 tile: 1 = denoise list, 0 = shadow list */
+    HR_SHADOWS_OUT_FINAL                 = 100 /* what output_ds() returns (src/ray_traced_shadows.cpp:135-155) */
+};
+
+HR_API void hr_shadows_default_params(hr_shadows_params* p);
+HR_API int  hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out); /* ctor, ray_traced_shadows.cpp:60-96 */
+HR_API int  hr_shadows_render(hr_pass* pass, const hr_frame* frame, const hr_shadows_params* params, void* stream); /* render(), :100-116 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray-traced ambient occlusion  (src/ray_traced_ao.{h,cpp}; shaders/ao/ *)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_ao_params { /* defaults: src/ray_traced_ao.h:51-110 */
+    float   ray_length;  /* 7.0  */
+    float   bias;        /* 0.3  */
+    float   alpha;       /* 0.01 */
+    float   power;       /* 1.2  */
+    int32_t blur_radius; /* 4    */
+    int32_t denoise;     /* 1    */
+} hr_ao_params;
+
+enum {
+    HR_AO_OUT_RAY_TRACE             = 0, /* R32_UINT mask */
+    HR_AO_OUT_TEMPORAL_ACCUMULATION = 1, /* R16F */
+    HR_AO_OUT_BILATERAL_BLUR        = 2, /* R16F */
+    HR_AO_OUT_UPSAMPLE              = 3, /* R16F full-res */
+    HR_AO_OUT_HISTORY_LENGTH        = 4, /* R16F */
+    HR_AO_OUT_TILE_FLAGS            = 6, /* R8_UINT */
+    HR_AO_OUT_FINAL                 = 100
+};
+
+HR_API void hr_ao_default_params(hr_ao_params* p);
+HR_API int  hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out);               /* ray_traced_ao.cpp:71-90 */
+HR_API int  hr_ao_render(hr_pass* pass, const hr_frame* frame, const hr_ao_params* params, void* stream); /* :98-112 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Common pass functions
+ * ---------------------------------------------------------------------------------------------- */
+/* output_ds() equivalent: borrowed device image, valid until the next render/destroy of this pass. */
+HR_API int hr_pass_output(hr_pass* pass, int which, hr_image* out);
+/* Synchronous device->host copy of an output on `stream` (waits for it). bytes must equal w*h*texel. */
+HR_API int hr_pass_download(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
+/* restart_accumulation() / clear_images() equivalent: next render behaves like first_frame for this pass's history. */
+HR_API int hr_pass_reset_history(hr_pass* pass);
+HR_API int hr_pass_destroy(hr_pass* pass);
+/* Per-stage GPU timings of the last render in ms (DW_SCOPED_SAMPLE equivalent, profiler.cpp:83-181).
+ * Enable with hr_ctx_set_profiling(ctx,1); names/ms arrays of capacity cap; returns count via *n. Synchronises. */
+HR_API int hr_ctx_set_profiling(hr_ctx* ctx, int enabled);
+HR_API int hr_pass_stage_times(hr_pass* pass, const char** names, float* ms, int cap, int* n);
+/* Test hook: key 1 = a-trous implementation (0 naive global-memory kernel, 1 shared-memory tiled kernel). */
+HR_API int hr_debug_set(int key, int value);
+/* Number of kernels this library launched since the context was created (bench.py gpu_launches). */
+HR_API uint64_t hr_ctx_launch_count(hr_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Screen-space row-band sharding across GPUs (new).  rank owns pass rows
+ * [row_begin, row_end) aligned to 8; the other rows are skipped by every stage except a halo.
+ * ---------------------------------------------------------------------------------------------- */
+HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world);
+/* Row range (at pass resolution, height H) owned by rank. */
+HR_API int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HR_API_H */

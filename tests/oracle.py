@@ -1,0 +1,221 @@
+"""ctypes binding + host sequencing for the CPU oracle (oracle/_build/liboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+`ShadowsOracle` / `AOOracle` replay RayTracedShadows::render (src/ray_traced_shadows.cpp:100-116, :938-1255) and
+RayTracedAO::render (src/ray_traced_ao.cpp:98-112, :829-1137) on the oracle's stage functions, with the same
+ping-pong / history bookkeeping.
+"""
+import ctypes as C
+import os
+import sys
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "hybrid-rendering_b200"))
+import pyhr  # noqa: E402
+
+LIB_ORACLE = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+
+class orc_gbuf(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("gb2", C.c_void_p), ("gb3", C.c_void_p), ("depth", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_ORACLE):
+            raise RuntimeError(f"{LIB_ORACLE} missing: run `make -C {ROOT}/oracle`")
+        L = C.CDLL(LIB_ORACLE)
+        L.orc_scene_create.restype = C.c_void_p
+        L.orc_scene_create.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        L.orc_scene_destroy.argtypes = [C.c_void_p]
+        L.orc_scene_set_brute.argtypes = [C.c_void_p, C.c_int]
+        L.orc_trace_any.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_det_sincos.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.orc_oct_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_sample_blue_noise.restype = C.c_float
+        L.orc_sample_blue_noise.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_build_mip.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6
+        P = C.c_void_p
+        F = C.c_float
+        I = C.c_int
+        L.orc_shadows_ray_trace.argtypes = [P, P, P, F, P, P, P]
+        L.orc_ao_ray_trace.argtypes = [P, P, P, F, F, P, P, P]
+        L.orc_shadows_temporal.argtypes = [P, P, P, P, P, P, F, F, P, P, P]
+        L.orc_shadows_atrous.argtypes = [P, P, P, I, I, F, F, F, F, P]
+        L.orc_upsample_scalar.argtypes = [P, P, P, I, F, F, P]
+        L.orc_ao_temporal.argtypes = [P, P, P, P, P, P, F, P, P, P]
+        L.orc_ao_bilateral_blur.argtypes = [P, P, P, P, I, I, I, P]
+        L.orc_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Scene:
+    def __init__(self, tri_verts9: np.ndarray, brute=False):
+        self.tris = np.ascontiguousarray(tri_verts9, np.float32)
+        self.h = lib().orc_scene_create(p(self.tris), self.tris.shape[0], int(brute))
+
+    def set_brute(self, b):
+        lib().orc_scene_set_brute(self.h, int(b))
+
+    def trace_any(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.empty(rays.shape[0], np.uint32)
+        lib().orc_trace_any(self.h, p(rays), rays.shape[0], p(out))
+        return out
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = rays.shape[0]
+        t = np.empty(n, np.float32)
+        prim = np.empty(n, np.uint32)
+        uv = np.empty((n, 2), np.float32)
+        lib().orc_trace_closest(self.h, p(rays), n, p(t), p(prim), p(uv))
+        return t, prim, uv
+
+    def __del__(self):
+        try:
+            lib().orc_scene_destroy(self.h)
+        except Exception:
+            pass
+
+
+class GBufMips:
+    """Host G-buffer with the NEAREST mip chain (oracle statement of g_buffer.cpp:236-244)."""
+
+    def __init__(self, g: "pyhr.GBufferHost", n_mips=3):
+        self.levels = [(g.W, g.H, g.gb2, g.gb3, g.depth)]
+        for _ in range(1, n_mips):
+            W, H, gb2, gb3, d = self.levels[-1]
+            w, h = max(W // 2, 1), max(H // 2, 1)
+            o2 = np.empty((h, w, 4), np.uint16)
+            o3 = np.empty((h, w, 4), np.uint16)
+            od = np.empty((h, w), np.float32)
+            lib().orc_build_mip(W, H, p(gb2), p(gb3), p(d), p(o2), p(o3), p(od))
+            self.levels.append((w, h, o2, o3, od))
+
+    def c(self, mip):
+        W, H, gb2, gb3, d = self.levels[mip]
+        return orc_gbuf(W, H, p(gb2), p(gb3), p(d))
+
+    def size(self, mip):
+        return self.levels[mip][0], self.levels[mip][1]
+
+
+def zero_gbuf_mips(W, H, n_mips=3):
+    return GBufMips(pyhr.GBufferHost(W, H), n_mips)
+
+
+class ShadowsOracle:
+    def __init__(self, W0, H0, scale=0):
+        self.W0, self.H0, self.scale = W0, H0, scale
+        self.W, self.H = W0, H0
+        for _ in range(scale):
+            self.W, self.H = max(self.W // 2, 1), max(self.H // 2, 1)
+        W, H = self.W, self.H
+        self.mask = np.zeros(((H + 3) // 4, (W + 7) // 8), np.uint32)
+        self.temporal = np.zeros((H, W, 2), np.uint16)
+        self.moments = [np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)]
+        self.prev_image = np.zeros((H, W, 2), np.uint16)
+        self.atrous = [np.zeros((H, W, 2), np.uint16), np.zeros((H, W, 2), np.uint16)]
+        self.tile_flags = np.zeros(((H + 7) // 8, (W + 7) // 8), np.uint8)
+        self.upsample = np.zeros((H0, W0), np.uint16) if scale else None
+        self.first = True
+        self.params = pyhr.hr_shadows_params()
+        pyhr.load_product  # noqa: B018  (defaults restated here so the oracle does not need the CUDA library)
+        P = self.params
+        P.bias, P.alpha, P.moments_alpha, P.phi_visibility, P.phi_normal, P.sigma_depth, P.power = 0.5, 0.01, 0.2, 10.0, 32.0, 1.0, 1.2
+        P.radius, P.filter_iterations, P.feedback_iteration, P.denoise = 1, 4, 1, 1
+        self.final = None
+
+    def render(self, scene: Scene, cur: GBufMips, prev: GBufMips, frame, bn):
+        L, P, pp = lib(), self.params, frame.ping_pong
+        sobol, sr = bn
+        if self.first:
+            self.prev_image[:] = 0
+            self.moments[1 - pp][:] = 0
+            self.first = False
+        gc, gp = cur.c(self.scale), prev.c(self.scale)
+        L.orc_shadows_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.bias, p(sobol), p(sr), p(self.mask))
+        self.final = self.mask
+        if not P.denoise:
+            return
+        L.orc_shadows_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.prev_image), p(self.moments[1 - pp]), C.byref(frame), P.alpha,
+                               P.moments_alpha, p(self.temporal), p(self.moments[pp]), p(self.tile_flags))
+        self.cur_moments = self.moments[pp]
+        ping = False
+        src = self.temporal
+        for i in range(P.filter_iterations):
+            write_idx = int(not ping)
+            power = P.power if i == P.filter_iterations - 1 else 0.0
+            L.orc_shadows_atrous(C.byref(gc), p(src), p(self.tile_flags), P.radius, 1 << i, P.phi_visibility, P.phi_normal, P.sigma_depth, power,
+                                 p(self.atrous[write_idx]))
+            ping = not ping
+            if P.feedback_iteration == i:
+                self.prev_image[:] = self.atrous[write_idx]
+            src = self.atrous[write_idx]
+        self.atrous_out = src
+        self.final = src
+        if self.scale:
+            g0 = cur.c(0)
+            L.orc_upsample_scalar(C.byref(g0), C.byref(gc), p(src), 2, 0.0, 0.0, p(self.upsample))
+            self.final = self.upsample
+
+
+class AOOracle:
+    def __init__(self, W0, H0, scale=1):
+        self.W0, self.H0, self.scale = W0, H0, scale
+        self.W, self.H = W0, H0
+        for _ in range(scale):
+            self.W, self.H = max(self.W // 2, 1), max(self.H // 2, 1)
+        W, H = self.W, self.H
+        self.mask = np.zeros(((H + 3) // 4, (W + 7) // 8), np.uint32)
+        self.color = [np.zeros((H, W), np.uint16), np.zeros((H, W), np.uint16)]
+        self.length = [np.zeros((H, W), np.uint16), np.zeros((H, W), np.uint16)]
+        self.blur = [np.zeros((H, W), np.uint16), np.zeros((H, W), np.uint16)]
+        self.tile_flags = np.zeros(((H + 7) // 8, (W + 7) // 8), np.uint8)
+        self.upsample = np.zeros((H0, W0), np.uint16) if scale else None
+        self.first = True
+        self.params = pyhr.hr_ao_params()
+        P = self.params
+        P.ray_length, P.bias, P.alpha, P.power, P.blur_radius, P.denoise = 7.0, 0.3, 0.01, 1.2, 4, 1
+        self.final = None
+
+    def render(self, scene: Scene, cur: GBufMips, prev: GBufMips, frame, bn):
+        L, P, pp = lib(), self.params, frame.ping_pong
+        sobol, sr = bn
+        if self.first:
+            self.color[1 - pp][:] = 0
+            self.length[1 - pp][:] = 0
+            self.first = False
+        gc, gp = cur.c(self.scale), prev.c(self.scale)
+        L.orc_ao_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, p(sobol), p(sr), p(self.mask))
+        self.final = self.mask
+        if not P.denoise:
+            return
+        L.orc_ao_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.color[1 - pp]), p(self.length[1 - pp]), C.byref(frame), P.alpha,
+                          p(self.color[pp]), p(self.length[pp]), p(self.tile_flags))
+        self.temporal = self.color[pp]
+        self.cur_length = self.length[pp]
+        zbp = np.array(frame.z_buffer_params[:], np.float32)
+        L.orc_ao_bilateral_blur(C.byref(gc), p(self.color[pp]), p(self.tile_flags), p(zbp), 1, 0, P.blur_radius, p(self.blur[0]))
+        L.orc_ao_bilateral_blur(C.byref(gc), p(self.blur[0]), p(self.tile_flags), p(zbp), 0, 1, P.blur_radius, p(self.blur[1]))
+        self.final = self.blur[1]
+        if self.scale:
+            g0 = cur.c(0)
+            L.orc_upsample_scalar(C.byref(g0), C.byref(gc), p(self.blur[1]), 1, 1.0, P.power, p(self.upsample))
+            self.final = self.upsample
+
+
+def h2f(a):
+    """uint16 half bits -> float32"""
+    return np.ascontiguousarray(a).view(np.float16).astype(np.float32)
