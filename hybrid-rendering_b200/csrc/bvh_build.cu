@@ -214,9 +214,11 @@ __global__ void k_pack_tiny(int n, const int* __restrict__ bounds, float4* __res
     }
     const float pad = ext * (1.0f / 65536.0f) + 1e-7f;
     out[0] = make_float4(lo[0] - pad, hi[0] + pad, lo[1] - pad, hi[1] + pad);
-    out[1] = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
-    out[2] = make_float4(lo[2] - pad, hi[2] + pad, FLT_MAX, -FLT_MAX);
-    out[3] = make_float4(__int_as_float(~((0 << 3) | (n - 1))), __int_as_float(~0x7FFFFFF8), 0.0f, 0.0f);
+    // child 1 is unused: a degenerate box far outside any scene (an inverted box would read as infinite in a min/max slab
+    // test) that still refers to a valid leaf, so even a visit is harmless.
+    out[1] = make_float4(1e30f, 1e30f, 1e30f, 1e30f);
+    out[2] = make_float4(lo[2] - pad, hi[2] + pad, 1e30f, 1e30f);
+    out[3] = make_float4(__int_as_float(~((0 << 3) | (n - 1))), __int_as_float(~((0 << 3) | 0)), 0.0f, 0.0f);
 }
 
 __global__ void k_pack_tris(const float* __restrict__ verts, const uint32_t* __restrict__ sorted_prim, uint32_t n, float4* __restrict__ out)

@@ -51,23 +51,33 @@ static GBufLevelDev level_view(const hr_ctx* ctx, int slot, int mip)
 }
 
 // ---- stage timing (DW_SCOPED_SAMPLE equivalent) ---------------------------------------------------------------
+static cudaEvent_t timer_event(hr_pass* p)
+{
+    cudaEvent_t e;
+    if (!p->timer.pool.empty()) { e = p->timer.pool.back(); p->timer.pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
 static void timer_begin(hr_pass* p, cudaStream_t st)
 {
     if (!p->ctx->profiling) return;
-    p->timer.names.clear();
-    p->timer.used = 0;
-    if (p->timer.ev.empty())
-    {
-        p->timer.ev.resize(32);
-        for (auto& e : p->timer.ev) cudaEventCreate(&e);
+    if (p->timer.recs.size() >= 1024)
+    { // nobody is reading: recycle the oldest record
+        for (auto e : p->timer.recs.front().ev) p->timer.pool.push_back(e);
+        p->timer.recs.erase(p->timer.recs.begin());
     }
-    cudaEventRecord(p->timer.ev[p->timer.used++], st);
+    p->timer.recs.emplace_back();
+    cudaEvent_t e = timer_event(p);
+    cudaEventRecord(e, st);
+    p->timer.recs.back().ev.push_back(e);
 }
 static void timer_mark(hr_pass* p, const char* name, cudaStream_t st)
 {
-    if (!p->ctx->profiling || p->timer.used >= (int)p->timer.ev.size()) return;
-    p->timer.names.push_back(name);
-    cudaEventRecord(p->timer.ev[p->timer.used++], st);
+    if (!p->ctx->profiling || p->timer.recs.empty()) return;
+    cudaEvent_t e = timer_event(p);
+    cudaEventRecord(e, st);
+    p->timer.recs.back().names.push_back(name);
+    p->timer.recs.back().ev.push_back(e);
 }
 
 extern "C" {
@@ -671,7 +681,8 @@ int hr_pass_destroy(hr_pass* p)
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (void* a : p->allocs) cudaFree(a);
-    for (auto& e : p->timer.ev) cudaEventDestroy(e);
+    for (auto& r : p->timer.recs) for (auto e : r.ev) cudaEventDestroy(e);
+    for (auto e : p->timer.pool) cudaEventDestroy(e);
     delete p;
     return HR_OK;
 }
@@ -680,15 +691,29 @@ int hr_pass_stage_times(hr_pass* p, const char** names, float* ms, int cap, int*
 {
     if (!p || !n) return HR_ERR_INVALID_ARG;
     *n = 0;
-    if (!p->ctx->profiling || p->timer.used < 2) return HR_OK;
-    cudaEventSynchronize(p->timer.ev[p->timer.used - 1]);
-    const int cnt = (int)p->timer.names.size();
-    for (int i = 0; i < cnt && i < cap; i++)
+    StageTimer& T = p->timer;
+    if (T.recs.empty()) return HR_OK;
+    std::vector<double> sum;
+    std::vector<int>    cnt;
+    T.last_names.clear();
+    for (auto& r : T.recs)
     {
-        float t = 0.0f;
-        cudaEventElapsedTime(&t, p->timer.ev[i], p->timer.ev[i + 1]);
-        if (names) names[i] = p->timer.names[i].c_str();
-        if (ms) ms[i] = t;
+        cudaEventSynchronize(r.ev.back());
+        for (size_t i = 0; i + 1 < r.ev.size(); i++)
+        {
+            float t = 0.0f;
+            cudaEventElapsedTime(&t, r.ev[i], r.ev[i + 1]);
+            if (i >= sum.size()) { sum.push_back(0.0); cnt.push_back(0); T.last_names.push_back(r.names[i]); }
+            sum[i] += t;
+            cnt[i]++;
+        }
+        for (auto e : r.ev) T.pool.push_back(e);
+    }
+    T.recs.clear();
+    for (size_t i = 0; i < sum.size() && (int)i < cap; i++)
+    {
+        if (names) names[i] = T.last_names[i].c_str();
+        if (ms) ms[i] = (float)(sum[i] / cnt[i]);
         (*n)++;
     }
     return HR_OK;

@@ -114,10 +114,11 @@ struct hr_scene {
 
 enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4 };
 
-struct StageTimer {
-    std::vector<std::string> names;
-    std::vector<cudaEvent_t> ev; // names.size()+1 events
-    int                      used = 0;
+struct StageTimer { // one Rec per profiled render; hr_pass_stage_times averages and recycles them
+    struct Rec { std::vector<std::string> names; std::vector<cudaEvent_t> ev; };
+    std::vector<Rec>         recs;
+    std::vector<cudaEvent_t> pool;
+    std::vector<std::string> last_names;
 };
 
 struct hr_pass {

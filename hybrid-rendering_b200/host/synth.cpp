@@ -243,11 +243,13 @@ void build_arcade(hrs_scene& s, int target_tris, uint32_t seed)
         n += 2L * fl * fl;
         if (emit) add_grid(s, { -30, 0, -8 }, { 60, 0, 0 }, { 0, 0, L + 16 }, fl, fl, { 0, 1, 0 }, mat(mi));
         mi++;
-        n += 2L * (fl / 2) * fl;
-        if (emit) add_grid(s, { -30, 2 * storey, -8 }, { 60, 0, 0 }, { 0, 0, L + 16 }, fl / 2, fl, { 0, -1, 0 }, mat(mi));
-        mi++;
         for (int side = -1; side <= 1; side += 2)
         {
+            // roof over the side aisles only: the nave (|x| < halfw) is open to the sky so the sun reaches the floor
+            n += 2L * (fl / 4) * fl;
+            float xr = side < 0 ? -30.0f : halfw;
+            if (emit) add_grid(s, { xr, 2 * storey, -8 }, { 30 - halfw, 0, 0 }, { 0, 0, L + 16 }, fl / 4, fl, { 0, -1, 0 }, mat(mi));
+            mi++;
             n += 2L * (fl / 4) * fl;
             float x0 = side < 0 ? -30.0f : halfw;
             if (emit) add_grid(s, { x0, storey, -8 }, { 30 - halfw, 0, 0 }, { 0, 0, L + 16 }, fl / 4, fl, { 0, 1, 0 }, mat(mi));
