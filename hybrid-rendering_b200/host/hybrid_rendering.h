@@ -1,0 +1,141 @@
+// hybrid_rendering.h — C++ host classes that keep the reference's pass interfaces on top of the C ABI (hr_api.h).
+//
+//   reference                                      here
+//   CommonResources (src/common.h:181-243)         hr::CommonResources  (hr_ctx + per-frame hr_frame + blue noise + scene)
+//   GBuffer         (src/g_buffer.h)               hr::GBuffer          (two device slots; output()/history() by ping_pong)
+//   RayTracedShadows(src/ray_traced_shadows.h)     hr::RayTracedShadows (ctor(common, gbuffer, scale); render(stream); output())
+//   RayTracedAO     (src/ray_traced_ao.h)          hr::RayTracedAO
+// Same method names and argument meaning; `dw::vk::CommandBuffer::Ptr` becomes a CUDA stream, descriptor sets become
+// hr_image views; construction errors throw std::runtime_error like the reference (common.cpp:350-353), render() does
+// not fail observably in the reference — here a failed launch throws as well.
+#pragma once
+#include "../../include/hr_api.h"
+#include "synth.h"
+#include <stdexcept>
+#include <string>
+
+namespace hr {
+
+enum RayTraceScale { RAY_TRACE_SCALE_FULL_RES = HR_SCALE_FULL, RAY_TRACE_SCALE_HALF_RES = HR_SCALE_HALF, RAY_TRACE_SCALE_QUARTER_RES = HR_SCALE_QUARTER }; // common.h:39-44
+
+inline void check(hr_ctx* ctx, int rc, const char* what)
+{
+    if (rc != HR_OK) throw std::runtime_error(std::string(what) + ": " + hr_last_error(ctx));
+}
+
+struct CommonResources {
+    hr_ctx*   ctx   = nullptr;
+    hr_scene* scene = nullptr;
+    // the fields the passes read every frame (common.h:186-191)
+    bool      first_frame = true;
+    bool      ping_pong   = false;
+    int32_t   num_frames  = 0;
+    hr_frame  frame {};
+    uint32_t  width, height;
+
+    CommonResources(int device, uint32_t w, uint32_t h) : width(w), height(h)
+    {
+        if (hr_init(device, &ctx) != HR_OK) throw std::runtime_error(std::string("hr_init: ") + hr_last_error(nullptr));
+    }
+    ~CommonResources()
+    {
+        if (scene) hr_scene_destroy(scene);
+        if (ctx) hr_shutdown(ctx);
+    }
+    CommonResources(const CommonResources&)            = delete;
+    CommonResources& operator=(const CommonResources&) = delete;
+
+    void set_blue_noise(const uint8_t* sobol, const uint8_t* scr_rank) { check(ctx, hr_bluenoise_set(ctx, sobol, scr_rank), "hr_bluenoise_set"); }
+    void load_scene(const hrs_scene* s)
+    { // CommonResources::load_mesh + RayTracedScene creation (common.cpp:340-534)
+        uint64_t nv, ni, nin, nm;
+        hrs_scene_counts(s, &nv, &ni, &nin, &nm);
+        check(ctx, hr_scene_build(ctx, hrs_scene_vertices(s), nv, hrs_scene_indices(s), ni, hrs_scene_instances(s), nin, hrs_scene_materials(s), nm, &scene),
+              "hr_scene_build");
+        check(ctx, hr_scene_set_current(ctx, scene), "hr_scene_set_current");
+    }
+    hr_scene* current_scene() { return scene; }
+    // HybridRendering::update_uniforms (main.cpp:937-972) for a look-at camera
+    void update_uniforms(const float cam_pos[3], const float cam_target[3], const hrs_light_desc* light)
+    {
+        hr_frame prev = frame;
+        hrs_make_frame(&frame, cam_pos, cam_target, (int)width, (int)height, light, first_frame ? nullptr : &prev, (uint32_t)num_frames);
+        frame.ping_pong   = ping_pong ? 1 : 0;
+        frame.first_frame = first_frame ? 1 : 0;
+    }
+    // end of HybridRendering::update (main.cpp:123-128)
+    void end_frame()
+    {
+        num_frames++;
+        first_frame = false;
+        ping_pong   = !ping_pong;
+    }
+};
+
+struct GBuffer {
+    CommonResources* common;
+    GBuffer(CommonResources* c) : common(c) { check(c->ctx, hr_gbuffer_create(c->ctx, (int)c->width, (int)c->height), "hr_gbuffer_create"); }
+    // GBuffer::render (g_buffer.cpp:39-189) replaced by: upload the CPU-written G-buffer of this frame into slot[ping_pong]
+    void render(const hr_gbuffer_desc* host_mip0, void* stream) { check(common->ctx, hr_gbuffer_upload(common->ctx, common->ping_pong ? 1 : 0, host_mip0, stream), "hr_gbuffer_upload"); }
+    void bind_device(const hr_gbuffer_desc* dev_mip0, void* stream) { check(common->ctx, hr_gbuffer_bind_device(common->ctx, common->ping_pong ? 1 : 0, dev_mip0, stream), "hr_gbuffer_bind_device"); }
+};
+
+class RayTracedShadows {
+public:
+    enum OutputType { OUTPUT_RAY_TRACE = 0, OUTPUT_TEMPORAL_ACCUMULATION = 1, OUTPUT_ATROUS = 2, OUTPUT_UPSAMPLE = 3 }; // ray_traced_shadows.h:10-16
+    RayTracedShadows(CommonResources* common, GBuffer* g_buffer, RayTraceScale scale = RAY_TRACE_SCALE_FULL_RES) : m_common(common), m_scale(scale)
+    {
+        (void)g_buffer;
+        hr_shadows_default_params(&params);
+        check(common->ctx, hr_shadows_create(common->ctx, (int)common->width, (int)common->height, scale, &m_pass), "hr_shadows_create");
+        m_width  = common->width >> scale;
+        m_height = common->height >> scale;
+    }
+    ~RayTracedShadows() { if (m_pass) hr_pass_destroy(m_pass); }
+    void       render(void* stream) { check(m_common->ctx, hr_shadows_render(m_pass, &m_common->frame, &params, stream), "hr_shadows_render"); }
+    hr_image   output_ds() const { return output(m_current_output_final ? 100 : (int)m_current_output); }
+    hr_image   output(int which) const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, which, &img), "hr_pass_output"); return img; }
+    uint32_t   width() const { return m_width; }
+    uint32_t   height() const { return m_height; }
+    RayTraceScale scale() const { return m_scale; }
+    OutputType current_output() const { return m_current_output; }
+    void       set_current_output(OutputType t) { m_current_output = t; m_current_output_final = false; }
+    hr_pass*   handle() { return m_pass; }
+    hr_shadows_params params; // the ImGui-bound members of the reference (ray_traced_shadows.cpp:120-131)
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+    RayTraceScale    m_scale;
+    uint32_t         m_width = 0, m_height = 0;
+    OutputType       m_current_output = OUTPUT_ATROUS;
+    bool             m_current_output_final = true;
+};
+
+class RayTracedAO {
+public:
+    enum OutputType { OUTPUT_RAY_TRACE = 0, OUTPUT_TEMPORAL_ACCUMULATION = 1, OUTPUT_BILATERAL_BLUR = 2, OUTPUT_UPSAMPLE = 3 }; // ray_traced_ao.h:10-16
+    RayTracedAO(CommonResources* common, GBuffer* g_buffer, RayTraceScale scale = RAY_TRACE_SCALE_HALF_RES) : m_common(common), m_scale(scale)
+    {
+        (void)g_buffer;
+        hr_ao_default_params(&params);
+        check(common->ctx, hr_ao_create(common->ctx, (int)common->width, (int)common->height, scale, &m_pass), "hr_ao_create");
+        m_width  = common->width >> scale;
+        m_height = common->height >> scale;
+    }
+    ~RayTracedAO() { if (m_pass) hr_pass_destroy(m_pass); }
+    void       render(void* stream) { check(m_common->ctx, hr_ao_render(m_pass, &m_common->frame, &params, stream), "hr_ao_render"); }
+    hr_image   output_ds() const { return output(100); }
+    hr_image   output(int which) const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, which, &img), "hr_pass_output"); return img; }
+    uint32_t   width() const { return m_width; }
+    uint32_t   height() const { return m_height; }
+    RayTraceScale scale() const { return m_scale; }
+    hr_pass*   handle() { return m_pass; }
+    hr_ao_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+    RayTraceScale    m_scale;
+    uint32_t         m_width = 0, m_height = 0;
+};
+
+} // namespace hr
