@@ -167,6 +167,8 @@ def main():
     g_host = pyhr.write_gbuffer(sc, f1, W, H, pinned=True)
 
     ctx = pyhr.Context(local_rank)
+    if os.environ.get("HR_ATROUS_IMPL"):  # A/B switch for kernel experiments (0 naive, 1 tiled, 2 chain = default)
+        ctx.lib.hr_debug_set(1, int(os.environ["HR_ATROUS_IMPL"]))
     ctx.set_bluenoise(*pyhr.blue_noise())
     scene_h = ctx.build_scene(sc)
     ctx.gbuffer_create(W, H)

@@ -124,6 +124,10 @@ __global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev
 #pragma unroll
                 for (int s = 0; s < 4; s++)
                 {
+                    // A tap with bilinear weight exactly 0 cannot change the result: it adds 0 to every sum, and if only
+                    // such taps are valid sumw = 0 < 0.01 sends us to the 3x3 fallback exactly as "no tap valid" does.
+                    // Static pixels (motion 0 => fx = fy = 0) therefore need 1 tap instead of 4.
+                    if (w4[s] == 0.0f) continue;
                     const int px = bx + (s & 1), py = by + (s >> 1);
                     const Tap t  = fetch_prev(prev, px, py);
                     if (tap_valid(t, cpos, cn, cmesh, hu, hv, fc.view_proj_inverse))

@@ -42,10 +42,12 @@ __device__ __forceinline__ bool ray_triangle(const float4 A, const float4 B, con
 struct SlabSetup { float idx, idy, idz, ox, oy, oz; };
 __device__ __forceinline__ SlabSetup slab_setup(const Ray& r)
 {
+    // |d| < 1e-18 is replaced by +-1e-18 for the BOX test only: with an infinite reciprocal the fma form
+    // lo*inf - o*inf turns into NaN/-inf and would reject boxes the ray is inside of (not conservative).
     SlabSetup s;
-    s.idx = 1.0f / r.d.x;
-    s.idy = 1.0f / r.d.y;
-    s.idz = 1.0f / r.d.z;
+    s.idx = 1.0f / (fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
+    s.idy = 1.0f / (fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
+    s.idz = 1.0f / (fabsf(r.d.z) > 1e-18f ? r.d.z : copysignf(1e-18f, r.d.z));
     s.ox  = r.o.x * s.idx;
     s.oy  = r.o.y * s.idy;
     s.oz  = r.o.z * s.idz;
