@@ -170,6 +170,11 @@ def main():
     if os.environ.get("HR_ATROUS_IMPL"):  # A/B switch for kernel experiments (0 naive, 1 tiled, 2 chain = default)
         ctx.lib.hr_debug_set(1, int(os.environ["HR_ATROUS_IMPL"]))
     ctx.set_bluenoise(*pyhr.blue_noise())
+    if world > 1:
+        # row-band sharding with the library's own NCCL exchange: rank 0 creates the ncclUniqueId, torch.distributed ships it
+        uid = [pyhr.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.shard_init(rank, world, uid[0])
     scene_h = ctx.build_scene(sc)
     ctx.gbuffer_create(W, H)
     sh = pyhr.Pass(ctx, "shadows", W, H, 0)

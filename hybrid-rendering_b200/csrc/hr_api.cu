@@ -492,8 +492,13 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     const int          pp  = f->ping_pong;
     const FrameConsts  fc  = make_consts(f);
     const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
-    const int          row0 = 0, row1 = p->H;
     const size_t       px = (size_t)p->W * p->H;
+    // row-band sharding (shard.cu): owned band [b0,b1); ray trace on band+-32, temporal / a-trous on band+-16:
+    // 17x17 mean needs mask rows +-8 beyond the temporal rows; 4 a-trous iterations at steps 1,2,4,8 erode +-15 rows.
+    int b0, b1, rt0, rt1, row0, row1;
+    hr_band(ctx, p->H, &b0, &b1);
+    hr_extend(b0, b1, ctx->world > 1 ? 32 : 0, p->H, &rt0, &rt1);
+    hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
     timer_begin(p, st);
 
     // clear_images (ray_traced_shadows.cpp:938-968): first frame => history image and moments[!pp] = 0
@@ -504,7 +509,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         p->first = false;
     }
     // ray_trace (:972-1011)
-    launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, row0, row1, st);
+    launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, rt0, rt1, st);
     ctx->launches++;
     timer_mark(p, "Ray Trace", st);
     set_view(p, HR_SHADOWS_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
@@ -551,7 +556,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         if (p->scale != HR_SCALE_FULL)
         { // upsample (:1219-1255)
             const GBufLevelDev g0 = level_view(ctx, pp, 0);
-            launch_upsample_scalar(g0, cur, last, 2, 0.0f, 0.0f, p->upsample_out, 0, p->H0, st);
+            launch_upsample_scalar(g0, cur, last, 2, 0.0f, 0.0f, p->upsample_out, b0 << p->scale, b1 >= p->H ? p->H0 : (b1 << p->scale), st);
             ctx->launches++;
             timer_mark(p, "Upsample", st);
             set_view(p, HR_SHADOWS_OUT_UPSAMPLE, p->upsample_out, p->W0, p->H0, HR_FMT_R16F);
@@ -560,6 +565,22 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
+    if (ctx->world > 1)
+    { // every rank ends up with the complete final output and the complete history (prev_image, moments) for the next frame
+        ExchangeItem it[4];
+        int          n = 0;
+        if (prm->denoise)
+        {
+            it[n++] = { p->prev_image, (size_t)p->W * 4, p->H, 0, 1, p->H };
+            it[n++] = { p->moments[pp], (size_t)p->W * 8, p->H, 0, 1, p->H };
+            if (final_ptr != p->prev_image && final_fmt == HR_FMT_RG16F) it[n++] = { final_ptr, (size_t)p->W * 4, p->H, 0, 1, p->H };
+            if (final_fmt == HR_FMT_R16F) it[n++] = { final_ptr, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
+        }
+        else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
+        rc = hr_shard_exchange(ctx, it, n, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Exchange", st);
+    }
     return HR_OK;
 }
 
@@ -602,8 +623,13 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     const int          pp  = f->ping_pong;
     const FrameConsts  fc  = make_consts(f);
     const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
-    const int          row0 = 0, row1 = p->H;
     const size_t       px = (size_t)p->W * p->H;
+    // row-band sharding: ray trace band+-32, temporal + horizontal blur band+-16, vertical blur (needs +-4 rows) band+-8
+    int b0, b1, rt0, rt1, row0, row1, v0, v1;
+    hr_band(ctx, p->H, &b0, &b1);
+    hr_extend(b0, b1, ctx->world > 1 ? 32 : 0, p->H, &rt0, &rt1);
+    hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
+    hr_extend(b0, b1, ctx->world > 1 ? 8 : 0, p->H, &v0, &v1);
     timer_begin(p, st);
     if (p->first)
     { // clear_images, ray_traced_ao.cpp:829-860
@@ -611,7 +637,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
         p->first = false;
     }
-    launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, row0, row1, st);
+    launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, rt0, rt1, st);
     ctx->launches++;
     timer_mark(p, "Ray Trace", st);
     set_view(p, HR_AO_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
@@ -624,7 +650,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         timer_mark(p, "Temporal Accumulation", st);
         // bilateral_blur (:1032-1137): pass labelled "Vertical" uses direction (1,0), then (0,1)
         launch_ao_blur(cur, p->ao_color[pp], p->tile_flags, f->z_buffer_params, 1, 0, prm->blur_radius, p->ao_blur[0], row0, row1, st);
-        launch_ao_blur(cur, p->ao_blur[0], p->tile_flags, f->z_buffer_params, 0, 1, prm->blur_radius, p->ao_blur[1], row0, row1, st);
+        launch_ao_blur(cur, p->ao_blur[0], p->tile_flags, f->z_buffer_params, 0, 1, prm->blur_radius, p->ao_blur[1], v0, v1, st);
         ctx->launches += 2;
         timer_mark(p, "Bilateral Blur", st);
         set_view(p, HR_AO_OUT_TEMPORAL_ACCUMULATION, p->ao_color[pp], p->W, p->H, HR_FMT_R16F);
@@ -635,7 +661,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         if (p->scale != HR_SCALE_FULL)
         { // upsample (:918-957)
             const GBufLevelDev g0 = level_view(ctx, pp, 0);
-            launch_upsample_scalar(g0, cur, p->ao_blur[1], 1, 1.0f, prm->power, p->upsample_out, 0, p->H0, st);
+            launch_upsample_scalar(g0, cur, p->ao_blur[1], 1, 1.0f, prm->power, p->upsample_out, b0 << p->scale, b1 >= p->H ? p->H0 : (b1 << p->scale), st);
             ctx->launches++;
             timer_mark(p, "Upsample", st);
             set_view(p, HR_AO_OUT_UPSAMPLE, p->upsample_out, p->W0, p->H0, HR_FMT_R16F);
@@ -644,6 +670,22 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
+    if (ctx->world > 1)
+    {
+        ExchangeItem it[4];
+        int          n = 0;
+        if (prm->denoise)
+        {
+            it[n++] = { p->ao_color[pp], (size_t)p->W * 2, p->H, 0, 1, p->H };
+            it[n++] = { p->ao_len[pp], (size_t)p->W * 2, p->H, 0, 1, p->H };
+            if (p->scale == HR_SCALE_FULL) it[n++] = { p->ao_blur[1], (size_t)p->W * 2, p->H, 0, 1, p->H };
+            else it[n++] = { p->upsample_out, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
+        }
+        else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
+        rc = hr_shard_exchange(ctx, it, n, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Exchange", st);
+    }
     return HR_OK;
 }
 
@@ -669,6 +711,21 @@ int hr_pass_download(hr_pass* p, int which, void* dst, size_t bytes, void* strea
     const size_t need = (size_t)img.width * img.height * texel_size(img.format);
     HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download: byte count mismatch");
     HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return HR_OK;
+}
+
+// Restore half of checkpoint / resume (the reference keeps its temporal history only in GPU images and has no such
+// facility): overwrite one of the pass's images, e.g. the history surfaces saved with hr_pass_download.
+int hr_pass_upload(hr_pass* p, int which, const void* src, size_t bytes, void* stream)
+{
+    hr_image img;
+    int      rc = hr_pass_output(p, which, &img);
+    if (rc != HR_OK) return rc;
+    hr_ctx*      ctx  = p->ctx;
+    const size_t need = (size_t)img.width * img.height * texel_size(img.format);
+    HR_REQUIRE(ctx, src && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_upload: byte count mismatch");
+    HR_CUDA(ctx, cudaMemcpyAsync(img.data, src, need, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     return HR_OK;
 }
@@ -730,6 +787,7 @@ int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end)
     return HR_OK;
 }
 
+// Band assignment without a communicator: the caller performs the exchange itself (tests emulate N ranks on one GPU).
 int hr_shard_config(hr_ctx* ctx, int rank, int world)
 {
     HR_REQUIRE(ctx, ctx && world >= 1 && rank >= 0 && rank < world, HR_ERR_INVALID_ARG, "hr_shard_config: bad rank/world");

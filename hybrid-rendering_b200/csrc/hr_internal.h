@@ -75,6 +75,7 @@ struct hr_ctx {
     hr_scene*    scene = nullptr;
     // sharding
     int          rank = 0, world = 1;
+    void*        nccl_comm = nullptr; // ncclComm_t when hr_shard_init was called (NCCL is dlopen'ed lazily, see shard.cu)
     // profiling
     bool         profiling = false;
     uint64_t     launches  = 0;
@@ -148,6 +149,22 @@ struct hr_pass {
     StageTimer timer;
     std::vector<void*> allocs;
 };
+
+// ---- row-band sharding (shard.cu) ---------------------------------------------------------------------
+// An image whose rows are owned band-wise by the ranks.  The band partition is defined on the PASS height `H`
+// (hr_shard_rows); the image's own rows are band << shift (full-res upsample outputs) or band / div (ray masks),
+// clamped to `rows` (the image's real height).
+struct ExchangeItem { void* base; size_t row_bytes; int H; int shift; int div; int rows; };
+// Rows of an image of height H owned by this context's rank (all rows when world == 1).
+void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1);
+// [b0 - halo, b1 + halo) clamped to [0, H); halo must be a multiple of 8 so tile alignment is kept.
+inline void hr_extend(int b0, int b1, int halo, int H, int* e0, int* e1)
+{
+    *e0 = b0 - halo < 0 ? 0 : b0 - halo;
+    *e1 = b1 + halo > H ? H : b1 + halo;
+}
+// Make every rank's copy of each image complete: rank r broadcasts its band of every item (one NCCL group).
+int hr_shard_exchange(hr_ctx* ctx, const ExchangeItem* items, int n, cudaStream_t st);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
 int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st);

@@ -346,7 +346,9 @@ void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 
 } // namespace
 
-int g_hr_atrous_impl = 2; // 0 = naive, 1 = tiled, 2 = chain / sliding window (hr_debug_set key 1)
+// 0 = naive, 1 = tiled (default: measured 64-105 us/iter at 4K), 2 = chain / sliding window (72-107 us: the extra registers
+// cost more occupancy than the saved shared-memory traffic buys; profiles/README.md).  hr_debug_set key 1.
+int g_hr_atrous_impl = 1;
 
 void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n,
                            float sigma_z, float power, __half2* out, int row0, int row1, cudaStream_t st)

@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "hr_scene_get_info", "hr_scene_rebuild", "hr_trace_any", "hr_trace_closest", "hr_gbuffer_create", "hr_gbuffer_upload",
     "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
-    "hr_pass_destroy", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows",
+    "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown",
 ]
 
 _product = None
@@ -134,6 +134,20 @@ def load_synth():
 
 class HrError(RuntimeError):
     pass
+
+
+def shard_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = load_product().hr_shard_unique_id(buf)
+    if rc != 0:
+        raise HrError(f"hr_shard_unique_id failed ({rc}): {load_product().hr_last_error(None).decode()}")
+    return buf.raw
+
+
+def shard_rows(H, rank, world):
+    b, e = C.c_int(), C.c_int()
+    load_product().hr_shard_rows(H, rank, world, C.byref(b), C.byref(e))
+    return b.value, e.value
 
 
 def _ptr(a):
@@ -303,6 +317,16 @@ class Context:
         self.check(self.lib.hr_gbuffer_download(self.h, slot, mip, which, _ptr(a), C.c_size_t(a.nbytes)), "hr_gbuffer_download")
         return a
 
+    def shard_config(self, rank, world):
+        self.check(self.lib.hr_shard_config(self.h, rank, world), "hr_shard_config")
+
+    def shard_init(self, rank, world, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self.check(self.lib.hr_shard_init(self.h, rank, world, buf), "hr_shard_init")
+
+    def shard_shutdown(self):
+        self.lib.hr_shard_shutdown(self.h)
+
     def launch_count(self):
         return int(self.lib.hr_ctx_launch_count(self.h))
 
@@ -340,6 +364,10 @@ class Pass:
         a = out if out is not None else np.empty(shape, np.dtype(dt))
         self.ctx.check(self.lib.hr_pass_download(self.h, which, _ptr(a), C.c_size_t(a.nbytes), C.c_void_p(stream)), "hr_pass_download")
         return a
+
+    def upload(self, which, a, stream=0):
+        a = np.ascontiguousarray(a)
+        self.ctx.check(self.lib.hr_pass_upload(self.h, which, _ptr(a), C.c_size_t(a.nbytes), C.c_void_p(stream)), "hr_pass_upload")
 
     def stage_times(self):
         names = (C.c_char_p * 32)()

@@ -261,6 +261,8 @@ HR_API int  hr_ao_render(hr_pass* pass, const hr_frame* frame, const hr_ao_param
 HR_API int hr_pass_output(hr_pass* pass, int which, hr_image* out);
 /* Synchronous device->host copy of an output on `stream` (waits for it). bytes must equal w*h*texel. */
 HR_API int hr_pass_download(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
+/* Checkpoint / resume of temporal history: hr_pass_download saves an image, hr_pass_upload restores it (synchronous). */
+HR_API int hr_pass_upload(hr_pass* pass, int which, const void* host_src, size_t bytes, void* stream);
 /* restart_accumulation() / clear_images() equivalent: next render behaves like first_frame for this pass's history. */
 HR_API int hr_pass_reset_history(hr_pass* pass);
 HR_API int hr_pass_destroy(hr_pass* pass);
@@ -277,7 +279,13 @@ HR_API uint64_t hr_ctx_launch_count(hr_ctx* ctx);
  * Screen-space row-band sharding across GPUs (new).  rank owns pass rows
  * [row_begin, row_end) aligned to 8; the other rows are skipped by every stage except a halo.
  * ---------------------------------------------------------------------------------------------- */
-HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world);
+HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world); /* band assignment only; the caller exchanges bands itself */
+/* NCCL-backed sharding: rank 0 obtains a 128-byte ncclUniqueId, every rank calls hr_shard_init with it (one process per
+ * GPU).  After every hr_*_render the ranks exchange their bands of the final output and of the temporal history with one
+ * NCCL group on the caller's stream, so each rank holds the complete, single-GPU-identical images. */
+HR_API int hr_shard_unique_id(void* out_128_bytes);
+HR_API int hr_shard_init(hr_ctx* ctx, int rank, int world, const void* unique_id_128_bytes);
+HR_API int hr_shard_shutdown(hr_ctx* ctx);
 /* Row range (at pass resolution, height H) owned by rank. */
 HR_API int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end);
 

@@ -136,6 +136,21 @@ class ShadowsOracle:
         P.bias, P.alpha, P.moments_alpha, P.phi_visibility, P.phi_normal, P.sigma_depth, P.power = 0.5, 0.01, 0.2, 10.0, 32.0, 1.0, 1.2
         P.radius, P.filter_iterations, P.feedback_iteration, P.denoise = 1, 4, 1, 1
         self.final = None
+        self.band = None  # (b0, b1): emulate a sharded rank — rows a rank would not compute are overwritten with garbage
+
+    def _poison(self, arr, halo, div=1, shift=0):
+        """Sharding emulation (tests/test_sharding_cpu.py): keep rows [b0-halo, b1+halo) of a stage output, trash the rest."""
+        if self.band is None:
+            return
+        b0, b1 = self.band
+        e0, e1 = max(b0 - halo, 0), min(b1 + halo, self.H)
+        if shift:
+            e0, e1 = e0 << shift, (arr.shape[0] if e1 >= self.H else e1 << shift)
+        e0, e1 = e0 // div, -(-e1 // div)
+        rng = np.random.default_rng(e0 * 7919 + e1)
+        for sl in (slice(0, e0), slice(e1, arr.shape[0])):
+            if arr[sl].size:
+                arr[sl] = rng.integers(0, 0x3C00, size=arr[sl].shape, dtype=np.uint32).astype(arr.dtype)
 
     def render(self, scene: Scene, cur: GBufMips, prev: GBufMips, frame, bn):
         L, P, pp = lib(), self.params, frame.ping_pong
@@ -146,12 +161,15 @@ class ShadowsOracle:
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
         L.orc_shadows_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.bias, p(sobol), p(sr), p(self.mask))
+        self._poison(self.mask, 32, div=4)
         self.final = self.mask
         if not P.denoise:
             return
         L.orc_shadows_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.prev_image), p(self.moments[1 - pp]), C.byref(frame), P.alpha,
                                P.moments_alpha, p(self.temporal), p(self.moments[pp]), p(self.tile_flags))
         self.cur_moments = self.moments[pp]
+        for a in (self.temporal, self.moments[pp], self.tile_flags):
+            self._poison(a, 16, div=8 if a is self.tile_flags else 1)
         ping = False
         src = self.temporal
         for i in range(P.filter_iterations):
@@ -159,6 +177,7 @@ class ShadowsOracle:
             power = P.power if i == P.filter_iterations - 1 else 0.0
             L.orc_shadows_atrous(C.byref(gc), p(src), p(self.tile_flags), P.radius, 1 << i, P.phi_visibility, P.phi_normal, P.sigma_depth, power,
                                  p(self.atrous[write_idx]))
+            self._poison(self.atrous[write_idx], 16)
             ping = not ping
             if P.feedback_iteration == i:
                 self.prev_image[:] = self.atrous[write_idx]
@@ -168,6 +187,7 @@ class ShadowsOracle:
         if self.scale:
             g0 = cur.c(0)
             L.orc_upsample_scalar(C.byref(g0), C.byref(gc), p(src), 2, 0.0, 0.0, p(self.upsample))
+            self._poison(self.upsample, 0, shift=self.scale)
             self.final = self.upsample
 
 
@@ -189,6 +209,9 @@ class AOOracle:
         P = self.params
         P.ray_length, P.bias, P.alpha, P.power, P.blur_radius, P.denoise = 7.0, 0.3, 0.01, 1.2, 4, 1
         self.final = None
+        self.band = None
+
+    _poison = ShadowsOracle._poison
 
     def render(self, scene: Scene, cur: GBufMips, prev: GBufMips, frame, bn):
         L, P, pp = lib(), self.params, frame.ping_pong
@@ -199,6 +222,7 @@ class AOOracle:
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
         L.orc_ao_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, p(sobol), p(sr), p(self.mask))
+        self._poison(self.mask, 32, div=4)
         self.final = self.mask
         if not P.denoise:
             return
@@ -206,13 +230,18 @@ class AOOracle:
                           p(self.color[pp]), p(self.length[pp]), p(self.tile_flags))
         self.temporal = self.color[pp]
         self.cur_length = self.length[pp]
+        for a in (self.color[pp], self.length[pp], self.tile_flags):
+            self._poison(a, 16, div=8 if a is self.tile_flags else 1)
         zbp = np.array(frame.z_buffer_params[:], np.float32)
         L.orc_ao_bilateral_blur(C.byref(gc), p(self.color[pp]), p(self.tile_flags), p(zbp), 1, 0, P.blur_radius, p(self.blur[0]))
+        self._poison(self.blur[0], 16)
         L.orc_ao_bilateral_blur(C.byref(gc), p(self.blur[0]), p(self.tile_flags), p(zbp), 0, 1, P.blur_radius, p(self.blur[1]))
+        self._poison(self.blur[1], 8)
         self.final = self.blur[1]
         if self.scale:
             g0 = cur.c(0)
             L.orc_upsample_scalar(C.byref(g0), C.byref(gc), p(self.blur[1]), 1, 1.0, P.power, p(self.upsample))
+            self._poison(self.upsample, 0, shift=self.scale)
             self.final = self.upsample
 
 

@@ -1,0 +1,130 @@
+"""Row-band sharding: N-rank results must be BIT-IDENTICAL to the single-GPU result.
+
+* test_sharded_emulation_*: N ranks emulated on one GPU (one hr_ctx per rank, hr_shard_config), the band exchange done by
+  the test through hr_pass_download / hr_pass_upload.  Runs on the single-GPU box.
+* test_nccl_*: real one-process-per-GPU run with the library's NCCL exchange (hr_shard_init); needs >= 2 GPUs
+  (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as O  # noqa: F401  (path setup)
+import pyhr
+
+pytestmark = pytest.mark.gpu
+
+W, H = 256, 144
+SH = dict(temporal=1, atrous=2, moments=4, prev=5, final=100)
+AO = dict(temporal=1, blur=2, length=4, final=100)
+
+
+def frames(n, pan_from=3):
+    f = None
+    for i in range(n):
+        dx = 0.0 if i < pan_from else 0.05 * (i - pan_from + 1)
+        f = pyhr.make_frame((dx, 14.0, 34.0), (dx, 3.0, 0.0), W, H, prev=f, num_frames=i)
+        yield f
+
+
+def make_rank(device, sc, sh_scale, ao_scale, rank=0, world=1):
+    c = pyhr.Context(device)
+    c.set_bluenoise(*pyhr.blue_noise())
+    c.build_scene(sc)
+    c.gbuffer_create(W, H)
+    if world > 1:
+        c.shard_config(rank, world)
+    return c, pyhr.Pass(c, "shadows", W, H, sh_scale), pyhr.Pass(c, "ao", W, H, ao_scale)
+
+
+def merge_bands(images, pass_h, world, shift=0):
+    """assemble the complete image from each rank's copy: rank r contributes its band (what the NCCL exchange does)"""
+    out = images[0].copy()
+    for r in range(world):
+        b, e = pyhr.shard_rows(pass_h, r, world)
+        e2 = out.shape[0] if e >= pass_h else e << shift
+        out[b << shift:e2] = images[r][b << shift:e2]
+    return out
+
+
+@pytest.mark.parametrize("world,sh_scale,ao_scale", [(2, 0, 1), (3, 0, 1), (4, 1, 0)])
+def test_sharded_emulation_bit_identical(world, sh_scale, ao_scale):
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ref = make_rank(0, sc, sh_scale, ao_scale)
+    ranks = [make_rank(0, sc, sh_scale, ao_scale, r, world) for r in range(world)]
+    sh_h, ao_h = H >> sh_scale, H >> ao_scale
+    for f in frames(7):
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        for c, sh, ao in [ref] + ranks:
+            c.gbuffer_upload(f.ping_pong, g)
+            sh.render(f)
+            ao.render(f)
+        # exchange: final output + history surfaces
+        for name, which, shift in (("prev", SH["prev"], 0), ("moments", SH["moments"], 0), ("final", SH["final"], sh_scale)):
+            merged = merge_bands([r[1].download(which) for r in ranks], sh_h, world, shift if name == "final" else 0)
+            assert np.array_equal(merged, ref[1].download(which)), f"shadows {name} differs (world={world}, frame {f.num_frames})"
+            for r in ranks:
+                r[1].upload(which, merged)
+        for name, which, shift in (("temporal", AO["temporal"], 0), ("length", AO["length"], 0), ("final", AO["final"], ao_scale)):
+            merged = merge_bands([r[2].download(which) for r in ranks], ao_h, world, shift if name == "final" else 0)
+            assert np.array_equal(merged, ref[2].download(which)), f"ao {name} differs (world={world}, frame {f.num_frames})"
+            for r in ranks:
+                r[2].upload(which, merged)
+    for c, sh, ao in [ref] + ranks:
+        sh.destroy()
+        ao.destroy()
+        c.close()
+
+
+def _nccl_worker(rank, world, uid, result_dir):
+    import torch
+    torch.cuda.set_device(rank)
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    c = pyhr.Context(rank)
+    c.set_bluenoise(*pyhr.blue_noise())
+    c.build_scene(sc)
+    c.gbuffer_create(W, H)
+    c.shard_init(rank, world, uid)
+    sh, ao = pyhr.Pass(c, "shadows", W, H, 0), pyhr.Pass(c, "ao", W, H, 1)
+    outs = []
+    for f in frames(6):
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        c.gbuffer_upload(f.ping_pong, g)
+        sh.render(f)
+        ao.render(f)
+        outs.append((sh.download(100), sh.download(SH["prev"]), sh.download(SH["moments"]), ao.download(100), ao.download(AO["temporal"])))
+    np.savez(os.path.join(result_dir, f"rank{rank}.npz"), **{f"f{i}_{j}": a for i, o in enumerate(outs) for j, a in enumerate(o)})
+    sh.destroy()
+    ao.destroy()
+    c.shard_shutdown()
+    c.close()
+
+
+def test_nccl_sharded_matches_single(tmp_path):
+    import torch
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    uid = pyhr.shard_unique_id()
+    mp.spawn(_nccl_worker, args=(world, uid, str(tmp_path)), nprocs=world, join=True)
+    # single-GPU reference in this process
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    c, sh, ao = make_rank(0, sc, 0, 1)
+    ref = []
+    for f in frames(6):
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        c.gbuffer_upload(f.ping_pong, g)
+        sh.render(f)
+        ao.render(f)
+        ref.append((sh.download(100), sh.download(SH["prev"]), sh.download(SH["moments"]), ao.download(100), ao.download(AO["temporal"])))
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
+        for i, o in enumerate(ref):
+            for j, a in enumerate(o):
+                assert np.array_equal(d[f"f{i}_{j}"], a), f"rank {r} frame {i} image {j} differs from the single-GPU result"
+    sh.destroy()
+    ao.destroy()
+    c.close()
