@@ -262,7 +262,11 @@ def main():
         atrous = [ms for name, ms in sh_stages if name.startswith("A-Trous")]
         at_ms = float(np.mean(atrous)) if atrous else None
         px = W * H
-        achieved = (ATROUS_BYTES_PER_PX * px / 1e9) / (at_ms / 1e3) if at_ms else None
+        # rows rank 0's a-trous launches cover: its band +- 16 halo rows when sharded, the whole image otherwise
+        b0, b1 = pyhr.shard_rows(H, 0, world)
+        at_rows = (min(b1 + 16, H) - max(b0 - 16, 0)) if world > 1 else H
+        at_px = W * at_rows
+        achieved = (ATROUS_BYTES_PER_PX * at_px / 1e9) / (at_ms / 1e3) if at_ms else None
         rays_per_frame = px + (W >> args.ao_scale) * (H >> args.ao_scale)  # upper bound: one ray per non-sky pixel per effect
         rt_ms = dict(sh_stages).get("Ray Trace", 0.0) + dict(ao_stages).get("Ray Trace", 0.0)
         line = {
@@ -272,7 +276,7 @@ def main():
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(g_host.nbytes()), "d2h_bytes_per_step": int(out_sh.nbytes + out_ao.nbytes)},
             "roofline": {"kernel": "k_atrous_tiled (shadows a-trous, K5)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                         "avg_launch_ms": at_ms, "algorithmic_bytes_per_launch": ATROUS_BYTES_PER_PX * px},
+                         "avg_launch_ms": at_ms, "algorithmic_bytes_per_launch": ATROUS_BYTES_PER_PX * at_px},
             "stages_ms": {"shadows": dict(sh_stages), "ao": dict(ao_stages)},
             "mrays_per_s": {"primary_rays_per_frame_upper_bound": rays_per_frame, "trace_kernels_ms": rt_ms,
                             "value": (rays_per_frame / 1e6) / (rt_ms / 1e3) if rt_ms else None},

@@ -738,6 +738,7 @@ int hr_pass_destroy(hr_pass* p)
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (void* a : p->allocs) cudaFree(a);
+    for (void* a : p->ddgi_grid_allocs) cudaFree(a);
     for (auto& r : p->timer.recs) for (auto e : r.ev) cudaEventDestroy(e);
     for (auto e : p->timer.pool) cudaEventDestroy(e);
     delete p;
@@ -797,3 +798,5 @@ int hr_shard_config(hr_ctx* ctx, int rank, int world)
 }
 
 } // extern "C"
+
+#include "hr_api_gi.inc"

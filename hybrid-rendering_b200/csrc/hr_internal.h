@@ -146,9 +146,47 @@ struct hr_pass {
     __half*   ao_color[2] = { nullptr, nullptr };
     __half*   ao_len[2] = { nullptr, nullptr };
     __half*   ao_blur[2] = { nullptr, nullptr };
+    // reflections (RGBA16F images as uint2)
+    uint2*    refl_rt = nullptr;
+    uint2*    refl_temporal[2] = { nullptr, nullptr }; // current_output[pp] (also the history of the next frame)
+    uint2*    refl_moments[2] = { nullptr, nullptr };
+    uint2*    refl_prev = nullptr;                     // prev_image (blur_as_input)
+    uint2*    refl_atrous[2] = { nullptr, nullptr };
+    uint2*    refl_upsample = nullptr;
+    // ddgi
+    hr_ddgi_uniforms ddgi_u {};
+    bool      ddgi_grid_valid = false;
+    const void* ddgi_scene = nullptr;
+    float     ddgi_key[4] = { 0, 0, 0, 0 };            // probe_distance, irradiance_oct, depth_oct, rays_per_probe
+    int       ddgi_mp = 0;                             // m_ping_pong (ddgi.cpp:103)
+    bool      ddgi_first = true;
+    uint2*    ddgi_radiance = nullptr;
+    uint2*    ddgi_dirdepth = nullptr;
+    uint2*    ddgi_irr[2] = { nullptr, nullptr };
+    uint32_t* ddgi_depth[2] = { nullptr, nullptr };
+    uint2*    ddgi_sample = nullptr;
+    std::vector<void*> ddgi_grid_allocs;
     StageTimer timer;
     std::vector<void*> allocs;
 };
+
+// rt_shade.cu / ddgi_update.cu / svgf_reflections.cu
+void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const void* irr_prev, const void* depth_prev, const hr_light& light, const float* rot16,
+                           uint32_t num_frames, uint32_t infinite_bounces, float gi_intensity, const float* sky3, int probe0, int probe1, void* radiance,
+                           void* dirdepth, cudaStream_t st);
+void launch_ddgi_probe_update(const hr_ddgi_uniforms& d, const void* radiance, const void* dirdepth, const void* prev_irr, const void* prev_depth, void* out_irr,
+                              void* out_depth, int first_frame, int probe0, int probe1, cudaStream_t st);
+void launch_ddgi_sample_probe_grid(const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms& d, const void* irr, const void* depth, float gi_intensity,
+                                   void* out, int row0, int row1, cudaStream_t st);
+void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
+                                  float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, int row0, int row1, cudaStream_t st);
+void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const void* hist, const void* hist_mom, const FrameConsts& fc,
+                                 float alpha, float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1,
+                                 cudaStream_t st);
+int  launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
+                               float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st);
+void launch_upsample_vec4(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st);
 
 // ---- row-band sharding (shard.cu) ---------------------------------------------------------------------
 // An image whose rows are owned band-wise by the ranks.  The band partition is defined on the PASS height `H`

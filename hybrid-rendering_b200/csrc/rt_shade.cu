@@ -1,0 +1,325 @@
+// rt_shade.cu — the two closest-hit ray-trace stages with hit shading.
+//   K18 gi/gi_ray_trace.{rgen,rchit,rmiss}                     (256 rays / probe -> radiance + direction/distance images)
+//   K12 reflections/reflections_ray_trace.{rgen,rchit,rmiss}   (1 reflection ray / pixel -> RGBA16F colour + ray length)
+// Hit shading: fetch_triangle / interpolated_vertex (scene_descriptor_set.glsl:117-160), direct_lighting
+// (lighting.glsl:117-196) with its shadow ray, evaluate_uber_brdf (brdf.glsl:130-142), DDGI infinite bounce
+// (gi_common.glsl:188-320).  Environment = constant colour (sky cubemap / IBL assets are not in the repository).
+//
+// BUILD NOTE: compiled with -fmad=false.  Everything that decides *which surface is hit or whether a shadow ray is
+// blocked* (ray directions, hit point, shading normal, shadow-ray origin) follows the deterministic fp32 rules of
+// det_math.cuh so that the binary visibility inside the shading is identical to the CPU oracle's; colours are
+// tolerance-checked.
+#include "gi_common.cuh"
+#include "traverse.cuh"
+
+namespace {
+
+using det::V3;
+using namespace trv;
+
+struct ShadeDev {
+    const float*       verts;    // n*9 world-space positions, primitive order
+    const float4*      vnormals; // n*3 world-space unit vertex normals
+    const uint32_t*    prim_mat;
+    const hr_material* materials;
+};
+
+struct Surface { V3 P, N; float3 albedo; float roughness, metallic; };
+
+__device__ __forceinline__ float3 to_f3(V3 v) { return make_float3(v.x, v.y, v.z); }
+
+__device__ __forceinline__ Surface fetch_surface(const ShadeDev& sd, uint32_t prim, float u, float v)
+{
+    const float* p  = sd.verts + 9ull * prim;
+    const float4 n0 = __ldg(sd.vnormals + 3ull * prim), n1 = __ldg(sd.vnormals + 3ull * prim + 1), n2 = __ldg(sd.vnormals + 3ull * prim + 2);
+    const float  b0 = 1.0f - u - v, b1 = u, b2 = v;
+    Surface      s;
+    s.P = det::add(det::add(det::scale(det::mk(__ldg(p), __ldg(p + 1), __ldg(p + 2)), b0), det::scale(det::mk(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5)), b1)),
+                   det::scale(det::mk(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8)), b2));
+    s.N = det::normalize(det::add(det::add(det::scale(det::mk(n0.x, n0.y, n0.z), b0), det::scale(det::mk(n1.x, n1.y, n1.z), b1)), det::scale(det::mk(n2.x, n2.y, n2.z), b2)));
+    const hr_material* m = sd.materials + __ldg(sd.prim_mat + prim);
+    s.albedo    = make_float3(m->albedo[0], m->albedo[1], m->albedo[2]);
+    s.roughness = fmaxf(m->roughness, 0.1f); // MIN_ROUGHNESS
+    s.metallic  = m->metallic;
+    return s;
+}
+
+// ---- brdf.glsl:36-142 (colour maths) ----------------------------------------------------------------------------------
+__device__ __forceinline__ float D_ggx(float ndoth, float alpha)
+{
+    const float a2 = alpha * alpha, denom = (ndoth * ndoth) * (a2 - 1.0f) + 1.0f;
+    return a2 / fmaxf(0.0001f, 3.14159265359f * denom * denom);
+}
+__device__ __forceinline__ float G1_schlick_ggx(float roughness, float ndotv)
+{
+    const float k = ((roughness + 1.0f) * (roughness + 1.0f)) / 8.0f;
+    return ndotv / fmaxf(0.0001f, ndotv * (1.0f - k) + k);
+}
+__device__ __forceinline__ float3 evaluate_uber_brdf(float3 diffuse_color, float roughness, V3 N, float3 F0, V3 Wo, V3 Wh, V3 Wi)
+{
+    using namespace gi;
+    const float NdotL = fmaxf(det::dot(N, Wi), 0.0f), NdotV = fmaxf(det::dot(N, Wo), 0.0f), NdotH = fmaxf(det::dot(N, Wh), 0.0f), VdotH = fmaxf(det::dot(Wi, Wh), 0.0f);
+    const float p5 = powf(1.0f - VdotH, 5.0f);
+    const float3 F = F0 + (f3(1, 1, 1) - F0) * p5;
+    const float spec = D_ggx(NdotH, roughness * roughness) * (G1_schlick_ggx(roughness, NdotL) * G1_schlick_ggx(roughness, NdotV)) / fmaxf(0.0001f, 4.0f * NdotL * NdotV);
+    return (f3(1, 1, 1) - F) * (diffuse_color * (1.0f / 3.14159265359f)) + F * spec;
+}
+
+// fetch_light_properties without SOFT_SHADOWS (lighting.glsl:6-111)
+__device__ __forceinline__ void fetch_light_properties_hard(const hr_light& L, V3 P, V3 N, float3& Li, V3& Wi, float& t_max, float& attenuation)
+{
+    const int type = (int)L.data3[0];
+    const V3  ldir = det::mk(L.data0[0], L.data0[1], L.data0[2]);
+    Li = make_float3(L.data2[0] * L.data0[3], L.data2[1] * L.data0[3], L.data2[2] * L.data0[3]);
+    if (type == 0) { Wi = ldir; t_max = 10000.0f; attenuation = 1.0f; }
+    else
+    {
+        const V3    to_light = det::sub(det::mk(L.data1[0], L.data1[1], L.data1[2]), P);
+        const float dist     = det::length(to_light);
+        Wi    = det::normalize(to_light);
+        t_max = dist;
+        if (type == 1) attenuation = 1.0f / (dist * dist);
+        else
+        {
+            const float e0 = L.data3[1], e1 = L.data3[2];
+            const float t = det::clampf((det::dot(Wi, ldir) - e0) / (e1 - e0), 0.0f, 1.0f);
+            attenuation   = (t * t * (3.0f - 2.0f * t)) / (dist * dist);
+        }
+    }
+    attenuation *= det::clampf(det::dot(N, Wi), 0.0f, 1.0f);
+}
+
+// direct_lighting, lighting.glsl:117-196
+__device__ float3 direct_lighting(const BvhDev& bvh, const hr_light& light, V3 Wo, V3 N, V3 P, float3 F0, float3 diffuse_color, float roughness, bool sky_light,
+                                  float r0, float r1, float3 sky)
+{
+    using namespace gi;
+    float3 Lo = f3(0, 0, 0);
+    Ray    sr;
+    sr.o    = det::add(P, det::scale(N, 0.1f));
+    sr.tmin = 0.01f;
+    {
+        float3 Li;
+        V3     Wi;
+        float  t_max, att;
+        fetch_light_properties_hard(light, P, N, Li, Wi, t_max, att);
+        const V3 Wh = det::normalize(det::add(Wo, Wi));
+        if (att > 0.0f)
+        {
+            sr.d    = Wi;
+            sr.tmax = t_max;
+            att *= trace_any(bvh, sr) ? 0.0f : 1.0f;
+        }
+        const float3 brdf = evaluate_uber_brdf(diffuse_color, roughness, N, F0, Wo, Wh, Wi);
+        Lo = Lo + (brdf * att) * Li;
+    }
+    if (sky_light)
+    {
+        const V3 Wi = det::sample_cosine_lobe(N, r0, r1);
+        const V3 Wh = det::normalize(det::add(Wo, Wi));
+        sr.d    = Wi;
+        sr.tmax = 10000.0f;
+        const float  vis  = trace_any(bvh, sr) ? 0.0f : 1.0f;
+        const float3 brdf = evaluate_uber_brdf(diffuse_color, roughness, N, F0, Wo, Wh, Wi);
+        Lo = Lo + brdf * (sky * vis);
+    }
+    return Lo;
+}
+
+__device__ float3 indirect_diffuse(const hr_ddgi_uniforms& d, const gi::AtlasDev& at, V3 Wo, V3 N, V3 P, float3 F0, float3 diffuse_color, float roughness,
+                                   float metallic, float gi_intensity)
+{
+    using namespace gi;
+    const float  ct = fmaxf(det::dot(N, Wo), 0.0f);
+    const float  p5 = powf(fmaxf(1.0f - ct, 0.0f), 5.0f), omr = 1.0f - roughness;
+    const float3 F  = F0 + (f3(fmaxf(omr, F0.x), fmaxf(omr, F0.y), fmaxf(omr, F0.z)) - F0) * p5;
+    const float3 kD = (f3(1, 1, 1) - F) * (1.0f - metallic);
+    const float3 irr = sample_irradiance(d, at, to_f3(P), to_f3(N), to_f3(Wo));
+    return (kD * diffuse_color) * irr * gi_intensity;
+}
+
+__device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& sd, const hr_light& light, const Ray& r, uint32_t prim, float u, float v, bool sky_light,
+                                            float r0, float r1, float3 sky, bool gi_on, const hr_ddgi_uniforms& d, const gi::AtlasDev& at, float gi_intensity)
+{
+    using namespace gi;
+    const Surface s  = fetch_surface(sd, prim, u, v);
+    const V3      Wo = det::scale(r.d, -1.0f);
+    const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;             // mix(0.04, albedo, metallic)
+    const float3  cd = (s.albedo * (f3(1, 1, 1) - F0)) * (1.0f - s.metallic) + f3(0, 0, 0) * s.metallic; // mix(albedo*(1-F0), 0, metallic)
+    float3        Lo = direct_lighting(bvh, light, Wo, s.N, s.P, F0, cd, s.roughness, sky_light, r0, r1, sky);
+    if (gi_on) Lo = Lo + indirect_diffuse(d, at, Wo, s.N, s.P, F0, cd, s.roughness, s.metallic, gi_intensity);
+    return Lo;
+}
+
+__device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d)
+{
+    const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+}
+
+// gi_ray_trace.rgen:61-72
+__device__ __forceinline__ V3 spherical_fibonacci(float i, float n)
+{
+    const float PHI = sqrtf(5.0f) * 0.5f + 0.5f;
+    const float a   = i * (PHI - 1.0f);
+    const float phi = 2.0f * 3.14159265359f * (a - floorf(a));
+    const float ct  = 1.0f - (2.0f * i + 1.0f) * (1.0f / n);
+    const float st  = sqrtf(det::clampf(1.0f - ct * ct, 0.0f, 1.0f));
+    float       sn, cs;
+    det::det_sincos(phi, &sn, &cs);
+    return det::mk(cs * st, sn * st, ct);
+}
+
+struct GiTraceParams { float rot[16]; uint32_t num_frames, infinite_bounces; float gi_intensity; float sky[3]; int probe0, probe1; };
+
+// K18: one block per probe, one thread per ray (blockDim = rays_per_probe rounded up to 32, looped if > 256)
+__global__ void __launch_bounds__(256) k_ddgi_ray_trace(BvhDev bvh, ShadeDev sd, hr_ddgi_uniforms d, gi::AtlasDev at, hr_light light, GiTraceParams P,
+                                                         uint2* __restrict__ radiance, uint2* __restrict__ dirdepth)
+{
+    const int probe = P.probe0 + blockIdx.x;
+    if (probe >= P.probe1) return;
+    const int cx = d.probe_counts[0], cxy = d.probe_counts[0] * d.probe_counts[1];
+    const V3  origin = det::mk(d.grid_step[0] * (float)(probe % cx) + d.grid_start_position[0], d.grid_step[1] * (float)((probe % cxy) / cx) + d.grid_start_position[1],
+                               d.grid_step[2] * (float)(probe / cxy) + d.grid_start_position[2]);
+    const float3 sky = make_float3(P.sky[0], P.sky[1], P.sky[2]);
+    for (int ray = threadIdx.x; ray < d.rays_per_probe; ray += blockDim.x)
+    {
+        const V3 sf = spherical_fibonacci((float)ray, (float)d.rays_per_probe);
+        Ray      r;
+        r.o = origin;
+        r.d = det::normalize(det::mk((P.rot[0] * sf.x + P.rot[4] * sf.y) + P.rot[8] * sf.z, (P.rot[1] * sf.x + P.rot[5] * sf.y) + P.rot[9] * sf.z,
+                                     (P.rot[2] * sf.x + P.rot[6] * sf.y) + P.rot[10] * sf.z));
+        r.tmin = 0.001f;
+        r.tmax = 10000.0f;
+        gi::RNG  rng = gi::rng_init((uint32_t)ray, (uint32_t)probe, P.num_frames);
+        float    t, u, v, hit_distance = 10000.0f;
+        uint32_t prim;
+        float3   L;
+        if (trace_closest(bvh, r, t, prim, u, v))
+        {
+            const float r0 = gi::next_float(rng), r1 = gi::next_float(rng);
+            L              = shade_hit(bvh, sd, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity);
+            hit_distance   = 0.001f + t;
+        }
+        else L = sky;
+        const size_t o = (size_t)probe * d.rays_per_probe + ray;
+        radiance[o] = pack_h4(L.x, L.y, L.z, 0.0f);
+        dirdepth[o] = pack_h4(r.d.x, r.d.y, r.d.z, hit_distance);
+    }
+}
+
+__device__ __forceinline__ V3 reflect(V3 I, V3 N) { return det::sub(I, det::scale(N, 2.0f * det::dot(N, I))); }
+
+// importance_sample_ggx, reflections_ray_trace.rgen:78-105
+__device__ __forceinline__ V3 importance_sample_ggx(float ex, float ey, V3 N, float roughness)
+{
+    const float a = roughness * roughness, m2 = a * a;
+    const float phi = 2.0f * 3.14159265359f * ex;
+    const float ct  = sqrtf((1.0f - ey) / (1.0f + (m2 - 1.0f) * ey));
+    const float st  = sqrtf(1.0f - ct * ct);
+    float       sn, cs;
+    det::det_sincos(phi, &sn, &cs);
+    const V3 H  = det::mk(cs * st, sn * st, ct);
+    const V3 up = fabsf(N.z) < 0.999f ? det::mk(0, 0, 1) : det::mk(1, 0, 0);
+    const V3 tangent   = det::normalize(det::cross(up, N));
+    const V3 bitangent = det::cross(N, tangent);
+    return det::normalize(det::add(det::add(det::scale(tangent, H.x), det::scale(bitangent, H.y)), det::scale(N, H.z)));
+}
+
+struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int row0, row1; };
+
+// K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
+__global__ void __launch_bounds__(256) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
+                                                                ReflTraceParams P, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk,
+                                                                uint2* __restrict__ out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7), y = P.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    if (x >= g.W || y >= g.H || y >= P.row1) return;
+    const size_t idx   = (size_t)y * g.W + x;
+    const float  depth = __ldg(g.depth + idx);
+    if (depth == 1.0f) { out[idx] = pack_h4(0.0f, 0.0f, 0.0f, -1.0f); return; }
+    const float  u = ((float)x + 0.5f) / (float)g.W, v = ((float)y + 0.5f) / (float)g.H;
+    const uint2  g2 = __ldg(g.gb2 + idx), g3 = __ldg(g.gb3 + idx);
+    const float2 e  = __half22float2(*reinterpret_cast<const __half2*>(&g2.x));
+    const float  roughness = __half22float2(*reinterpret_cast<const __half2*>(&g3.x)).x;
+    const V3     Pw = det::world_position_from_depth(u, v, depth, fc.view_proj_inverse);
+    const V3     N  = det::octohedral_to_direction(e.x, e.y);
+    const V3     Wo = det::normalize(det::sub(det::mk(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]), Pw));
+    const float3 sky = make_float3(P.sky[0], P.sky[1], P.sky[2]);
+    Ray          r;
+    r.o    = det::add(Pw, det::scale(N, P.bias));
+    r.tmin = 0.001f;
+    r.tmax = 10000.0f;
+    float3 color = make_float3(0, 0, 0);
+    float  ray_length = -1.0f;
+    bool   trace = false;
+    if (roughness < 0.05f) { r.d = reflect(det::scale(Wo, -1.0f), N); trace = true; }
+    else if (roughness > 0.75f && P.approximate_with_ddgi == 1)
+    {
+        const V3 R = reflect(det::scale(Wo, -1.0f), N);
+        using namespace gi;
+        color = sample_irradiance(d, at, to_f3(Pw), to_f3(R), to_f3(Wo)) * P.rough_ddgi_intensity;
+    }
+    else
+    {
+        const float ex = det::sample_blue_noise(x, y, (int)fc.num_frames, 0, sobol, srk) * P.trim;
+        const float ey = det::sample_blue_noise(x, y, (int)fc.num_frames, 1, sobol, srk) * P.trim;
+        const V3    Wh = importance_sample_ggx(ex, ey, N, roughness);
+        r.d   = reflect(det::scale(Wo, -1.0f), Wh);
+        trace = true;
+    }
+    if (trace)
+    {
+        float    t, hu, hv;
+        uint32_t prim;
+        if (trace_closest(bvh, r, t, prim, hu, hv))
+        {
+            color      = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity);
+            ray_length = 0.001f + t;
+        }
+        else color = sky;
+    }
+    out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), ray_length);
+}
+
+ShadeDev shade_view(const hr_scene* sc)
+{
+    ShadeDev s;
+    s.verts     = sc->d_tri_verts;
+    s.vnormals  = sc->d_vnormals;
+    s.prim_mat  = sc->d_prim_mat;
+    s.materials = sc->d_materials;
+    return s;
+}
+
+} // namespace
+
+void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const void* irr_prev, const void* depth_prev, const hr_light& light, const float* rot16,
+                           uint32_t num_frames, uint32_t infinite_bounces, float gi_intensity, const float* sky3, int probe0, int probe1, void* radiance,
+                           void* dirdepth, cudaStream_t st)
+{
+    if (probe1 <= probe0) return;
+    GiTraceParams P;
+    memcpy(P.rot, rot16, 64);
+    P.num_frames = num_frames; P.infinite_bounces = infinite_bounces; P.gi_intensity = gi_intensity;
+    P.sky[0] = sky3[0]; P.sky[1] = sky3[1]; P.sky[2] = sky3[2];
+    P.probe0 = probe0; P.probe1 = probe1;
+    gi::AtlasDev at { (const uint2*)irr_prev, (const uint32_t*)depth_prev };
+    int threads = d.rays_per_probe < 256 ? ((d.rays_per_probe + 31) / 32) * 32 : 256;
+    k_ddgi_ray_trace<<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth);
+}
+
+void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
+                                  float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, int row0, int row1, cudaStream_t st)
+{
+    if (row1 <= row0) return;
+    ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1 };
+    hr_ddgi_uniforms du;
+    memset(&du, 0, sizeof(du));
+    if (d) du = *d;
+    gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
+    dim3         grid((g.W + 31) / 32, (row1 - row0 + 7) / 8);
+    k_reflections_ray_trace<<<grid, 256, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+}

@@ -1,0 +1,174 @@
+// traverse.cuh — software BVH traversal shared by every ray-tracing kernel (trace.cu, rt_shade.cu).
+// Replaces rayQueryEXT / traceRayEXT over the driver TLAS (ray_query.glsl:6-59, reflections_ray_trace.rgen:150,165,
+// gi_ray_trace.rgen:96).  MUST be compiled with -fmad=false: ray_triangle is part of the deterministic chain
+// (det_math.cuh); the slab test uses explicit fmaf and only has to be conservative (boxes are padded at build time).
+#pragma once
+#include "det_math.cuh"
+#include "hr_internal.h"
+
+namespace trv {
+
+using det::V3;
+
+
+struct Ray { V3 o, d; float tmin, tmax; };
+
+// Moeller-Trumbore, fixed operation order (see oracle/orc_scene.h::ray_triangle for the CPU statement).
+__device__ __forceinline__ bool ray_triangle(const float4 A, const float4 B, const float4 C, const Ray& r, float& t, float& u, float& v)
+{
+    const V3    v0 = det::mk(A.x, A.y, A.z), e1 = det::mk(B.x, B.y, B.z), e2 = det::mk(C.x, C.y, C.z);
+    const V3    p   = det::cross(r.d, e2);
+    const float dt  = det::dot(e1, p);
+    if (dt == 0.0f) return false;
+    const float inv = 1.0f / dt;
+    const V3    tv  = det::sub(r.o, v0);
+    u               = det::dot(tv, p) * inv;
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    const V3 q = det::cross(tv, e1);
+    v          = det::dot(r.d, q) * inv;
+    if (!(v >= 0.0f && u + v <= 1.0f)) return false;
+    t = det::dot(e2, q) * inv;
+    return t > r.tmin && t < r.tmax;
+}
+
+#define STACK_SIZE 64
+#define SENTINEL 0x7FFFFFFF
+
+struct SlabSetup { float idx, idy, idz, ox, oy, oz; };
+__device__ __forceinline__ SlabSetup slab_setup(const Ray& r)
+{
+    // |d| < 1e-18 is replaced by +-1e-18 for the BOX test only: with an infinite reciprocal the fma form
+    // lo*inf - o*inf turns into NaN/-inf and would reject boxes the ray is inside of (not conservative).
+    SlabSetup s;
+    s.idx = 1.0f / (fabsf(r.d.x) > 1e-18f ? r.d.x : copysignf(1e-18f, r.d.x));
+    s.idy = 1.0f / (fabsf(r.d.y) > 1e-18f ? r.d.y : copysignf(1e-18f, r.d.y));
+    s.idz = 1.0f / (fabsf(r.d.z) > 1e-18f ? r.d.z : copysignf(1e-18f, r.d.z));
+    s.ox  = r.o.x * s.idx;
+    s.oy  = r.o.y * s.idy;
+    s.oz  = r.o.z * s.idz;
+    return s;
+}
+
+// Tests both children of a node; returns entry distances. fminf/fmaxf drop NaNs (0*inf) => conservative.
+__device__ __forceinline__ void node_test(const float4* __restrict__ nodes, int node, const SlabSetup& s, float tmin, float tmax, bool& h0, bool& h1,
+                                          float& tn0, float& tn1, int& c0, int& c1)
+{
+    const float4 n0 = __ldg(nodes + 4ull * node + 0);
+    const float4 n1 = __ldg(nodes + 4ull * node + 1);
+    const float4 nz = __ldg(nodes + 4ull * node + 2);
+    const float4 ch = __ldg(nodes + 4ull * node + 3);
+    c0 = __float_as_int(ch.x);
+    c1 = __float_as_int(ch.y);
+    float ax = fmaf(n0.x, s.idx, -s.ox), bx = fmaf(n0.y, s.idx, -s.ox);
+    float ay = fmaf(n0.z, s.idy, -s.oy), by = fmaf(n0.w, s.idy, -s.oy);
+    float az = fmaf(nz.x, s.idz, -s.oz), bz = fmaf(nz.y, s.idz, -s.oz);
+    tn0      = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    h0       = tn0 <= tf;
+    ax = fmaf(n1.x, s.idx, -s.ox); bx = fmaf(n1.y, s.idx, -s.ox);
+    ay = fmaf(n1.z, s.idy, -s.oy); by = fmaf(n1.w, s.idy, -s.oy);
+    az = fmaf(nz.z, s.idz, -s.oz); bz = fmaf(nz.w, s.idz, -s.oz);
+    tn1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    tf  = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    h1  = tn1 <= tf;
+}
+
+// Any-hit traversal (while-while). Returns true as soon as one triangle is hit in (tmin, tmax).
+static __device__ bool trace_any(const BvhDev& bvh, const Ray& r)
+{
+    int       stack[STACK_SIZE];
+    int       sp = 0;
+    stack[sp++]  = SENTINEL;
+    int             node = 0;
+    const SlabSetup s    = slab_setup(r);
+    while (node != SENTINEL)
+    {
+        while (node >= 0 && node != SENTINEL)
+        {
+            bool  h0, h1;
+            float t0, t1;
+            int   c0, c1;
+            node_test(bvh.nodes, node, s, r.tmin, r.tmax, h0, h1, t0, t1, c0, c1);
+            if (!h0 && !h1) node = stack[--sp];
+            else
+            {
+                node = h0 ? c0 : c1;
+                if (h0 && h1)
+                {
+                    if (t1 < t0) { int tmp = c1; c1 = node; node = tmp; }
+                    if (sp < STACK_SIZE) stack[sp++] = c1;
+                }
+            }
+        }
+        if (node < 0)
+        {
+            const int leaf  = ~node;
+            const int first = leaf >> 3, cnt = (leaf & 7) + 1;
+            for (int k = 0; k < cnt; k++)
+            {
+                const float4 A = __ldg(bvh.tris + 3ull * (first + k));
+                const float4 B = __ldg(bvh.tris + 3ull * (first + k) + 1);
+                const float4 C = __ldg(bvh.tris + 3ull * (first + k) + 2);
+                float        t, u, v;
+                if (ray_triangle(A, B, C, r, t, u, v)) return true;
+            }
+            node = stack[--sp];
+        }
+    }
+    return false;
+}
+
+// Closest hit; ties broken by the lowest primitive index (order independent).
+static __device__ bool trace_closest(const BvhDev& bvh, const Ray& r, float& best_t, uint32_t& best_prim, float& best_u, float& best_v)
+{
+    int stack[STACK_SIZE];
+    int sp      = 0;
+    stack[sp++] = SENTINEL;
+    int node    = 0;
+    best_t      = r.tmax;
+    best_prim   = 0xFFFFFFFFu;
+    best_u = best_v = 0.0f;
+    const SlabSetup s = slab_setup(r);
+    while (node != SENTINEL)
+    {
+        while (node >= 0 && node != SENTINEL)
+        {
+            bool  h0, h1;
+            float t0, t1;
+            int   c0, c1;
+            node_test(bvh.nodes, node, s, r.tmin, best_t, h0, h1, t0, t1, c0, c1);
+            if (!h0 && !h1) node = stack[--sp];
+            else
+            {
+                node = h0 ? c0 : c1;
+                if (h0 && h1)
+                {
+                    if (t1 < t0) { int tmp = c1; c1 = node; node = tmp; }
+                    if (sp < STACK_SIZE) stack[sp++] = c1;
+                }
+            }
+        }
+        if (node < 0)
+        {
+            const int leaf  = ~node;
+            const int first = leaf >> 3, cnt = (leaf & 7) + 1;
+            for (int k = 0; k < cnt; k++)
+            {
+                const float4 A = __ldg(bvh.tris + 3ull * (first + k));
+                const float4 B = __ldg(bvh.tris + 3ull * (first + k) + 1);
+                const float4 C = __ldg(bvh.tris + 3ull * (first + k) + 2);
+                float        t, u, v;
+                if (ray_triangle(A, B, C, r, t, u, v))
+                {
+                    const uint32_t prim = __float_as_uint(A.w);
+                    if (t < best_t || (t == best_t && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; }
+                }
+            }
+            node = stack[--sp];
+        }
+    }
+    return best_prim != 0xFFFFFFFFu;
+}
+
+
+} // namespace trv

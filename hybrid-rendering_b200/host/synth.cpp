@@ -492,6 +492,20 @@ void hrs_scene_world_triangles(const hrs_scene* s, float* out9, uint32_t* prim_i
     }
 }
 
+void hrs_scene_world_normals(const hrs_scene* s, float* out9, uint32_t* prim_material)
+{
+    for (size_t i = 0; i < s->tris.size(); i++)
+    {
+        const hrs_scene::Tri& t = s->tris[i];
+        if (out9)
+        {
+            float* o = out9 + 9 * i;
+            o[0] = t.n0.x; o[1] = t.n0.y; o[2] = t.n0.z; o[3] = t.n1.x; o[4] = t.n1.y; o[5] = t.n1.z; o[6] = t.n2.x; o[7] = t.n2.y; o[8] = t.n2.z;
+        }
+        if (prim_material) prim_material[i] = s->instances[t.inst].material_idx;
+    }
+}
+
 void hrs_default_light(hrs_light_desc* l)
 {
     memset(l, 0, sizeof(*l));

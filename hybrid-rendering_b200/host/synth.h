@@ -35,6 +35,8 @@ HR_API void               hrs_scene_bounds(const hrs_scene* s, float mn[3], floa
 /* World-space triangle soup, 9 floats per triangle, in the primitive order hr_scene_build uses
  * (instances in order, triangles in index order).  prim_instance (optional): instance index per triangle. */
 HR_API void hrs_scene_world_triangles(const hrs_scene* s, float* out9, uint32_t* prim_instance);
+/* World-space unit vertex normals (9 floats per triangle) and material index per triangle, same primitive order. */
+HR_API void hrs_scene_world_normals(const hrs_scene* s, float* out9, uint32_t* prim_material);
 
 /* Fill hr_frame like HybridRendering::update_uniforms (src/main.cpp:937-972) + create_camera (:248-255):
  * perspective(60 deg, W/H, 1, 1000), jitter 0.  prev == NULL => first frame (prev_view_proj = identity, first_frame = 1). */

@@ -88,6 +88,8 @@ ABI_SYMBOLS = [
     "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown",
+    "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
+    "hr_reflections_render",
 ]
 
 _product = None
@@ -124,6 +126,7 @@ def load_synth():
             getattr(lib, n).argtypes = [C.c_void_p]
         lib.hrs_scene_bounds.argtypes = [C.c_void_p, c_float_p, c_float_p]
         lib.hrs_scene_world_triangles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.hrs_scene_world_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.hrs_default_light.argtypes = [C.POINTER(hrs_light_desc)]
         lib.hrs_make_frame.argtypes = [C.POINTER(hr_frame), c_float_p, c_float_p, C.c_int, C.c_int, C.POINTER(hrs_light_desc), C.POINTER(hr_frame), C.c_uint32]
         lib.hrs_write_gbuffer.argtypes = [C.c_void_p, C.POINTER(hr_frame), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -187,6 +190,17 @@ class SynthScene:
         inst = np.empty(self.n_tris, np.uint32)
         self.lib.hrs_scene_world_triangles(self.h, _ptr(tri), _ptr(inst))
         return tri, inst
+
+    def world_normals(self):
+        nrm = np.empty((self.n_tris, 9), np.float32)
+        mat = np.empty(self.n_tris, np.uint32)
+        self.lib.hrs_scene_world_normals(self.h, _ptr(nrm), _ptr(mat))
+        return nrm, mat
+
+    def materials_array(self):
+        n = self.n_materials
+        buf = (hr_material * n).from_address(self.lib.hrs_scene_materials(self.h))
+        return buf
 
     def bounds(self):
         mn = (C.c_float * 3)()
@@ -383,3 +397,70 @@ class Pass:
         if self.h:
             self.lib.hr_pass_destroy(self.h)
             self.h = None
+
+
+class hr_ddgi_uniforms(C.Structure):
+    _fields_ = [("grid_start_position", C.c_float * 3), ("grid_step", C.c_float * 3), ("probe_counts", C.c_int32 * 3), ("max_distance", C.c_float),
+                ("depth_sharpness", C.c_float), ("hysteresis", C.c_float), ("normal_bias", C.c_float), ("energy_preservation", C.c_float),
+                ("irradiance_probe_side_length", C.c_int32), ("irradiance_texture_width", C.c_int32), ("irradiance_texture_height", C.c_int32),
+                ("depth_probe_side_length", C.c_int32), ("depth_texture_width", C.c_int32), ("depth_texture_height", C.c_int32),
+                ("rays_per_probe", C.c_int32), ("visibility_test", C.c_int32)]
+
+
+class hr_ddgi_params(C.Structure):
+    _fields_ = [("infinite_bounces", C.c_int32), ("infinite_bounce_intensity", C.c_float), ("rays_per_probe", C.c_int32), ("visibility_test", C.c_int32),
+                ("probe_distance", C.c_float), ("recursive_energy_preservation", C.c_float), ("irradiance_oct_size", C.c_int32), ("depth_oct_size", C.c_int32),
+                ("hysteresis", C.c_float), ("depth_sharpness", C.c_float), ("normal_bias", C.c_float), ("gi_intensity", C.c_float), ("sky_color", C.c_float * 3)]
+
+
+class hr_reflections_params(C.Structure):
+    _fields_ = [("bias", C.c_float), ("trim", C.c_float), ("sample_gi", C.c_int32), ("approximate_with_ddgi", C.c_int32), ("gi_intensity", C.c_float),
+                ("rough_ddgi_intensity", C.c_float), ("ibl_indirect_specular_intensity", C.c_float), ("alpha", C.c_float), ("moments_alpha", C.c_float),
+                ("blur_as_input", C.c_int32), ("phi_color", C.c_float), ("phi_normal", C.c_float), ("sigma_depth", C.c_float), ("radius", C.c_int32),
+                ("filter_iterations", C.c_int32), ("feedback_iteration", C.c_int32), ("denoise", C.c_int32), ("sky_color", C.c_float * 3)]
+
+
+def rotation_matrix(angle, axis):
+    """glm::mat4_cast(glm::angleAxis(angle, normalize(axis))) as 16 column-major floats (ddgi.cpp:788)"""
+    ax = np.asarray(axis, np.float64)
+    ax = ax / np.linalg.norm(ax)
+    c, s, t = np.cos(angle), np.sin(angle), 1.0 - np.cos(angle)
+    x, y, z = ax
+    R = np.array([[t * x * x + c, t * x * y - s * z, t * x * z + s * y], [t * x * y + s * z, t * y * y + c, t * y * z - s * x],
+                  [t * x * z - s * y, t * y * z + s * x, t * z * z + c]])
+    M = np.eye(4)
+    M[:3, :3] = R
+    return np.ascontiguousarray(M.T.reshape(16), np.float32)  # column-major
+
+
+class DDGIPass(Pass):
+    def __init__(self, ctx: Context, W, H, scale=0):
+        self.ctx, self.kind, self.lib = ctx, "ddgi", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_ddgi_create(ctx.h, W, H, scale, C.byref(h)), "hr_ddgi_create")
+        self.h = h
+        self.params = hr_ddgi_params()
+        self.lib.hr_ddgi_default_params(C.byref(self.params))
+
+    def render(self, frame: hr_frame, rot16, stream=0):
+        rot16 = np.ascontiguousarray(rot16, np.float32)
+        self.ctx.check(self.lib.hr_ddgi_render(self.h, C.byref(frame), C.byref(self.params), _ptr(rot16), C.c_void_p(stream)), "hr_ddgi_render")
+
+    def uniforms(self):
+        u = hr_ddgi_uniforms()
+        self.ctx.check(self.lib.hr_ddgi_get_uniforms(self.h, C.byref(u)), "hr_ddgi_get_uniforms")
+        return u
+
+
+class ReflectionsPass(Pass):
+    def __init__(self, ctx: Context, W, H, scale=1):
+        self.ctx, self.kind, self.lib = ctx, "reflections", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_reflections_create(ctx.h, W, H, scale, C.byref(h)), "hr_reflections_create")
+        self.h = h
+        self.params = hr_reflections_params()
+        self.lib.hr_reflections_default_params(C.byref(self.params))
+
+    def render(self, frame: hr_frame, ddgi: DDGIPass = None, stream=0):
+        self.ctx.check(self.lib.hr_reflections_render(self.h, C.byref(frame), C.byref(self.params), ddgi.h if ddgi is not None else None, C.c_void_p(stream)),
+                       "hr_reflections_render")

@@ -255,6 +255,101 @@ HR_API int  hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass*
 HR_API int  hr_ao_render(hr_pass* pass, const hr_frame* frame, const hr_ao_params* params, void* stream); /* :98-112 */
 
 /* ------------------------------------------------------------------------------------------------
+ * DDGI  (src/ddgi.{h,cpp}; shaders/gi/ *)
+ * ---------------------------------------------------------------------------------------------- */
+/* DDGIUniforms, src/ddgi.cpp:14-32 <-> gi_common.glsl:10-28 (scalar layout, 88 bytes) */
+typedef struct hr_ddgi_uniforms {
+    float   grid_start_position[3];
+    float   grid_step[3];
+    int32_t probe_counts[3];
+    float   max_distance;
+    float   depth_sharpness;
+    float   hysteresis;
+    float   normal_bias;
+    float   energy_preservation;
+    int32_t irradiance_probe_side_length;
+    int32_t irradiance_texture_width;
+    int32_t irradiance_texture_height;
+    int32_t depth_probe_side_length;
+    int32_t depth_texture_width;
+    int32_t depth_texture_height;
+    int32_t rays_per_probe;
+    int32_t visibility_test;
+} hr_ddgi_uniforms;
+
+typedef struct hr_ddgi_params { /* defaults: src/ddgi.h:52-115; per-scene overrides src/main.cpp:1084-1145 */
+    int32_t infinite_bounces;          /* 1    */
+    float   infinite_bounce_intensity; /* 1.7  */
+    int32_t rays_per_probe;            /* 256  */
+    int32_t visibility_test;           /* 1    */
+    float   probe_distance;            /* 1.0 (4.0 test scenes, 50.0 Sponza) */
+    float   recursive_energy_preservation; /* 0.85 */
+    int32_t irradiance_oct_size;       /* 8    */
+    int32_t depth_oct_size;            /* 16   */
+    float   hysteresis;                /* 0.98 */
+    float   depth_sharpness;           /* 50   */
+    float   normal_bias;               /* 0.25 */
+    float   gi_intensity;              /* 1.0 (sample_probe_grid) */
+    float   sky_color[3];              /* constant-colour environment replacing the sky cubemap (ENVIRONMENT "None" = 0) */
+} hr_ddgi_params;
+
+enum {
+    HR_DDGI_OUT_RADIANCE        = 0, /* RGBA16F rays_per_probe x num_probes  (gi_ray_trace.rgen:98) */
+    HR_DDGI_OUT_DIRECTION_DEPTH = 1, /* RGBA16F rays_per_probe x num_probes  (:99) */
+    HR_DDGI_OUT_IRRADIANCE      = 2, /* RGBA16F atlas written this frame */
+    HR_DDGI_OUT_DEPTH           = 3, /* RG16F atlas written this frame */
+    HR_DDGI_OUT_SAMPLE          = 4, /* RGBA16F per-pixel irradiance (gi_sample_probe_grid.comp) */
+    HR_DDGI_OUT_FINAL           = 100
+};
+
+HR_API void hr_ddgi_default_params(hr_ddgi_params* p);
+HR_API int  hr_ddgi_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out); /* ddgi.cpp:60-76 */
+/* render(), ddgi.cpp:89-104.  random_orientation: column-major mat4 (the reference draws it from std::mt19937 seeded by
+ * std::random_device, ddgi.cpp:73,788 — non-deterministic; the caller supplies it).  The probe grid is (re)initialised from
+ * the current scene's bounds when the scene or probe_distance / oct sizes / rays_per_probe change (ddgi.cpp:150-169). */
+HR_API int hr_ddgi_render(hr_pass* pass, const hr_frame* frame, const hr_ddgi_params* params, const float* random_orientation16, void* stream);
+HR_API int hr_ddgi_get_uniforms(hr_pass* pass, hr_ddgi_uniforms* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ray-traced reflections  (src/ray_traced_reflections.{h,cpp}; shaders/reflections/ *)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_reflections_params { /* defaults: src/ray_traced_reflections.h:51-123 */
+    float   bias;                  /* 0.5  */
+    float   trim;                  /* 0.8  */
+    int32_t sample_gi;             /* 1    */
+    int32_t approximate_with_ddgi; /* 1    */
+    float   gi_intensity;          /* 0.5  */
+    float   rough_ddgi_intensity;  /* 0.5  */
+    float   ibl_indirect_specular_intensity; /* 0.05; needs prefiltered environment + BRDF LUT assets: term is 0 here */
+    float   alpha;                 /* 0.01 */
+    float   moments_alpha;         /* 0.2  */
+    int32_t blur_as_input;         /* 0    */
+    float   phi_color;             /* 10   */
+    float   phi_normal;            /* 32   */
+    float   sigma_depth;           /* 1    */
+    int32_t radius;                /* 1    */
+    int32_t filter_iterations;     /* 4    */
+    int32_t feedback_iteration;    /* 1    */
+    int32_t denoise;               /* 1    */
+    float   sky_color[3];          /* miss colour (skybox cubemap replaced by a constant) */
+} hr_reflections_params;
+
+enum {
+    HR_REFLECTIONS_OUT_RAY_TRACE             = 0, /* RGBA16F (rgb clamped to 0.7, a = ray length or -1) */
+    HR_REFLECTIONS_OUT_TEMPORAL_ACCUMULATION = 1, /* RGBA16F (rgb, variance) */
+    HR_REFLECTIONS_OUT_ATROUS                = 2, /* RGBA16F */
+    HR_REFLECTIONS_OUT_UPSAMPLE              = 3, /* RGBA16F full-res */
+    HR_REFLECTIONS_OUT_MOMENTS               = 4, /* RGBA16F (m1, m2, history length, 0) */
+    HR_REFLECTIONS_OUT_TILE_FLAGS            = 6, /* R8_UINT: 1 = denoise list, 0 = copy list */
+    HR_REFLECTIONS_OUT_FINAL                 = 100
+};
+
+HR_API void hr_reflections_default_params(hr_reflections_params* p);
+HR_API int  hr_reflections_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out); /* ray_traced_reflections.cpp:67-103 */
+/* render(cmd_buf, DDGI*), ray_traced_reflections.cpp:107-123; ddgi may be NULL (then sample_gi / approximate_with_ddgi are off). */
+HR_API int hr_reflections_render(hr_pass* pass, const hr_frame* frame, const hr_reflections_params* params, hr_pass* ddgi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Common pass functions
  * ---------------------------------------------------------------------------------------------- */
 /* output_ds() equivalent: borrowed device image, valid until the next render/destroy of this pass. */

@@ -51,6 +51,20 @@ def lib():
         L.orc_ao_temporal.argtypes = [P, P, P, P, P, P, F, P, P, P]
         L.orc_ao_bilateral_blur.argtypes = [P, P, P, P, I, I, I, P]
         L.orc_num_threads.restype = C.c_int
+        L.orc_shading_create.restype = C.c_void_p
+        L.orc_shading_create.argtypes = [P, P, P, P, C.c_size_t, P, C.c_size_t]
+        L.orc_shading_destroy.argtypes = [P]
+        U = C.c_uint32
+        L.orc_ddgi_ray_trace.argtypes = [P, P, P, P, U, F, P, P, P, P, P]
+        L.orc_ddgi_probe_update.argtypes = [P, P, P, P, I, I, P]
+        L.orc_ddgi_border_update.argtypes = [P, I, P]
+        L.orc_ddgi_sample_probe_grid.argtypes = [P, P, P, P, P, F, P]
+        L.orc_reflections_ray_trace.argtypes = [P, P, P, F, F, I, I, F, F, P, P, P, P, P, P, P]
+        L.orc_reflections_temporal.argtypes = [P, P, P, P, P, P, F, F, I, P, P, P]
+        L.orc_reflections_atrous.argtypes = [P, P, P, I, I, F, F, F, I, P]
+        L.orc_upsample_vec4.argtypes = [P, P, P, P]
+        L.orc_rng_sequence.restype = U
+        L.orc_rng_sequence.argtypes = [U, U, U, P, I]
         _lib = L
     return _lib
 
@@ -248,3 +262,137 @@ class AOOracle:
 def h2f(a):
     """uint16 half bits -> float32"""
     return np.ascontiguousarray(a).view(np.float16).astype(np.float32)
+
+
+class ShadingScene:
+    """oracle-side scene with shading data (positions, vertex normals, materials) in primitive order"""
+
+    def __init__(self, synth_scene, brute=False):
+        tri, _ = synth_scene.world_triangles()
+        nrm, mat = synth_scene.world_normals()
+        self.scene = Scene(tri, brute)
+        self.tri, self.nrm, self.mat = tri, nrm, mat
+        self.synth = synth_scene
+        mats = synth_scene.materials_array()
+        self.h = lib().orc_shading_create(self.scene.h, p(tri), p(nrm), p(mat), tri.shape[0], C.cast(mats, C.c_void_p), synth_scene.n_materials)
+
+    def __del__(self):
+        try:
+            lib().orc_shading_destroy(self.h)
+        except Exception:
+            pass
+
+
+def ddgi_uniforms_from(params, bounds_min, bounds_max):
+    """initialize_probe_grid + update_properties_ubo (ddgi.cpp:150-169, :738-763)"""
+    u = pyhr.hr_ddgi_uniforms()
+    for a in range(3):
+        ln = np.float32(bounds_max[a]) - np.float32(bounds_min[a])
+        u.probe_counts[a] = int(np.float32(ln) / np.float32(params.probe_distance)) + 2
+        u.grid_start_position[a] = float(bounds_min[a])
+        u.grid_step[a] = params.probe_distance
+    cx, cy, cz = u.probe_counts[0], u.probe_counts[1], u.probe_counts[2]
+    u.max_distance = params.probe_distance * 1.5
+    u.depth_sharpness, u.hysteresis, u.normal_bias = params.depth_sharpness, params.hysteresis, params.normal_bias
+    u.energy_preservation = params.recursive_energy_preservation
+    u.irradiance_probe_side_length, u.depth_probe_side_length = params.irradiance_oct_size, params.depth_oct_size
+    u.irradiance_texture_width = (params.irradiance_oct_size + 2) * cx * cy + 2
+    u.irradiance_texture_height = (params.irradiance_oct_size + 2) * cz + 2
+    u.depth_texture_width = (params.depth_oct_size + 2) * cx * cy + 2
+    u.depth_texture_height = (params.depth_oct_size + 2) * cz + 2
+    u.rays_per_probe, u.visibility_test = params.rays_per_probe, params.visibility_test
+    return u
+
+
+class DDGIOracle:
+    """DDGI::render, src/ddgi.cpp:89-104"""
+
+    def __init__(self, W0, H0, scale, params, bounds_min, bounds_max):
+        self.W, self.H, self.scale = W0 >> scale, H0 >> scale, scale
+        self.params = params
+        self.u = ddgi_uniforms_from(params, bounds_min, bounds_max)
+        u = self.u
+        self.total = u.probe_counts[0] * u.probe_counts[1] * u.probe_counts[2]
+        self.radiance = np.zeros((self.total, u.rays_per_probe, 4), np.uint16)
+        self.dirdepth = np.zeros((self.total, u.rays_per_probe, 4), np.uint16)
+        self.irr = [np.zeros((u.irradiance_texture_height, u.irradiance_texture_width, 4), np.uint16) for _ in range(2)]
+        self.dep = [np.zeros((u.depth_texture_height, u.depth_texture_width, 2), np.uint16) for _ in range(2)]
+        self.sample = np.zeros((self.H, self.W, 4), np.uint16)
+        self.mp, self.first = 0, True
+
+    def render(self, ss: ShadingScene, cur: GBufMips, frame, rot16):
+        L, P, u, mp = lib(), self.params, self.u, self.mp
+        sky = np.array(P.sky_color[:], np.float32)
+        rot = np.ascontiguousarray(rot16, np.float32)
+        inf = 1 if (P.infinite_bounces and not self.first) else 0
+        L.orc_ddgi_ray_trace(ss.h, C.byref(u), C.byref(frame), p(rot), inf, P.infinite_bounce_intensity, p(sky), p(self.irr[1 - mp]), p(self.dep[1 - mp]),
+                             p(self.radiance), p(self.dirdepth))
+        ff = 1 if self.first else 0
+        L.orc_ddgi_probe_update(C.byref(u), p(self.radiance), p(self.dirdepth), p(self.irr[1 - mp]), ff, 0, p(self.irr[mp]))
+        L.orc_ddgi_probe_update(C.byref(u), p(self.radiance), p(self.dirdepth), p(self.dep[1 - mp]), ff, 1, p(self.dep[mp]))
+        L.orc_ddgi_border_update(C.byref(u), 0, p(self.irr[mp]))
+        L.orc_ddgi_border_update(C.byref(u), 1, p(self.dep[mp]))
+        gc = cur.c(self.scale)
+        L.orc_ddgi_sample_probe_grid(C.byref(gc), C.byref(frame), C.byref(u), p(self.irr[mp]), p(self.dep[mp]), P.gi_intensity, p(self.sample))
+        self.cur_irr, self.cur_dep = self.irr[mp], self.dep[mp]
+        self.first = False
+        self.mp = 1 - mp
+
+
+class ReflectionsOracle:
+    """RayTracedReflections::render, src/ray_traced_reflections.cpp:107-123"""
+
+    def __init__(self, W0, H0, scale, params):
+        self.W0, self.H0, self.scale = W0, H0, scale
+        self.W, self.H = W0 >> scale, H0 >> scale
+        W, H = self.W, self.H
+        self.params = params
+        self.rt = np.zeros((H, W, 4), np.uint16)
+        self.temporal = [np.zeros((H, W, 4), np.uint16) for _ in range(2)]
+        self.moments = [np.zeros((H, W, 4), np.uint16) for _ in range(2)]
+        self.prev_image = np.zeros((H, W, 4), np.uint16)
+        self.atrous = [np.zeros((H, W, 4), np.uint16) for _ in range(2)]
+        self.tile_flags = np.zeros(((H + 7) // 8, (W + 7) // 8), np.uint8)
+        self.upsample = np.zeros((H0, W0, 4), np.uint16) if scale else None
+        self.first = True
+        self.final = None
+
+    def render(self, ss: ShadingScene, cur: GBufMips, prev: GBufMips, frame, bn, ddgi: DDGIOracle = None):
+        L, P, pp = lib(), self.params, frame.ping_pong
+        sobol, sr = bn
+        if self.first:
+            self.prev_image[:] = 0
+            self.moments[1 - pp][:] = 0
+            self.temporal[1 - pp][:] = 0
+        have_gi = ddgi is not None
+        sample_gi = 1 if (P.sample_gi and have_gi and not self.first) else 0
+        approx = 1 if (P.approximate_with_ddgi and have_gi and not self.first) else 0
+        sky = np.array(P.sky_color[:], np.float32)
+        gc, gp = cur.c(self.scale), prev.c(self.scale)
+        # reflections read the atlas DDGI wrote this frame (ddgi.cpp:100-103,135-138)
+        up = C.byref(ddgi.u) if have_gi else None
+        irr = p(ddgi.cur_irr) if have_gi else None
+        dep = p(ddgi.cur_dep) if have_gi else None
+        L.orc_reflections_ray_trace(ss.h, C.byref(gc), C.byref(frame), P.bias, P.trim, sample_gi, approx, P.gi_intensity, P.rough_ddgi_intensity, p(sky), p(sobol), p(sr),
+                                    up, irr, dep, p(self.rt))
+        self.final = self.rt
+        self.first = False
+        if not P.denoise:
+            return
+        hist = self.prev_image if P.blur_as_input else self.temporal[1 - pp]
+        L.orc_reflections_temporal(C.byref(gc), C.byref(gp), p(self.rt), p(hist), p(self.moments[1 - pp]), C.byref(frame), P.alpha, P.moments_alpha, approx,
+                                   p(self.temporal[pp]), p(self.moments[pp]), p(self.tile_flags))
+        self.cur_temporal, self.cur_moments = self.temporal[pp], self.moments[pp]
+        src, toggle = self.temporal[pp], 1
+        for i in range(P.filter_iterations):
+            dst = self.atrous[toggle]
+            L.orc_reflections_atrous(C.byref(gc), p(src), p(self.tile_flags), P.radius, 1 << i, P.phi_color, P.phi_normal, P.sigma_depth, approx, p(dst))
+            if P.blur_as_input and i == P.feedback_iteration:
+                self.prev_image[:] = dst
+            src, toggle = dst, 1 - toggle
+        self.atrous_out = src
+        self.final = src
+        if self.scale:
+            g0 = cur.c(0)
+            L.orc_upsample_vec4(C.byref(g0), C.byref(gc), p(src), p(self.upsample))
+            self.final = self.upsample
