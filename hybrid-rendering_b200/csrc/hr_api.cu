@@ -121,6 +121,8 @@ int hr_shutdown(hr_ctx* ctx)
     cudaFree(ctx->d_sobol);
     cudaFree(ctx->d_scr_rank);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
+    if (ctx->nccl_comm) hr_shard_shutdown(ctx);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
     return HR_OK;
 }
@@ -501,6 +503,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
     timer_begin(p, st);
 
+    if (!prm->denoise || p->first) hr_wait_exchange(p, st); // the exchanged image (mask / cleared history) is rewritten right away
     // clear_images (ray_traced_shadows.cpp:938-968): first frame => history image and moments[!pp] = 0
     if (p->first)
     {
@@ -518,6 +521,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     if (prm->denoise)
     {
         // temporal_accumulation (:1041-1090); reset_args (:1015-1037) is subsumed by the per-tile flag image
+        hr_wait_exchange(p, st); // last frame's band exchange of prev_image / moments (overlapped with the ray trace above)
         launch_shadows_temporal(cur, prev, p->mask, p->prev_image, p->moments[!pp], fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp],
                                 p->tile_flags, row0, row1, st);
         ctx->launches++;
@@ -577,7 +581,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
             if (final_fmt == HR_FMT_R16F) it[n++] = { final_ptr, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
         else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
-        rc = hr_shard_exchange(ctx, it, n, st);
+        rc = hr_shard_exchange(p, it, n, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Exchange", st);
     }
@@ -631,6 +635,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
     hr_extend(b0, b1, ctx->world > 1 ? 8 : 0, p->H, &v0, &v1);
     timer_begin(p, st);
+    if (!prm->denoise || p->first) hr_wait_exchange(p, st);
     if (p->first)
     { // clear_images, ray_traced_ao.cpp:829-860
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_len[!pp], 0, px * sizeof(__half), st));
@@ -645,6 +650,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
     if (prm->denoise)
     {
+        hr_wait_exchange(p, st);
         launch_ao_temporal(cur, prev, p->mask, p->ao_color[!pp], p->ao_len[!pp], fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
         timer_mark(p, "Temporal Accumulation", st);
@@ -682,7 +688,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
             else it[n++] = { p->upsample_out, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
         else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
-        rc = hr_shard_exchange(ctx, it, n, st);
+        rc = hr_shard_exchange(p, it, n, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Exchange", st);
     }
@@ -698,6 +704,8 @@ int hr_pass_output(hr_pass* p, int which, hr_image* out)
     HR_REQUIRE(ctx, p && out && which >= 0 && which < 128, HR_ERR_INVALID_ARG, "hr_pass_output: bad argument");
     const hr_pass::Img& v = p->out_view[which];
     HR_REQUIRE(ctx, v.p != nullptr, HR_ERR_NOT_READY, "hr_pass_output: output not produced by the last render");
+    // a borrowed pointer may be consumed on any stream: finish a pending band exchange first (sharded runs only)
+    if (p->xchg_pending && p->ev_done) { cudaEventSynchronize(p->ev_done); p->xchg_pending = false; }
     out->data = v.p; out->width = v.w; out->height = v.h; out->format = v.fmt;
     return HR_OK;
 }
@@ -710,6 +718,7 @@ int hr_pass_download(hr_pass* p, int which, void* dst, size_t bytes, void* strea
     hr_ctx*      ctx  = p->ctx;
     const size_t need = (size_t)img.width * img.height * texel_size(img.format);
     HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download: byte count mismatch");
+    hr_wait_exchange(p, (cudaStream_t)stream);
     HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     return HR_OK;
@@ -725,6 +734,7 @@ int hr_pass_upload(hr_pass* p, int which, const void* src, size_t bytes, void* s
     hr_ctx*      ctx  = p->ctx;
     const size_t need = (size_t)img.width * img.height * texel_size(img.format);
     HR_REQUIRE(ctx, src && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_upload: byte count mismatch");
+    hr_wait_exchange(p, (cudaStream_t)stream);
     HR_CUDA(ctx, cudaMemcpyAsync(img.data, src, need, cudaMemcpyHostToDevice, (cudaStream_t)stream));
     HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     return HR_OK;
@@ -739,6 +749,8 @@ int hr_pass_destroy(hr_pass* p)
     cudaDeviceSynchronize();
     for (void* a : p->allocs) cudaFree(a);
     for (void* a : p->ddgi_grid_allocs) cudaFree(a);
+    if (p->ev_ready) cudaEventDestroy(p->ev_ready);
+    if (p->ev_done) cudaEventDestroy(p->ev_done);
     for (auto& r : p->timer.recs) for (auto e : r.ev) cudaEventDestroy(e);
     for (auto e : p->timer.pool) cudaEventDestroy(e);
     delete p;

@@ -76,6 +76,7 @@ struct hr_ctx {
     // sharding
     int          rank = 0, world = 1;
     void*        nccl_comm = nullptr; // ncclComm_t when hr_shard_init was called (NCCL is dlopen'ed lazily, see shard.cu)
+    cudaStream_t comm_stream = nullptr; // band exchanges run here, overlapped with the next pass / next frame's ray trace
     // profiling
     bool         profiling = false;
     uint64_t     launches  = 0;
@@ -166,6 +167,11 @@ struct hr_pass {
     uint32_t* ddgi_depth[2] = { nullptr, nullptr };
     uint2*    ddgi_sample = nullptr;
     std::vector<void*> ddgi_grid_allocs;
+    // asynchronous band exchange (shard.cu): ev_ready = pass kernels done on the caller's stream, ev_done = exchange done on
+    // ctx->comm_stream.  Whoever next touches an exchanged image (next frame's temporal stage, hr_pass_output/download)
+    // first makes its stream wait on ev_done (hr_wait_exchange).
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool        xchg_pending = false;
     StageTimer timer;
     std::vector<void*> allocs;
 };
@@ -202,7 +208,10 @@ inline void hr_extend(int b0, int b1, int halo, int H, int* e0, int* e1)
     *e1 = b1 + halo > H ? H : b1 + halo;
 }
 // Make every rank's copy of each image complete: rank r broadcasts its band of every item (one NCCL group).
-int hr_shard_exchange(hr_ctx* ctx, const ExchangeItem* items, int n, cudaStream_t st);
+// Asynchronous: enqueued on ctx->comm_stream after everything already enqueued on `st`; completion is p->ev_done.
+int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t st);
+// Make `st` wait for the pass's pending exchange (no-op when nothing is pending).
+void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
 int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st);

@@ -73,10 +73,25 @@ void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1)
     hr_shard_rows(H, ctx->rank, ctx->world, b0, b1);
 }
 
-int hr_shard_exchange(hr_ctx* ctx, const ExchangeItem* items, int n, cudaStream_t st)
+void hr_wait_exchange(hr_pass* p, cudaStream_t st)
 {
+    if (p && p->xchg_pending && p->ev_done) cudaStreamWaitEvent(st, p->ev_done, 0);
+}
+
+int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t caller)
+{
+    hr_ctx* ctx = p->ctx;
     if (ctx->world <= 1 || !ctx->nccl_comm) return HR_OK;
     NcclApi& N = nccl();
+    if (!ctx->comm_stream) HR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    if (!p->ev_ready)
+    {
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_done, cudaEventDisableTiming));
+    }
+    HR_CUDA(ctx, cudaEventRecord(p->ev_ready, caller));
+    HR_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, p->ev_ready, 0));
+    cudaStream_t st = ctx->comm_stream;
     HR_NCCL(ctx, N.GroupStart());
     for (int i = 0; i < n; i++)
         for (int r = 0; r < ctx->world; r++)
@@ -92,6 +107,8 @@ int hr_shard_exchange(hr_ctx* ctx, const ExchangeItem* items, int n, cudaStream_
             HR_NCCL(ctx, N.Broadcast(p, p, (size_t)(re - rb) * items[i].row_bytes, ncclUint8, r, (ncclComm_t)ctx->nccl_comm, st));
         }
     HR_NCCL(ctx, N.GroupEnd());
+    HR_CUDA(ctx, cudaEventRecord(p->ev_done, st));
+    p->xchg_pending = true;
     return HR_OK;
 }
 

@@ -17,7 +17,7 @@ struct hrs_scene {
     std::vector<hr_instance> instances;
     std::vector<hr_material> materials;
     // derived: world-space soup + BVH for primary visibility
-    struct Tri { V3 v0, e1, e2; V3 n0, n1, n2; uint32_t inst; };
+    struct Tri { V3 v0, e1, e2; V3 n0, n1, n2; uint32_t inst; V3 v1, v2; }; // v1, v2: the original vertices (v0 + e1 != v1 in fp32)
     struct Node { float lo[3], hi[3]; int left, right, first, count; };
     std::vector<Tri>  tris;     // primitive order (instances in order, triangles in index order)
     std::vector<Tri>  bvh_tris; // BVH leaf order
@@ -341,7 +341,7 @@ void hrs_scene::finalize()
                 mul_point(model, nin, no);
                 n[j] = normalize(V3 { no[0], no[1], no[2] });
             }
-            tris.push_back({ p[0], p[1] - p[0], p[2] - p[0], n[0], n[1], n[2], ii });
+            tris.push_back({ p[0], p[1] - p[0], p[2] - p[0], n[0], n[1], n[2], ii, p[1], p[2] });
         }
     }
     size_t n = tris.size();
@@ -350,7 +350,7 @@ void hrs_scene::finalize()
     bmax = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
     for (size_t i = 0; i < n; i++)
     {
-        V3 a = tris[i].v0, b = a + tris[i].e1, c = a + tris[i].e2;
+        V3 a = tris[i].v0, b = tris[i].v1, c = tris[i].v2;
         tmin[i] = { std::min({ a.x, b.x, c.x }), std::min({ a.y, b.y, c.y }), std::min({ a.z, b.z, c.z }) };
         tmax[i] = { std::max({ a.x, b.x, c.x }), std::max({ a.y, b.y, c.y }), std::max({ a.z, b.z, c.z }) };
         cen[i]  = (tmin[i] + tmax[i]) * 0.5f;
@@ -482,7 +482,7 @@ void hrs_scene_world_triangles(const hrs_scene* s, float* out9, uint32_t* prim_i
     for (size_t i = 0; i < s->tris.size(); i++)
     {
         const hrs_scene::Tri& t = s->tris[i];
-        V3 a = t.v0, b = t.v0 + t.e1, c = t.v0 + t.e2;
+        V3 a = t.v0, b = t.v1, c = t.v2;
         if (out9)
         {
             float* o = out9 + 9 * i;
