@@ -349,6 +349,8 @@ void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 // 0 = naive, 1 = tiled (default: measured 64-105 us/iter at 4K), 2 = chain / sliding window (72-107 us: the extra registers
 // cost more occupancy than the saved shared-memory traffic buys; profiles/README.md).  hr_debug_set key 1.
 int g_hr_atrous_impl = 1;
+bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n, float sigma_z,
+                              float power, uint32_t* out, int row0, int row1, cudaStream_t st); // svgf_atrous_v3.cu (impl 3: packed fp32x2)
 
 void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n,
                            float sigma_z, float power, __half2* out, int row0, int row1, cudaStream_t st)
@@ -357,7 +359,8 @@ void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8
     AtrousParams P { g.W, g.H, step, radius, phi_vis, phi_n, sigma_z, power, row0, row1 };
     const uint32_t* i32 = reinterpret_cast<const uint32_t*>(in);
     uint32_t*       o32 = reinterpret_cast<uint32_t*>(out);
-    const bool tiled_ok = g_hr_atrous_impl == 1 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8) && (row0 % TILE_H == 0 || true);
+    const bool tiled_ok = g_hr_atrous_impl != 0 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8);
+    if (g_hr_atrous_impl == 3 && launch_shadows_atrous_v3(g, i32, tile_flags, radius, step, phi_vis, phi_n, sigma_z, power, o32, row0, row1, st)) return;
     const bool chain_ok = g_hr_atrous_impl == 2 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8) && row0 % 8 == 0;
     if (chain_ok)
     {

@@ -1,0 +1,204 @@
+// svgf_atrous_v3.cu — shadows a-trous (K4+K5, shadows_denoise_atrous.comp:94-174) with packed fp32x2 arithmetic.
+//
+// The scalar tiled kernel (svgf_atrous.cu) is instruction-issue bound (ncu r1b: 54 % issue-active, 13 % DRAM): ~23 FP32
+// instructions per tap.  Blackwell (sm_100) has packed two-wide fp32 instructions (FFMA2 / FMUL2 / FADD2, exposed as
+// __ffma2_rn / __fmul2_rn / __fadd2_rn): this kernel lets every thread filter TWO horizontally adjacent pixels and keeps
+// each per-pixel quantity of the pair in one 64-bit register pair, so one issue slot does the work for both pixels.
+// Shared memory holds the staged tile as six fp32 planes (nx, ny, nz, z*log2e/sigma, visibility, variance); an aligned
+// LDS.64 fetches the same plane value for both pixels of a pair (taps at even column offsets), odd offsets (STEP = 1,
+// dx = +-1) use two LDS.32 straight into the register pair.  Out-of-image cells are staged with a zero normal (weight 0,
+// = the reference's `inside` test) and zero variance (texelFetch robust-access zeros).
+#include "glsl_fast.cuh"
+#include "hr_internal.h"
+
+namespace {
+
+using namespace gf;
+
+constexpr int TW3 = 64, TH3 = 16;
+
+struct V3Params {
+    int   W, H;
+    float c_sigma;   // log2(e) / sigma_depth
+    float c_phi0;    // -log2(e) / phi_visibility
+    float power;
+    int   row0, row1;
+};
+
+__device__ __forceinline__ float2 ld_pair(const float* __restrict__ plane, int idx, bool aligned)
+{
+    if (aligned) return *reinterpret_cast<const float2*>(plane + idx);
+    return make_float2(plane[idx], plane[idx + 1]);
+}
+
+struct PairCell { float2 nx, ny, nz, zs, vis, var; };
+
+template <int STEP>
+__global__ void __launch_bounds__(256) k_atrous_v3(GBufLevelDev g, const uint32_t* __restrict__ in, const uint8_t* __restrict__ tile_flags, V3Params P,
+                                                    uint32_t* __restrict__ out)
+{
+    extern __shared__ float smem_f[];
+    constexpr int PADL = STEP + (STEP & 1);             // even left pad => even region column for even image column
+    constexpr int RW   = (TW3 + PADL + STEP + 1) & ~1;  // even row pitch keeps LDS.64 alignment on every row
+    constexpr int RH   = TH3 + 2 * STEP;
+    constexpr int PL   = RW * RH;
+    float* s_nx = smem_f;
+    float* s_ny = s_nx + PL;
+    float* s_nz = s_ny + PL;
+    float* s_zs = s_nz + PL;
+    float* s_vi = s_zs + PL;
+    float* s_va = s_vi + PL;
+    __shared__ uint32_t s_tf;
+
+    const int W = P.W, H = P.H;
+    const int x0 = blockIdx.x * TW3, y0 = P.row0 + blockIdx.y * TH3;
+    const int TWt = (W + 7) >> 3, THt = (H + 7) >> 3;
+    if (threadIdx.x < 32)
+    {
+        const int  tx = (x0 >> 3) + (threadIdx.x & 7), ty = (y0 >> 3) + (threadIdx.x >> 3);
+        const bool f  = threadIdx.x < 16 && tx < TWt && ty < THt && tile_flags[(size_t)ty * TWt + tx] != 0;
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
+        if (threadIdx.x == 0) s_tf = b;
+    }
+    __syncthreads();
+    const uint32_t tf = s_tf;
+
+    if (tf != 0)
+    {
+        const uint32_t* gb2w = reinterpret_cast<const uint32_t*>(g.gb2);
+        const uint32_t* gb3w = reinterpret_cast<const uint32_t*>(g.gb3);
+        for (int i = threadIdx.x; i < PL; i += 256)
+        {
+            const int rx = i % RW, ry = i / RW;
+            const int px = x0 - PADL + rx, py = y0 - STEP + ry;
+            float nx = 0.0f, ny = 0.0f, nz = 0.0f, zs = 0.0f, vi = 0.0f, va = 0.0f;
+            if (px >= 0 && py >= 0 && px < W && py < H)
+            {
+                const size_t pi = (size_t)py * W + px;
+                const float2 e  = h2_to_f2(__ldg(gb2w + 2 * pi));
+                const float2 zz = h2_to_f2(__ldg(gb3w + 2 * pi + 1));
+                const float2 iv = h2_to_f2(__ldg(in + pi));
+                const float3 n  = octohedral_to_direction(e.x, e.y);
+                nx = n.x; ny = n.y; nz = n.z;
+                zs = zz.y * P.c_sigma;
+                vi = iv.x; va = iv.y;
+            }
+            s_nx[i] = nx; s_ny[i] = ny; s_nz[i] = nz; s_zs[i] = zs; s_vi[i] = vi; s_va[i] = va;
+        }
+    }
+    __syncthreads();
+
+    const int lx2 = threadIdx.x & 31, lyb = threadIdx.x >> 5; // 32 pixel pairs x 8 rows, 2 rows per thread
+    const int x = x0 + 2 * lx2;
+    const float2 neg1 = make_float2(-1.0f, -1.0f), nl2e = make_float2(-1.44269504f, -1.44269504f);
+    const float  LK1 = -0.5849625007f, LK2 = -1.1699250014f; // log2(2/3), log2(4/9): kernel weights folded into the exponent
+#pragma unroll
+    for (int k = 0; k < TH3 / 8; k++)
+    {
+        const int ly = lyb + 8 * k, y = y0 + ly;
+        if (x >= W || y >= H || y >= P.row1) continue;
+        const size_t idx  = (size_t)y * W + x;
+        const bool   has1 = x + 1 < W;
+        if (!((tf >> ((ly >> 3) * 8 + (lx2 >> 2))) & 1u))
+        {
+            out[idx] = 0u;
+            if (has1) out[idx + 1] = 0u;
+            continue;
+        }
+        const int ci = (ly + STEP) * RW + 2 * lx2 + PADL;
+        PairCell  c;
+        c.nx = ld_pair(s_nx, ci, true); c.ny = ld_pair(s_ny, ci, true); c.nz = ld_pair(s_nz, ci, true);
+        c.zs = ld_pair(s_zs, ci, true); c.vis = ld_pair(s_vi, ci, true); c.var = ld_pair(s_va, ci, true);
+        // compute_variance_center for both pixels: columns ci-1 .. ci+2, rows -1..+1; weights {1/4,1/8,1/16}
+        float2 vbar;
+        {
+            const float a0 = s_va[ci - RW - 1], d0 = s_va[ci - RW + 2];
+            const float2 m0 = ld_pair(s_va, ci - RW, true);
+            const float a1 = s_va[ci - 1], d1 = s_va[ci + 2];
+            const float a2 = s_va[ci + RW - 1], d2 = s_va[ci + RW + 2];
+            const float2 m2 = ld_pair(s_va, ci + RW, true);
+            vbar.x = 0.25f * c.var.x + 0.125f * (a1 + c.var.y + m0.x + m2.x) + 0.0625f * (a0 + m0.y + a2 + m2.y);
+            vbar.y = 0.25f * c.var.y + 0.125f * (c.var.x + d1 + m0.y + m2.y) + 0.0625f * (m0.x + d0 + m2.x + d2);
+        }
+        const float2 cphi = make_float2(P.c_phi0 * rsqrtf(fmaxf(1e-10f + vbar.x, 1e-30f)), P.c_phi0 * rsqrtf(fmaxf(1e-10f + vbar.y, 1e-30f)));
+        float2 sumw = make_float2(1.0f, 1.0f), s0 = c.vis, s1 = c.var;
+#pragma unroll
+        for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+            for (int xx = -1; xx <= 1; xx++)
+            {
+                if (xx == 0 && yy == 0) continue;
+                const float lk      = (xx != 0 && yy != 0) ? LK2 : LK1;
+                const int   si      = ci + yy * STEP * RW + xx * STEP;
+                const bool  aligned = ((xx * STEP) & 1) == 0;
+                PairCell    s;
+                s.nx = ld_pair(s_nx, si, aligned); s.ny = ld_pair(s_ny, si, aligned); s.nz = ld_pair(s_nz, si, aligned);
+                s.zs = ld_pair(s_zs, si, aligned); s.vis = ld_pair(s_vi, si, aligned); s.var = ld_pair(s_va, si, aligned);
+                const float2 dz = __ffma2_rn(s.zs, neg1, c.zs);
+                float2       wZ;
+                wZ.x = fast_exp2(-fabsf(dz.x));
+                wZ.y = fast_exp2(-fabsf(dz.y));
+                const float2 dl = __ffma2_rn(s.vis, neg1, c.vis);
+                float2       ea;
+                ea.x = fmaf(fabsf(dl.x), cphi.x, lk);
+                ea.y = fmaf(fabsf(dl.y), cphi.y, lk);
+                ea   = __ffma2_rn(wZ, nl2e, ea);
+                float2 e;
+                e.x = fast_exp2(ea.x);
+                e.y = fast_exp2(ea.y);
+                float2 nd = __fmul2_rn(c.nz, s.nz);
+                nd        = __ffma2_rn(c.ny, s.ny, nd);
+                nd        = __ffma2_rn(c.nx, s.nx, nd);
+                nd.x      = fmaxf(nd.x, 0.0f);
+                nd.y      = fmaxf(nd.y, 0.0f);
+                float2 p = __fmul2_rn(nd, nd);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                const float2 wk = __fmul2_rn(e, p);
+                sumw = __fadd2_rn(sumw, wk);
+                s0   = __ffma2_rn(wk, s.vis, s0);
+                s1   = __ffma2_rn(__fmul2_rn(wk, wk), s.var, s1);
+            }
+        const float2 inv = make_float2(fast_rcp(sumw.x), fast_rcp(sumw.y));
+        float2       o0 = __fmul2_rn(s0, inv), o1 = __fmul2_rn(__fmul2_rn(s1, inv), inv);
+        if (P.power != 0.0f) { o0.x = pow_pos(o0.x, P.power); o0.y = pow_pos(o0.y, P.power); }
+        // sky pixels (linear z < 0) pass the input through
+        const uint32_t r0 = c.zs.x < 0.0f ? f2_to_h2(c.vis.x, c.var.x) : f2_to_h2(o0.x, o1.x);
+        const uint32_t r1 = c.zs.y < 0.0f ? f2_to_h2(c.vis.y, c.var.y) : f2_to_h2(o0.y, o1.y);
+        if (has1) *reinterpret_cast<uint2*>(out + idx) = make_uint2(r0, r1); // idx even (W even is required by the launcher)
+        else out[idx] = r0;
+    }
+}
+
+template <int STEP>
+void launch_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, const V3Params& P, uint32_t* out, cudaStream_t st)
+{
+    constexpr int PADL = STEP + (STEP & 1);
+    constexpr int RW   = (TW3 + PADL + STEP + 1) & ~1;
+    constexpr int RH   = TH3 + 2 * STEP;
+    const size_t  smem = (size_t)RW * RH * 6 * sizeof(float);
+    static bool   configured = false;
+    if (!configured) { cudaFuncSetAttribute(k_atrous_v3<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    dim3 grid((P.W + TW3 - 1) / TW3, (P.row1 - P.row0 + TH3 - 1) / TH3);
+    k_atrous_v3<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
+}
+
+} // namespace
+
+// returns false when this variant does not support the configuration (caller falls back to the scalar kernels)
+bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n, float sigma_z,
+                              float power, uint32_t* out, int row0, int row1, cudaStream_t st)
+{
+    if (radius != 1 || phi_n != 32.0f || (g.W & 1) || row0 % 8 != 0 || !(step == 1 || step == 2 || step == 4 || step == 8)) return false;
+    V3Params P { g.W, g.H, 1.44269504f / sigma_z, -1.44269504f / phi_vis, power, row0, row1 };
+    switch (step)
+    {
+        case 1: launch_v3<1>(g, in, tile_flags, P, out, st); break;
+        case 2: launch_v3<2>(g, in, tile_flags, P, out, st); break;
+        case 4: launch_v3<4>(g, in, tile_flags, P, out, st); break;
+        default: launch_v3<8>(g, in, tile_flags, P, out, st); break;
+    }
+    return true;
+}

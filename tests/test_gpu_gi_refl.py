@@ -70,7 +70,7 @@ def run(scene_kind, n_frames, refl_scale, with_ddgi, light=None, cam=None, pan_f
             if i == 0:
                 u = dd.uniforms()
                 assert bytes(u) == bytes(odd.u), "DDGIUniforms differ"
-            dird_c, dird_o = dd.download(1), odd.dirdepth
+            dird_c, dird_o = dd.download(1).view(np.uint16), odd.dirdepth
             assert np.array_equal(dird_c, dird_o.reshape(dird_c.shape)), f"frame {i}: probe ray direction / hit distance not exact"
             close(f16(dd.download(0)), O.h2f(odd.radiance).reshape(-1, odd.u.rays_per_probe, 4), f"frame {i} ddgi radiance", 2e-3, 0.05)
             close(f16(dd.download(2)), O.h2f(odd.cur_irr), f"frame {i} irradiance atlas")

@@ -241,7 +241,7 @@ def test_atrous_tiled_equals_naive_and_oracle_1080p():
     osh = O.ShadowsOracle(W, H, 0)
     f, prev_g = None, O.zero_gbuf_mips(W, H)
     outs = {}
-    for impl in (1, 0):
+    for impl in (1, 0, 3):
         c.lib.hr_debug_set(1, impl)
         sh.reset_history()
         f = None
@@ -261,6 +261,8 @@ def test_atrous_tiled_equals_naive_and_oracle_1080p():
     assert np.array_equal(sh.download(0), osh.mask)
     ref = O.h2f(osh.final)
     assert rmse(outs[1], outs[0]) <= 2e-4 and np.abs(outs[1] - outs[0]).max() <= 2e-3
+    assert rmse(outs[3], outs[0]) <= 2e-4 and np.abs(outs[3] - outs[0]).max() <= 2e-3  # packed fp32x2 kernel
+    assert rmse(outs[3], ref) <= 1e-3
     assert rmse(outs[1], ref) <= 1e-3
     assert 0.02 < ref[..., 0].mean() < 0.98
     sh.destroy()
