@@ -118,6 +118,7 @@ def main():
     ap.add_argument("--tris", type=int, default=262144)
     ap.add_argument("--ao-scale", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the shadows+AO+DDGI+reflections leg")
     args = ap.parse_args()
     W, H = args.width, args.height
     rank = int(os.environ.get("RANK", "0"))
@@ -250,10 +251,57 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    # ---- full hybrid pipeline (BASELINE config 4 pass set at 1 spp): shadows + AO + DDGI (4096 probes x 256 rays) + reflections -----
+    full = None
+    if not args.no_full:
+        dd = pyhr.DDGIPass(ctx, W, H, 0)
+        rf = pyhr.ReflectionsPass(ctx, W, H, 1)
+        dd.params.probe_distance, dd.params.normal_bias = 4.2, 0.5  # arcade bounds 60 x 28.6 x 128 => 16 x 8 x 32 = 4096 probes
+        for P in (dd.params, rf.params):
+            P.sky_color[0], P.sky_color[1], P.sky_color[2] = 0.3, 0.4, 0.6
+        rng = np.random.default_rng(1234)
+
+        def step_full():
+            f = next_frame()
+            ctx.gbuffer_bind_device(f.ping_pong, dev_desc, stream)
+            sh.render(f, stream)
+            ao.render(f, stream)
+            ax = rng.uniform(-1, 1, 3)
+            dd.render(f, pyhr.rotation_matrix(float(rng.uniform(0, 2 * np.pi)), ax / np.linalg.norm(ax)), stream)
+            rf.render(f, dd, stream)
+
+        for _ in range(12):
+            step_full()
+        barrier()
+        ctx.set_profiling(True)
+        for p_ in (sh, ao):
+            p_.stage_times()
+        f0e, f1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0e.record()
+        for _ in range(args.steps):
+            step_full()
+        f1e.record()
+        barrier()
+        ms_full = f0e.elapsed_time(f1e)
+        dd_st, rf_st = dict(dd.stage_times()), dict(rf.stage_times())
+        ctx.set_profiling(False)
+        ra = [v for k_, v in rf_st.items() if k_.startswith("A-Trous")]
+        ra_ms = float(np.mean(ra)) if ra else None
+        rb0, rb1 = pyhr.shard_rows(H // 2, 0, world)
+        r_rows = (min(rb1 + 16, H // 2) - max(rb0 - 16, 0)) if world > 1 else H // 2
+        r_bytes = 36.0 * (W // 2) * r_rows  # RGBA16F 8 + GB2 8 + GB3 8 + depth 4 read, RGBA16F 8 written
+        n_probes = 1
+        u_ = dd.uniforms()
+        n_probes = u_.probe_counts[0] * u_.probe_counts[1] * u_.probe_counts[2]
+        full = {"ms_total": ms_full, "ddgi": dd_st, "reflections": rf_st, "refl_atrous_ms": ra_ms, "refl_atrous_bytes": r_bytes, "probes": n_probes,
+                "rays_per_probe": int(u_.rays_per_probe)}
+        dd.destroy()
+        rf.destroy()
+
+    t = torch.tensor([ms_total, ms_e2e, full["ms_total"] if full else 0.0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, ms_full_max = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         fps = args.steps / (ms_total / 1e3)
@@ -281,6 +329,19 @@ def main():
             "mrays_per_s": {"primary_rays_per_frame_upper_bound": rays_per_frame, "trace_kernels_ms": rt_ms,
                             "value": (rays_per_frame / 1e6) / (rt_ms / 1e3) if rt_ms else None},
         }
+        if full:
+            ra_ach = (full["refl_atrous_bytes"] / 1e9) / (full["refl_atrous_ms"] / 1e3) if full["refl_atrous_ms"] else None
+            n_gi_rays = full["probes"] * full["rays_per_probe"]
+            line["full_pipeline"] = {
+                "passes": ["shadows(full)", "ao(half)", f"ddgi({full['probes']} probes x {full['rays_per_probe']} rays, full-res sample)", "reflections(half)"],
+                "value": args.steps / (ms_full_max / 1e3), "unit": "frames/s", "ms_per_step": ms_full_max / args.steps,
+                "stages_ms": {"ddgi": full["ddgi"], "reflections": full["reflections"]},
+                "roofline_reflections_atrous": {"kernel": "k_refl_atrous (K16)", "bound": "hbm", "achieved": ra_ach, "peak": peak, "unit": "GB/s",
+                                                "frac": (ra_ach / peak) if ra_ach else None, "avg_launch_ms": full["refl_atrous_ms"],
+                                                "algorithmic_bytes_per_launch": full["refl_atrous_bytes"]},
+                "mrays_per_s": {"ddgi_primary": (n_gi_rays / 1e6) / (full["ddgi"].get("Ray Trace", 0.0) / 1e3) if full["ddgi"].get("Ray Trace") else None,
+                                "reflections_primary_upper_bound": ((W // 2) * (H // 2) / 1e6) / (full["reflections"].get("Ray Trace", 0.0) / 1e3)
+                                if full["reflections"].get("Ray Trace") else None}}
         if not args.no_cpu_baseline and world == 1:
             sw, shh = W // 4, H // 4
             cfps, threads, secs = oracle_fps(sw, shh, args.tris, 2, (W * H) / (sw * shh))

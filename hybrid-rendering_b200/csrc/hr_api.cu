@@ -10,6 +10,7 @@
 static std::string g_last_error;
 static std::mutex  g_err_mutex;
 extern int         g_hr_atrous_impl;
+extern int         g_hr_trace_impl;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -136,6 +137,7 @@ const char* hr_last_error(hr_ctx* ctx)
 int hr_debug_set(int key, int value)
 {
     if (key == 1) { g_hr_atrous_impl = value; return HR_OK; }
+    if (key == 2) { g_hr_trace_impl = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 

@@ -348,7 +348,9 @@ void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 
 // 0 = naive, 1 = tiled (default: measured 64-105 us/iter at 4K), 2 = chain / sliding window (72-107 us: the extra registers
 // cost more occupancy than the saved shared-memory traffic buys; profiles/README.md).  hr_debug_set key 1.
-int g_hr_atrous_impl = 1;
+// 3 = packed fp32x2 pixel-pair kernel (svgf_atrous_v3.cu; default: 53-85 us/iter, 47 % of HBM peak); it falls back to the
+// scalar tiled kernel for odd widths / phi_normal != 32.
+int g_hr_atrous_impl = 3;
 bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n, float sigma_z,
                               float power, uint32_t* out, int row0, int row1, cudaStream_t st); // svgf_atrous_v3.cu (impl 3: packed fp32x2)
 

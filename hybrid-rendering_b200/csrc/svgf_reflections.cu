@@ -105,20 +105,12 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
             const float  cmesh = g3.z, curvature = g3.y;
             const float3 cpos = world_position_from_depth(tu, tv, depth, fc.view_proj_inverse);
             // compute_history_coord, reprojection.glsl:101-111
-            float hfx = (float)x + g2.z * fw, hfy = (float)y + g2.w * fh;
+            float hfx = rn_mad(g2.z, fw, (float)x), hfy = rn_mad(g2.w, fh, (float)y);
             if (ray_length > 0.0f && curvature == 0.0f)
-            { // virtual_point_reprojection :78-97 (tex_coord = coord / size, no +0.5)
-                const float3 ro  = world_position_from_depth((float)x / fw, (float)y / fh, depth, fc.view_proj_inverse);
-                float3       cr  = make_float3(ro.x - fc.cam_pos[0], ro.y - fc.cam_pos[1], ro.z - fc.cam_pos[2]);
-                const float  len = sqrtf(dot3(cr, cr));
-                const float  il  = 1.0f / len;
-                const float  tt  = len + ray_length;
-                const float3 ph  = make_float3(fc.cam_pos[0] + cr.x * il * tt, fc.cam_pos[1] + cr.y * il * tt, fc.cam_pos[2] + cr.z * il * tt);
-                const float* M   = fc.prev_view_proj;
-                const float  cx = M[0] * ph.x + M[4] * ph.y + M[8] * ph.z + M[12], cy = M[1] * ph.x + M[5] * ph.y + M[9] * ph.z + M[13];
-                const float  cw = M[3] * ph.x + M[7] * ph.y + M[11] * ph.z + M[15];
-                hfx = (cx / cw * 0.5f + 0.5f) * fw;
-                hfy = (cy / cw * 0.5f + 0.5f) * fh;
+            { // virtual_point_reprojection :78-97 — exactly rounded: it lands on texel corners for a static camera
+                const float2 vp = rn_virtual_point_reprojection(x, y, fw, fh, depth, ray_length, fc.cam_pos, fc.view_proj_inverse, fc.prev_view_proj);
+                hfx = vp.x;
+                hfy = vp.y;
             }
             const int   hcx = (int)hfx, hcy = (int)hfy; // ivec2(reprojected_coord) :171
             const float hu = tu + g2.z, hv = tv + g2.w;

@@ -107,8 +107,8 @@ __global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev
             const float3 cn = octohedral_to_direction(g2.x, g2.y);
             const float  cmesh = g3.x;
             const float3 cpos  = world_position_from_depth(tu, tv, depth, fc.view_proj_inverse);
-            const float  hfx = (float)x + g2.z * fw, hfy = (float)y + g2.w * fh;   // history_coord_floor (:176)
-            const int    hcx = (int)(hfx + 0.5f), hcy = (int)(hfy + 0.5f);         // history_coord (:175)
+            const float  hfx = rn_mad(g2.z, fw, (float)x), hfy = rn_mad(g2.w, fh, (float)y); // history_coord_floor (:176), exactly rounded
+            const int    hcx = (int)__fadd_rn(hfx, 0.5f), hcy = (int)__fadd_rn(hfy, 0.5f);       // history_coord (:175)
             const float  hu = tu + g2.z, hv = tv + g2.w;                           // history_tex_coord (:177)
             const bool   in_frame = inside(hcx, hcy, W, H);                        // out_of_frame_disocclusion_check on history_coord
             const int    bx = (int)hfx, by = (int)hfy;                             // ivec2(history_coord_floor) truncates
