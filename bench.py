@@ -170,6 +170,8 @@ def main():
     ctx = pyhr.Context(local_rank)
     if os.environ.get("HR_ATROUS_IMPL"):  # A/B switch for kernel experiments (0 naive, 1 tiled, 2 chain = default)
         ctx.lib.hr_debug_set(1, int(os.environ["HR_ATROUS_IMPL"]))
+    if os.environ.get("HR_TRACE_IMPL"):  # 0 one warp per 8x4 block, 1 persistent threads + compaction (default)
+        ctx.lib.hr_debug_set(2, int(os.environ["HR_TRACE_IMPL"]))
     ctx.set_bluenoise(*pyhr.blue_noise())
     if world > 1:
         # row-band sharding with the library's own NCCL exchange: rank 0 creates the ncclUniqueId, torch.distributed ships it

@@ -106,7 +106,7 @@ __global__ void k_build_mip(int W, int H, const uint2* __restrict__ gb2, const u
 
 } // namespace
 
-void launch_ao_blur(const GBufLevelDev& g, const __half* in, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, __half* out,
+void launch_ao_blur_v1(const GBufLevelDev& g, const __half* in, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, __half* out,
                     int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
@@ -115,7 +115,7 @@ void launch_ao_blur(const GBufLevelDev& g, const __half* in, const uint8_t* tile
     k_ao_blur<<<grid, 256, 0, st>>>(g, in, tile_flags, P, out);
 }
 
-void launch_upsample_scalar(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, int in_channels, float sky_value, float power, __half* out,
+void launch_upsample_scalar_v1(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, int in_channels, float sky_value, float power, __half* out,
                             int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;

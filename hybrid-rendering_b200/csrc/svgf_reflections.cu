@@ -385,9 +385,12 @@ int launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8
     return 0;
 }
 
+bool launch_upsample_vec4_v2(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st); // svgf_misc_v2.cu
+
 void launch_upsample_vec4(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
+    if (launch_upsample_vec4_v2(g0, gm, in, out, row0, row1, st)) return; // shared-memory staged variant
     UpParams P { g0.W, g0.H, gm.W, gm.H, row0, row1 };
     dim3     grid((g0.W + 31) / 32, (row1 - row0 + 7) / 8);
     k_upsample_vec4<<<grid, 256, 0, st>>>(g0, gm, (const uint2*)in, P, (uint2*)out);

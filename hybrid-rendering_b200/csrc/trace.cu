@@ -278,7 +278,10 @@ __global__ void k_trace_closest(BvhDev bvh, const float* __restrict__ rays, size
 
 static inline dim3 mask_grid(int W, int mrow0, int mrow1) { return dim3(((W + 7) / 8 + 3) / 4, (mrow1 - mrow0 + 1) / 2, 1); }
 
-int g_hr_trace_impl = 1; // 0 = one warp per 8x4 block, 1 = persistent threads + ray compaction + LDS stack (hr_debug_set key 2)
+// 0 = one warp per 8x4 block (default), 1 = persistent threads + ray compaction + LDS stack (hr_debug_set key 2).
+// Measured at 4K (profiles/README.md): shadows 585 us vs 712 us, AO 223 us vs 333 us — on this workload the 8x4 blocks are
+// almost uniformly active (coherent surfaces), so compaction buys little and the queue / refill bookkeeping costs more.
+int g_hr_trace_impl = 0;
 
 static const size_t kPtSmem = sizeof(QRay) * PT_WARPS * PT_QUEUE + sizeof(int) * SM_STACK * PT_WARPS * 32 + sizeof(uint32_t) * PT_WARPS * 4;
 

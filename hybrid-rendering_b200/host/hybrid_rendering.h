@@ -138,4 +138,58 @@ private:
     uint32_t         m_width = 0, m_height = 0;
 };
 
+// DDGI (src/ddgi.h): ctor(backend, common, g_buffer, scale); render(cmd_buf); current_read_ds(); probe_counts(); restart_accumulation()
+class DDGI {
+public:
+    DDGI(CommonResources* common, GBuffer* g_buffer, RayTraceScale scale = RAY_TRACE_SCALE_FULL_RES) : m_common(common), m_scale(scale)
+    {
+        (void)g_buffer;
+        hr_ddgi_default_params(&params);
+        check(common->ctx, hr_ddgi_create(common->ctx, (int)common->width, (int)common->height, scale, &m_pass), "hr_ddgi_create");
+    }
+    ~DDGI() { if (m_pass) hr_pass_destroy(m_pass); }
+    // random_orientation replaces the std::mt19937(std::random_device()) draw of ddgi.cpp:73,788 (the caller seeds it)
+    void     render(const float* random_orientation16, void* stream) { check(m_common->ctx, hr_ddgi_render(m_pass, &m_common->frame, &params, random_orientation16, stream), "hr_ddgi_render"); }
+    hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, HR_DDGI_OUT_FINAL, &img), "hr_pass_output"); return img; }
+    hr_image current_read_ds(int which /* HR_DDGI_OUT_IRRADIANCE or _DEPTH */) const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, which, &img), "hr_pass_output"); return img; }
+    void     probe_counts(int out[3]) const { hr_ddgi_uniforms u; check(m_common->ctx, hr_ddgi_get_uniforms(m_pass, &u), "hr_ddgi_get_uniforms"); out[0] = u.probe_counts[0]; out[1] = u.probe_counts[1]; out[2] = u.probe_counts[2]; }
+    void     restart_accumulation() { hr_pass_reset_history(m_pass); } // ddgi.h:33
+    void     set_probe_distance(float v) { params.probe_distance = v; }
+    void     set_normal_bias(float v) { params.normal_bias = v; }
+    RayTraceScale scale() const { return m_scale; }
+    hr_pass* handle() { return m_pass; }
+    hr_ddgi_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+    RayTraceScale    m_scale;
+};
+
+// RayTracedReflections (src/ray_traced_reflections.h): render(cmd_buf, DDGI*)
+class RayTracedReflections {
+public:
+    enum OutputType { OUTPUT_RAY_TRACE = 0, OUTPUT_TEMPORAL_ACCUMULATION = 1, OUTPUT_ATROUS = 2, OUTPUT_UPSAMPLE = 3 };
+    RayTracedReflections(CommonResources* common, GBuffer* g_buffer, RayTraceScale scale = RAY_TRACE_SCALE_HALF_RES) : m_common(common), m_scale(scale)
+    {
+        (void)g_buffer;
+        hr_reflections_default_params(&params);
+        check(common->ctx, hr_reflections_create(common->ctx, (int)common->width, (int)common->height, scale, &m_pass), "hr_reflections_create");
+        m_width  = common->width >> scale;
+        m_height = common->height >> scale;
+    }
+    ~RayTracedReflections() { if (m_pass) hr_pass_destroy(m_pass); }
+    void     render(void* stream, DDGI* ddgi) { check(m_common->ctx, hr_reflections_render(m_pass, &m_common->frame, &params, ddgi ? ddgi->handle() : nullptr, stream), "hr_reflections_render"); }
+    hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, HR_REFLECTIONS_OUT_FINAL, &img), "hr_pass_output"); return img; }
+    uint32_t width() const { return m_width; }
+    uint32_t height() const { return m_height; }
+    RayTraceScale scale() const { return m_scale; }
+    hr_pass* handle() { return m_pass; }
+    hr_reflections_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+    RayTraceScale    m_scale;
+    uint32_t         m_width = 0, m_height = 0;
+};
+
 } // namespace hr
