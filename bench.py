@@ -170,15 +170,20 @@ def main():
     ctx = pyhr.Context(local_rank)
     if os.environ.get("HR_ATROUS_IMPL"):  # A/B switch for kernel experiments (0 naive, 1 tiled, 2 chain = default)
         ctx.lib.hr_debug_set(1, int(os.environ["HR_ATROUS_IMPL"]))
-    if os.environ.get("HR_TRACE_IMPL"):  # 0 one warp per 8x4 block, 1 persistent threads + compaction (default)
+    if os.environ.get("HR_TRACE_IMPL"):  # 0 one warp per 8x4 block (default), 1 persistent threads + compaction
         ctx.lib.hr_debug_set(2, int(os.environ["HR_TRACE_IMPL"]))
+    if os.environ.get("HR_BVH_QUALITY"):  # 0 Karras radix tree, 1 PLOC (default); must be set before the scene build
+        ctx.lib.hr_debug_set(3, int(os.environ["HR_BVH_QUALITY"]))
     ctx.set_bluenoise(*pyhr.blue_noise())
     if world > 1:
         # row-band sharding with the library's own NCCL exchange: rank 0 creates the ncclUniqueId, torch.distributed ships it
         uid = [pyhr.shard_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.shard_init(rank, world, uid[0])
+    t_b = time.perf_counter()
     scene_h = ctx.build_scene(sc)
+    torch.cuda.synchronize()
+    print(f"[bench] scene build (upload + BVH): {(time.perf_counter() - t_b) * 1e3:.2f} ms", file=sys.stderr)
     ctx.gbuffer_create(W, H)
     sh = pyhr.Pass(ctx, "shadows", W, H, 0)
     ao = pyhr.Pass(ctx, "ao", W, H, args.ao_scale)
@@ -324,7 +329,7 @@ def main():
             "warmup": max(args.warmup, 3) + 30, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (fp16 storage)", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(g_host.nbytes()), "d2h_bytes_per_step": int(out_sh.nbytes + out_ao.nbytes)},
-            "roofline": {"kernel": "k_atrous_tiled (shadows a-trous, K5)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_atrous_v3 (shadows a-trous, K5)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "avg_launch_ms": at_ms, "algorithmic_bytes_per_launch": ATROUS_BYTES_PER_PX * at_px},
             "stages_ms": {"shadows": dict(sh_stages), "ao": dict(ao_stages)},

@@ -11,6 +11,17 @@
 //   6. k_pack         traversal layout: 64-byte nodes holding both child boxes; sub-trees with <= LEAF_MAX
 //                     triangles are collapsed into one leaf (their triangles are contiguous in Morton order)
 //
+// Topology: hr_debug_set(3, q).  q = 0: Karras radix tree (steps 4-5, fastest build, used by nothing by default).
+// q = 1 (default): PLOC — parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton-sorted leaves:
+// every round each cluster finds the neighbour within +-PLOC_R array slots that minimises the surface area of the union,
+// mutual nearest neighbours are merged, the cluster array is compacted (cub scan) and the loop ends when one cluster is
+// left.  The bottom-up agglomeration follows the surface-area heuristic much more closely than Morton-prefix splits
+// (fewer node visits per ray).  Hit results do not depend on the topology: any-hit is an existence test and closest-hit
+// ties resolve to the lowest primitive index, so the visibility masks stay bit-exact with either builder.
+// Internal node ids are handed out downwards from n-2 so that the last merge (the root) is node 0; after the tree is
+// complete every leaf walks to the root to find its depth-first position, which makes the triangles of every subtree
+// contiguous again (needed for the <= LEAF_MAX leaf collapse) and gives the (first,last) range of every node.
+//
 // Node layout (4 x float4):  n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
 //                            nz = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   ch = (int c0, int c1, -, -) as bits
 // child >= 0: internal node index;  child < 0: leaf, ~child = (first_tri << 3) | (count - 1).
@@ -18,6 +29,7 @@
 // Boxes are padded by 2^-16 of the scene extent so the slab test is conservative w.r.t. the fp32 ray/triangle test.
 #include "hr_internal.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cfloat>
 
 #define LEAF_MAX 4
@@ -232,6 +244,196 @@ __global__ void k_pack_tris(const float* __restrict__ verts, const uint32_t* __r
     out[3ull * k + 2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
 }
 
+
+// ---- PLOC -------------------------------------------------------------------------------------------------------------
+#define PLOC_R 24
+#define PLOC_T 256
+
+struct Cluster { float4 lo, hi; }; // lo.w = node id bits (leaf k = n-1+k), hi.w = triangle count bits
+
+__global__ void k_ploc_init(int n, const float* __restrict__ tri_aabb, const uint32_t* __restrict__ sorted_prim, Cluster* __restrict__ out, int* __restrict__ parent)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float* b = tri_aabb + 6ull * sorted_prim[k];
+    Cluster      c;
+    c.lo   = make_float4(b[0], b[1], b[2], __int_as_float(n - 1 + k));
+    c.hi   = make_float4(b[3], b[4], b[5], __int_as_float(1));
+    out[k] = c;
+    if (k == 0) parent[0] = -1;
+}
+
+// nearest neighbour (smallest union surface area, ties -> lowest index) within +-PLOC_R slots
+__global__ void __launch_bounds__(PLOC_T) k_ploc_nn(const Cluster* __restrict__ c, int m, int* __restrict__ nn)
+{
+    __shared__ float s[6][PLOC_T + 2 * PLOC_R];
+    const int base = blockIdx.x * PLOC_T - PLOC_R;
+    for (int t = threadIdx.x; t < PLOC_T + 2 * PLOC_R; t += PLOC_T)
+    {
+        const int j = base + t;
+        if (j >= 0 && j < m)
+        {
+            const float4 lo = c[j].lo, hi = c[j].hi;
+            s[0][t] = lo.x; s[1][t] = lo.y; s[2][t] = lo.z;
+            s[3][t] = hi.x; s[4][t] = hi.y; s[5][t] = hi.z;
+        }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * PLOC_T + threadIdx.x;
+    if (i >= m) return;
+    const int   ti = threadIdx.x + PLOC_R;
+    const float lx = s[0][ti], ly = s[1][ti], lz = s[2][ti], hx = s[3][ti], hy = s[4][ti], hz = s[5][ti];
+    float       best = FLT_MAX;
+    int         bj = -1;
+    const int   j0 = max(i - PLOC_R, 0), j1 = min(i + PLOC_R, m - 1);
+    for (int j = j0; j <= j1; j++)
+    {
+        if (j == i) continue;
+        const int   t  = j - base;
+        const float dx = fmaxf(hx, s[3][t]) - fminf(lx, s[0][t]);
+        const float dy = fmaxf(hy, s[4][t]) - fminf(ly, s[1][t]);
+        const float dz = fmaxf(hz, s[5][t]) - fminf(lz, s[2][t]);
+        const float a  = dx * dy + dy * dz + dz * dx;
+        if (a < best) { best = a; bj = j; }
+    }
+    nn[i] = bj;
+}
+
+// flags packed as (merges << 32 | survivors) so one scan yields both the new node index and the compacted slot
+__global__ void k_ploc_flags(int m, const int* __restrict__ nn, unsigned long long* __restrict__ flags)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int  j      = nn[i];
+    const bool mutual = j >= 0 && nn[j] == i;
+    const unsigned long long merge = (mutual && i < j) ? 1ull : 0ull, survive = (mutual && i > j) ? 0ull : 1ull;
+    flags[i] = (merge << 32) | survive;
+}
+
+__global__ void k_ploc_apply(int m, int n, const Cluster* __restrict__ cin, const int* __restrict__ nn, const unsigned long long* __restrict__ flags,
+                             const unsigned long long* __restrict__ scan, int node_base, Cluster* __restrict__ cout, int2* __restrict__ children,
+                             int* __restrict__ parent, float* __restrict__ node_aabb, int* __restrict__ sizes, int* __restrict__ counts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const unsigned long long f = flags[i], sc = scan[i];
+    if (i == m - 1)
+    {
+        counts[0] = (int)((sc + f) & 0xFFFFFFFFull); // survivors
+        counts[1] = (int)((sc + f) >> 32);           // merges
+    }
+    if (!(f & 1ull)) return; // absorbed by its partner
+    Cluster a = cin[i];
+    if (f >> 32)
+    {
+        const Cluster b    = cin[nn[i]];
+        const int     node = node_base - 1 - (int)(sc >> 32);
+        const int     ia = __float_as_int(a.lo.w), ib = __float_as_int(b.lo.w);
+        const int     sz = __float_as_int(a.hi.w) + __float_as_int(b.hi.w);
+        children[node] = make_int2(ia, ib);
+        parent[ia]     = node;
+        parent[ib]     = node;
+        sizes[node]    = sz;
+        a.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), __int_as_float(node));
+        a.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), __int_as_float(sz));
+        float* o = node_aabb + 6ull * node;
+        o[0] = a.lo.x; o[1] = a.lo.y; o[2] = a.lo.z; o[3] = a.hi.x; o[4] = a.hi.y; o[5] = a.hi.z;
+    }
+    cout[(int)(sc & 0xFFFFFFFFull)] = a;
+}
+
+// depth-first offset of every node / leaf: sum of the left siblings' triangle counts along the path to the root
+__global__ void k_ploc_offsets(int n, const int2* __restrict__ children, const int* __restrict__ parent, const int* __restrict__ sizes,
+                               const uint32_t* __restrict__ sorted_prim, int2* __restrict__ ranges, int* __restrict__ leaf_pos, uint32_t* __restrict__ new_prim)
+{
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= 2 * n - 1) return;
+    int off = 0, cur = id, p;
+    while ((p = parent[cur]) >= 0)
+    {
+        const int2 c = children[p];
+        if (c.y == cur) off += c.x >= n - 1 ? 1 : sizes[c.x];
+        cur = p;
+    }
+    if (id < n - 1) ranges[id] = make_int2(off, off + sizes[id] - 1);
+    else
+    {
+        leaf_pos[id - (n - 1)] = off;
+        new_prim[off]          = sorted_prim[id - (n - 1)];
+    }
+}
+
+__global__ void k_ploc_remap(int n, int2* __restrict__ children, const int* __restrict__ leaf_pos)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int2 c = children[i];
+    if (c.x >= n - 1) c.x = n - 1 + leaf_pos[c.x - (n - 1)];
+    if (c.y >= n - 1) c.y = n - 1 + leaf_pos[c.y - (n - 1)];
+    children[i] = c;
+}
+
+} // namespace
+
+int g_hr_bvh_quality = 1;
+
+namespace {
+
+// Builds children / ranges / node_aabb (and the depth-first primitive order in sc->d_vals) with PLOC.
+// Returns HR_OK, a negative hr_status on a CUDA error, or 1 if the round cap is hit (caller falls back to the radix tree).
+int ploc_build(hr_scene* sc, cudaStream_t st)
+{
+    hr_ctx*   ctx = sc->ctx;
+    const int n   = (int)sc->n_tris;
+    const int T   = 256;
+    // scratch: 2 cluster arrays, nn, flags, scan, counts, cub temp
+    size_t scan_tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, n, st);
+    const size_t o_c0 = 0, o_c1 = o_c0 + sizeof(Cluster) * n, o_nn = o_c1 + sizeof(Cluster) * n, o_fl = o_nn + ((sizeof(int) * n + 15) & ~size_t(15)),
+                 o_sc = o_fl + 8ull * n, o_cnt = o_sc + 8ull * n, o_tmp = o_cnt + 16, total = o_tmp + scan_tmp;
+    if (total > sc->ploc_bytes)
+    {
+        if (sc->d_ploc) cudaFree(sc->d_ploc);
+        sc->d_ploc = nullptr;
+        HR_CUDA(ctx, cudaMalloc(&sc->d_ploc, total));
+        sc->ploc_bytes = total;
+    }
+    char*    base = (char*)sc->d_ploc;
+    Cluster* c[2] = { (Cluster*)(base + o_c0), (Cluster*)(base + o_c1) };
+    int*     nn   = (int*)(base + o_nn);
+    unsigned long long *flags = (unsigned long long*)(base + o_fl), *scan = (unsigned long long*)(base + o_sc);
+    int*     counts = (int*)(base + o_cnt);
+    int*     sizes  = sc->d_flags; // n-1 ints, unused by this builder otherwise
+
+    k_ploc_init<<<(n + T - 1) / T, T, 0, st>>>(n, sc->d_tri_aabb, sc->d_vals_sorted, c[0], sc->d_parent);
+    ctx->launches++;
+    int m = n, node_base = n - 1, cur = 0, rounds = 0;
+    while (m > 1)
+    {
+        if (++rounds > 1024) return 1;
+        const int g = (m + T - 1) / T;
+        k_ploc_nn<<<(m + PLOC_T - 1) / PLOC_T, PLOC_T, 0, st>>>(c[cur], m, nn);
+        k_ploc_flags<<<g, T, 0, st>>>(m, nn, flags);
+        HR_CUDA(ctx, cub::DeviceScan::ExclusiveSum(base + o_tmp, scan_tmp, flags, scan, m, st));
+        k_ploc_apply<<<g, T, 0, st>>>(m, n, c[cur], nn, flags, scan, node_base, c[cur ^ 1], sc->d_children, sc->d_parent, sc->d_node_aabb, sizes, counts);
+        ctx->launches += 4;
+        int h[2];
+        HR_CUDA(ctx, cudaMemcpyAsync(h, counts, sizeof(h), cudaMemcpyDeviceToHost, st));
+        HR_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h[1] <= 0 || h[0] != m - h[1]) return 1;
+        m = h[0];
+        node_base -= h[1];
+        cur ^= 1;
+    }
+    if (node_base != 0) return 1;
+    int* leaf_pos = reinterpret_cast<int*>(sc->d_keys); // the unsorted keys / values are dead after the radix sort
+    k_ploc_offsets<<<(2 * n - 1 + T - 1) / T, T, 0, st>>>(n, sc->d_children, sc->d_parent, sizes, sc->d_vals_sorted, sc->d_ranges, leaf_pos, sc->d_vals);
+    k_ploc_remap<<<(n - 1 + T - 1) / T, T, 0, st>>>(n, sc->d_children, leaf_pos);
+    ctx->launches += 2;
+    HR_CHECK_LAUNCH(ctx);
+    return HR_OK;
+}
+
 } // namespace
 
 int hr_bvh_build(hr_scene* sc, cudaStream_t st)
@@ -255,15 +457,28 @@ int hr_bvh_build(hr_scene* sc, cudaStream_t st)
     }
     HR_CUDA(ctx, cub::DeviceRadixSort::SortPairs(sc->d_sort_tmp, sc->sort_tmp_bytes, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
                                                  (int)n, 0, 63, st));
+    const uint32_t* prim_order = sc->d_vals_sorted;
     if (n > LEAF_MAX)
     {
         const int gi = (int)((n - 1 + T - 1) / T);
-        HR_CUDA(ctx, cudaMemsetAsync(sc->d_flags, 0, sizeof(int) * (n - 1), st));
-        k_hierarchy<<<gi, T, 0, st>>>(sc->d_keys_sorted, (int)n, sc->d_children, sc->d_ranges, sc->d_parent);
-        k_fit<<<gb, T, 0, st>>>(sc->d_tri_aabb, sc->d_vals_sorted, (int)n, sc->d_children, sc->d_parent, sc->d_node_aabb, sc->d_flags);
-        k_pack_nodes<<<gi, T, 0, st>>>((int)n, sc->d_children, sc->d_ranges, sc->d_tri_aabb, sc->d_vals_sorted, sc->d_node_aabb, sc->d_bounds_i, sc->d_nodes);
+        bool      ploc = false;
+        if (g_hr_bvh_quality >= 1)
+        {
+            const int rc = ploc_build(sc, st);
+            if (rc < 0) return rc; // CUDA error, already recorded (rc > 0: round cap hit, fall back to the radix tree)
+            ploc = rc == HR_OK;
+        }
+        if (ploc) prim_order = sc->d_vals;
+        else
+        {
+            HR_CUDA(ctx, cudaMemsetAsync(sc->d_flags, 0, sizeof(int) * (n - 1), st));
+            k_hierarchy<<<gi, T, 0, st>>>(sc->d_keys_sorted, (int)n, sc->d_children, sc->d_ranges, sc->d_parent);
+            k_fit<<<gb, T, 0, st>>>(sc->d_tri_aabb, sc->d_vals_sorted, (int)n, sc->d_children, sc->d_parent, sc->d_node_aabb, sc->d_flags);
+            ctx->launches += 2;
+        }
+        k_pack_nodes<<<gi, T, 0, st>>>((int)n, sc->d_children, sc->d_ranges, sc->d_tri_aabb, prim_order, sc->d_node_aabb, sc->d_bounds_i, sc->d_nodes);
         sc->n_nodes = n - 1;
-        ctx->launches += 3;
+        ctx->launches += 1;
     }
     else
     {
@@ -271,7 +486,7 @@ int hr_bvh_build(hr_scene* sc, cudaStream_t st)
         sc->n_nodes = 1;
         ctx->launches += 1;
     }
-    k_pack_tris<<<gb, T, 0, st>>>(sc->d_tri_verts, sc->d_vals_sorted, n, sc->d_tris);
+    k_pack_tris<<<gb, T, 0, st>>>(sc->d_tri_verts, prim_order, n, sc->d_tris);
     ctx->launches += 1;
     HR_CHECK_LAUNCH(ctx);
     return HR_OK;

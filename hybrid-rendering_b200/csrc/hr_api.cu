@@ -11,6 +11,7 @@ static std::string g_last_error;
 static std::mutex  g_err_mutex;
 extern int         g_hr_atrous_impl;
 extern int         g_hr_trace_impl;
+extern int         g_hr_bvh_quality;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -138,6 +139,7 @@ int hr_debug_set(int key, int value)
 {
     if (key == 1) { g_hr_atrous_impl = value; return HR_OK; }
     if (key == 2) { g_hr_trace_impl = value; return HR_OK; }
+    if (key == 3) { g_hr_bvh_quality = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 
@@ -276,7 +278,7 @@ int hr_scene_destroy(hr_scene* sc)
     if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
     void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
                      sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_tris,
-                     sc->d_materials, sc->d_sort_tmp };
+                     sc->d_materials, sc->d_sort_tmp, sc->d_ploc };
     for (void* p : ptrs) cudaFree(p);
     delete sc;
     return HR_OK;

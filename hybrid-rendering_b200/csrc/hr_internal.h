@@ -103,6 +103,8 @@ struct hr_scene {
     int*      d_flags    = nullptr;  // n-1
     void*     d_sort_tmp = nullptr;
     size_t    sort_tmp_bytes = 0;
+    void*     d_ploc = nullptr;      // PLOC builder scratch (cluster ping-pong, nearest neighbours, scan)
+    size_t    ploc_bytes = 0;
     // outputs
     float4*   d_nodes = nullptr;     // n_nodes*4
     float4*   d_tris  = nullptr;     // n*3

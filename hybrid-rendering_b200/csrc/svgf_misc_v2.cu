@@ -47,6 +47,10 @@ __global__ void __launch_bounds__(256) k_ao_blur_v2(GBufLevelDev g, const __half
             s_gauss[threadIdx.x] = (1.0f / sqrtf(2.0f * 3.14159265359f * dev * dev)) * __expf(-(i * i) / (2.0f * dev * dev));
         }
     }
+    const int   lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int   x = x0 + lx, y = y0 + ly;
+    const bool  inb = x < W && y < H && y < P.row1;
+    const float cdepth = inb ? __ldg(g.depth + (size_t)y * W + x) : 1.0f; // requested before the staging loop (overlapping round trips)
     __syncthreads();
     const uint32_t tf = s_tf;
     if (tf != 0)
@@ -69,13 +73,11 @@ __global__ void __launch_bounds__(256) k_ao_blur_v2(GBufLevelDev g, const __half
         }
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= W || y >= H || y >= P.row1) return;
+    if (!inb) return;
     const size_t idx = (size_t)y * W + x;
     const __half one = __float2half_rn(1.0f);
     if (!((tf >> (lx >> 3)) & 1u)) { out[idx] = one; return; } // image cleared to 1.0, tile not dispatched (ray_traced_ao.cpp:1055)
-    if (__ldg(g.depth + idx) == 1.0f) { out[idx] = one; return; }
+    if (cdepth == 1.0f) { out[idx] = one; return; }
     const int    ci = (ly + oy) * RW + lx + ox;
     const float4 c  = s_nz[ci];
     float        total_ao = s_ao[ci], total_w = 1.0f;
@@ -116,6 +118,16 @@ __global__ void __launch_bounds__(256) k_upsample_v2(GBufLevelDev g0, GBufLevelD
     const int cx_min = nearest(((float)x0 + 0.5f) / (float)P.W0 - tsx, P.Wm), cx_max = nearest(((float)x1 + 0.5f) / (float)P.W0 + tsx, P.Wm);
     const int cy_min = nearest(((float)y0 + 0.5f) / (float)P.H0 - tsy, P.Hm), cy_max = nearest(((float)y1 + 0.5f) / (float)P.H0 + tsy, P.Hm);
     const int rw = cx_max - cx_min + 1, rh = cy_max - cy_min + 1; // <= 19 x 7 for scale >= 1 (host checks)
+    // the pixel's own G-buffer words are requested before the staging loop so both round trips to HBM overlap
+    const int    x = x0 + (threadIdx.x & 31), y = y0 + (threadIdx.x >> 5);
+    const bool   inb = x < P.W0 && y < P.H0 && y < P.row1;
+    const size_t idx = (size_t)y * P.W0 + x;
+    uint32_t     hz_raw = 0u, he_raw = 0u;
+    if (inb)
+    {
+        hz_raw = __ldg(reinterpret_cast<const uint32_t*>(g0.gb3 + idx) + 1);
+        he_raw = __ldg(reinterpret_cast<const uint32_t*>(g0.gb2 + idx));
+    }
     for (int i = threadIdx.x; i < rw * rh; i += 256)
     {
         const int    rx = i % rw, ry = i / rw;
@@ -128,17 +140,15 @@ __global__ void __launch_bounds__(256) k_upsample_v2(GBufLevelDev g0, GBufLevelD
         else s_v1[ry * UP_RW + rx] = __half2float(__ldg(reinterpret_cast<const __half*>(in) + ci * in_channels));
     }
     __syncthreads();
-    const int x = x0 + (threadIdx.x & 31), y = y0 + (threadIdx.x >> 5);
-    if (x >= P.W0 || y >= P.H0 || y >= P.row1) return;
-    const size_t idx = (size_t)y * P.W0 + x;
-    const float  hz  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g0.gb3 + idx) + 1)).y;
+    if (!inb) return;
+    const float hz = h2_to_f2(hz_raw).y;
     if (hz == -1.0f)
     {
         if (C == 4) reinterpret_cast<uint2*>(out)[idx] = make_uint2(0u, 0u);
         else reinterpret_cast<__half*>(out)[idx] = __float2half_rn(P.sky_value);
         return;
     }
-    const float2 he = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g0.gb2 + idx)));
+    const float2 he = h2_to_f2(he_raw);
     const float3 hn = octohedral_to_direction(he.x, he.y);
     const float  tu = ((float)x + 0.5f) / (float)P.W0, tv = ((float)y + 0.5f) / (float)P.H0;
     const float  kx[4] = { 0.0f, 1.0f, -1.0f, 0.0f }, ky[4] = { 1.0f, 0.0f, 0.0f, -1.0f };

@@ -39,11 +39,44 @@ __device__ __forceinline__ Tap fetch_prev(const GBufLevelDev& p, int x, int y)
     return t;
 }
 
+struct TapRaw { uint32_t e, g3; float depth; };
+
+__device__ __forceinline__ TapRaw fetch_prev_raw(const GBufLevelDev& p, size_t i)
+{
+    TapRaw r;
+    r.e     = __ldg(reinterpret_cast<const uint32_t*>(p.gb2 + i));
+    r.g3    = __ldg(reinterpret_cast<const uint32_t*>(p.gb3 + i) + 1); // (mesh id, linear z)
+    r.depth = __ldg(p.depth + i);
+    return r;
+}
+
+__device__ __forceinline__ Tap decode_tap(const TapRaw& r)
+{ // all-zero words decode to the out-of-bounds texel: normal oct(0,0), mesh id 0, depth 0
+    Tap          t;
+    const float2 e = h2_to_f2(r.e);
+    t.n       = octohedral_to_direction(e.x, e.y);
+    t.mesh_id = h2_to_f2(r.g3).x;
+    t.depth   = r.depth;
+    return t;
+}
+
+// world_position_from_depth (common.glsl:175-186) with an approximate reciprocal: only feeds the 5.0-unit plane-distance test
+__device__ __forceinline__ float3 world_position_from_depth_fast(float u, float v, float d, const float* __restrict__ M)
+{
+    const float sx = u * 2.0f - 1.0f, sy = v * 2.0f - 1.0f;
+    const float wx = M[0] * sx + M[4] * sy + M[8] * d + M[12];
+    const float wy = M[1] * sx + M[5] * sy + M[9] * d + M[13];
+    const float wz = M[2] * sx + M[6] * sy + M[10] * d + M[14];
+    const float ww = M[3] * sx + M[7] * sy + M[11] * d + M[15];
+    const float iw = fast_rcp(ww);
+    return make_float3(wx * iw, wy * iw, wz * iw);
+}
+
 // is_reprojection_valid, reprojection.glsl:52-67 (frame test hoisted by the caller)
 __device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 cur_n, float cur_mesh, float hu, float hv, const float* vpi)
 {
     if (!(cur_mesh == t.mesh_id)) return false;
-    const float3 hp = world_position_from_depth(hu, hv, t.depth, vpi);
+    const float3 hp = world_position_from_depth_fast(hu, hv, t.depth, vpi);
     const float3 d  = make_float3(cur_pos.x - hp.x, cur_pos.y - hp.y, cur_pos.z - hp.z);
     if (fabsf(dot3(d, cur_n)) > 5.0f) return false; // PLANE_DISTANCE
     const float nd = fabsf(dot3(cur_n, t.n));
@@ -53,7 +86,7 @@ __device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 c
 
 // MODE 0: shadows (history RG16F .r, moments RGBA16F (m1,m2,N,0)); MODE 1: AO (history R16F, length R16F)
 template <int MODE>
-__global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const void* __restrict__ hist_img,
+__global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const void* __restrict__ hist_img,
                                                    const void* __restrict__ hist_aux, FrameConsts fc, float alpha_p, float moments_alpha_p,
                                                    void* __restrict__ out_img, void* __restrict__ out_aux, uint8_t* __restrict__ tile_flags, int row0, int row1)
 {
@@ -80,6 +113,19 @@ __global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev
         }
         s_rows[r] = bits;
     }
+    // the pixel's own G-buffer words are requested before the barriers so their HBM round trip overlaps the mask fetch
+    const int    x = x0 + lx, y = y0 + ly;
+    const bool   inb = x < W && y < H && y < row1;
+    const size_t idx = (size_t)y * W + x;
+    float        depth = 1.0f;
+    uint2        g2raw = make_uint2(0u, 0u);
+    uint32_t     g3raw = 0u;
+    if (inb)
+    {
+        depth = __ldg(cur.depth + idx);
+        g2raw = __ldg(cur.gb2 + idx);
+        g3raw = __ldg(reinterpret_cast<const uint32_t*>(cur.gb3 + idx) + 1);
+    }
     __syncthreads();
     {   // horizontal 17-wide window counts (columns lx .. lx+16 of the 48-wide region) for region rows ly, ly+8, ly+16
         const unsigned long long win = 0x1FFFFull << lx;
@@ -88,80 +134,84 @@ __global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev
     }
     __syncthreads();
 
-    const int x = x0 + lx, y = y0 + ly;
-    bool      flag = false;
-    if (x < W && y < H && y < row1)
+    bool flag = false;
+    if (inb)
     {
-        // neighborhood_mean: rows ly .. ly+16 of the per-row 17-wide counts (separable: 3 popcll per thread instead of 17)
-        int cnt = 0;
-#pragma unroll
-        for (int r = 0; r < 17; r++) cnt += s_h[ly + r][lx];
-        const float mean = (float)cnt / 289.0f;
-
-        const size_t idx   = (size_t)y * W + x;
-        const float  depth = __ldg(cur.depth + idx);
-        float        o0 = 0.0f, o1 = 0.0f, m0 = 0.0f, m1 = 0.0f, hlen = 0.0f;
+        float o0 = 0.0f, o1 = 0.0f, m0 = 0.0f, m1 = 0.0f, hlen = 0.0f;
         if (MODE == 1) o0 = 1.0f;
         if (depth != 1.0f)
         {
             const float vis = (float)((s_rows[ly + 8] >> (lx + 8)) & 1ull);
             // ---- reproject(), reprojection.glsl:115-328 ----
             const float  fw = (float)W, fh = (float)H;
-            const float  tu = ((float)x + 0.5f) / fw, tv = ((float)y + 0.5f) / fh;
-            const float4 g2 = h4_to_f4(__ldg(cur.gb2 + idx));
-            const float2 g3 = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(cur.gb3 + idx) + 1));
-            const float3 cn = octohedral_to_direction(g2.x, g2.y);
-            const float  cmesh = g3.x;
-            const float3 cpos  = world_position_from_depth(tu, tv, depth, fc.view_proj_inverse);
+            const float  tu = ((float)x + 0.5f) * fast_rcp(fw), tv = ((float)y + 0.5f) * fast_rcp(fh);
+            const float4 g2 = h4_to_f4(g2raw);
+            const float  cmesh = h2_to_f2(g3raw).x;
             const float  hfx = rn_mad(g2.z, fw, (float)x), hfy = rn_mad(g2.w, fh, (float)y); // history_coord_floor (:176), exactly rounded
             const int    hcx = (int)__fadd_rn(hfx, 0.5f), hcy = (int)__fadd_rn(hfy, 0.5f);       // history_coord (:175)
             const float  hu = tu + g2.z, hv = tv + g2.w;                           // history_tex_coord (:177)
             const bool   in_frame = inside(hcx, hcy, W, H);                        // out_of_frame_disocclusion_check on history_coord
             const int    bx = (int)hfx, by = (int)hfy;                             // ivec2(history_coord_floor) truncates
 
-            float hcol = 0.0f, hm0 = 0.0f, hm1 = 0.0f;
+            float hcol = 0.0f, hm0 = 0.0f, hm1 = 0.0f, hist_len = 0.0f;
             bool  valid = false;
             if (in_frame)
             {
+                // all history-side loads of the common path (<= 4 bilinear taps + history length) are issued back to back,
+                // before any of the validity arithmetic, so they share one HBM round trip
                 const float fx = hfx - floorf(hfx), fy = hfy - floorf(hfy);
                 const float w4[4] = { (1 - fx) * (1 - fy), fx * (1 - fy), (1 - fx) * fy, fx * fy };
+                {
+                    const size_t hi = (size_t)hcy * W + hcx;
+                    if (MODE == 0) hist_len = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + hi) + 1)).x;
+                    else hist_len = __half2float(__ldg(reinterpret_cast<const __half*>(hist_aux) + hi));
+                }
+                TapRaw   tr[4];
+                uint32_t hraw[4], mraw[4];
+#pragma unroll
+                for (int s = 0; s < 4; s++)
+                {
+                    tr[s]   = TapRaw { 0u, 0u, 0.0f };
+                    hraw[s] = 0u;
+                    mraw[s] = 0u;
+                    // A tap with bilinear weight exactly 0 cannot change the result: it adds 0 to every sum, and if only
+                    // such taps are valid sumw = 0 < 0.01 sends us to the 3x3 fallback exactly as "no tap valid" does.
+                    // Static pixels (motion 0 => fx = fy = 0) therefore need 1 tap instead of 4.
+                    const int px = bx + (s & 1), py = by + (s >> 1);
+                    if (w4[s] != 0.0f && inside(px, py, W, H))
+                    { // texelFetch out of bounds => zeros
+                        const size_t pi = (size_t)py * W + px;
+                        tr[s] = fetch_prev_raw(prev, pi);
+                        if (MODE == 0)
+                        {
+                            hraw[s] = __ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi);
+                            mraw[s] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi));
+                        }
+                        else hraw[s] = __half_as_ushort(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
+                    }
+                }
+                const float3 cn   = octohedral_to_direction(g2.x, g2.y);
+                const float3 cpos = world_position_from_depth_fast(tu, tv, depth, fc.view_proj_inverse);
                 float sumw = 0.0f;
                 bool  any  = false;
 #pragma unroll
                 for (int s = 0; s < 4; s++)
                 {
-                    // A tap with bilinear weight exactly 0 cannot change the result: it adds 0 to every sum, and if only
-                    // such taps are valid sumw = 0 < 0.01 sends us to the 3x3 fallback exactly as "no tap valid" does.
-                    // Static pixels (motion 0 => fx = fy = 0) therefore need 1 tap instead of 4.
                     if (w4[s] == 0.0f) continue;
-                    const int px = bx + (s & 1), py = by + (s >> 1);
-                    const Tap t  = fetch_prev(prev, px, py);
-                    if (tap_valid(t, cpos, cn, cmesh, hu, hv, fc.view_proj_inverse))
+                    if (tap_valid(decode_tap(tr[s]), cpos, cn, cmesh, hu, hv, fc.view_proj_inverse))
                     {
                         any = true;
-                        float hv0 = 0.0f, a0 = 0.0f, a1 = 0.0f;
-                        if (inside(px, py, W, H))
-                        {
-                            const size_t pi = (size_t)py * W + px;
-                            if (MODE == 0)
-                            {
-                                hv0 = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi)).x;
-                                const float2 mm = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi)));
-                                a0 = mm.x;
-                                a1 = mm.y;
-                            }
-                            else hv0 = __half2float(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
-                        }
-                        hcol += w4[s] * hv0;
-                        hm0 += w4[s] * a0;
-                        hm1 += w4[s] * a1;
+                        const float2 hh = h2_to_f2(hraw[s]), mm = h2_to_f2(mraw[s]);
+                        hcol += w4[s] * hh.x;
+                        hm0 += w4[s] * mm.x;
+                        hm1 += w4[s] * mm.y;
                         sumw += w4[s];
                     }
                 }
                 if (any)
                 {
                     valid = sumw >= 0.01f;
-                    if (valid) { hcol /= sumw; hm0 /= sumw; hm1 /= sumw; }
+                    if (valid) { const float inv = fast_rcp(sumw); hcol *= inv; hm0 *= inv; hm1 *= inv; }
                     else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
                 }
                 if (!valid)
@@ -189,28 +239,27 @@ __global__ void __launch_bounds__(256) k_temporal(GBufLevelDev cur, GBufLevelDev
                                 cntv += 1.0f;
                             }
                         }
-                    if (cntv > 0.0f) { valid = true; hcol /= cntv; hm0 /= cntv; hm1 /= cntv; }
+                    if (cntv > 0.0f) { valid = true; const float inv = fast_rcp(cntv); hcol *= inv; hm0 *= inv; hm1 *= inv; }
                 }
             }
-            float hist_len = 0.0f;
-            if (valid)
-            { // history_coord is inside the frame here
-                const size_t hi = (size_t)hcy * W + hcx;
-                if (MODE == 0) hist_len = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + hi) + 1)).x;
-                else hist_len = __half2float(__ldg(reinterpret_cast<const __half*>(hist_aux) + hi));
-            }
-            else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
+            if (!valid) { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; hist_len = 0.0f; }
             // ---- accumulate ----
             hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
+            const float ihlen = fast_rcp(hlen);
             if (valid)
             {
-                const float sd = sqrtf(fmaxf(mean - mean * mean, 0.0f));
-                hcol           = fminf(fmaxf(hcol, mean - 0.5f * sd), mean + 0.5f * sd);
+                // neighborhood_mean: rows ly .. ly+16 of the per-row 17-wide counts (separable: 3 popcll per thread instead of 17)
+                int cnt = 0;
+#pragma unroll
+                for (int r = 0; r < 17; r++) cnt += s_h[ly + r][lx];
+                const float mean = (float)cnt * (1.0f / 289.0f);
+                const float sd   = sqrtf(fmaxf(mean - mean * mean, 0.0f));
+                hcol             = fminf(fmaxf(hcol, mean - 0.5f * sd), mean + 0.5f * sd);
             }
-            const float alpha = valid ? fmaxf(alpha_p, 1.0f / hlen) : 1.0f;
+            const float alpha = valid ? fmaxf(alpha_p, ihlen) : 1.0f;
             if (MODE == 0)
             {
-                const float am = valid ? fmaxf(moments_alpha_p, 1.0f / hlen) : 1.0f;
+                const float am = valid ? fmaxf(moments_alpha_p, ihlen) : 1.0f;
                 m0 = hm0 * (1.0f - am) + vis * am;
                 m1 = hm1 * (1.0f - am) + (vis * vis) * am;
                 o1 = fmaxf(0.0f, m1 - m0 * m0);

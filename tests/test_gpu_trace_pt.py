@@ -1,6 +1,8 @@
-"""The persistent-threads traversal kernel (warp ray compaction + shared-memory stack, hr_debug_set(2, 1)) must produce the
-same bit-exact visibility masks as the oracle — it is not the default (the plain one-warp-per-8x4-block kernel is faster
-on coherent primary-surface rays) but it is a supported variant."""
+"""Non-default traversal / BVH variants must produce the same bit-exact visibility masks as the oracle:
+  * hr_debug_set(2, 1): persistent-threads traversal kernel (warp ray compaction + shared-memory stack) — not the default
+    (the plain one-warp-per-8x4-block kernel is faster on coherent primary-surface rays) but a supported variant;
+  * hr_debug_set(3, 0): Karras radix-tree topology instead of the default PLOC agglomerative build (hit results must not
+    depend on the BVH topology)."""
 import numpy as np
 import pytest
 
@@ -10,18 +12,19 @@ import pyhr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("dbg_key,dbg_val,dbg_default", [(2, 1, 0), (3, 0, 1)], ids=["persistent-traversal", "lbvh-topology"])
 @pytest.mark.parametrize("scene_kind,tris,W,H,cam", [
     (pyhr.SCENE_SHADOWS_TEST, 0, 256, 144, ((0.0, 14.0, 34.0), (0.0, 3.0, 0.0))),
     (pyhr.SCENE_ARCADE, 30000, 200, 104, ((0.0, 9.0, -4.0), (2.0, 7.0, 60.0))),  # width not a multiple of 32: partial super-blocks
 ])
-def test_persistent_traversal_masks_bit_exact(scene_kind, tris, W, H, cam):
+def test_variant_masks_bit_exact(scene_kind, tris, W, H, cam, dbg_key, dbg_val, dbg_default):
     sc = pyhr.SynthScene(scene_kind, tris)
     tri, _ = sc.world_triangles()
     osc = O.Scene(tri, brute=sc.n_tris <= 4096)
     bn = pyhr.blue_noise()
     ctx = pyhr.Context(0)
     try:
-        ctx.lib.hr_debug_set(2, 1)
+        ctx.lib.hr_debug_set(dbg_key, dbg_val)
         ctx.set_bluenoise(*bn)
         ctx.build_scene(sc)
         ctx.gbuffer_create(W, H)
@@ -40,11 +43,11 @@ def test_persistent_traversal_masks_bit_exact(scene_kind, tris, W, H, cam):
             cur = O.GBufMips(g)
             osh.render(osc, cur, cur, f, bn)
             oao.render(osc, cur, cur, f, bn)
-            assert np.array_equal(sh.download(0), osh.mask), f"frame {i}: shadows mask (persistent kernel)"
-            assert np.array_equal(ao.download(0), oao.mask), f"frame {i}: AO mask (persistent kernel)"
+            assert np.array_equal(sh.download(0), osh.mask), f"frame {i}: shadows mask (variant {dbg_key}={dbg_val})"
+            assert np.array_equal(ao.download(0), oao.mask), f"frame {i}: AO mask (variant {dbg_key}={dbg_val})"
             assert osh.mask.any() and oao.mask.any()
         sh.destroy()
         ao.destroy()
     finally:
-        ctx.lib.hr_debug_set(2, 0)
+        ctx.lib.hr_debug_set(dbg_key, dbg_default)
         ctx.close()
