@@ -3,6 +3,7 @@
 //   RayTracedShadows::render  src/ray_traced_shadows.cpp:100-116 (+ stages :938-1255)
 //   RayTracedAO::render       src/ray_traced_ao.cpp:98-112      (+ stages :829-1137)
 #include "hr_internal.h"
+#include <utility>
 #include <cstdarg>
 #include <cstring>
 #include <mutex>
@@ -120,6 +121,10 @@ int hr_shutdown(hr_ctx* ctx)
         }
         for (int k = 0; k < 4; k++) cudaFree(ctx->owned_mip0[s][k]);
     }
+    for (int k = 0; k < 4; k++) cudaFree(ctx->staging_mip0[k]);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->ev_staged) cudaEventDestroy(ctx->ev_staged);
+    if (ctx->ev_storage_free) cudaEventDestroy(ctx->ev_storage_free);
     cudaFree(ctx->d_sobol);
     cudaFree(ctx->d_scr_rank);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
@@ -362,6 +367,62 @@ static int gbuffer_copy_in(hr_ctx* ctx, int slot, const hr_gbuffer_desc* src, cu
 
 int hr_gbuffer_upload(hr_ctx* ctx, int slot, const hr_gbuffer_desc* host, void* stream) { return gbuffer_copy_in(ctx, slot, host, cudaMemcpyHostToDevice, (cudaStream_t)stream); }
 int hr_gbuffer_copy_from_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev, void* stream) { return gbuffer_copy_in(ctx, slot, dev, cudaMemcpyDeviceToDevice, (cudaStream_t)stream); }
+
+// Streaming host frames.  PCIe moves ~24 B/pixel per frame (199 MB at 4K, ~3.6 ms on a Gen5 x16 link) — longer than the
+// frame's kernels — so the upload of frame N+1 has to overlap the render of frame N.  The G-buffer is double buffered by
+// design (current / previous, src/g_buffer.cpp:236-244), and slot (N+1)%2 is still being read as "previous" while frame N
+// renders, so the copy goes to a third surface on the library's upload stream; commit swaps that surface with the slot's
+// storage.  The storage handed back by the swap was last read by renders already enqueued on `stream`: an event recorded
+// there gates the next staged upload.
+int hr_gbuffer_stage_upload(hr_ctx* ctx, const hr_gbuffer_desc* host)
+{
+    HR_REQUIRE(ctx, ctx && host, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_upload: bad argument");
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_stage_upload: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, host->width == ctx->gb_w && host->height == ctx->gb_h, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_upload: size mismatch");
+    HR_REQUIRE(ctx, host->gb2 && host->gb3 && host->depth, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_upload: gb2/gb3/depth are required");
+    HR_REQUIRE(ctx, !ctx->staged_pending, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_upload: a staged frame is already waiting for hr_gbuffer_commit_staged");
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->gb_w * ctx->gb_h;
+    if (!ctx->upload_stream)
+    {
+        HR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_storage_free, cudaEventDisableTiming));
+        const size_t bytes[4] = { px * 4, px * 8, px * 8, px * 4 };
+        for (int k = 0; k < 4; k++)
+        {
+            HR_CUDA(ctx, cudaMalloc(&ctx->staging_mip0[k], bytes[k]));
+            HR_CUDA(ctx, cudaMemset(ctx->staging_mip0[k], 0, bytes[k]));
+        }
+    }
+    if (ctx->storage_free_recorded) HR_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_storage_free, 0));
+    if (host->gb1) HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[0], host->gb1, px * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[1], host->gb2, px * 8, cudaMemcpyHostToDevice, ctx->upload_stream));
+    HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[2], host->gb3, px * 8, cudaMemcpyHostToDevice, ctx->upload_stream));
+    HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[3], host->depth, px * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    HR_CUDA(ctx, cudaEventRecord(ctx->ev_staged, ctx->upload_stream));
+    ctx->staged_pending = true;
+    return HR_OK;
+}
+
+int hr_gbuffer_commit_staged(hr_ctx* ctx, int slot, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && (slot == 0 || slot == 1), HR_ERR_INVALID_ARG, "hr_gbuffer_commit_staged: bad argument");
+    HR_REQUIRE(ctx, ctx->staged_pending, HR_ERR_NOT_READY, "hr_gbuffer_commit_staged: no staged frame (call hr_gbuffer_stage_upload first)");
+    cudaStream_t st = (cudaStream_t)stream;
+    // everything enqueued on `stream` so far may still read the storage we are about to recycle as the staging surface
+    HR_CUDA(ctx, cudaEventRecord(ctx->ev_storage_free, st));
+    ctx->storage_free_recorded = true;
+    HR_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_staged, 0));
+    GBufSlot& s = ctx->slot[slot];
+    for (int k = 0; k < 4; k++) std::swap(ctx->owned_mip0[slot][k], ctx->staging_mip0[k]);
+    s.gb1[0]   = ctx->owned_mip0[slot][0];
+    s.gb2[0]   = ctx->owned_mip0[slot][1];
+    s.gb3[0]   = ctx->owned_mip0[slot][2];
+    s.depth[0] = (float*)ctx->owned_mip0[slot][3];
+    ctx->staged_pending = false;
+    return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, st);
+}
 
 int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev, void* stream)
 {
@@ -711,6 +772,20 @@ int hr_pass_output(hr_pass* p, int which, hr_image* out)
     // a borrowed pointer may be consumed on any stream: finish a pending band exchange first (sharded runs only)
     if (p->xchg_pending && p->ev_done) { cudaEventSynchronize(p->ev_done); p->xchg_pending = false; }
     out->data = v.p; out->width = v.w; out->height = v.h; out->format = v.fmt;
+    return HR_OK;
+}
+
+// hr_pass_download without the host synchronisation: the caller orders it with its own stream / event waits.
+int hr_pass_download_async(hr_pass* p, int which, void* dst, size_t bytes, void* stream)
+{
+    hr_image img;
+    int      rc = hr_pass_output(p, which, &img);
+    if (rc != HR_OK) return rc;
+    hr_ctx*      ctx  = p->ctx;
+    const size_t need = (size_t)img.width * img.height * texel_size(img.format);
+    HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download_async: byte count mismatch");
+    hr_wait_exchange(p, (cudaStream_t)stream);
+    HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return HR_OK;
 }
 

@@ -71,6 +71,13 @@ struct hr_ctx {
     int          gb_w = 0, gb_h = 0;
     GBufSlot     slot[2];
     void*        owned_mip0[2][4] = {}; // library-owned mip0 storage (gb1,gb2,gb3,depth) kept when a slot is bound zero-copy
+    // streaming host frames: a third mip0 surface receives frame N+1 over PCIe (upload_stream) while frame N renders;
+    // hr_gbuffer_commit_staged swaps it with a slot's storage (no copy)
+    void*        staging_mip0[4] = {};
+    bool         staging_has_gb1 = false, staged_pending = false;
+    cudaStream_t upload_stream = nullptr;
+    cudaEvent_t  ev_staged = nullptr, ev_storage_free = nullptr;
+    bool         storage_free_recorded = false;
     // scene
     hr_scene*    scene = nullptr;
     // sharding

@@ -180,6 +180,110 @@ __global__ void __launch_bounds__(256) k_upsample_v2(GBufLevelDev g0, GBufLevelD
     }
 }
 
+
+// ---- exact 2x upsample ------------------------------------------------------------------------------------------------
+// W0 == 2*Wm and H0 == 2*Hm (the reference's half-resolution passes on even frame sizes).  textureLod NEAREST of
+// uv + (+-1 coarse texel) with uv = (x + 0.5) / W0 lands on coarse texel (x >> 1) +- 1 (fraction .25 / .75, far from the
+// rounding edge), clamped to the image: the four pixels of a 2x2 quad share their four taps.  One thread = one quad:
+// 16-byte loads of its two G-buffer rows, taps decoded once per CTA into shared memory, no per-pixel address arithmetic.
+template <int C>
+__global__ void __launch_bounds__(256) k_upsample_2x(GBufLevelDev g0, GBufLevelDev gm, const void* __restrict__ in, int in_channels, UpParams P, void* __restrict__ out)
+{
+    constexpr int RW = 34, RH = 10;
+    __shared__ float4 s_nz[RW * RH];
+    __shared__ float4 s_val[C == 4 ? RW * RH : 1];
+    __shared__ float  s_v1[C == 1 ? RW * RH : 1];
+    const int  lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int  cx0 = blockIdx.x * 32, cy0 = (P.row0 >> 1) + blockIdx.y * 8;
+    const int  cx = cx0 + lx, cy = cy0 + ly, x = 2 * cx, y = 2 * cy;
+    const bool inb = cx < P.Wm && y < P.row1;
+    uint4      a2[2], a3[2];
+    if (inb)
+    {
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+        {
+            const size_t i = (size_t)(y + r) * P.W0 + x; // even => 16-byte aligned
+            a2[r] = __ldg(reinterpret_cast<const uint4*>(g0.gb2 + i));
+            a3[r] = __ldg(reinterpret_cast<const uint4*>(g0.gb3 + i));
+        }
+    }
+    for (int i = threadIdx.x; i < RW * RH; i += 256)
+    {
+        const int    rx = i % RW, ry = i / RW;
+        const int    gx = min(max(cx0 - 1 + rx, 0), P.Wm - 1), gy = min(max(cy0 - 1 + ry, 0), P.Hm - 1);
+        const size_t ci = (size_t)gy * P.Wm + gx;
+        const float2 e  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(gm.gb2 + ci)));
+        const float  z  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(gm.gb3 + ci) + 1)).y;
+        const float3 n  = octohedral_to_direction(e.x, e.y);
+        s_nz[i] = make_float4(n.x, n.y, n.z, z);
+        if (C == 4) s_val[i] = h4_to_f4(__ldg(reinterpret_cast<const uint2*>(in) + ci));
+        else s_v1[i] = __half2float(__ldg(reinterpret_cast<const __half*>(in) + ci * in_channels));
+    }
+    __syncthreads();
+    if (!inb) return;
+    // tap order of the reference kernel: (0,+1) (+1,0) (-1,0) (0,-1)
+    const int ti[4] = { (ly + 2) * RW + lx + 1, (ly + 1) * RW + lx + 2, (ly + 1) * RW + lx, ly * RW + lx + 1 };
+    float4    c[4], v4[4];
+    float     v1[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+    {
+        c[t] = s_nz[ti[t]];
+        if (C == 4) v4[t] = s_val[ti[t]];
+        else v1[t] = s_v1[ti[t]];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+    {
+        uint32_t o1[2];
+        uint2    o4[2];
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+        {
+            const float hz = h2_to_f2(q ? a3[r].w : a3[r].y).y;
+            if (hz == -1.0f)
+            {
+                o1[q] = __half_as_ushort(__float2half_rn(P.sky_value));
+                o4[q] = make_uint2(0u, 0u);
+                continue;
+            }
+            const float2 he = h2_to_f2(q ? a2[r].z : a2[r].x);
+            const float3 hn = octohedral_to_direction(he.x, he.y);
+            float        up[4] = { 0, 0, 0, 0 }, tw = 0.0f;
+#pragma unroll
+            for (int t = 0; t < 4; t++)
+            {
+                if (c[t].w == -1.0f) continue; // coarse texel is sky
+                const float wZ = fast_exp2(-1.44269504f * fabsf(hz - c[t].w));
+                const float w  = fast_exp2(fmaf(wZ, -1.44269504f, -1.44269504f)) * pow32(__saturatef(hn.x * c[t].x + hn.y * c[t].y + hn.z * c[t].z));
+                if (C == 4)
+                {
+                    up[0] = fmaf(v4[t].x, w, up[0]); up[1] = fmaf(v4[t].y, w, up[1]); up[2] = fmaf(v4[t].z, w, up[2]); up[3] = fmaf(v4[t].w, w, up[3]);
+                }
+                else up[0] = fmaf(v1[t], w, up[0]);
+                tw += w;
+            }
+            const float inv = 1.0f / fmaxf(tw, 0.00000001f);
+            if (C == 4) o4[q] = pack_h4(up[0] * inv, up[1] * inv, up[2] * inv, up[3] * inv);
+            else
+            {
+                float rr = up[0] * inv;
+                if (P.power != 0.0f) rr = pow_pos(rr, P.power);
+                o1[q] = __half_as_ushort(__float2half_rn(rr));
+            }
+        }
+        const size_t oi = (size_t)(y + r) * P.W0 + x;
+        if (C == 4) reinterpret_cast<uint4*>(out)[oi >> 1] = make_uint4(o4[0].x, o4[0].y, o4[1].x, o4[1].y);
+        else reinterpret_cast<uint32_t*>(out)[oi >> 1] = o1[0] | (o1[1] << 16);
+    }
+}
+
+bool upsample_is_2x(const GBufLevelDev& g0, const GBufLevelDev& gm, int row0, int row1)
+{
+    return g0.W == 2 * gm.W && g0.H == 2 * gm.H && (row0 & 1) == 0 && (row1 & 1) == 0;
+}
+
 // the staged footprint must fit UP_RW x UP_RH: true when the coarse image is at most 2x smaller... i.e. 32 full-res columns
 // map to <= 32*Wm/W0 + 3 coarse columns
 bool upsample_fits(const GBufLevelDev& g0, const GBufLevelDev& gm)
@@ -209,8 +313,14 @@ void launch_upsample_scalar(const GBufLevelDev& g0, const GBufLevelDev& gm, cons
                             int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
-    if (!upsample_fits(g0, gm)) { launch_upsample_scalar_v1(g0, gm, in, in_channels, sky_value, power, out, row0, row1, st); return; }
     UpParams P { g0.W, g0.H, gm.W, gm.H, row0, row1, sky_value, power };
+    if (upsample_is_2x(g0, gm, row0, row1))
+    {
+        dim3 grid2((gm.W + 31) / 32, ((row1 - row0) / 2 + 7) / 8);
+        k_upsample_2x<1><<<grid2, 256, 0, st>>>(g0, gm, in, in_channels, P, out);
+        return;
+    }
+    if (!upsample_fits(g0, gm)) { launch_upsample_scalar_v1(g0, gm, in, in_channels, sky_value, power, out, row0, row1, st); return; }
     dim3     grid((g0.W + 31) / 32, (row1 - row0 + 7) / 8);
     k_upsample_v2<1><<<grid, 256, 0, st>>>(g0, gm, in, in_channels, P, out);
 }
@@ -218,8 +328,14 @@ void launch_upsample_scalar(const GBufLevelDev& g0, const GBufLevelDev& gm, cons
 // returns false if the footprint does not fit (caller uses its v1 kernel)
 bool launch_upsample_vec4_v2(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st)
 {
-    if (!upsample_fits(g0, gm)) return false;
     UpParams P { g0.W, g0.H, gm.W, gm.H, row0, row1, 0.0f, 0.0f };
+    if (upsample_is_2x(g0, gm, row0, row1))
+    {
+        dim3 grid2((gm.W + 31) / 32, ((row1 - row0) / 2 + 7) / 8);
+        k_upsample_2x<4><<<grid2, 256, 0, st>>>(g0, gm, in, 4, P, out);
+        return true;
+    }
+    if (!upsample_fits(g0, gm)) return false;
     dim3     grid((g0.W + 31) / 32, (row1 - row0 + 7) / 8);
     k_upsample_v2<4><<<grid, 256, 0, st>>>(g0, gm, in, 4, P, out);
     return true;

@@ -53,12 +53,17 @@ __device__ __forceinline__ SlabSetup slab_setup(const Ray& r)
 __device__ __forceinline__ void node_test(const float4* __restrict__ nodes, int node, const SlabSetup& s, float tmin, float tmax, bool& h0, bool& h1,
                                           float& tn0, float& tn1, int& c0, int& c1)
 {
-    const float4 n0 = __ldg(nodes + 4ull * node + 0);
-    const float4 n1 = __ldg(nodes + 4ull * node + 1);
-    const float4 nz = __ldg(nodes + 4ull * node + 2);
-    const float4 ch = __ldg(nodes + 4ull * node + 3);
-    c0 = __float_as_int(ch.x);
-    c1 = __float_as_int(ch.y);
+    // The 64-byte node is fetched with two 256-bit loads (sm_100 LDG.E.256): the child indices travel with the z slabs, so
+    // they cannot be sunk below the box tests by the scheduler (a second L1 round trip per traversal step otherwise).
+    const float4* np = nodes + 4ull * node;
+    float4        n0, n1, nz;
+    float         pad0, pad1;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w)
+                 : "l"(np));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+                 : "=f"(nz.x), "=f"(nz.y), "=f"(nz.z), "=f"(nz.w), "=r"(c0), "=r"(c1), "=f"(pad0), "=f"(pad1)
+                 : "l"(np));
     float ax = fmaf(n0.x, s.idx, -s.ox), bx = fmaf(n0.y, s.idx, -s.ox);
     float ay = fmaf(n0.z, s.idy, -s.oy), by = fmaf(n0.w, s.idy, -s.oy);
     float az = fmaf(nz.x, s.idz, -s.oz), bz = fmaf(nz.y, s.idz, -s.oz);

@@ -85,6 +85,7 @@ HR_FMT = {1: ("<u4", 1), 2: ("<f2", 1), 3: ("<f2", 2), 4: ("<f2", 4), 5: ("u1", 
 ABI_SYMBOLS = [
     "hr_init", "hr_shutdown", "hr_last_error", "hr_version", "hr_bluenoise_set", "hr_scene_build", "hr_scene_destroy", "hr_scene_set_current",
     "hr_scene_get_info", "hr_scene_rebuild", "hr_trace_any", "hr_trace_closest", "hr_gbuffer_create", "hr_gbuffer_upload",
+    "hr_gbuffer_stage_upload", "hr_gbuffer_commit_staged", "hr_pass_download_async",
     "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown",
@@ -312,6 +313,14 @@ class Context:
         d = g.desc()
         self.check(self.lib.hr_gbuffer_upload(self.h, slot, C.byref(d), C.c_void_p(stream)), "hr_gbuffer_upload")
 
+    def gbuffer_stage_upload(self, g: GBufferHost):
+        """Start the PCIe copy of the NEXT frame's (pinned) G-buffer on the library's upload stream; returns immediately."""
+        d = g.desc()
+        self.check(self.lib.hr_gbuffer_stage_upload(self.h, C.byref(d)), "hr_gbuffer_stage_upload")
+
+    def gbuffer_commit_staged(self, slot, stream=0):
+        self.check(self.lib.hr_gbuffer_commit_staged(self.h, slot, C.c_void_p(stream)), "hr_gbuffer_commit_staged")
+
     def gbuffer_copy_from_device(self, slot, desc: hr_gbuffer_desc, stream=0):
         self.check(self.lib.hr_gbuffer_copy_from_device(self.h, slot, C.byref(desc), C.c_void_p(stream)), "hr_gbuffer_copy_from_device")
 
@@ -378,6 +387,11 @@ class Pass:
         a = out if out is not None else np.empty(shape, np.dtype(dt))
         self.ctx.check(self.lib.hr_pass_download(self.h, which, _ptr(a), C.c_size_t(a.nbytes), C.c_void_p(stream)), "hr_pass_download")
         return a
+
+    def download_async(self, which, out, stream=0):
+        """Enqueue the device -> host copy on `stream` without synchronising (out: pinned array of the image's size)."""
+        self.ctx.check(self.lib.hr_pass_download_async(self.h, which, _ptr(out), C.c_size_t(out.nbytes), C.c_void_p(stream)), "hr_pass_download_async")
+        return out
 
     def upload(self, which, a, stream=0):
         a = np.ascontiguousarray(a)

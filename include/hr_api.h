@@ -177,6 +177,14 @@ typedef struct hr_gbuffer_desc {
 HR_API int hr_gbuffer_create(hr_ctx* ctx, int width, int height);
 /* Host -> device copy of mip 0 into slot, then NEAREST mip chain on device (g_buffer.cpp:236-244). Async on stream. */
 HR_API int hr_gbuffer_upload(hr_ctx* ctx, int slot, const hr_gbuffer_desc* host_mip0, void* stream);
+/* Streaming host frames (copy / compute overlap).  hr_gbuffer_stage_upload starts the host -> device copy of the NEXT
+ * frame's mip 0 into a third, library-owned surface on the library's own upload stream and returns immediately (pinned
+ * host memory required for the copy to be asynchronous; the host buffers must stay untouched until the frame was
+ * committed and `stream` reached that point).  hr_gbuffer_commit_staged makes `stream` wait for that copy, swaps the
+ * staged surface into `slot` (pointer swap, no copy) and builds the mip chain on `stream` — afterwards the slot behaves
+ * exactly as after hr_gbuffer_upload.  One staged frame at a time: stage, commit, stage, commit ... */
+HR_API int hr_gbuffer_stage_upload(hr_ctx* ctx, const hr_gbuffer_desc* host_mip0);
+HR_API int hr_gbuffer_commit_staged(hr_ctx* ctx, int slot, void* stream);
 /* Device -> device variant (inputs already resident in HBM). */
 HR_API int hr_gbuffer_copy_from_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev_mip0, void* stream);
 /* Zero-copy: bind caller-owned device mip-0 images as slot; the library only builds mips 1.. from them. */
@@ -356,6 +364,8 @@ HR_API int hr_reflections_render(hr_pass* pass, const hr_frame* frame, const hr_
 HR_API int hr_pass_output(hr_pass* pass, int which, hr_image* out);
 /* Synchronous device->host copy of an output on `stream` (waits for it). bytes must equal w*h*texel. */
 HR_API int hr_pass_download(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
+/* Same copy enqueued on `stream` without the host synchronisation (pinned host_dst; the caller synchronises). */
+HR_API int hr_pass_download_async(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
 /* Checkpoint / resume of temporal history: hr_pass_download saves an image, hr_pass_upload restores it (synchronous). */
 HR_API int hr_pass_upload(hr_pass* pass, int which, const void* host_src, size_t bytes, void* stream);
 /* restart_accumulation() / clear_images() equivalent: next render behaves like first_frame for this pass's history. */
