@@ -182,6 +182,9 @@ def main():
         uid = [pyhr.shard_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.shard_init(rank, world, uid[0])
+        # the denoised frame stays distributed: every rank keeps (and, in the e2e leg, downloads) its own band; the temporal
+        # history is read through peer mappings, so no per-frame collective is left on the data path
+        ctx.shard_set_gather(False)
     t_b = time.perf_counter()
     scene_h = ctx.build_scene(sc)
     torch.cuda.synchronize()
@@ -198,8 +201,9 @@ def main():
     d_depth = torch.from_numpy(g_host.depth).cuda()
     dev_desc = pyhr.hr_gbuffer_desc(W, H, d_gb1.data_ptr(), d_gb2.data_ptr(), d_gb3.data_ptr(), d_depth.data_ptr())
 
-    out_sh = torch.empty((H, W, 2), dtype=torch.float16).pin_memory().numpy()
-    out_ao = torch.empty((H, W), dtype=torch.float16).pin_memory().numpy()
+    band0, band1 = pyhr.shard_rows(H, rank, world)  # this rank's rows of the full-resolution outputs
+    out_sh = torch.empty((band1 - band0, W, 2), dtype=torch.float16).pin_memory().numpy()
+    out_ao = torch.empty((band1 - band0, W), dtype=torch.float16).pin_memory().numpy()
 
     state = {"f": f1, "n": 2}
 
@@ -219,8 +223,9 @@ def main():
         ctx.gbuffer_upload(f.ping_pong, g_host, stream)
         sh.render(f, stream)
         ao.render(f, stream)
-        sh.download(100, stream, out_sh)
-        ao.download(100, stream, out_ao)
+        sh.download_rows_async(100, band0, band1, out_sh, stream)
+        ao.download_rows_async(100, band0, band1, out_ao, stream)
+        torch.cuda.current_stream().synchronize()
 
     def step_e2e():
         # streaming host frames: this frame's G-buffer was staged (PCIe copy on the library's upload stream) while the
@@ -230,8 +235,8 @@ def main():
         ctx.gbuffer_stage_upload(g_host)
         sh.render(f, stream)
         ao.render(f, stream)
-        sh.download_async(100, out_sh, stream)
-        ao.download_async(100, out_ao, stream)
+        sh.download_rows_async(100, band0, band1, out_sh, stream)
+        ao.download_rows_async(100, band0, band1, out_ao, stream)
 
     # history warm-up to steady state (both slots bound, history length saturates at 32)
     ctx.gbuffer_bind_device(0, dev_desc, stream)
@@ -332,8 +337,13 @@ def main():
         rf.destroy()
 
     t = torch.tensor([ms_total, ms_e2e, full["ms_total"] if full else 0.0], dtype=torch.float64, device="cuda")
+    # per-rank sum of the profiled stage times of one frame: shows the load imbalance between the row bands
+    busy = torch.tensor([sum(ms for _, ms in sh_stages), sum(ms for _, ms in ao_stages), dict(sh_stages).get("Ray Trace", 0.0) + dict(ao_stages).get("Ray Trace", 0.0)],
+                        dtype=torch.float64, device="cuda")
+    busy_all = [busy.clone() for _ in range(world)]
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_gather(busy_all, busy)
     ms_total, ms_e2e, ms_full_max = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
@@ -354,9 +364,10 @@ def main():
             "metric": "denoised frames/s @4K (shadows+AO, 1 spp, full SVGF)", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3) + 30, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (fp16 storage)", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(g_host.nbytes()), "d2h_bytes_per_step": int(out_sh.nbytes + out_ao.nbytes),
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(g_host.nbytes()), "d2h_bytes_per_step": int(W * H * 6),
                     "mode": "streamed: hr_gbuffer_stage_upload of frame N+1 overlaps the render of frame N (pinned host buffers)",
                     "serial_value": args.steps / (ms_e2e_serial / 1e3)},
+            "rank_stage_sums_ms": [{"shadows": round(float(b[0]), 4), "ao": round(float(b[1]), 4), "ray_trace": round(float(b[2]), 4)} for b in busy_all],
             "roofline": {"kernel": "k_atrous_v3 (shadows a-trous, K5)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "avg_launch_ms": at_ms, "algorithmic_bytes_per_launch": ATROUS_BYTES_PER_PX * at_px},

@@ -538,12 +538,15 @@ int hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** o
     A(pass_alloc(p, p->temporal_out, px));
     A(pass_alloc(p, p->moments[0], px));
     A(pass_alloc(p, p->moments[1], px));
-    A(pass_alloc(p, p->prev_image, px));
+    A(pass_alloc(p, p->prev_image[0], px));
+    A(pass_alloc(p, p->prev_image[1], px));
     A(pass_alloc(p, p->atrous[0], px));
     A(pass_alloc(p, p->atrous[1], px));
     A(pass_alloc(p, p->tile_flags, tw * th));
     if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
 #undef A
+    void* hist[4] = { p->prev_image[0], p->prev_image[1], p->moments[0], p->moments[1] };
+    hr_peer_register(p, hist, 4);
     return HR_OK;
 }
 
@@ -568,11 +571,21 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
     timer_begin(p, st);
 
-    if (!prm->denoise || p->first) hr_wait_exchange(p, st); // the exchanged image (mask / cleared history) is rewritten right away
-    // clear_images (ray_traced_shadows.cpp:938-968): first frame => history image and moments[!pp] = 0
+    if (ctx->world > 1 && ctx->nccl_comm && !p->peers_linked)
+    { // first sharded render: map the peers' history images (collective, shard.cu)
+        rc = hr_peer_link_ipc(p, st);
+        if (rc != HR_OK) return rc;
+    }
+    const int  epoch      = ++p->epoch;
+    const bool no_history = p->first;
+    bool       signalled  = false;
+    hr_wait_exchange(p, st); // last frame's gather of the final output (side stream) reads images this frame rewrites
+    // clear_images (ray_traced_shadows.cpp:938-968): first frame => history image and moments[!pp] = 0.  The reprojection
+    // kernel is told not to read any history on that frame (same values as reading the cleared images, and no peer can be
+    // caught reading a surface while it is being cleared); hr_pass_reset_history must be called on all ranks together.
     if (p->first)
     {
-        HR_CUDA(ctx, cudaMemsetAsync(p->prev_image, 0, px * sizeof(__half2), st));
+        HR_CUDA(ctx, cudaMemsetAsync(p->prev_image[!pp], 0, px * sizeof(__half2), st));
         HR_CUDA(ctx, cudaMemsetAsync(p->moments[!pp], 0, px * sizeof(uint2), st));
         p->first = false;
     }
@@ -585,41 +598,60 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
     if (prm->denoise)
     {
-        // temporal_accumulation (:1041-1090); reset_args (:1015-1037) is subsumed by the per-tile flag image
-        hr_wait_exchange(p, st); // last frame's band exchange of prev_image / moments (overlapped with the ray trace above)
-        launch_shadows_temporal(cur, prev, p->mask, p->prev_image, p->moments[!pp], fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp],
-                                p->tile_flags, row0, row1, st);
+        // temporal_accumulation (:1041-1090); reset_args (:1015-1037) is subsumed by the per-tile flag image.
+        // History = prev_image[!pp] / moments[!pp] of whichever rank owns the reprojected row (peer history, shard.cu):
+        // wait until every peer has finished writing them (tick epoch-1), overlapped with the ray trace above.
+        HistPeers hist;
+        hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
+        if (!no_history)
+        {
+            rc = hr_peer_wait(p, epoch - 1, st);
+            if (rc != HR_OK) return rc;
+        }
+        launch_shadows_temporal(cur, prev, p->mask, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
         timer_mark(p, "Temporal Accumulation", st);
         // a_trous_filter (:1094-1215).  The reference ping-pongs image[0]/image[1] and copies the output of
-        // feedback_iteration into prev_image; here that iteration writes prev_image directly and the next one reads it.
+        // feedback_iteration into prev_image; here that iteration writes this frame's history image directly and the next
+        // one reads it.  prev_image is double buffered by frame parity (peers may still read last frame's).
+        __half2* const hist_out = p->prev_image[pp];
         const __half2* in      = p->temporal_out;
         __half2*       last    = p->temporal_out;
         int            toggle  = 1; // reference: first write_idx = 1
+        bool           fed_back = false;
         for (int i = 0; i < prm->filter_iterations; i++)
         {
-            __half2* dst = (i == prm->feedback_iteration) ? p->prev_image : p->atrous[toggle];
-            if (i == prm->filter_iterations - 1 && dst == p->prev_image)
+            __half2* dst = (i == prm->feedback_iteration) ? hist_out : p->atrous[toggle];
+            if (i == prm->filter_iterations - 1 && dst == hist_out)
             { // final output must not alias the history image: filter into atrous[], then copy (reference semantics)
                 dst = p->atrous[toggle];
             }
             const float power = (i == prm->filter_iterations - 1) ? prm->power : 0.0f;
             launch_shadows_atrous(cur, in, p->tile_flags, prm->radius, 1 << i, prm->phi_visibility, prm->phi_normal, prm->sigma_depth, power, dst, row0, row1, st);
             ctx->launches++;
-            if (i == prm->feedback_iteration && dst != p->prev_image)
-                HR_CUDA(ctx, cudaMemcpyAsync(p->prev_image, dst, px * sizeof(__half2), cudaMemcpyDeviceToDevice, st));
+            if (i == prm->feedback_iteration)
+            {
+                if (dst != hist_out) HR_CUDA(ctx, cudaMemcpyAsync(hist_out, dst, px * sizeof(__half2), cudaMemcpyDeviceToDevice, st));
+                fed_back = true;
+                // both history images of this frame (moments[pp] from the temporal stage, prev_image[pp]) are complete
+                rc = hr_peer_signal(p, epoch, st);
+                if (rc != HR_OK) return rc;
+                signalled = true;
+            }
             in     = dst;
             last   = dst;
             toggle = !toggle;
             static const char* names[8] = { "A-Trous 0", "A-Trous 1", "A-Trous 2", "A-Trous 3", "A-Trous 4", "A-Trous 5", "A-Trous 6", "A-Trous 7" };
             timer_mark(p, names[i], st);
         }
-        if (prm->feedback_iteration < 0 || prm->feedback_iteration >= prm->filter_iterations)
-        { /* no feedback: prev_image keeps its previous contents, like the reference */ }
+        if (!fed_back)
+        { // no feedback: the history image keeps its previous contents, like the reference's single prev_image
+            HR_CUDA(ctx, cudaMemcpyAsync(hist_out, p->prev_image[!pp], px * sizeof(__half2), cudaMemcpyDeviceToDevice, st));
+        }
         set_view(p, HR_SHADOWS_OUT_TEMPORAL_ACCUMULATION, p->temporal_out, p->W, p->H, HR_FMT_RG16F);
         set_view(p, HR_SHADOWS_OUT_ATROUS, last, p->W, p->H, HR_FMT_RG16F);
         set_view(p, HR_SHADOWS_OUT_MOMENTS, p->moments[pp], p->W, p->H, HR_FMT_RGBA16F);
-        set_view(p, HR_SHADOWS_OUT_PREV_IMAGE, p->prev_image, p->W, p->H, HR_FMT_RG16F);
+        set_view(p, HR_SHADOWS_OUT_PREV_IMAGE, hist_out, p->W, p->H, HR_FMT_RG16F);
         set_view(p, HR_SHADOWS_OUT_TILE_FLAGS, p->tile_flags, (p->W + 7) / 8, (p->H + 7) / 8, HR_FMT_R8_UINT);
         final_ptr = last; final_w = p->W; final_h = p->H; final_fmt = HR_FMT_RG16F;
         if (p->scale != HR_SCALE_FULL)
@@ -632,17 +664,20 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
             final_ptr = p->upsample_out; final_w = p->W0; final_h = p->H0; final_fmt = HR_FMT_R16F;
         }
     }
+    if (!signalled)
+    {
+        rc = hr_peer_signal(p, epoch, st);
+        if (rc != HR_OK) return rc;
+    }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
-    if (ctx->world > 1)
-    { // every rank ends up with the complete final output and the complete history (prev_image, moments) for the next frame
-        ExchangeItem it[4];
+    if (ctx->world > 1 && ctx->gather_final)
+    { // every rank ends up with the complete final output (the history stays distributed: peer history, shard.cu)
+        ExchangeItem it[2];
         int          n = 0;
         if (prm->denoise)
         {
-            it[n++] = { p->prev_image, (size_t)p->W * 4, p->H, 0, 1, p->H };
-            it[n++] = { p->moments[pp], (size_t)p->W * 8, p->H, 0, 1, p->H };
-            if (final_ptr != p->prev_image && final_fmt == HR_FMT_RG16F) it[n++] = { final_ptr, (size_t)p->W * 4, p->H, 0, 1, p->H };
+            if (final_fmt == HR_FMT_RG16F) it[n++] = { final_ptr, (size_t)p->W * 4, p->H, 0, 1, p->H };
             if (final_fmt == HR_FMT_R16F) it[n++] = { final_ptr, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
         else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
@@ -678,6 +713,8 @@ int hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
     A(pass_alloc(p, p->tile_flags, tw * th));
     if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
 #undef A
+    void* hist[4] = { p->ao_color[0], p->ao_color[1], p->ao_len[0], p->ao_len[1] };
+    hr_peer_register(p, hist, 4);
     return HR_OK;
 }
 
@@ -700,9 +737,16 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
     hr_extend(b0, b1, ctx->world > 1 ? 8 : 0, p->H, &v0, &v1);
     timer_begin(p, st);
-    if (!prm->denoise || p->first) hr_wait_exchange(p, st);
+    if (ctx->world > 1 && ctx->nccl_comm && !p->peers_linked)
+    {
+        rc = hr_peer_link_ipc(p, st);
+        if (rc != HR_OK) return rc;
+    }
+    const int  epoch      = ++p->epoch;
+    const bool no_history = p->first;
+    hr_wait_exchange(p, st);
     if (p->first)
-    { // clear_images, ray_traced_ao.cpp:829-860
+    { // clear_images, ray_traced_ao.cpp:829-860 (see hr_shadows_render for the first-frame / peer rules)
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_len[!pp], 0, px * sizeof(__half), st));
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
         p->first = false;
@@ -713,11 +757,22 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     set_view(p, HR_AO_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
     void* final_ptr = p->mask;
     int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
+    bool  signalled = false;
     if (prm->denoise)
     {
-        hr_wait_exchange(p, st);
-        launch_ao_temporal(cur, prev, p->mask, p->ao_color[!pp], p->ao_len[!pp], fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
+        // history = ao_color[!pp] / ao_len[!pp] of the rank that owns the reprojected row (peer history, shard.cu)
+        HistPeers hist;
+        hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
+        if (!no_history)
+        {
+            rc = hr_peer_wait(p, epoch - 1, st);
+            if (rc != HR_OK) return rc;
+        }
+        launch_ao_temporal(cur, prev, p->mask, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
+        rc = hr_peer_signal(p, epoch, st); // this frame's history (ao_color[pp], ao_len[pp]) is complete
+        if (rc != HR_OK) return rc;
+        signalled = true;
         timer_mark(p, "Temporal Accumulation", st);
         // bilateral_blur (:1032-1137): pass labelled "Vertical" uses direction (1,0), then (0,1)
         launch_ao_blur(cur, p->ao_color[pp], p->tile_flags, f->z_buffer_params, 1, 0, prm->blur_radius, p->ao_blur[0], row0, row1, st);
@@ -739,16 +794,19 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
             final_ptr = p->upsample_out; final_w = p->W0; final_h = p->H0; final_fmt = HR_FMT_R16F;
         }
     }
+    if (!signalled)
+    {
+        rc = hr_peer_signal(p, epoch, st);
+        if (rc != HR_OK) return rc;
+    }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
-    if (ctx->world > 1)
+    if (ctx->world > 1 && ctx->gather_final)
     {
         ExchangeItem it[4];
         int          n = 0;
         if (prm->denoise)
         {
-            it[n++] = { p->ao_color[pp], (size_t)p->W * 2, p->H, 0, 1, p->H };
-            it[n++] = { p->ao_len[pp], (size_t)p->W * 2, p->H, 0, 1, p->H };
             if (p->scale == HR_SCALE_FULL) it[n++] = { p->ao_blur[1], (size_t)p->W * 2, p->H, 0, 1, p->H };
             else it[n++] = { p->upsample_out, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
@@ -789,6 +847,21 @@ int hr_pass_download_async(hr_pass* p, int which, void* dst, size_t bytes, void*
     return HR_OK;
 }
 
+// Rows [row0,row1) of an image (a rank's own band of a distributed output), asynchronous like hr_pass_download_async.
+int hr_pass_download_rows_async(hr_pass* p, int which, int row0, int row1, void* dst, size_t bytes, void* stream)
+{
+    hr_image img;
+    int      rc = hr_pass_output(p, which, &img);
+    if (rc != HR_OK) return rc;
+    hr_ctx* ctx = p->ctx;
+    HR_REQUIRE(ctx, row0 >= 0 && row1 >= row0 && row1 <= img.height, HR_ERR_INVALID_ARG, "hr_pass_download_rows_async: bad row range");
+    const size_t row_bytes = (size_t)img.width * texel_size(img.format), need = row_bytes * (size_t)(row1 - row0);
+    HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download_rows_async: byte count mismatch");
+    hr_wait_exchange(p, (cudaStream_t)stream);
+    if (need) HR_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(img.data) + row_bytes * row0, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return HR_OK;
+}
+
 int hr_pass_download(hr_pass* p, int which, void* dst, size_t bytes, void* stream)
 {
     hr_image img;
@@ -826,6 +899,7 @@ int hr_pass_destroy(hr_pass* p)
     if (!p) return HR_ERR_INVALID_ARG;
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
+    hr_peer_unlink(p);
     for (void* a : p->allocs) cudaFree(a);
     for (void* a : p->ddgi_grid_allocs) cudaFree(a);
     if (p->ev_ready) cudaEventDestroy(p->ev_ready);

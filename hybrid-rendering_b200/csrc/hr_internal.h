@@ -51,6 +51,19 @@ struct FrameConsts {           // what kernels need from hr_frame (passed by val
 };
 
 // ---- objects ----------------------------------------------------------------------------------------
+#define HR_MAX_RANKS 8
+
+// Temporal history as the reprojection kernels see it (shard.cu, "peer history").  Row y of the previous frame's history
+// images lives on the rank that owns y (band_end[r] = first row NOT owned by ranks 0..r); img[r] / aux[r] are that rank's
+// full-size images — this GPU's own for r == self, NVLink peer mappings (CUDA IPC) otherwise.  Single GPU: world = 1.
+// no_history: first frame after creation / hr_pass_reset_history — every history texel reads as 0 (cleared images).
+struct HistPeers {
+    const void* img[HR_MAX_RANKS];
+    const void* aux[HR_MAX_RANKS];
+    int         band_end[HR_MAX_RANKS];
+    int         world, self, no_history;
+};
+
 struct GBufSlot {
     void*  gb1[HR_MAX_MIPS]   = {};
     void*  gb2[HR_MAX_MIPS]   = {};
@@ -83,6 +96,7 @@ struct hr_ctx {
     // sharding
     int          rank = 0, world = 1;
     void*        nccl_comm = nullptr; // ncclComm_t when hr_shard_init was called (NCCL is dlopen'ed lazily, see shard.cu)
+    bool         gather_final = true;   // all-gather every pass's final output after the render (hr_shard_set_gather)
     cudaStream_t comm_stream = nullptr; // band exchanges run here, overlapped with the next pass / next frame's ray trace
     // profiling
     bool         profiling = false;
@@ -148,7 +162,7 @@ struct hr_pass {
     uint32_t* mask = nullptr;
     __half2*  temporal_out = nullptr;
     uint2*    moments[2] = { nullptr, nullptr };
-    __half2*  prev_image = nullptr;
+    __half2*  prev_image[2] = { nullptr, nullptr }; // [ping_pong]: written by frame N's feedback iteration, read by frame N+1's temporal
     __half2*  atrous[2] = { nullptr, nullptr };
     uint8_t*  tile_flags = nullptr;
     __half*   upsample_out = nullptr;
@@ -181,6 +195,16 @@ struct hr_pass {
     // first makes its stream wait on ev_done (hr_wait_exchange).
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool        xchg_pending = false;
+    // peer history (shard.cu): the history images of every rank mapped into this process, and the frame ticks that order
+    // "rank q finished writing frame N's history" before "rank r's frame N+1 reprojection reads it"
+    bool        peers_linked = false, peers_ipc = false;
+    int         n_hist = 0;                          // history images registered (shadows: prev_image[2], moments[2]; AO: colour[2], length[2])
+    void*       hist_local[4] = {};
+    void*       hist_peer[HR_MAX_RANKS][4] = {};     // [rank][image]; own rank = hist_local
+    int*        sync_ticks = nullptr;                // [HR_MAX_RANKS] ticks written by the peers into THIS rank's memory
+    int*        peer_ticks[HR_MAX_RANKS] = {};       // the peers' tick arrays (we write slot [self])
+    int*        sync_error = nullptr;                // set by the wait kernel on time-out
+    int         epoch = 0;                           // renders of this pass so far
     StageTimer timer;
     std::vector<void*> allocs;
 };
@@ -208,6 +232,13 @@ void launch_upsample_vec4(const GBufLevelDev& g0, const GBufLevelDev& gm, const 
 // (hr_shard_rows); the image's own rows are band << shift (full-res upsample outputs) or band / div (ray masks),
 // clamped to `rows` (the image's real height).
 struct ExchangeItem { void* base; size_t row_bytes; int H; int shift; int div; int rows; };
+// peer history (shard.cu)
+void hr_peer_register(hr_pass* p, void* const* imgs, int n);
+int  hr_peer_link_ipc(hr_pass* p, cudaStream_t st);
+void hr_peer_unlink(hr_pass* p);
+void hr_peer_hist(const hr_pass* p, int img_k, int aux_k, int H, bool no_history, HistPeers* out);
+int  hr_peer_wait(hr_pass* p, int tick, cudaStream_t st);
+int  hr_peer_signal(hr_pass* p, int tick, cudaStream_t st);
 // Rows of an image of height H owned by this context's rank (all rows when world == 1).
 void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1);
 // [b0 - halo, b1 + halo) clamped to [0, H); halo must be a multiple of 8 so tile alignment is kept.
@@ -227,6 +258,7 @@ int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st
 int hr_bvh_build(hr_scene* sc, cudaStream_t st);
 BvhDev hr_bvh_view(const hr_scene* sc);
 
+
 void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                               uint32_t* mask, int row0, int row1, cudaStream_t st);
 void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
@@ -234,14 +266,14 @@ void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameCo
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st);
 void launch_trace_closest(const BvhDev& bvh, const float* rays, size_t n, float* out_t, uint32_t* out_prim, float* out_uv, cudaStream_t st);
 
-void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half2* prev_image, const uint2* prev_moments,
+void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const HistPeers& hist,
                              const FrameConsts& fc, float alpha, float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags,
                              int row0, int row1, cudaStream_t st);
 void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n,
                            float sigma_z, float power, __half2* out, int row0, int row1, cudaStream_t st);
 void launch_upsample_scalar(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, int in_channels, float sky_value, float power,
                             __half* out, int row0, int row1, cudaStream_t st);
-void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half* prev_ao, const __half* prev_len,
+void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const HistPeers& hist,
                         const FrameConsts& fc, float alpha, __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
 void launch_ao_blur(const GBufLevelDev& g, const __half* in, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, __half* out,
                     int row0, int row1, cudaStream_t st);

@@ -4,19 +4,26 @@
 // One process per GPU.  A pass image of height H is split into `world` contiguous bands of whole 8-row tiles
 // (hr_shard_rows).  Every rank keeps a full replica of the G-buffer, the BVH and the blue-noise tables, computes all
 // stages on its band plus a recompute halo (rays and stencils are pure functions of replicated inputs, so the halo is
-// exact), and after the last stage of a pass the ranks exchange their bands of
-//   * the pass's final output (the denoised frame every rank ends up with), and
-//   * the temporal history surfaces the next frame's reprojection gathers from (prev_image / moments, AO colour /
-//     history length), because reprojection may read any row under camera motion,
-// with one NCCL group of per-band broadcasts (an all-gather with unequal counts: 2160 rows = 270 tiles do not divide
-// evenly by 8).  After the exchange every rank holds exactly the images a single GPU would hold: the 1/2/4/8-GPU
-// results are bit-identical (tests/test_gpu_multi.py).
+// exact).  Two things cross GPUs:
+//   * PEER HISTORY (shadows / AO): next frame's reprojection may read ANY row of the history images under camera motion.
+//     Instead of all-gathering ~16 B/pixel of history every frame, each rank keeps only its band and maps every peer's
+//     history images into its address space (CUDA IPC over NVLink / NVSwitch); the temporal kernel fetches a history
+//     texel from the GPU that owns its row (HistPeers) — the exchange is fused into the kernel and moves exactly the
+//     texels the reprojection touches (a few boundary rows for a static camera).  Ordering is a per-pass frame tick:
+//     after its last history write of frame N a rank stores N into every peer's tick array (st.release.sys); before
+//     the reprojection of frame N+1 a one-warp kernel spins (ld.acquire.sys, 2 s time-out) until every peer's tick
+//     is >= N.  History images are double buffered by frame parity, so that wait also covers the write-after-read hazard.
+//   * the pass's FINAL OUTPUT (optional, hr_shard_set_gather; on by default): one NCCL group of per-band broadcasts (an
+//     all-gather with unequal counts: 2160 rows = 270 tiles do not divide evenly by 8) on a side stream, so every rank
+//     ends up with the complete denoised frame.  The reflections / DDGI passes still exchange their history this way.
+// The 1/2/4/8-GPU results are bit-identical to the single-GPU result (tests/test_gpu_multi.py).
 //
 // NCCL is dlopen'ed on first use so the single-GPU library has no NCCL dependency; inside a PyTorch process the
 // already-loaded torch-bundled libnccl.so.2 is picked up.
 #include "hr_internal.h"
 #include <dlfcn.h>
 #include <nccl.h>
+#include <vector>
 
 namespace {
 
@@ -28,6 +35,7 @@ struct NcclApi {
     ncclResult_t (*GroupStart)()                                                                               = nullptr;
     ncclResult_t (*GroupEnd)()                                                                                 = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)       = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)            = nullptr;
     const char* (*GetErrorString)(ncclResult_t)                                                                = nullptr;
     bool ok = false;
 };
@@ -50,9 +58,10 @@ NcclApi& nccl()
     LOAD(GroupStart, "ncclGroupStart");
     LOAD(GroupEnd, "ncclGroupEnd");
     LOAD(Broadcast, "ncclBroadcast");
+    LOAD(AllGather, "ncclAllGather");
     LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast && api.GetErrorString;
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast && api.AllGather && api.GetErrorString;
     return api;
 }
 
@@ -112,6 +121,173 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
     return HR_OK;
 }
 
+
+// ---- peer history -----------------------------------------------------------------------------------------------------
+namespace {
+
+struct TickPtrs { int* p[HR_MAX_RANKS]; };
+
+__global__ void k_peer_signal(TickPtrs peers, int world, int self, int tick)
+{
+    const int r = threadIdx.x;
+    if (r >= world || r == self || !peers.p[r]) return;
+    __threadfence_system(); // the history writes of the kernels before us in stream order become visible system-wide first
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.p[r] + self), "r"(tick) : "memory");
+}
+
+__global__ void k_peer_wait(const int* __restrict__ ticks, int world, int self, int tick, int* err)
+{
+    const int r = threadIdx.x;
+    if (r >= world || r == self) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;)
+    {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ticks + r) : "memory");
+        if (v >= tick) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) { *err = 1 + r; break; } // a peer died or the ranks render different frame counts: do not hang the GPU
+        __nanosleep(200);
+    }
+}
+
+int peer_alloc_ticks(hr_pass* p)
+{
+    hr_ctx* ctx = p->ctx;
+    if (p->sync_ticks) return HR_OK;
+    HR_CUDA(ctx, cudaMalloc((void**)&p->sync_ticks, sizeof(int) * HR_MAX_RANKS));
+    HR_CUDA(ctx, cudaMemset(p->sync_ticks, 0, sizeof(int) * HR_MAX_RANKS));
+    HR_CUDA(ctx, cudaHostAlloc((void**)&p->sync_error, sizeof(int), cudaHostAllocMapped));
+    *p->sync_error = 0;
+    return HR_OK;
+}
+
+} // namespace
+
+void hr_peer_register(hr_pass* p, void* const* imgs, int n)
+{
+    p->n_hist = n;
+    for (int k = 0; k < n; k++) p->hist_local[k] = imgs[k];
+}
+
+// Collective over the NCCL communicator: all-gather the CUDA IPC handles of this pass's history images and tick array,
+// map every peer's.  Called from the first sharded render of the pass (all ranks render their passes in the same order).
+int hr_peer_link_ipc(hr_pass* p, cudaStream_t st)
+{
+    hr_ctx* ctx = p->ctx;
+    if (p->peers_linked || ctx->world <= 1 || !ctx->nccl_comm || p->n_hist == 0) return HR_OK;
+    NcclApi& N = nccl();
+    int      rc = peer_alloc_ticks(p);
+    if (rc != HR_OK) return rc;
+    const int    nh = p->n_hist + 1, world = ctx->world;
+    const size_t hb = sizeof(cudaIpcMemHandle_t), mine = hb * nh;
+    std::vector<cudaIpcMemHandle_t> h(nh), all((size_t)nh * world);
+    for (int k = 0; k < p->n_hist; k++) HR_CUDA(ctx, cudaIpcGetMemHandle(&h[k], p->hist_local[k]));
+    HR_CUDA(ctx, cudaIpcGetMemHandle(&h[p->n_hist], p->sync_ticks));
+    char *d_send = nullptr, *d_recv = nullptr;
+    HR_CUDA(ctx, cudaMalloc((void**)&d_send, mine));
+    HR_CUDA(ctx, cudaMalloc((void**)&d_recv, mine * world));
+    HR_CUDA(ctx, cudaMemcpyAsync(d_send, h.data(), mine, cudaMemcpyHostToDevice, st));
+    HR_NCCL(ctx, N.AllGather(d_send, d_recv, mine, ncclUint8, (ncclComm_t)ctx->nccl_comm, st));
+    HR_CUDA(ctx, cudaMemcpyAsync(all.data(), d_recv, mine * world, cudaMemcpyDeviceToHost, st));
+    HR_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(d_send);
+    cudaFree(d_recv);
+    for (int r = 0; r < world; r++)
+    {
+        if (r == ctx->rank)
+        {
+            for (int k = 0; k < p->n_hist; k++) p->hist_peer[r][k] = p->hist_local[k];
+            p->peer_ticks[r] = p->sync_ticks;
+            continue;
+        }
+        for (int k = 0; k < nh; k++)
+        {
+            void* m = nullptr;
+            HR_CUDA(ctx, cudaIpcOpenMemHandle(&m, all[(size_t)r * nh + k], cudaIpcMemLazyEnablePeerAccess));
+            if (k < p->n_hist) p->hist_peer[r][k] = m;
+            else p->peer_ticks[r] = (int*)m;
+        }
+    }
+    p->peers_linked = true;
+    p->peers_ipc    = true;
+    return HR_OK;
+}
+
+void hr_peer_unlink(hr_pass* p)
+{
+    if (p->peers_ipc)
+        for (int r = 0; r < HR_MAX_RANKS; r++)
+        {
+            if (r == p->ctx->rank) continue;
+            for (int k = 0; k < p->n_hist; k++)
+                if (p->hist_peer[r][k]) cudaIpcCloseMemHandle(p->hist_peer[r][k]);
+            if (p->peer_ticks[r]) cudaIpcCloseMemHandle(p->peer_ticks[r]);
+        }
+    p->peers_linked = p->peers_ipc = false;
+    if (p->sync_ticks) cudaFree(p->sync_ticks);
+    if (p->sync_error) cudaFreeHost(p->sync_error);
+    p->sync_ticks = nullptr;
+    p->sync_error = nullptr;
+}
+
+// History table for the reprojection kernel: images `img_k` / `aux_k` of every rank, rows split like hr_shard_rows(H).
+void hr_peer_hist(const hr_pass* p, int img_k, int aux_k, int H, bool no_history, HistPeers* out)
+{
+    const hr_ctx* ctx = p->ctx;
+    HistPeers     hp {};
+    hp.no_history = no_history ? 1 : 0;
+    if (p->peers_linked && ctx->world > 1)
+    {
+        hp.world = ctx->world;
+        hp.self  = ctx->rank;
+        for (int r = 0; r < ctx->world; r++)
+        {
+            int b, e;
+            hr_shard_rows(H, r, ctx->world, &b, &e);
+            hp.img[r]      = p->hist_peer[r][img_k];
+            hp.aux[r]      = p->hist_peer[r][aux_k];
+            hp.band_end[r] = e;
+        }
+    }
+    else
+    { // single GPU, or band emulation where the caller moves the bands itself (hr_shard_config + hr_pass_upload)
+        hp.world       = 1;
+        hp.self        = 0;
+        hp.img[0]      = p->hist_local[img_k];
+        hp.aux[0]      = p->hist_local[aux_k];
+        hp.band_end[0] = H;
+    }
+    *out = hp;
+}
+
+int hr_peer_wait(hr_pass* p, int tick, cudaStream_t st)
+{
+    if (!p->peers_linked || p->ctx->world <= 1 || tick <= 0) return HR_OK;
+    hr_ctx* ctx = p->ctx;
+    if (p->sync_error && *p->sync_error)
+    {
+        hr_set_error(ctx, "peer history: timed out waiting for rank %d's frame tick (peer stopped, or ranks rendered different frame counts)", *p->sync_error - 1);
+        return HR_ERR_NCCL;
+    }
+    int* d_err = nullptr;
+    HR_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_err, p->sync_error, 0));
+    k_peer_wait<<<1, 32, 0, st>>>(p->sync_ticks, ctx->world, ctx->rank, tick, d_err);
+    ctx->launches++;
+    return HR_OK;
+}
+
+int hr_peer_signal(hr_pass* p, int tick, cudaStream_t st)
+{
+    if (!p->peers_linked || p->ctx->world <= 1) return HR_OK;
+    TickPtrs t {};
+    for (int r = 0; r < p->ctx->world; r++) t.p[r] = p->peer_ticks[r];
+    k_peer_signal<<<1, 32, 0, st>>>(t, p->ctx->world, p->ctx->rank, tick);
+    p->ctx->launches++;
+    return HR_OK;
+}
+
 extern "C" {
 
 int hr_shard_unique_id(void* out_128_bytes)
@@ -140,6 +316,36 @@ int hr_shard_init(hr_ctx* ctx, int rank, int world, const void* unique_id_128_by
     ncclComm_t comm;
     HR_NCCL(ctx, N.CommInitRank(&comm, world, id, rank));
     ctx->nccl_comm = comm;
+    return HR_OK;
+}
+
+// Same-process peers (N ranks emulated on one GPU, or a multi-GPU single-process host): rank `rank`'s history lives in
+// `peer`'s images.  Every pass of the group must be linked with every other before the first sharded render.
+int hr_shard_link_local(hr_pass* pass, int rank, hr_pass* peer)
+{
+    if (!pass || !peer) return HR_ERR_INVALID_ARG;
+    hr_ctx* ctx = pass->ctx;
+    HR_REQUIRE(ctx, rank >= 0 && rank < ctx->world && rank < HR_MAX_RANKS && pass->kind == peer->kind && pass->n_hist == peer->n_hist && pass->n_hist > 0 &&
+                        pass->W == peer->W && pass->H == peer->H && !pass->peers_ipc,
+               HR_ERR_INVALID_ARG, "hr_shard_link_local: passes do not match (kind / size / rank) or the pass has no peer history");
+    int rc = peer_alloc_ticks(pass);
+    if (rc != HR_OK) return rc;
+    rc = peer_alloc_ticks(peer);
+    if (rc != HR_OK) return rc;
+    for (int k = 0; k < pass->n_hist; k++) pass->hist_peer[rank][k] = peer->hist_local[k];
+    pass->peer_ticks[rank] = peer->sync_ticks;
+    for (int k = 0; k < pass->n_hist; k++) pass->hist_peer[ctx->rank][k] = pass->hist_local[k];
+    pass->peer_ticks[ctx->rank] = pass->sync_ticks;
+    bool all = true;
+    for (int r = 0; r < ctx->world; r++) all = all && pass->peer_ticks[r] != nullptr;
+    pass->peers_linked = all;
+    return HR_OK;
+}
+
+int hr_shard_set_gather(hr_ctx* ctx, int gather_final_output)
+{
+    if (!ctx) return HR_ERR_INVALID_ARG;
+    ctx->gather_final = gather_final_output != 0;
     return HR_OK;
 }
 

@@ -84,10 +84,35 @@ __device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 c
     return true;
 }
 
+// ---- history fetches through the owner table (HistPeers, hr_internal.h) ----
+// Rows owned by this GPU use the read-only path; rows owned by a peer are read over NVLink with L1 bypassed (the mapping
+// is rewritten by the peer every frame).  A warp's 32 pixels share their row in the static case, so the branch is uniform.
+__device__ __forceinline__ int owner_of(const HistPeers& hp, int row)
+{
+    int o = 0;
+#pragma unroll
+    for (int r = 0; r < HR_MAX_RANKS - 1; r++) o += (r < hp.world - 1 && row >= hp.band_end[r]) ? 1 : 0;
+    return o;
+}
+__device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const HistPeers& hp, int row, size_t word_index)
+{
+    if (hp.no_history) return 0u;
+    const int       o = hp.world > 1 ? owner_of(hp, row) : 0;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tab[o]) + word_index;
+    return o == hp.self ? __ldg(p) : __ldcg(p);
+}
+__device__ __forceinline__ uint32_t hist_ld16(const void* const* tab, const HistPeers& hp, int row, size_t half_index)
+{
+    if (hp.no_history) return 0u;
+    const int             o = hp.world > 1 ? owner_of(hp, row) : 0;
+    const unsigned short* p = reinterpret_cast<const unsigned short*>(tab[o]) + half_index;
+    return o == hp.self ? __ldg(p) : __ldcg(p);
+}
+
 // MODE 0: shadows (history RG16F .r, moments RGBA16F (m1,m2,N,0)); MODE 1: AO (history R16F, length R16F)
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const void* __restrict__ hist_img,
-                                                   const void* __restrict__ hist_aux, FrameConsts fc, float alpha_p, float moments_alpha_p,
+__global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const HistPeers hp,
+                                                   FrameConsts fc, float alpha_p, float moments_alpha_p,
                                                    void* __restrict__ out_img, void* __restrict__ out_aux, uint8_t* __restrict__ tile_flags, int row0, int row1)
 {
     __shared__ unsigned long long s_rows[24];
@@ -163,8 +188,8 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                 const float w4[4] = { (1 - fx) * (1 - fy), fx * (1 - fy), (1 - fx) * fy, fx * fy };
                 {
                     const size_t hi = (size_t)hcy * W + hcx;
-                    if (MODE == 0) hist_len = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + hi) + 1)).x;
-                    else hist_len = __half2float(__ldg(reinterpret_cast<const __half*>(hist_aux) + hi));
+                    if (MODE == 0) hist_len = h2_to_f2(hist_ld32(hp.aux, hp, hcy, 2 * hi + 1)).x;
+                    else hist_len = __half2float(__ushort_as_half((unsigned short)hist_ld16(hp.aux, hp, hcy, hi)));
                 }
                 TapRaw   tr[4];
                 uint32_t hraw[4], mraw[4];
@@ -184,10 +209,10 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                         tr[s] = fetch_prev_raw(prev, pi);
                         if (MODE == 0)
                         {
-                            hraw[s] = __ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi);
-                            mraw[s] = __ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi));
+                            hraw[s] = hist_ld32(hp.img, hp, py, pi);
+                            mraw[s] = hist_ld32(hp.aux, hp, py, 2 * pi);
                         }
-                        else hraw[s] = __half_as_ushort(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
+                        else hraw[s] = hist_ld16(hp.img, hp, py, pi);
                     }
                 }
                 const float3 cn   = octohedral_to_direction(g2.x, g2.y);
@@ -229,12 +254,12 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                                     const size_t pi = (size_t)py * W + px;
                                     if (MODE == 0)
                                     {
-                                        hcol += h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_img) + pi)).x;
-                                        const float2 mm = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint2*>(hist_aux) + pi)));
+                                        hcol += h2_to_f2(hist_ld32(hp.img, hp, py, pi)).x;
+                                        const float2 mm = h2_to_f2(hist_ld32(hp.aux, hp, py, 2 * pi));
                                         hm0 += mm.x;
                                         hm1 += mm.y;
                                     }
-                                    else hcol += __half2float(__ldg(reinterpret_cast<const __half*>(hist_img) + pi));
+                                    else hcol += __half2float(__ushort_as_half((unsigned short)hist_ld16(hp.img, hp, py, pi)));
                                 }
                                 cntv += 1.0f;
                             }
@@ -296,19 +321,18 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
 
 } // namespace
 
-void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half2* prev_image, const uint2* prev_moments,
-                             const FrameConsts& fc, float alpha, float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags,
-                             int row0, int row1, cudaStream_t st)
+void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const HistPeers& hist, const FrameConsts& fc, float alpha,
+                             float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
     dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_temporal<0><<<grid, 256, 0, st>>>(cur, prev, mask, prev_image, prev_moments, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
+    k_temporal<0><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
 }
 
-void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const __half* prev_ao, const __half* prev_len,
-                        const FrameConsts& fc, float alpha, __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
+void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const HistPeers& hist, const FrameConsts& fc, float alpha,
+                        __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
     dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_temporal<1><<<grid, 256, 0, st>>>(cur, prev, mask, prev_ao, prev_len, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
+    k_temporal<1><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
 }

@@ -85,10 +85,10 @@ HR_FMT = {1: ("<u4", 1), 2: ("<f2", 1), 3: ("<f2", 2), 4: ("<f2", 4), 5: ("u1", 
 ABI_SYMBOLS = [
     "hr_init", "hr_shutdown", "hr_last_error", "hr_version", "hr_bluenoise_set", "hr_scene_build", "hr_scene_destroy", "hr_scene_set_current",
     "hr_scene_get_info", "hr_scene_rebuild", "hr_trace_any", "hr_trace_closest", "hr_gbuffer_create", "hr_gbuffer_upload",
-    "hr_gbuffer_stage_upload", "hr_gbuffer_commit_staged", "hr_pass_download_async",
+    "hr_gbuffer_stage_upload", "hr_gbuffer_commit_staged", "hr_pass_download_async", "hr_pass_download_rows_async",
     "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
-    "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown",
+    "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
     "hr_reflections_render",
 ]
@@ -340,6 +340,9 @@ class Context:
         self.check(self.lib.hr_gbuffer_download(self.h, slot, mip, which, _ptr(a), C.c_size_t(a.nbytes)), "hr_gbuffer_download")
         return a
 
+    def shard_set_gather(self, on):
+        self.check(self.lib.hr_shard_set_gather(self.h, int(on)), "hr_shard_set_gather")
+
     def shard_config(self, rank, world):
         self.check(self.lib.hr_shard_config(self.h, rank, world), "hr_shard_config")
 
@@ -387,6 +390,16 @@ class Pass:
         a = out if out is not None else np.empty(shape, np.dtype(dt))
         self.ctx.check(self.lib.hr_pass_download(self.h, which, _ptr(a), C.c_size_t(a.nbytes), C.c_void_p(stream)), "hr_pass_download")
         return a
+
+    def download_rows_async(self, which, row0, row1, out, stream=0):
+        """rows [row0,row1) of the image into `out` (pinned, exactly that many rows), no synchronisation"""
+        self.ctx.check(self.lib.hr_pass_download_rows_async(self.h, which, row0, row1, _ptr(out), C.c_size_t(out.nbytes), C.c_void_p(stream)),
+                       "hr_pass_download_rows_async")
+        return out
+
+    def link_local(self, rank, peer):
+        """same-process peer history: rank `rank`'s band of this pass's history lives in `peer` (hr_shard_link_local)"""
+        self.ctx.check(self.lib.hr_shard_link_local(self.h, rank, peer.h), "hr_shard_link_local")
 
     def download_async(self, which, out, stream=0):
         """Enqueue the device -> host copy on `stream` without synchronising (out: pinned array of the image's size)."""

@@ -366,6 +366,8 @@ HR_API int hr_pass_output(hr_pass* pass, int which, hr_image* out);
 HR_API int hr_pass_download(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
 /* Same copy enqueued on `stream` without the host synchronisation (pinned host_dst; the caller synchronises). */
 HR_API int hr_pass_download_async(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
+/* Rows [row0,row1) only — e.g. a rank's own band (hr_shard_rows, scaled to the image) of an output left distributed. */
+HR_API int hr_pass_download_rows_async(hr_pass* pass, int which, int row0, int row1, void* host_dst, size_t bytes, void* stream);
 /* Checkpoint / resume of temporal history: hr_pass_download saves an image, hr_pass_upload restores it (synchronous). */
 HR_API int hr_pass_upload(hr_pass* pass, int which, const void* host_src, size_t bytes, void* stream);
 /* restart_accumulation() / clear_images() equivalent: next render behaves like first_frame for this pass's history. */
@@ -394,6 +396,17 @@ HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world); /* band assignment
 HR_API int hr_shard_unique_id(void* out_128_bytes);
 HR_API int hr_shard_init(hr_ctx* ctx, int rank, int world, const void* unique_id_128_bytes);
 HR_API int hr_shard_shutdown(hr_ctx* ctx);
+/* After hr_shard_init the shadows / AO temporal history stays distributed: every rank keeps the rows of its band and the
+ * reprojection kernel reads a history texel from the GPU that owns its row (peer mappings over NVLink, set up on the
+ * first render of each pass — all ranks must create and render their passes in the same order, and call
+ * hr_pass_reset_history together).  hr_pass_output / hr_pass_download of history and intermediate images are therefore
+ * valid on the rank's own band only.  The FINAL output (which = 100) of every pass is all-gathered after each render
+ * unless this is switched off (gather_final_output = 0: every rank keeps just its band of the frame). */
+HR_API int hr_shard_set_gather(hr_ctx* ctx, int gather_final_output);
+/* Same-process peers (N ranks emulated on one GPU with hr_shard_config, or several GPUs driven by one process): declare
+ * that rank `rank`'s band of this pass's history lives in `peer`.  Link every pass with every other rank's pass before
+ * the first render; the ranks' renders of a frame may then run in any order / on any streams. */
+HR_API int hr_shard_link_local(hr_pass* pass, int rank, hr_pass* peer);
 /* Row range (at pass resolution, height H) owned by rank. */
 HR_API int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end);
 

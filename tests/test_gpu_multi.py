@@ -2,8 +2,11 @@
 
 * test_sharded_emulation_*: N ranks emulated on one GPU (one hr_ctx per rank, hr_shard_config), the band exchange done by
   the test through hr_pass_download / hr_pass_upload.  Runs on the single-GPU box.
-* test_nccl_*: real one-process-per-GPU run with the library's NCCL exchange (hr_shard_init); needs >= 2 GPUs
-  (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+* test_peer_history_emulation_*: the same N emulated ranks, but linked with hr_shard_link_local: nothing is moved by the
+  test — every rank's reprojection kernel pulls history texels from the rank that owns their row (the production
+  multi-GPU data path, minus CUDA IPC).  Runs on the single-GPU box.
+* test_nccl_*: real one-process-per-GPU run (hr_shard_init): peer history over CUDA IPC / NVLink + the NCCL gather of the
+  final output; needs >= 2 GPUs (`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
 """
 import os
 import sys
@@ -21,11 +24,12 @@ SH = dict(temporal=1, atrous=2, moments=4, prev=5, final=100)
 AO = dict(temporal=1, blur=2, length=4, final=100)
 
 
-def frames(n, pan_from=3):
+def frames(n, pan_from=3, vertical=0.0):
     f = None
     for i in range(n):
         dx = 0.0 if i < pan_from else 0.05 * (i - pan_from + 1)
-        f = pyhr.make_frame((dx, 14.0, 34.0), (dx, 3.0, 0.0), W, H, prev=f, num_frames=i)
+        dy = 0.0 if i < pan_from else vertical * (i - pan_from + 1)  # vertical motion: reprojection taps cross band borders
+        f = pyhr.make_frame((dx, 14.0 + dy, 34.0), (dx, 3.0 - dy, 0.0), W, H, prev=f, num_frames=i)
         yield f
 
 
@@ -78,6 +82,36 @@ def test_sharded_emulation_bit_identical(world, sh_scale, ao_scale):
         c.close()
 
 
+@pytest.mark.parametrize("world,sh_scale,ao_scale", [(2, 0, 1), (5, 0, 0), (8, 1, 1)])
+def test_peer_history_emulation_bit_identical(world, sh_scale, ao_scale):
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ref = make_rank(0, sc, sh_scale, ao_scale)
+    ranks = [make_rank(0, sc, sh_scale, ao_scale, r, world) for r in range(world)]
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                ranks[r][1].link_local(q, ranks[q][1])
+                ranks[r][2].link_local(q, ranks[q][2])
+    sh_h, ao_h = H >> sh_scale, H >> ao_scale
+    for f in frames(8, pan_from=2, vertical=0.35):
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        for c, sh, ao in [ref] + ranks:
+            c.gbuffer_upload(f.ping_pong, g)
+            sh.render(f)
+            ao.render(f)
+        for name, which, shift in (("prev", SH["prev"], 0), ("moments", SH["moments"], 0), ("final", SH["final"], sh_scale)):
+            merged = merge_bands([r[1].download(which) for r in ranks], sh_h, world, shift if name == "final" else 0)
+            assert np.array_equal(merged, ref[1].download(which)), f"shadows {name} differs (world={world}, frame {f.num_frames})"
+        for name, which, shift in (("temporal", AO["temporal"], 0), ("length", AO["length"], 0), ("final", AO["final"], ao_scale)):
+            merged = merge_bands([r[2].download(which) for r in ranks], ao_h, world, shift if name == "final" else 0)
+            assert np.array_equal(merged, ref[2].download(which)), f"ao {name} differs (world={world}, frame {f.num_frames})"
+    for c, sh, ao in [ref] + ranks:
+        sh.destroy()
+        ao.destroy()
+    for c, sh, ao in [ref] + ranks:
+        c.close()
+
+
 def _nccl_worker(rank, world, uid, result_dir):
     import torch
     torch.cuda.set_device(rank)
@@ -89,7 +123,7 @@ def _nccl_worker(rank, world, uid, result_dir):
     c.shard_init(rank, world, uid)
     sh, ao = pyhr.Pass(c, "shadows", W, H, 0), pyhr.Pass(c, "ao", W, H, 1)
     outs = []
-    for f in frames(6):
+    for f in frames(6, vertical=0.35):
         g = pyhr.write_gbuffer(sc, f, W, H)
         c.gbuffer_upload(f.ping_pong, g)
         sh.render(f)
@@ -114,17 +148,25 @@ def test_nccl_sharded_matches_single(tmp_path):
     sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
     c, sh, ao = make_rank(0, sc, 0, 1)
     ref = []
-    for f in frames(6):
+    for f in frames(6, vertical=0.35):
         g = pyhr.write_gbuffer(sc, f, W, H)
         c.gbuffer_upload(f.ping_pong, g)
         sh.render(f)
         ao.render(f)
         ref.append((sh.download(100), sh.download(SH["prev"]), sh.download(SH["moments"]), ao.download(100), ao.download(AO["temporal"])))
+    # image j: 0 shadows final (gathered: complete on every rank), 1 prev_image, 2 moments, 3 AO final (gathered, full-res),
+    # 4 AO temporal — the history images stay distributed (peer history): each rank holds its own band
+    band_h = {1: H, 2: H, 4: H >> 1}
     for r in range(world):
         d = np.load(os.path.join(str(tmp_path), f"rank{r}.npz"))
         for i, o in enumerate(ref):
             for j, a in enumerate(o):
-                assert np.array_equal(d[f"f{i}_{j}"], a), f"rank {r} frame {i} image {j} differs from the single-GPU result"
+                got = d[f"f{i}_{j}"]
+                if j in band_h:
+                    b, e = pyhr.shard_rows(band_h[j], r, world)
+                    assert np.array_equal(got[b:e], a[b:e]), f"rank {r} frame {i} image {j}: own band differs from the single-GPU result"
+                else:
+                    assert np.array_equal(got, a), f"rank {r} frame {i} image {j} differs from the single-GPU result"
     sh.destroy()
     ao.destroy()
     c.close()
