@@ -94,23 +94,27 @@ __device__ __forceinline__ int owner_of(const HistPeers& hp, int row)
     for (int r = 0; r < HR_MAX_RANKS - 1; r++) o += (r < hp.world - 1 && row >= hp.band_end[r]) ? 1 : 0;
     return o;
 }
+template <bool PEER>
 __device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const HistPeers& hp, int row, size_t word_index)
 {
     if (hp.no_history) return 0u;
-    const int       o = hp.world > 1 ? owner_of(hp, row) : 0;
+    if (!PEER) return __ldg(reinterpret_cast<const uint32_t*>(tab[0]) + word_index);
+    const int       o = owner_of(hp, row);
     const uint32_t* p = reinterpret_cast<const uint32_t*>(tab[o]) + word_index;
     return o == hp.self ? __ldg(p) : __ldcg(p);
 }
+template <bool PEER>
 __device__ __forceinline__ uint32_t hist_ld16(const void* const* tab, const HistPeers& hp, int row, size_t half_index)
 {
     if (hp.no_history) return 0u;
-    const int             o = hp.world > 1 ? owner_of(hp, row) : 0;
+    if (!PEER) return __ldg(reinterpret_cast<const unsigned short*>(tab[0]) + half_index);
+    const int             o = owner_of(hp, row);
     const unsigned short* p = reinterpret_cast<const unsigned short*>(tab[o]) + half_index;
     return o == hp.self ? __ldg(p) : __ldcg(p);
 }
 
 // MODE 0: shadows (history RG16F .r, moments RGBA16F (m1,m2,N,0)); MODE 1: AO (history R16F, length R16F)
-template <int MODE>
+template <int MODE, bool PEER>
 __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint32_t* __restrict__ mask, const HistPeers hp,
                                                    FrameConsts fc, float alpha_p, float moments_alpha_p,
                                                    void* __restrict__ out_img, void* __restrict__ out_aux, uint8_t* __restrict__ tile_flags, int row0, int row1)
@@ -188,8 +192,8 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                 const float w4[4] = { (1 - fx) * (1 - fy), fx * (1 - fy), (1 - fx) * fy, fx * fy };
                 {
                     const size_t hi = (size_t)hcy * W + hcx;
-                    if (MODE == 0) hist_len = h2_to_f2(hist_ld32(hp.aux, hp, hcy, 2 * hi + 1)).x;
-                    else hist_len = __half2float(__ushort_as_half((unsigned short)hist_ld16(hp.aux, hp, hcy, hi)));
+                    if (MODE == 0) hist_len = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, hcy, 2 * hi + 1)).x;
+                    else hist_len = __half2float(__ushort_as_half((unsigned short)hist_ld16<PEER>(hp.aux, hp, hcy, hi)));
                 }
                 TapRaw   tr[4];
                 uint32_t hraw[4], mraw[4];
@@ -209,10 +213,10 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                         tr[s] = fetch_prev_raw(prev, pi);
                         if (MODE == 0)
                         {
-                            hraw[s] = hist_ld32(hp.img, hp, py, pi);
-                            mraw[s] = hist_ld32(hp.aux, hp, py, 2 * pi);
+                            hraw[s] = hist_ld32<PEER>(hp.img, hp, py, pi);
+                            mraw[s] = hist_ld32<PEER>(hp.aux, hp, py, 2 * pi);
                         }
-                        else hraw[s] = hist_ld16(hp.img, hp, py, pi);
+                        else hraw[s] = hist_ld16<PEER>(hp.img, hp, py, pi);
                     }
                 }
                 const float3 cn   = octohedral_to_direction(g2.x, g2.y);
@@ -254,12 +258,12 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                                     const size_t pi = (size_t)py * W + px;
                                     if (MODE == 0)
                                     {
-                                        hcol += h2_to_f2(hist_ld32(hp.img, hp, py, pi)).x;
-                                        const float2 mm = h2_to_f2(hist_ld32(hp.aux, hp, py, 2 * pi));
+                                        hcol += h2_to_f2(hist_ld32<PEER>(hp.img, hp, py, pi)).x;
+                                        const float2 mm = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, py, 2 * pi));
                                         hm0 += mm.x;
                                         hm1 += mm.y;
                                     }
-                                    else hcol += __half2float(__ushort_as_half((unsigned short)hist_ld16(hp.img, hp, py, pi)));
+                                    else hcol += __half2float(__ushort_as_half((unsigned short)hist_ld16<PEER>(hp.img, hp, py, pi)));
                                 }
                                 cntv += 1.0f;
                             }
@@ -326,7 +330,8 @@ void launch_shadows_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, 
 {
     if (row1 <= row0) return;
     dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_temporal<0><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
+    if (hist.world > 1) k_temporal<0, true><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
+    else k_temporal<0, false><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, moments_alpha, out, moments_out, tile_flags, row0, row1);
 }
 
 void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint32_t* mask, const HistPeers& hist, const FrameConsts& fc, float alpha,
@@ -334,5 +339,6 @@ void launch_ao_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const
 {
     if (row1 <= row0) return;
     dim3 grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_temporal<1><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
+    if (hist.world > 1) k_temporal<1, true><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
+    else k_temporal<1, false><<<grid, 256, 0, st>>>(cur, prev, mask, hist, fc, alpha, 0.0f, out, len_out, tile_flags, row0, row1);
 }
