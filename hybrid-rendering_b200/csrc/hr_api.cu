@@ -479,6 +479,19 @@ static int pass_alloc(hr_pass* p, T*& ptr, size_t count, int fill_byte = 0)
     return HR_OK;
 }
 
+// multi-GPU ray-trace sharing (shard.cu): second ray-mask image (frame parity), cost tables, device-side row partition
+static int pass_alloc_rt_share(hr_pass* p)
+{
+    const size_t mw = (p->W + 7) / 8, mh = (p->H + 3) / 4;
+    int          rc;
+    p->mask_pp[0] = p->mask;
+    if ((rc = pass_alloc(p, p->mask_pp[1], mw * mh)) != HR_OK) return rc;
+    if ((rc = pass_alloc(p, p->rt_cost_all, 2 * mh)) != HR_OK) return rc;
+    if ((rc = pass_alloc(p, p->rt_cost_acc, mh)) != HR_OK) return rc;
+    if ((rc = pass_alloc(p, p->rt_bounds, (size_t)HR_MAX_RANKS + 1)) != HR_OK) return rc;
+    return HR_OK;
+}
+
 static void set_view(hr_pass* p, int which, void* ptr, int w, int h, int fmt)
 {
     p->out_view[which].p   = ptr;
@@ -545,8 +558,10 @@ int hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** o
     A(pass_alloc(p, p->tile_flags, tw * th));
     if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
 #undef A
-    void* hist[4] = { p->prev_image[0], p->prev_image[1], p->moments[0], p->moments[1] };
-    hr_peer_register(p, hist, 4);
+    rc = pass_alloc_rt_share(p);
+    if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; }
+    void* hist[7] = { p->prev_image[0], p->prev_image[1], p->moments[0], p->moments[1], p->mask_pp[0], p->mask_pp[1], p->rt_cost_all };
+    hr_peer_register(p, hist, 7);
     return HR_OK;
 }
 
@@ -589,12 +604,32 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         HR_CUDA(ctx, cudaMemsetAsync(p->moments[!pp], 0, px * sizeof(uint2), st));
         p->first = false;
     }
-    // ray_trace (:972-1011)
-    launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, rt0, rt1, st);
-    ctx->launches++;
-    timer_mark(p, "Ray Trace", st);
-    set_view(p, HR_SHADOWS_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
-    void* final_ptr = p->mask;
+    // ray_trace (:972-1011).  Linked to peers: this rank traces its cost-balanced share of the WHOLE image and stores the
+    // mask words into every rank's mask image (no halo re-trace); otherwise its band +- 32 rows into its own image.
+    RtShare    rts;
+    const bool shared_rt = hr_rt_share(p, epoch & 1, &rts);
+    uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
+    if (shared_rt)
+    {
+        launch_shadows_ray_trace_shared(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, rts, st);
+        ctx->launches++;
+        rc = hr_rt_share_finish(p, epoch & 1, epoch, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Ray Trace", st);
+        rc = hr_peer_wait(p, 1, epoch, st); // every rank's share of this frame's mask (and cost table) has arrived
+        if (rc != HR_OK) return rc;
+        rc = hr_rt_partition(p, epoch & 1, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Mask Exchange Wait", st);
+    }
+    else
+    {
+        launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, mask, rt0, rt1, st);
+        ctx->launches++;
+        timer_mark(p, "Ray Trace", st);
+    }
+    set_view(p, HR_SHADOWS_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = mask;
     int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
     if (prm->denoise)
     {
@@ -605,10 +640,10 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
         if (!no_history)
         {
-            rc = hr_peer_wait(p, epoch - 1, st);
+            rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;
         }
-        launch_shadows_temporal(cur, prev, p->mask, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
+        launch_shadows_temporal(cur, prev, mask, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
         timer_mark(p, "Temporal Accumulation", st);
         // a_trous_filter (:1094-1215).  The reference ping-pongs image[0]/image[1] and copies the output of
@@ -634,7 +669,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
                 if (dst != hist_out) HR_CUDA(ctx, cudaMemcpyAsync(hist_out, dst, px * sizeof(__half2), cudaMemcpyDeviceToDevice, st));
                 fed_back = true;
                 // both history images of this frame (moments[pp] from the temporal stage, prev_image[pp]) are complete
-                rc = hr_peer_signal(p, epoch, st);
+                rc = hr_peer_signal(p, 0, epoch, st);
                 if (rc != HR_OK) return rc;
                 signalled = true;
             }
@@ -666,12 +701,12 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     }
     if (!signalled)
     {
-        rc = hr_peer_signal(p, epoch, st);
+        rc = hr_peer_signal(p, 0, epoch, st);
         if (rc != HR_OK) return rc;
     }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
-    if (ctx->world > 1 && ctx->gather_final)
+    if (ctx->world > 1 && ctx->gather_final && !(shared_rt && !prm->denoise))
     { // every rank ends up with the complete final output (the history stays distributed: peer history, shard.cu)
         ExchangeItem it[2];
         int          n = 0;
@@ -680,7 +715,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
             if (final_fmt == HR_FMT_RG16F) it[n++] = { final_ptr, (size_t)p->W * 4, p->H, 0, 1, p->H };
             if (final_fmt == HR_FMT_R16F) it[n++] = { final_ptr, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
-        else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
+        else it[n++] = { mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
         rc = hr_shard_exchange(p, it, n, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Exchange", st);
@@ -713,8 +748,10 @@ int hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
     A(pass_alloc(p, p->tile_flags, tw * th));
     if (scale != HR_SCALE_FULL) A(pass_alloc(p, p->upsample_out, (size_t)p->W0 * p->H0));
 #undef A
-    void* hist[4] = { p->ao_color[0], p->ao_color[1], p->ao_len[0], p->ao_len[1] };
-    hr_peer_register(p, hist, 4);
+    rc = pass_alloc_rt_share(p);
+    if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; }
+    void* hist[7] = { p->ao_color[0], p->ao_color[1], p->ao_len[0], p->ao_len[1], p->mask_pp[0], p->mask_pp[1], p->rt_cost_all };
+    hr_peer_register(p, hist, 7);
     return HR_OK;
 }
 
@@ -751,11 +788,30 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
         p->first = false;
     }
-    launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->mask, rt0, rt1, st);
-    ctx->launches++;
-    timer_mark(p, "Ray Trace", st);
-    set_view(p, HR_AO_OUT_RAY_TRACE, p->mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
-    void* final_ptr = p->mask;
+    RtShare    rts;
+    const bool shared_rt = hr_rt_share(p, epoch & 1, &rts); // see hr_shadows_render
+    uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
+    if (shared_rt)
+    {
+        launch_ao_ray_trace_shared(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, rts, st);
+        ctx->launches++;
+        rc = hr_rt_share_finish(p, epoch & 1, epoch, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Ray Trace", st);
+        rc = hr_peer_wait(p, 1, epoch, st);
+        if (rc != HR_OK) return rc;
+        rc = hr_rt_partition(p, epoch & 1, st);
+        if (rc != HR_OK) return rc;
+        timer_mark(p, "Mask Exchange Wait", st);
+    }
+    else
+    {
+        launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, mask, rt0, rt1, st);
+        ctx->launches++;
+        timer_mark(p, "Ray Trace", st);
+    }
+    set_view(p, HR_AO_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = mask;
     int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
     bool  signalled = false;
     if (prm->denoise)
@@ -765,12 +821,12 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
         if (!no_history)
         {
-            rc = hr_peer_wait(p, epoch - 1, st);
+            rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;
         }
-        launch_ao_temporal(cur, prev, p->mask, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
+        launch_ao_temporal(cur, prev, mask, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
-        rc = hr_peer_signal(p, epoch, st); // this frame's history (ao_color[pp], ao_len[pp]) is complete
+        rc = hr_peer_signal(p, 0, epoch, st); // this frame's history (ao_color[pp], ao_len[pp]) is complete
         if (rc != HR_OK) return rc;
         signalled = true;
         timer_mark(p, "Temporal Accumulation", st);
@@ -796,12 +852,12 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     }
     if (!signalled)
     {
-        rc = hr_peer_signal(p, epoch, st);
+        rc = hr_peer_signal(p, 0, epoch, st);
         if (rc != HR_OK) return rc;
     }
     set_view(p, 100, final_ptr, final_w, final_h, final_fmt);
     HR_CHECK_LAUNCH(ctx);
-    if (ctx->world > 1 && ctx->gather_final)
+    if (ctx->world > 1 && ctx->gather_final && !(shared_rt && !prm->denoise))
     {
         ExchangeItem it[4];
         int          n = 0;
@@ -810,7 +866,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
             if (p->scale == HR_SCALE_FULL) it[n++] = { p->ao_blur[1], (size_t)p->W * 2, p->H, 0, 1, p->H };
             else it[n++] = { p->upsample_out, (size_t)p->W0 * 2, p->H, p->scale, 1, p->H0 };
         }
-        else it[n++] = { p->mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
+        else it[n++] = { mask, (size_t)((p->W + 7) / 8) * 4, p->H, 0, 4, (p->H + 3) / 4 };
         rc = hr_shard_exchange(p, it, n, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Exchange", st);

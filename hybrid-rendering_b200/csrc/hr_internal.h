@@ -52,6 +52,7 @@ struct FrameConsts {           // what kernels need from hr_frame (passed by val
 
 // ---- objects ----------------------------------------------------------------------------------------
 #define HR_MAX_RANKS 8
+#define HR_MAX_SHARED 8
 
 // Temporal history as the reprojection kernels see it (shard.cu, "peer history").  Row y of the previous frame's history
 // images lives on the rank that owns y (band_end[r] = first row NOT owned by ranks 0..r); img[r] / aux[r] are that rank's
@@ -198,10 +199,15 @@ struct hr_pass {
     // peer history (shard.cu): the history images of every rank mapped into this process, and the frame ticks that order
     // "rank q finished writing frame N's history" before "rank r's frame N+1 reprojection reads it"
     bool        peers_linked = false, peers_ipc = false;
-    int         n_hist = 0;                          // history images registered (shadows: prev_image[2], moments[2]; AO: colour[2], length[2])
-    void*       hist_local[4] = {};
-    void*       hist_peer[HR_MAX_RANKS][4] = {};     // [rank][image]; own rank = hist_local
-    int*        sync_ticks = nullptr;                // [HR_MAX_RANKS] ticks written by the peers into THIS rank's memory
+    int         n_hist = 0;                          // shared images: 0-3 history (shadows: prev_image[2], moments[2]; AO: colour[2], length[2]),
+                                                     // 4-5 ray mask [frame parity], 6 ray-trace cost table [2][mask rows]
+    void*       hist_local[HR_MAX_SHARED] = {};
+    void*       hist_peer[HR_MAX_RANKS][HR_MAX_SHARED] = {}; // [rank][image]; own rank = hist_local
+    int*        sync_ticks = nullptr;                // [2][HR_MAX_RANKS] ticks written by the peers into THIS rank's memory: [0] history, [1] ray trace
+    uint32_t*   mask_pp[2] = { nullptr, nullptr };   // ray mask by frame parity (mask_pp[0] == mask); peers push their rows into both copies' owner
+    uint32_t*   rt_cost_all = nullptr;               // [2][MH] per-mask-row trace cost of the frame (all ranks' rows, pushed by their owners)
+    uint32_t*   rt_cost_acc = nullptr;               // [MH] this rank's accumulation scratch (atomicAdd per warp), drained by the push kernel
+    int*        rt_bounds = nullptr;                 // [world+1] mask-row partition of the NEXT frame's ray trace (device side, cost balanced)
     int*        peer_ticks[HR_MAX_RANKS] = {};       // the peers' tick arrays (we write slot [self])
     int*        sync_error = nullptr;                // set by the wait kernel on time-out
     int         epoch = 0;                           // renders of this pass so far
@@ -237,8 +243,24 @@ void hr_peer_register(hr_pass* p, void* const* imgs, int n);
 int  hr_peer_link_ipc(hr_pass* p, cudaStream_t st);
 void hr_peer_unlink(hr_pass* p);
 void hr_peer_hist(const hr_pass* p, int img_k, int aux_k, int H, bool no_history, HistPeers* out);
-int  hr_peer_wait(hr_pass* p, int tick, cudaStream_t st);
-int  hr_peer_signal(hr_pass* p, int tick, cudaStream_t st);
+int  hr_peer_wait(hr_pass* p, int which, int tick, cudaStream_t st);   // which: 0 history ticks, 1 ray-trace ticks
+int  hr_peer_signal(hr_pass* p, int which, int tick, cudaStream_t st);
+// Cost-balanced ray trace over the whole image with the masks pushed to every peer (trace.cu / shard.cu).
+struct RtShare {
+    uint32_t*   mask[HR_MAX_RANKS]; // every rank's mask image of this frame's parity
+    const int*  bounds;             // [world+1] mask-row partition (device)
+    uint32_t*   cost_acc;           // [MH] local cost accumulation
+    int         world, self;
+};
+// most mask rows one rank may be handed: 3x the uniform share (the whole image for world <= 3)
+inline int hr_rt_share_cap(int MH, int world) { const int c = 3 * ((MH + world - 1) / world) + 2; return c < MH ? c : MH; }
+bool hr_rt_share(hr_pass* p, int parity, RtShare* out); // false when the pass is not linked to peers
+int  hr_rt_share_finish(hr_pass* p, int parity, int tick, cudaStream_t st); // push costs, signal the ray-trace tick
+int  hr_rt_partition(hr_pass* p, int parity, cudaStream_t st);              // next frame's bounds from this frame's complete cost table
+void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
+                                     const RtShare& sh, cudaStream_t st);
+void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
+                                const uint8_t* sr, const RtShare& sh, cudaStream_t st);
 // Rows of an image of height H owned by this context's rank (all rows when world == 1).
 void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1);
 // [b0 - halo, b1 + halo) clamped to [0, H); halo must be a multiple of 8 so tile alignment is kept.

@@ -123,16 +123,84 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
 
 
 // ---- peer history -----------------------------------------------------------------------------------------------------
+static int rt_init_bounds(hr_pass* p);
+
 namespace {
 
 struct TickPtrs { int* p[HR_MAX_RANKS]; };
 
-__global__ void k_peer_signal(TickPtrs peers, int world, int self, int tick)
+__global__ void k_peer_signal(TickPtrs peers, int world, int self, int slot, int tick)
 {
     const int r = threadIdx.x;
     if (r >= world || r == self || !peers.p[r]) return;
-    __threadfence_system(); // the history writes of the kernels before us in stream order become visible system-wide first
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.p[r] + self), "r"(tick) : "memory");
+    __threadfence_system(); // the writes of the kernels before us in stream order become visible system-wide first
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.p[r] + slot * HR_MAX_RANKS + self), "r"(tick) : "memory");
+}
+
+// ---- cost-balanced ray-trace partition ----
+struct CostPtrs { uint32_t* p[HR_MAX_RANKS]; };
+
+// drain this rank's accumulation scratch into every rank's cost table (rows [bounds[self], bounds[self+1]) of table `parity`)
+__global__ void k_rt_push_cost(CostPtrs all, const int* __restrict__ bounds, uint32_t* __restrict__ acc, int world, int self, int parity, int MH)
+{
+    const int b0 = bounds[self], b1 = bounds[self + 1];
+    for (int row = b0 + blockIdx.x * blockDim.x + threadIdx.x; row < b1; row += gridDim.x * blockDim.x)
+    {
+        const uint32_t v = acc[row];
+        acc[row]         = 0u;
+        for (int r = 0; r < world; r++) all.p[r][(size_t)parity * MH + row] = v;
+    }
+}
+
+// One warp: bounds[k] = first mask row whose cost prefix reaches k/world of the total; every rank computes the same table
+// from the same (complete) cost table.  Shares are clamped to [1, cap] rows so the fixed launch grid covers them.
+__global__ void k_rt_partition(const uint32_t* __restrict__ cost, int MH, int world, int cap, int* __restrict__ bounds)
+{
+    __shared__ unsigned long long s_prefix[1024 + 1];
+    const int lane = threadIdx.x;
+    // chunked inclusive scan by one warp (MH <= a few thousand)
+    const int chunk = (MH + 31) / 32;
+    unsigned long long local = 0;
+    for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) local += cost[i];
+    unsigned long long incl = local;
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long run = incl - local;
+    // boundaries: lane k (1..world-1) searches its target; done cooperatively through shared prefix when MH is small
+    if (MH <= 1024)
+    {
+        for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) { run += cost[i]; s_prefix[i + 1] = run; }
+        if (lane == 0) s_prefix[0] = 0;
+        __syncwarp();
+    }
+    if (lane == 0)
+    {
+        int prev = 0;
+        bounds[0] = 0;
+        for (int k = 1; k < world; k++)
+        {
+            int b;
+            if (total == 0 || MH > 1024) b = (int)(((long long)MH * k) / world); // no cost information: uniform split
+            else
+            {
+                const unsigned long long target = (total * (unsigned long long)k) / (unsigned long long)world;
+                int lo = prev, hi = MH; // first row index b with prefix[b] >= target
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] >= target) hi = mid; else lo = mid + 1; }
+                b = lo;
+            }
+            b = max(b, prev + 1);                   // at least one row per rank
+            b = min(b, prev + cap);                 // the launch grid covers at most `cap` rows
+            b = min(b, MH - (world - k));           // leave a row for each remaining rank
+            b = max(b, MH - (world - k) * cap);     // the remaining ranks must be able to cover the rest
+            bounds[k] = b;
+            prev      = b;
+        }
+        bounds[world] = MH;
+    }
 }
 
 __global__ void k_peer_wait(const int* __restrict__ ticks, int world, int self, int tick, int* err)
@@ -156,8 +224,8 @@ int peer_alloc_ticks(hr_pass* p)
 {
     hr_ctx* ctx = p->ctx;
     if (p->sync_ticks) return HR_OK;
-    HR_CUDA(ctx, cudaMalloc((void**)&p->sync_ticks, sizeof(int) * HR_MAX_RANKS));
-    HR_CUDA(ctx, cudaMemset(p->sync_ticks, 0, sizeof(int) * HR_MAX_RANKS));
+    HR_CUDA(ctx, cudaMalloc((void**)&p->sync_ticks, sizeof(int) * 2 * HR_MAX_RANKS));
+    HR_CUDA(ctx, cudaMemset(p->sync_ticks, 0, sizeof(int) * 2 * HR_MAX_RANKS));
     HR_CUDA(ctx, cudaHostAlloc((void**)&p->sync_error, sizeof(int), cudaHostAllocMapped));
     *p->sync_error = 0;
     return HR_OK;
@@ -210,6 +278,7 @@ int hr_peer_link_ipc(hr_pass* p, cudaStream_t st)
             else p->peer_ticks[r] = (int*)m;
         }
     }
+    if (p->rt_bounds) { rc = rt_init_bounds(p); if (rc != HR_OK) return rc; }
     p->peers_linked = true;
     p->peers_ipc    = true;
     return HR_OK;
@@ -262,7 +331,7 @@ void hr_peer_hist(const hr_pass* p, int img_k, int aux_k, int H, bool no_history
     *out = hp;
 }
 
-int hr_peer_wait(hr_pass* p, int tick, cudaStream_t st)
+int hr_peer_wait(hr_pass* p, int which, int tick, cudaStream_t st)
 {
     if (!p->peers_linked || p->ctx->world <= 1 || tick <= 0) return HR_OK;
     hr_ctx* ctx = p->ctx;
@@ -273,18 +342,63 @@ int hr_peer_wait(hr_pass* p, int tick, cudaStream_t st)
     }
     int* d_err = nullptr;
     HR_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_err, p->sync_error, 0));
-    k_peer_wait<<<1, 32, 0, st>>>(p->sync_ticks, ctx->world, ctx->rank, tick, d_err);
+    k_peer_wait<<<1, 32, 0, st>>>(p->sync_ticks + which * HR_MAX_RANKS, ctx->world, ctx->rank, tick, d_err);
     ctx->launches++;
     return HR_OK;
 }
 
-int hr_peer_signal(hr_pass* p, int tick, cudaStream_t st)
+int hr_peer_signal(hr_pass* p, int which, int tick, cudaStream_t st)
 {
     if (!p->peers_linked || p->ctx->world <= 1) return HR_OK;
     TickPtrs t {};
     for (int r = 0; r < p->ctx->world; r++) t.p[r] = p->peer_ticks[r];
-    k_peer_signal<<<1, 32, 0, st>>>(t, p->ctx->world, p->ctx->rank, tick);
+    k_peer_signal<<<1, 32, 0, st>>>(t, p->ctx->world, p->ctx->rank, which, tick);
     p->ctx->launches++;
+    return HR_OK;
+}
+
+// ---- shared ray mask + cost-balanced partition ------------------------------------------------------------------------
+static int rt_init_bounds(hr_pass* p)
+{ // first frame: uniform split of the mask rows
+    hr_ctx*   ctx = p->ctx;
+    const int MH = (p->H + 3) / 4, world = ctx->world;
+    int       h[HR_MAX_RANKS + 1];
+    for (int k = 0; k <= world; k++) h[k] = (int)(((long long)MH * k) / world);
+    HR_CUDA(ctx, cudaMemcpy(p->rt_bounds, h, sizeof(int) * (world + 1), cudaMemcpyHostToDevice));
+    return HR_OK;
+}
+
+bool hr_rt_share(hr_pass* p, int parity, RtShare* out)
+{
+    hr_ctx* ctx = p->ctx;
+    if (!p->peers_linked || ctx->world <= 1 || p->n_hist < 7) return false;
+    RtShare sh {};
+    for (int r = 0; r < ctx->world; r++) sh.mask[r] = static_cast<uint32_t*>(p->hist_peer[r][4 + parity]);
+    sh.bounds   = p->rt_bounds;
+    sh.cost_acc = p->rt_cost_acc;
+    sh.world    = ctx->world;
+    sh.self     = ctx->rank;
+    *out        = sh;
+    return true;
+}
+
+int hr_rt_share_finish(hr_pass* p, int parity, int tick, cudaStream_t st)
+{
+    hr_ctx*   ctx = p->ctx;
+    const int MH  = (p->H + 3) / 4;
+    CostPtrs  c {};
+    for (int r = 0; r < ctx->world; r++) c.p[r] = static_cast<uint32_t*>(p->hist_peer[r][6]);
+    k_rt_push_cost<<<4, 256, 0, st>>>(c, p->rt_bounds, p->rt_cost_acc, ctx->world, ctx->rank, parity, MH);
+    ctx->launches++;
+    return hr_peer_signal(p, 1, tick, st);
+}
+
+int hr_rt_partition(hr_pass* p, int parity, cudaStream_t st)
+{
+    hr_ctx*   ctx = p->ctx;
+    const int MH  = (p->H + 3) / 4;
+    k_rt_partition<<<1, 32, 0, st>>>(p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, hr_rt_share_cap(MH, ctx->world), p->rt_bounds);
+    ctx->launches++;
     return HR_OK;
 }
 
@@ -339,6 +453,7 @@ int hr_shard_link_local(hr_pass* pass, int rank, hr_pass* peer)
     bool all = true;
     for (int r = 0; r < ctx->world; r++) all = all && pass->peer_ticks[r] != nullptr;
     pass->peers_linked = all;
+    if (all && pass->rt_bounds) return rt_init_bounds(pass);
     return HR_OK;
 }
 

@@ -24,17 +24,12 @@ __device__ __forceinline__ float2 load_oct_normal(const uint2* gb2, size_t idx)
     return __half22float2(h);
 }
 
-// MODE 0 = shadows (K1), 1 = AO (K7).  Block = 256 threads = 8 warps; warp w covers mask word (bx*4 + (w&3), by*2 + (w>>2)).
+// one pixel of K1 (MODE 0) / K7 (MODE 1): 1 = the ray reached the light / left the AO radius unoccluded
 template <int MODE>
-__global__ void __launch_bounds__(256) k_ray_trace_mask(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
-                                                         const uint8_t* __restrict__ sr, uint32_t* __restrict__ mask, int mrow0, int mrow1)
+__device__ __forceinline__ uint32_t trace_pixel(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+                                                const uint8_t* __restrict__ sr, int x, int y)
 {
-    const int MW   = (g.W + 7) >> 3;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mx = blockIdx.x * 4 + (warp & 3), my = mrow0 + blockIdx.y * 2 + (warp >> 2);
-    if (mx >= MW || my >= mrow1) return; // whole warp exits together
-    const int x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-    uint32_t  result = 0;
+    uint32_t result = 0;
     if (x < g.W && y < g.H)
     {
         const size_t idx   = (size_t)y * g.W + x;
@@ -65,8 +60,43 @@ __global__ void __launch_bounds__(256) k_ray_trace_mask(GBufLevelDev g, BvhDev b
             }
         }
     }
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, result != 0);
+    return result;
+}
+
+// MODE 0 = shadows (K1), 1 = AO (K7).  Block = 256 threads = 8 warps; warp w covers mask word (bx*4 + (w&3), by*2 + (w>>2)).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ray_trace_mask(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+                                                         const uint8_t* __restrict__ sr, uint32_t* __restrict__ mask, int mrow0, int mrow1)
+{
+    const int MW   = (g.W + 7) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mx = blockIdx.x * 4 + (warp & 3), my = mrow0 + blockIdx.y * 2 + (warp >> 2);
+    if (mx >= MW || my >= mrow1) return; // whole warp exits together
+    const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+    const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
     if (lane == 0) mask[(size_t)my * MW + mx] = word;
+}
+
+// Multi-GPU variant (shard.cu, "shared mask"): this rank traces mask rows [bounds[self], bounds[self+1]) — a partition of
+// the whole image balanced on last frame's measured cost, read from device memory — and stores every mask word into the
+// mask image of EVERY rank (peer stores over NVLink, 1 bit / pixel), so that no rank re-traces a halo.  Each warp adds
+// its residency time to the mask row's cost, the input of the next frame's partition.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+                                                                const uint8_t* __restrict__ sr, RtShare sh)
+{
+    const long long t0 = clock64();
+    const int MW   = (g.W + 7) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
+    const int mx = blockIdx.x * 4 + (warp & 3), my = mrow0 + blockIdx.y * 2 + (warp >> 2);
+    if (mx >= MW || my >= mrow1) return; // whole warp exits together
+    const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+    const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
+    if (lane < sh.world) sh.mask[lane][(size_t)my * MW + mx] = word;
+    if (lane == 0) atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -321,6 +351,25 @@ void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameCo
     if (mrow1 <= mrow0) return;
     if (g_hr_trace_impl == 1) { launch_pt<1>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1, st); return; }
     k_ray_trace_mask<1><<<mask_grid(g.W, mrow0, mrow1), 256, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1);
+}
+
+// grid: every rank can be handed at most RT_SHARE_CAP times the uniform share of mask rows (hr_rt_partition clamps)
+static inline dim3 shared_grid(int W, int H, int world)
+{
+    const int MH = (H + 3) / 4, cap = hr_rt_share_cap(MH, world);
+    return dim3(((W + 7) / 8 + 3) / 4, (cap + 1) / 2, 1);
+}
+
+void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
+                                     const RtShare& sh, cudaStream_t st)
+{
+    k_ray_trace_mask_shared<0><<<shared_grid(g.W, g.H, sh.world), 256, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
+}
+
+void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
+                                const uint8_t* sr, const RtShare& sh, cudaStream_t st)
+{
+    k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), 256, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
 }
 
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st)

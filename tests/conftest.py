@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# the peer-history emulation tests run up to 8 emulated ranks on concurrent streams of one GPU: give every stream its own
+# hardware queue (must be set before the CUDA context exists)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "hybrid-rendering_b200"))

@@ -13,6 +13,7 @@ import sys
 
 import numpy as np
 import pytest
+import torch
 
 import oracle as O  # noqa: F401  (path setup)
 import pyhr
@@ -93,12 +94,25 @@ def test_peer_history_emulation_bit_identical(world, sh_scale, ao_scale):
                 ranks[r][1].link_local(q, ranks[q][1])
                 ranks[r][2].link_local(q, ranks[q][2])
     sh_h, ao_h = H >> sh_scale, H >> ao_scale
+    # Linked ranks wait for each other inside a frame (the ray masks are traced cooperatively: every rank traces its
+    # cost-balanced share of the whole image and pushes it to all peers), so the emulated ranks must be able to run
+    # concurrently: one CUDA stream per rank (conftest.py raises CUDA_DEVICE_MAX_CONNECTIONS so they get separate queues).
+    streams = [torch.cuda.Stream() for _ in range(world)]
     for f in frames(8, pan_from=2, vertical=0.35):
         g = pyhr.write_gbuffer(sc, f, W, H)
-        for c, sh, ao in [ref] + ranks:
-            c.gbuffer_upload(f.ping_pong, g)
-            sh.render(f)
-            ao.render(f)
+        ref[0].gbuffer_upload(f.ping_pong, g)
+        ref[1].render(f)
+        ref[2].render(f)
+        for (c, sh, ao), st in zip(ranks, streams):
+            c.gbuffer_upload(f.ping_pong, g, st.cuda_stream)
+        for (c, sh, ao), st in zip(ranks, streams):
+            sh.render(f, st.cuda_stream)
+        for (c, sh, ao), st in zip(ranks, streams):
+            ao.render(f, st.cuda_stream)
+        torch.cuda.synchronize()
+        for r in ranks:  # the complete ray mask is on every rank
+            assert np.array_equal(r[1].download(0), ref[1].download(0)), f"shadows mask differs (world={world}, frame {f.num_frames})"
+            assert np.array_equal(r[2].download(0), ref[2].download(0)), f"ao mask differs (world={world}, frame {f.num_frames})"
         for name, which, shift in (("prev", SH["prev"], 0), ("moments", SH["moments"], 0), ("final", SH["final"], sh_scale)):
             merged = merge_bands([r[1].download(which) for r in ranks], sh_h, world, shift if name == "final" else 0)
             assert np.array_equal(merged, ref[1].download(which)), f"shadows {name} differs (world={world}, frame {f.num_frames})"
