@@ -405,7 +405,9 @@ HR_API int hr_shard_shutdown(hr_ctx* ctx);
 HR_API int hr_shard_set_gather(hr_ctx* ctx, int gather_final_output);
 /* Same-process peers (N ranks emulated on one GPU with hr_shard_config, or several GPUs driven by one process): declare
  * that rank `rank`'s band of this pass's history lives in `peer`.  Link every pass with every other rank's pass before
- * the first render; the ranks' renders of a frame may then run in any order / on any streams. */
+ * the first render, give every rank its own stream (the ranks wait for each other's ray masks inside a frame, so their
+ * kernels must be able to run concurrently) and run the process with CUDA_MODULE_LOADING=EAGER (a lazily loaded kernel's
+ * first launch synchronises the context, which stalls until the peer time-out while another rank's wait kernel spins). */
 HR_API int hr_shard_link_local(hr_pass* pass, int rank, hr_pass* peer);
 /* Row range (at pass resolution, height H) owned by rank. */
 HR_API int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end);

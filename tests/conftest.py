@@ -6,6 +6,9 @@ import pytest
 # the peer-history emulation tests run up to 8 emulated ranks on concurrent streams of one GPU: give every stream its own
 # hardware queue (must be set before the CUDA context exists)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and load every kernel when the library is loaded: with lazy loading the FIRST launch of a kernel synchronises the
+# context, which dead-locks (until the 2 s peer time-out) while another emulated rank's wait kernel is spinning
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
