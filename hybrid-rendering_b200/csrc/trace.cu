@@ -63,14 +63,17 @@ __device__ __forceinline__ uint32_t trace_pixel(const GBufLevelDev& g, const Bvh
     return result;
 }
 
-// MODE 0 = shadows (K1), 1 = AO (K7).  Block = 256 threads = 8 warps; warp w covers mask word (bx*4 + (w&3), by*2 + (w>>2)).
+// MODE 0 = shadows (K1), 1 = AO (K7).  Block = RT_CTA_WARPS warps; warp w covers mask word (bx*RT_CTA_WARPS + w, by).
+// Small CTAs on purpose: ray costs are heavy-tailed and a CTA's slot (registers) is only recycled when its slowest warp
+// is done — with 8-warp CTAs the kernel ran its last ~20 % at a fraction of the occupancy.
+#define RT_CTA_WARPS 2
 template <int MODE>
-__global__ void __launch_bounds__(256) k_ray_trace_mask(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+__global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
                                                          const uint8_t* __restrict__ sr, uint32_t* __restrict__ mask, int mrow0, int mrow1)
 {
     const int MW   = (g.W + 7) >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mx = blockIdx.x * 4 + (warp & 3), my = mrow0 + blockIdx.y * 2 + (warp >> 2);
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
     if (mx >= MW || my >= mrow1) return; // whole warp exits together
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
     const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
@@ -83,14 +86,14 @@ __global__ void __launch_bounds__(256) k_ray_trace_mask(GBufLevelDev g, BvhDev b
 // mask image of EVERY rank (peer stores over NVLink, 1 bit / pixel), so that no rank re-traces a halo.  Each warp adds
 // its residency time to the mask row's cost, the input of the next frame's partition.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+__global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
                                                                 const uint8_t* __restrict__ sr, RtShare sh)
 {
     const long long t0 = clock64();
     const int MW   = (g.W + 7) >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
-    const int mx = blockIdx.x * 4 + (warp & 3), my = mrow0 + blockIdx.y * 2 + (warp >> 2);
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
     if (mx >= MW || my >= mrow1) return; // whole warp exits together
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
     const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
@@ -306,7 +309,7 @@ __global__ void k_trace_closest(BvhDev bvh, const float* __restrict__ rays, size
 
 } // namespace
 
-static inline dim3 mask_grid(int W, int mrow0, int mrow1) { return dim3(((W + 7) / 8 + 3) / 4, (mrow1 - mrow0 + 1) / 2, 1); }
+static inline dim3 mask_grid(int W, int mrow0, int mrow1) { return dim3(((W + 7) / 8 + RT_CTA_WARPS - 1) / RT_CTA_WARPS, mrow1 - mrow0, 1); }
 
 // 0 = one warp per 8x4 block (default), 1 = persistent threads + ray compaction + LDS stack (hr_debug_set key 2).
 // Measured at 4K (profiles/README.md): shadows 585 us vs 712 us, AO 223 us vs 333 us — on this workload the 8x4 blocks are
@@ -341,7 +344,7 @@ void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const Fr
     const int mrow0 = row0 / 4, mrow1 = (row1 + 3) / 4;
     if (mrow1 <= mrow0) return;
     if (g_hr_trace_impl == 1) { launch_pt<0>(g, bvh, fc, bias, 0.0f, sobol, sr, mask, mrow0, mrow1, st); return; }
-    k_ray_trace_mask<0><<<mask_grid(g.W, mrow0, mrow1), 256, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, mask, mrow0, mrow1);
+    k_ray_trace_mask<0><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, mask, mrow0, mrow1);
 }
 
 void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
@@ -350,26 +353,26 @@ void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameCo
     const int mrow0 = row0 / 4, mrow1 = (row1 + 3) / 4;
     if (mrow1 <= mrow0) return;
     if (g_hr_trace_impl == 1) { launch_pt<1>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1, st); return; }
-    k_ray_trace_mask<1><<<mask_grid(g.W, mrow0, mrow1), 256, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1);
+    k_ray_trace_mask<1><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1);
 }
 
 // grid: every rank can be handed at most RT_SHARE_CAP times the uniform share of mask rows (hr_rt_partition clamps)
 static inline dim3 shared_grid(int W, int H, int world)
 {
     const int MH = (H + 3) / 4, cap = hr_rt_share_cap(MH, world);
-    return dim3(((W + 7) / 8 + 3) / 4, (cap + 1) / 2, 1);
+    return dim3(((W + 7) / 8 + RT_CTA_WARPS - 1) / RT_CTA_WARPS, cap, 1);
 }
 
 void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                                      const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<0><<<shared_grid(g.W, g.H, sh.world), 256, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
+    k_ray_trace_mask_shared<0><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
 }
 
 void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
                                 const uint8_t* sr, const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), 256, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
+    k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
 }
 
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st)
