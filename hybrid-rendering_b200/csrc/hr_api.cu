@@ -13,6 +13,7 @@ static std::mutex  g_err_mutex;
 extern int         g_hr_atrous_impl;
 extern int         g_hr_trace_impl;
 extern int         g_hr_bvh_quality;
+extern int         g_hr_force_shared_rt;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -145,6 +146,7 @@ int hr_debug_set(int key, int value)
     if (key == 1) { g_hr_atrous_impl = value; return HR_OK; }
     if (key == 2) { g_hr_trace_impl = value; return HR_OK; }
     if (key == 3) { g_hr_bvh_quality = value; return HR_OK; }
+    if (key == 4) { g_hr_force_shared_rt = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 
@@ -488,7 +490,7 @@ static int pass_alloc_rt_share(hr_pass* p)
     if ((rc = pass_alloc(p, p->mask_pp[1], mw * mh)) != HR_OK) return rc;
     if ((rc = pass_alloc(p, p->rt_cost_all, 2 * mh)) != HR_OK) return rc;
     if ((rc = pass_alloc(p, p->rt_cost_acc, mh)) != HR_OK) return rc;
-    if ((rc = pass_alloc(p, p->rt_bounds, (size_t)HR_MAX_RANKS + 1)) != HR_OK) return rc;
+    if ((rc = pass_alloc(p, p->rt_bounds, (size_t)HR_MAX_RANKS + 4)) != HR_OK) return rc; // + job counter, push-blocks-done counter
     return HR_OK;
 }
 
@@ -616,9 +618,8 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         rc = hr_rt_share_finish(p, epoch & 1, epoch, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Ray Trace", st);
-        rc = hr_peer_wait(p, 1, epoch, st); // every rank's share of this frame's mask (and cost table) has arrived
-        if (rc != HR_OK) return rc;
-        rc = hr_rt_partition(p, epoch & 1, st);
+        // every rank's share of this frame's mask (and cost table) has arrived, and last frame's history is complete
+        rc = hr_rt_wait_partition(p, epoch & 1, epoch, (prm->denoise && !no_history) ? epoch - 1 : 0, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Mask Exchange Wait", st);
     }
@@ -638,7 +639,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         // wait until every peer has finished writing them (tick epoch-1), overlapped with the ray trace above.
         HistPeers hist;
         hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
-        if (!no_history)
+        if (!no_history && !shared_rt)
         {
             rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;
@@ -798,9 +799,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         rc = hr_rt_share_finish(p, epoch & 1, epoch, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Ray Trace", st);
-        rc = hr_peer_wait(p, 1, epoch, st);
-        if (rc != HR_OK) return rc;
-        rc = hr_rt_partition(p, epoch & 1, st);
+        rc = hr_rt_wait_partition(p, epoch & 1, epoch, (prm->denoise && !no_history) ? epoch - 1 : 0, st);
         if (rc != HR_OK) return rc;
         timer_mark(p, "Mask Exchange Wait", st);
     }
@@ -819,7 +818,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         // history = ao_color[!pp] / ao_len[!pp] of the rank that owns the reprojected row (peer history, shard.cu)
         HistPeers hist;
         hr_peer_hist(p, !pp, 2 + !pp, p->H, no_history, &hist);
-        if (!no_history)
+        if (!no_history && !shared_rt)
         {
             rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;

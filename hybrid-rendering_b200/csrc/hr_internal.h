@@ -207,7 +207,7 @@ struct hr_pass {
     uint32_t*   mask_pp[2] = { nullptr, nullptr };   // ray mask by frame parity (mask_pp[0] == mask); peers push their rows into both copies' owner
     uint32_t*   rt_cost_all = nullptr;               // [2][MH] per-mask-row trace cost of the frame (all ranks' rows, pushed by their owners)
     uint32_t*   rt_cost_acc = nullptr;               // [MH] this rank's accumulation scratch (atomicAdd per warp), drained by the push kernel
-    int*        rt_bounds = nullptr;                 // [world+1] mask-row partition of the NEXT frame's ray trace (device side, cost balanced)
+    int*        rt_bounds = nullptr;                 // [world+1] mask-row partition of the NEXT frame's ray trace (device side, cost balanced); [HR_MAX_RANKS+1] = job counter, [+2] = push blocks done
     int*        peer_ticks[HR_MAX_RANKS] = {};       // the peers' tick arrays (we write slot [self])
     int*        sync_error = nullptr;                // set by the wait kernel on time-out
     int         epoch = 0;                           // renders of this pass so far
@@ -247,16 +247,15 @@ int  hr_peer_wait(hr_pass* p, int which, int tick, cudaStream_t st);   // which:
 int  hr_peer_signal(hr_pass* p, int which, int tick, cudaStream_t st);
 // Cost-balanced ray trace over the whole image with the masks pushed to every peer (trace.cu / shard.cu).
 struct RtShare {
-    uint32_t*   mask[HR_MAX_RANKS]; // every rank's mask image of this frame's parity
-    const int*  bounds;             // [world+1] mask-row partition (device)
-    uint32_t*   cost_acc;           // [MH] local cost accumulation
-    int         world, self;
+    uint32_t*     mask_local; // this rank's mask image of this frame's parity (k_rt_push copies the share to the peers)
+    const int*    bounds;     // [world+1] mask-row partition (device)
+    uint32_t*     cost_acc;   // [MH] local cost accumulation
+    unsigned int* counter;    // job counter (reset by k_rt_push after the frame)
+    int           world, self;
 };
-// most mask rows one rank may be handed: 3x the uniform share (the whole image for world <= 3)
-inline int hr_rt_share_cap(int MH, int world) { const int c = 3 * ((MH + world - 1) / world) + 2; return c < MH ? c : MH; }
 bool hr_rt_share(hr_pass* p, int parity, RtShare* out); // false when the pass is not linked to peers
 int  hr_rt_share_finish(hr_pass* p, int parity, int tick, cudaStream_t st); // push costs, signal the ray-trace tick
-int  hr_rt_partition(hr_pass* p, int parity, cudaStream_t st);              // next frame's bounds from this frame's complete cost table
+int  hr_rt_wait_partition(hr_pass* p, int parity, int rt_tick, int hist_tick, cudaStream_t st); // wait for the peers' ticks, then next frame's bounds
 void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                                      const RtShare& sh, cudaStream_t st);
 void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,

@@ -137,31 +137,94 @@ __global__ void k_peer_signal(TickPtrs peers, int world, int self, int slot, int
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(peers.p[r] + slot * HR_MAX_RANKS + self), "r"(tick) : "memory");
 }
 
-// ---- cost-balanced ray-trace partition ----
+// ---- cooperative ray trace: push of the traced share + cost-balanced partition ----
 struct CostPtrs { uint32_t* p[HR_MAX_RANKS]; };
+struct MaskPtrs { uint32_t* p[HR_MAX_RANKS]; };
 
-// drain this rank's accumulation scratch into every rank's cost table (rows [bounds[self], bounds[self+1]) of table `parity`)
-__global__ void k_rt_push_cost(CostPtrs all, const int* __restrict__ bounds, uint32_t* __restrict__ acc, int world, int self, int parity, int MH)
+// After the ray-trace kernel: copy this rank's share of the mask image (rows [bounds[self], bounds[self+1])) into every
+// peer's mask image with wide stores, drain the cost accumulation into every rank's cost table, reset the job counter,
+// and — from the last block to finish — publish the ray-trace tick to the peers.
+__global__ void __launch_bounds__(256) k_rt_push(MaskPtrs masks, CostPtrs costs, int* __restrict__ ctl, uint32_t* __restrict__ acc, TickPtrs ticks, int world, int self,
+                                                 int parity, int MH, int MW, int tick)
 {
-    const int b0 = bounds[self], b1 = bounds[self + 1];
-    for (int row = b0 + blockIdx.x * blockDim.x + threadIdx.x; row < b1; row += gridDim.x * blockDim.x)
+    const int    b0 = ctl[self], b1 = ctl[self + 1];
+    const size_t first = (size_t)b0 * MW, n = (size_t)(b1 - b0) * MW;
+    const uint32_t* src = masks.p[self] + first;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    if ((MW & 3) == 0)
+    { // rows are 16-byte multiples and the images 256-byte aligned
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        for (size_t i = tid; i < n / 4; i += nthr)
+        {
+            const uint4 v = s4[i];
+            for (int r = 0; r < world; r++)
+                if (r != self) reinterpret_cast<uint4*>(masks.p[r] + first)[i] = v;
+        }
+    }
+    else
+        for (size_t i = tid; i < n; i += nthr)
+        {
+            const uint32_t v = src[i];
+            for (int r = 0; r < world; r++)
+                if (r != self) masks.p[r][first + i] = v;
+        }
+    if (blockIdx.x == 0)
+        for (int row = b0 + threadIdx.x; row < b1; row += blockDim.x)
+        {
+            const uint32_t v = acc[row];
+            acc[row]         = 0u;
+            for (int r = 0; r < world; r++) costs.p[r][(size_t)parity * MH + row] = v;
+        }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0)
     {
-        const uint32_t v = acc[row];
-        acc[row]         = 0u;
-        for (int r = 0; r < world; r++) all.p[r][(size_t)parity * MH + row] = v;
+        const int done = atomicAdd(ctl + HR_MAX_RANKS + 2, 1);
+        s_last         = done == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0)
+    {
+        ctl[HR_MAX_RANKS + 2] = 0; // blocks-done counter
+        ctl[HR_MAX_RANKS + 1] = 0; // ray-trace job counter (the kernel of this frame is complete: same stream)
+    }
+    const int r = threadIdx.x;
+    if (r < world && r != self && ticks.p[r])
+    {
+        __threadfence_system(); // all blocks' stores (ordered before their atomicAdd) are visible before the tick
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ticks.p[r] + 1 * HR_MAX_RANKS + self), "r"(tick) : "memory");
     }
 }
 
-// One warp: bounds[k] = first mask row whose cost prefix reaches k/world of the total; every rank computes the same table
-// from the same (complete) cost table.  Shares are clamped to [1, cap] rows so the fixed launch grid covers them.
-__global__ void k_rt_partition(const uint32_t* __restrict__ cost, int MH, int world, int cap, int* __restrict__ bounds)
+// One warp.  Lanes spin until every peer's ray-trace tick reached `rt_tick` and its history tick `hist_tick` (2 s time-out),
+// then the warp computes next frame's partition: bounds[k] = first mask row whose cost prefix reaches k/world of the total.
+// Every rank computes the same table from the same (complete) cost table.
+__global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, int hist_tick, int* err, const uint32_t* __restrict__ cost, int MH, int world, int self,
+                                    int* __restrict__ bounds)
 {
     __shared__ unsigned long long s_prefix[1024 + 1];
     const int lane = threadIdx.x;
-    // chunked inclusive scan by one warp (MH <= a few thousand)
-    const int chunk = (MH + 31) / 32;
+    if (lane < world && lane != self)
+    {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;)
+        {
+            int v, h = hist_tick;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ticks + HR_MAX_RANKS + lane) : "memory");
+            if (hist_tick > 0) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(h) : "l"(ticks + lane) : "memory");
+            if (v >= rt_tick && h >= hist_tick) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { *err = 1 + lane; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncwarp();
+    const int          chunk = (MH + 31) / 32;
     unsigned long long local = 0;
-    for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) local += cost[i];
+    for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) local += __ldcg(cost + i);
     unsigned long long incl = local;
     for (int o = 1; o < 32; o <<= 1)
     {
@@ -169,17 +232,16 @@ __global__ void k_rt_partition(const uint32_t* __restrict__ cost, int MH, int wo
         if (lane >= o) incl += v;
     }
     const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    unsigned long long run = incl - local;
-    // boundaries: lane k (1..world-1) searches its target; done cooperatively through shared prefix when MH is small
+    unsigned long long       run   = incl - local;
     if (MH <= 1024)
     {
-        for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) { run += cost[i]; s_prefix[i + 1] = run; }
+        for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) { run += __ldcg(cost + i); s_prefix[i + 1] = run; }
         if (lane == 0) s_prefix[0] = 0;
-        __syncwarp();
     }
+    __syncwarp();
     if (lane == 0)
     {
-        int prev = 0;
+        int prev  = 0;
         bounds[0] = 0;
         for (int k = 1; k < world; k++)
         {
@@ -192,10 +254,8 @@ __global__ void k_rt_partition(const uint32_t* __restrict__ cost, int MH, int wo
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] >= target) hi = mid; else lo = mid + 1; }
                 b = lo;
             }
-            b = max(b, prev + 1);                   // at least one row per rank
-            b = min(b, prev + cap);                 // the launch grid covers at most `cap` rows
-            b = min(b, MH - (world - k));           // leave a row for each remaining rank
-            b = max(b, MH - (world - k) * cap);     // the remaining ranks must be able to cover the rest
+            b = max(b, prev + 1);         // at least one row per rank
+            b = min(b, MH - (world - k)); // leave a row for each remaining rank
             bounds[k] = b;
             prev      = b;
         }
@@ -368,36 +428,62 @@ static int rt_init_bounds(hr_pass* p)
     return HR_OK;
 }
 
+int g_hr_force_shared_rt = 0; // hr_debug_set(4, 1): run the cooperative ray-trace kernel on a single GPU (overhead A/B)
+
 bool hr_rt_share(hr_pass* p, int parity, RtShare* out)
 {
     hr_ctx* ctx = p->ctx;
-    if (!p->peers_linked || ctx->world <= 1 || p->n_hist < 7) return false;
+    const bool forced = g_hr_force_shared_rt && ctx->world == 1 && p->n_hist >= 7;
+    if (forced && !p->hist_peer[0][6])
+    {
+        for (int k = 0; k < p->n_hist; k++) p->hist_peer[0][k] = p->hist_local[k];
+        if (rt_init_bounds(p) != HR_OK) return false;
+    }
+    if (!forced && (!p->peers_linked || ctx->world <= 1 || p->n_hist < 7)) return false;
     RtShare sh {};
-    for (int r = 0; r < ctx->world; r++) sh.mask[r] = static_cast<uint32_t*>(p->hist_peer[r][4 + parity]);
-    sh.bounds   = p->rt_bounds;
-    sh.cost_acc = p->rt_cost_acc;
-    sh.world    = ctx->world;
-    sh.self     = ctx->rank;
-    *out        = sh;
+    sh.mask_local = static_cast<uint32_t*>(p->hist_local[4 + parity]);
+    sh.bounds     = p->rt_bounds;
+    sh.cost_acc   = p->rt_cost_acc;
+    sh.counter    = reinterpret_cast<unsigned int*>(p->rt_bounds + HR_MAX_RANKS + 1);
+    sh.world      = ctx->world;
+    sh.self       = ctx->rank;
+    *out          = sh;
     return true;
 }
 
 int hr_rt_share_finish(hr_pass* p, int parity, int tick, cudaStream_t st)
 {
     hr_ctx*   ctx = p->ctx;
-    const int MH  = (p->H + 3) / 4;
+    const int MH = (p->H + 3) / 4, MW = (p->W + 7) / 8;
     CostPtrs  c {};
-    for (int r = 0; r < ctx->world; r++) c.p[r] = static_cast<uint32_t*>(p->hist_peer[r][6]);
-    k_rt_push_cost<<<4, 256, 0, st>>>(c, p->rt_bounds, p->rt_cost_acc, ctx->world, ctx->rank, parity, MH);
+    MaskPtrs  m {};
+    TickPtrs  t {};
+    for (int r = 0; r < ctx->world; r++)
+    {
+        c.p[r] = static_cast<uint32_t*>(p->hist_peer[r][6]);
+        m.p[r] = static_cast<uint32_t*>(p->hist_peer[r][4 + parity]);
+        t.p[r] = p->peer_ticks[r];
+    }
+    k_rt_push<<<ctx->world > 1 ? 32 : 1, 256, 0, st>>>(m, c, p->rt_bounds, p->rt_cost_acc, t, ctx->world, ctx->rank, parity, MH, MW, tick);
     ctx->launches++;
-    return hr_peer_signal(p, 1, tick, st);
+    return HR_OK;
 }
 
-int hr_rt_partition(hr_pass* p, int parity, cudaStream_t st)
+int hr_rt_wait_partition(hr_pass* p, int parity, int rt_tick, int hist_tick, cudaStream_t st)
 {
     hr_ctx*   ctx = p->ctx;
     const int MH  = (p->H + 3) / 4;
-    k_rt_partition<<<1, 32, 0, st>>>(p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, hr_rt_share_cap(MH, ctx->world), p->rt_bounds);
+    int*      d_err = nullptr;
+    if (ctx->world > 1)
+    {
+        if (p->sync_error && *p->sync_error)
+        {
+            hr_set_error(ctx, "peer sync: timed out waiting for rank %d's frame tick (peer stopped, or ranks rendered different frame counts)", *p->sync_error - 1);
+            return HR_ERR_NCCL;
+        }
+        HR_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_err, p->sync_error, 0));
+    }
+    k_rt_wait_partition<<<1, 32, 0, st>>>(p->sync_ticks, rt_tick, hist_tick, d_err, p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, ctx->rank, p->rt_bounds);
     ctx->launches++;
     return HR_OK;
 }

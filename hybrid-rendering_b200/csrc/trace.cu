@@ -81,25 +81,39 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelD
     if (lane == 0) mask[(size_t)my * MW + mx] = word;
 }
 
-// Multi-GPU variant (shard.cu, "shared mask"): this rank traces mask rows [bounds[self], bounds[self+1]) — a partition of
-// the whole image balanced on last frame's measured cost, read from device memory — and stores every mask word into the
-// mask image of EVERY rank (peer stores over NVLink, 1 bit / pixel), so that no rank re-traces a halo.  Each warp adds
-// its residency time to the mask row's cost, the input of the next frame's partition.
+// Multi-GPU variant (shard.cu, "cooperative ray trace"): this rank traces mask rows [bounds[self], bounds[self+1]) — a
+// partition of the WHOLE image balanced on last frame's measured cost, read from device memory, so the host never needs
+// to know it.  The grid is a fixed set of resident warps that pull 8x4-pixel jobs (row-major: neighbouring warps work on
+// neighbouring blocks) from an atomic counter until the share is done: the same launch covers any share size without
+// empty CTAs.  Mask words go to this rank's own mask image; k_rt_push (shard.cu) then copies the share to every peer
+// with wide stores.  Each job adds its duration to its mask row's cost, the input of the next frame's partition.
 template <int MODE>
 __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
                                                                 const uint8_t* __restrict__ sr, RtShare sh)
 {
-    const long long t0 = clock64();
-    const int MW   = (g.W + 7) >> 3;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MW    = (g.W + 7) >> 3;
+    const int lane  = threadIdx.x & 31;
     const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
-    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
-    if (mx >= MW || my >= mrow1) return; // whole warp exits together
-    const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
-    const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
-    if (lane < sh.world) sh.mask[lane][(size_t)my * MW + mx] = word;
-    if (lane == 0) atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
+    const int n_jobs = (mrow1 - mrow0) * MW;
+    int job = 0;
+    if (lane == 0) job = (int)atomicAdd(sh.counter, 1u);
+    job = __shfl_sync(0xFFFFFFFFu, job, 0);
+    while (job < n_jobs)
+    {
+        int next = 0;
+        if (lane == 0) next = (int)atomicAdd(sh.counter, 1u); // fetched early: its latency hides behind this job's traversal
+        const long long t0 = clock64();
+        const int my = mrow0 + job / MW, mx = job - (job / MW) * MW;
+        const int x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+        const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+        const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
+        if (lane == 0)
+        {
+            sh.mask_local[(size_t)my * MW + mx] = word;
+            atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
+        }
+        job = __shfl_sync(0xFFFFFFFFu, next, 0);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -356,23 +370,32 @@ void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameCo
     k_ray_trace_mask<1><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1);
 }
 
-// grid: every rank can be handed at most RT_SHARE_CAP times the uniform share of mask rows (hr_rt_partition clamps)
-static inline dim3 shared_grid(int W, int H, int world)
+// fixed grid of resident CTAs (occupancy x SM count); the job loop covers whatever share the device-side partition assigns
+template <int MODE>
+static dim3 shared_grid()
 {
-    const int MH = (H + 3) / 4, cap = hr_rt_share_cap(MH, world);
-    return dim3(((W + 7) / 8 + RT_CTA_WARPS - 1) / RT_CTA_WARPS, cap, 1);
+    static int ctas = 0;
+    if (!ctas)
+    {
+        int dev = 0, sms = 148, per_sm = 8;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_trace_mask_shared<MODE>, RT_CTA_WARPS * 32, 0);
+        ctas = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    return dim3(ctas, 1, 1);
 }
 
 void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                                      const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<0><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
+    k_ray_trace_mask_shared<0><<<shared_grid<0>(), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
 }
 
 void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
                                 const uint8_t* sr, const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
+    k_ray_trace_mask_shared<1><<<shared_grid<1>(), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
 }
 
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st)
