@@ -250,9 +250,10 @@ struct RtShare {
     uint32_t*     mask_local; // this rank's mask image of this frame's parity (k_rt_push copies the share to the peers)
     const int*    bounds;     // [world+1] mask-row partition (device)
     uint32_t*     cost_acc;   // [MH] local cost accumulation
-    unsigned int* counter;    // job counter (reset by k_rt_push after the frame)
     int           world, self;
 };
+// most mask rows one rank may be handed: twice the uniform share (+4); the whole image for world <= 2
+inline int hr_rt_share_cap(int MH, int world) { const int c = 2 * ((MH + world - 1) / world) + 4; return c < MH ? c : MH; }
 bool hr_rt_share(hr_pass* p, int parity, RtShare* out); // false when the pass is not linked to peers
 int  hr_rt_share_finish(hr_pass* p, int parity, int tick, cudaStream_t st); // push costs, signal the ray-trace tick
 int  hr_rt_wait_partition(hr_pass* p, int parity, int rt_tick, int hist_tick, cudaStream_t st); // wait for the peers' ticks, then next frame's bounds

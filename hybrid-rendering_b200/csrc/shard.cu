@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(256) k_rt_push(MaskPtrs masks, CostPtrs costs,
     if (threadIdx.x == 0)
     {
         ctl[HR_MAX_RANKS + 2] = 0; // blocks-done counter
-        ctl[HR_MAX_RANKS + 1] = 0; // ray-trace job counter (the kernel of this frame is complete: same stream)
     }
     const int r = threadIdx.x;
     if (r < world && r != self && ticks.p[r])
@@ -202,7 +201,7 @@ __global__ void __launch_bounds__(256) k_rt_push(MaskPtrs masks, CostPtrs costs,
 // then the warp computes next frame's partition: bounds[k] = first mask row whose cost prefix reaches k/world of the total.
 // Every rank computes the same table from the same (complete) cost table.
 __global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, int hist_tick, int* err, const uint32_t* __restrict__ cost, int MH, int world, int self,
-                                    int* __restrict__ bounds)
+                                    int cap, int* __restrict__ bounds)
 {
     __shared__ unsigned long long s_prefix[1024 + 1];
     const int lane = threadIdx.x;
@@ -254,8 +253,10 @@ __global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, 
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] >= target) hi = mid; else lo = mid + 1; }
                 b = lo;
             }
-            b = max(b, prev + 1);         // at least one row per rank
-            b = min(b, MH - (world - k)); // leave a row for each remaining rank
+            b = max(b, prev + 1);               // at least one row per rank
+            b = min(b, prev + cap);             // the fixed launch grid covers at most `cap` rows
+            b = min(b, MH - (world - k));       // leave a row for each remaining rank
+            b = max(b, MH - (world - k) * cap); // the remaining ranks must be able to cover the rest
             bounds[k] = b;
             prev      = b;
         }
@@ -444,7 +445,6 @@ bool hr_rt_share(hr_pass* p, int parity, RtShare* out)
     sh.mask_local = static_cast<uint32_t*>(p->hist_local[4 + parity]);
     sh.bounds     = p->rt_bounds;
     sh.cost_acc   = p->rt_cost_acc;
-    sh.counter    = reinterpret_cast<unsigned int*>(p->rt_bounds + HR_MAX_RANKS + 1);
     sh.world      = ctx->world;
     sh.self       = ctx->rank;
     *out          = sh;
@@ -483,7 +483,8 @@ int hr_rt_wait_partition(hr_pass* p, int parity, int rt_tick, int hist_tick, cud
         }
         HR_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_err, p->sync_error, 0));
     }
-    k_rt_wait_partition<<<1, 32, 0, st>>>(p->sync_ticks, rt_tick, hist_tick, d_err, p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, ctx->rank, p->rt_bounds);
+    k_rt_wait_partition<<<1, 32, 0, st>>>(p->sync_ticks, rt_tick, hist_tick, d_err, p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, ctx->rank,
+                                         hr_rt_share_cap(MH, ctx->world), p->rt_bounds);
     ctx->launches++;
     return HR_OK;
 }

@@ -83,36 +83,27 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelD
 
 // Multi-GPU variant (shard.cu, "cooperative ray trace"): this rank traces mask rows [bounds[self], bounds[self+1]) — a
 // partition of the WHOLE image balanced on last frame's measured cost, read from device memory, so the host never needs
-// to know it.  The grid is a fixed set of resident warps that pull 8x4-pixel jobs (row-major: neighbouring warps work on
-// neighbouring blocks) from an atomic counter until the share is done: the same launch covers any share size without
-// empty CTAs.  Mask words go to this rank's own mask image; k_rt_push (shard.cu) then copies the share to every peer
-// with wide stores.  Each job adds its duration to its mask row's cost, the input of the next frame's partition.
+// to know it: the launch grid covers the largest share the partition kernel may hand out (hr_rt_share_cap) and CTAs past
+// the end of the share exit at once (a persistent job-loop variant was measured 14 % slower than letting the hardware
+// schedule 2-warp CTAs).  Mask words go to this rank's own mask image; k_rt_push (shard.cu) then copies the share to
+// every peer with wide stores.  Each warp adds its duration to its mask row's cost, the input of the next partition.
 template <int MODE>
 __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
                                                                 const uint8_t* __restrict__ sr, RtShare sh)
 {
-    const int MW    = (g.W + 7) >> 3;
-    const int lane  = threadIdx.x & 31;
+    const long long t0 = clock64();
+    const int MW   = (g.W + 7) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
-    const int n_jobs = (mrow1 - mrow0) * MW;
-    int job = 0;
-    if (lane == 0) job = (int)atomicAdd(sh.counter, 1u);
-    job = __shfl_sync(0xFFFFFFFFu, job, 0);
-    while (job < n_jobs)
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
+    if (mx >= MW || my >= mrow1) return; // whole warp exits together
+    const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+    const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
+    if (lane == 0)
     {
-        int next = 0;
-        if (lane == 0) next = (int)atomicAdd(sh.counter, 1u); // fetched early: its latency hides behind this job's traversal
-        const long long t0 = clock64();
-        const int my = mrow0 + job / MW, mx = job - (job / MW) * MW;
-        const int x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-        const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
-        const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
-        if (lane == 0)
-        {
-            sh.mask_local[(size_t)my * MW + mx] = word;
-            atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
-        }
-        job = __shfl_sync(0xFFFFFFFFu, next, 0);
+        sh.mask_local[(size_t)my * MW + mx] = word;
+        atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
     }
 }
 
@@ -370,32 +361,23 @@ void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameCo
     k_ray_trace_mask<1><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, mask, mrow0, mrow1);
 }
 
-// fixed grid of resident CTAs (occupancy x SM count); the job loop covers whatever share the device-side partition assigns
-template <int MODE>
-static dim3 shared_grid()
+// the grid covers the largest share hr_rt_wait_partition may hand to one rank
+static inline dim3 shared_grid(int W, int H, int world)
 {
-    static int ctas = 0;
-    if (!ctas)
-    {
-        int dev = 0, sms = 148, per_sm = 8;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_trace_mask_shared<MODE>, RT_CTA_WARPS * 32, 0);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    return dim3(ctas, 1, 1);
+    const int MH = (H + 3) / 4;
+    return dim3(((W + 7) / 8 + RT_CTA_WARPS - 1) / RT_CTA_WARPS, hr_rt_share_cap(MH, world), 1);
 }
 
 void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                                      const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<0><<<shared_grid<0>(), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
+    k_ray_trace_mask_shared<0><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, sh);
 }
 
 void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
                                 const uint8_t* sr, const RtShare& sh, cudaStream_t st)
 {
-    k_ray_trace_mask_shared<1><<<shared_grid<1>(), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
+    k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
 }
 
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st)
