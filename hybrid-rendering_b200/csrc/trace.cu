@@ -95,8 +95,9 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBu
     const int MW   = (g.W + 7) >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
-    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
-    if (mx >= MW || my >= mrow1) return; // whole warp exits together
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp;
+    if (mx >= MW || mrow0 + (int)blockIdx.y >= mrow1) return; // whole warp exits together
+    const int      my = __ldg(sh.order + mrow0 + blockIdx.y); // the share's rows, most expensive first
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
     const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
     const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
