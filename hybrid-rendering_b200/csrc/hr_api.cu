@@ -490,7 +490,6 @@ static int pass_alloc_rt_share(hr_pass* p)
     if ((rc = pass_alloc(p, p->mask_pp[1], mw * mh)) != HR_OK) return rc;
     if ((rc = pass_alloc(p, p->rt_cost_all, 2 * mh)) != HR_OK) return rc;
     if ((rc = pass_alloc(p, p->rt_cost_acc, mh)) != HR_OK) return rc;
-    if ((rc = pass_alloc(p, p->rt_order, mh)) != HR_OK) return rc;
     if ((rc = pass_alloc(p, p->rt_bounds, (size_t)HR_MAX_RANKS + 4)) != HR_OK) return rc; // + job counter, push-blocks-done counter
     return HR_OK;
 }

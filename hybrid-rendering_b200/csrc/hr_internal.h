@@ -206,7 +206,6 @@ struct hr_pass {
     int*        sync_ticks = nullptr;                // [2][HR_MAX_RANKS] ticks written by the peers into THIS rank's memory: [0] history, [1] ray trace
     uint32_t*   mask_pp[2] = { nullptr, nullptr };   // ray mask by frame parity (mask_pp[0] == mask); peers push their rows into both copies' owner
     uint32_t*   rt_cost_all = nullptr;               // [2][MH] per-mask-row trace cost of the frame (all ranks' rows, pushed by their owners)
-    int*        rt_order = nullptr;                  // [MH] each share's mask rows sorted by last frame's cost (heavy first)
     uint32_t*   rt_cost_acc = nullptr;               // [MH] this rank's accumulation scratch (atomicAdd per warp), drained by the push kernel
     int*        rt_bounds = nullptr;                 // [world+1] mask-row partition of the NEXT frame's ray trace (device side, cost balanced); [HR_MAX_RANKS+1] = job counter, [+2] = push blocks done
     int*        peer_ticks[HR_MAX_RANKS] = {};       // the peers' tick arrays (we write slot [self])
@@ -251,7 +250,6 @@ struct RtShare {
     uint32_t*     mask_local; // this rank's mask image of this frame's parity (k_rt_push copies the share to the peers)
     const int*    bounds;     // [world+1] mask-row partition (device)
     uint32_t*     cost_acc;   // [MH] local cost accumulation
-    const int*    order;      // [MH] the shares' rows, most expensive first (position bounds[r] + i = i-th row of rank r's share)
     int           world, self;
 };
 // most mask rows one rank may be handed: twice the uniform share (+4); the whole image for world <= 2

@@ -197,98 +197,70 @@ __global__ void __launch_bounds__(256) k_rt_push(MaskPtrs masks, CostPtrs costs,
     }
 }
 
-// One CTA.  Warp 0: lanes spin until every peer's ray-trace tick reached `rt_tick` and its history tick `hist_tick` (2 s
-// time-out), then compute next frame's partition: bounds[k] = first mask row whose cost prefix reaches k/world of the
-// total (shares clamped to [1, cap] rows so the fixed launch grid covers them).  All threads: order[] = each share's rows
-// sorted by cost, most expensive first — the ray-trace grid walks its share in that order so the heavy rows are not what
-// the kernel is still waiting for at its tail.  Every rank computes the same tables from the same (complete) cost table.
-__global__ void __launch_bounds__(1024) k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, int hist_tick, int* err, const uint32_t* __restrict__ cost,
-                                                            int MH, int world, int self, int cap, int* __restrict__ bounds, int* __restrict__ order)
+// One warp.  Lanes spin until every peer's ray-trace tick reached `rt_tick` and its history tick `hist_tick` (2 s time-out),
+// then the warp computes next frame's partition: bounds[k] = first mask row whose cost prefix reaches k/world of the total.
+// Every rank computes the same table from the same (complete) cost table.
+__global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, int hist_tick, int* err, const uint32_t* __restrict__ cost, int MH, int world, int self,
+                                    int cap, int* __restrict__ bounds)
 {
     __shared__ unsigned long long s_prefix[1024 + 1];
-    __shared__ uint32_t           s_cost[1024];
-    __shared__ int                s_bounds[HR_MAX_RANKS + 1];
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 32)
+    const int lane = threadIdx.x;
+    if (lane < world && lane != self)
     {
-        if (lane < world && lane != self)
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;)
         {
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            for (;;)
-            {
-                int v, h = hist_tick;
-                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ticks + HR_MAX_RANKS + lane) : "memory");
-                if (hist_tick > 0) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(h) : "l"(ticks + lane) : "memory");
-                if (v >= rt_tick && h >= hist_tick) break;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-                if (t1 - t0 > 2000000000ull) { *err = 1 + lane; break; }
-                __nanosleep(100);
-            }
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-    const bool small = MH <= 1024;
-    if (small && tid < MH) s_cost[tid] = __ldcg(cost + tid);
-    __syncthreads();
-    if (tid < 32)
-    {
-        const int          chunk = (MH + 31) / 32;
-        unsigned long long local = 0;
-        if (small)
-            for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) local += s_cost[i];
-        unsigned long long incl = local;
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned long long       run   = incl - local;
-        if (small)
-        {
-            for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) { run += s_cost[i]; s_prefix[i + 1] = run; }
-            if (lane == 0) s_prefix[0] = 0;
-        }
-        __syncwarp();
-        if (lane == 0)
-        {
-            int prev    = 0;
-            s_bounds[0] = 0;
-            for (int k = 1; k < world; k++)
-            {
-                int b;
-                if (total == 0 || !small) b = (int)(((long long)MH * k) / world); // no cost information: uniform split
-                else
-                {
-                    const unsigned long long target = (total * (unsigned long long)k) / (unsigned long long)world;
-                    int lo = prev, hi = MH; // first row index b with prefix[b] >= target
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] >= target) hi = mid; else lo = mid + 1; }
-                    b = lo;
-                }
-                b = max(b, prev + 1);               // at least one row per rank
-                b = min(b, prev + cap);             // the fixed launch grid covers at most `cap` rows
-                b = min(b, MH - (world - k));       // leave a row for each remaining rank
-                b = max(b, MH - (world - k) * cap); // the remaining ranks must be able to cover the rest
-                s_bounds[k] = b;
-                prev        = b;
-            }
-            s_bounds[world] = MH;
-            for (int k = 0; k <= world; k++) bounds[k] = s_bounds[k];
+            int v, h = hist_tick;
+            asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ticks + HR_MAX_RANKS + lane) : "memory");
+            if (hist_tick > 0) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(h) : "l"(ticks + lane) : "memory");
+            if (v >= rt_tick && h >= hist_tick) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) { *err = 1 + lane; break; }
+            __nanosleep(100);
         }
     }
-    __syncthreads();
-    for (int i = tid; i < MH; i += blockDim.x)
+    __syncwarp();
+    const int          chunk = (MH + 31) / 32;
+    unsigned long long local = 0;
+    for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) local += __ldcg(cost + i);
+    unsigned long long incl = local;
+    for (int o = 1; o < 32; o <<= 1)
     {
-        if (!small) { order[i] = i; continue; }
-        int k = 0;
-        while (k < world - 1 && i >= s_bounds[k + 1]) k++;
-        const int      b0 = s_bounds[k], b1 = s_bounds[k + 1];
-        const uint32_t c  = s_cost[i];
-        int            rank = 0;
-        for (int j = b0; j < b1; j++) rank += (s_cost[j] > c || (s_cost[j] == c && j < i)) ? 1 : 0;
-        order[b0 + rank] = i;
+        const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned long long       run   = incl - local;
+    if (MH <= 1024)
+    {
+        for (int i = lane * chunk; i < min((lane + 1) * chunk, MH); i++) { run += __ldcg(cost + i); s_prefix[i + 1] = run; }
+        if (lane == 0) s_prefix[0] = 0;
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        int prev  = 0;
+        bounds[0] = 0;
+        for (int k = 1; k < world; k++)
+        {
+            int b;
+            if (total == 0 || MH > 1024) b = (int)(((long long)MH * k) / world); // no cost information: uniform split
+            else
+            {
+                const unsigned long long target = (total * (unsigned long long)k) / (unsigned long long)world;
+                int lo = prev, hi = MH; // first row index b with prefix[b] >= target
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] >= target) hi = mid; else lo = mid + 1; }
+                b = lo;
+            }
+            b = max(b, prev + 1);               // at least one row per rank
+            b = min(b, prev + cap);             // the fixed launch grid covers at most `cap` rows
+            b = min(b, MH - (world - k));       // leave a row for each remaining rank
+            b = max(b, MH - (world - k) * cap); // the remaining ranks must be able to cover the rest
+            bounds[k] = b;
+            prev      = b;
+        }
+        bounds[world] = MH;
     }
 }
 
@@ -454,9 +426,6 @@ static int rt_init_bounds(hr_pass* p)
     int       h[HR_MAX_RANKS + 1];
     for (int k = 0; k <= world; k++) h[k] = (int)(((long long)MH * k) / world);
     HR_CUDA(ctx, cudaMemcpy(p->rt_bounds, h, sizeof(int) * (world + 1), cudaMemcpyHostToDevice));
-    std::vector<int> ident(MH);
-    for (int i = 0; i < MH; i++) ident[i] = i;
-    HR_CUDA(ctx, cudaMemcpy(p->rt_order, ident.data(), sizeof(int) * MH, cudaMemcpyHostToDevice));
     return HR_OK;
 }
 
@@ -476,7 +445,6 @@ bool hr_rt_share(hr_pass* p, int parity, RtShare* out)
     sh.mask_local = static_cast<uint32_t*>(p->hist_local[4 + parity]);
     sh.bounds     = p->rt_bounds;
     sh.cost_acc   = p->rt_cost_acc;
-    sh.order      = p->rt_order;
     sh.world      = ctx->world;
     sh.self       = ctx->rank;
     *out          = sh;
@@ -515,8 +483,8 @@ int hr_rt_wait_partition(hr_pass* p, int parity, int rt_tick, int hist_tick, cud
         }
         HR_CUDA(ctx, cudaHostGetDevicePointer((void**)&d_err, p->sync_error, 0));
     }
-    k_rt_wait_partition<<<1, 1024, 0, st>>>(p->sync_ticks, rt_tick, hist_tick, d_err, p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, ctx->rank,
-                                           hr_rt_share_cap(MH, ctx->world), p->rt_bounds, p->rt_order);
+    k_rt_wait_partition<<<1, 32, 0, st>>>(p->sync_ticks, rt_tick, hist_tick, d_err, p->rt_cost_all + (size_t)parity * MH, MH, ctx->world, ctx->rank,
+                                         hr_rt_share_cap(MH, ctx->world), p->rt_bounds);
     ctx->launches++;
     return HR_OK;
 }

@@ -84,8 +84,9 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelD
 // Multi-GPU variant (shard.cu, "cooperative ray trace"): this rank traces mask rows [bounds[self], bounds[self+1]) — a
 // partition of the WHOLE image balanced on last frame's measured cost, read from device memory, so the host never needs
 // to know it: the launch grid covers the largest share the partition kernel may hand out (hr_rt_share_cap) and CTAs past
-// the end of the share exit at once (a persistent job-loop variant was measured 14 % slower than letting the hardware
-// schedule 2-warp CTAs).  Mask words go to this rank's own mask image; k_rt_push (shard.cu) then copies the share to
+// the end of the share exit at once (measured alternatives, both ~14 % slower on one GPU: a persistent job loop over an
+// atomic counter, and walking the share's rows most-expensive-first — the row-major walk keeps neighbouring rows, i.e.
+// the same BVH nodes and G-buffer sectors, in flight together).  Mask words go to this rank's own mask image; k_rt_push (shard.cu) then copies the share to
 // every peer with wide stores.  Each warp adds its duration to its mask row's cost, the input of the next partition.
 template <int MODE>
 __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
@@ -95,9 +96,8 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBu
     const int MW   = (g.W + 7) >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mrow0 = __ldg(sh.bounds + sh.self), mrow1 = __ldg(sh.bounds + sh.self + 1);
-    const int mx = blockIdx.x * RT_CTA_WARPS + warp;
-    if (mx >= MW || mrow0 + (int)blockIdx.y >= mrow1) return; // whole warp exits together
-    const int      my = __ldg(sh.order + mrow0 + blockIdx.y); // the share's rows, most expensive first
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
+    if (mx >= MW || my >= mrow1) return; // whole warp exits together
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
     const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
     const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
