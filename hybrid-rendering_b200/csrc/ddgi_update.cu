@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(256) k_sample_probe_grid(GBufLevelDev g, Frame
     const float  u = ((float)x + 0.5f) / (float)g.W, v = ((float)y + 0.5f) / (float)g.H;
     const float* M = fc.view_proj_inverse;
     const float  sx = u * 2.0f - 1.0f, sy = v * 2.0f - 1.0f;
-    const float  ww = M[3] * sx + M[7] * sy + M[11] * depth + M[15];
-    const float3 P  = f3((M[0] * sx + M[4] * sy + M[8] * depth + M[12]) / ww, (M[1] * sx + M[5] * sy + M[9] * depth + M[13]) / ww, (M[2] * sx + M[6] * sy + M[10] * depth + M[14]) / ww);
+    const float  iw = __fdividef(1.0f, M[3] * sx + M[7] * sy + M[11] * depth + M[15]);
+    const float3 P  = f3((M[0] * sx + M[4] * sy + M[8] * depth + M[12]) * iw, (M[1] * sx + M[5] * sy + M[9] * depth + M[13]) * iw, (M[2] * sx + M[6] * sy + M[10] * depth + M[14]) * iw);
     const float2 e  = h2f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb2 + idx)));
     float3       N  = f3(e.x, e.y, 1.0f - fabsf(e.x) - fabsf(e.y));
     if (N.z < 0.0f)
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_sample_probe_grid(GBufLevelDev g, Frame
     }
     N = normalize(N);
     const float3 Wo = normalize(f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]) - P);
-    const float3 ir = sample_irradiance(d, at, P, N, Wo) * gi_intensity;
+    const float3 ir = sample_irradiance<8>(d, at, P, N, Wo) * gi_intensity;
     out[idx] = pack_h4(ir.x, ir.y, ir.z, 1.0f);
 }
 

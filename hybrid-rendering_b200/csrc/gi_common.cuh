@@ -111,55 +111,99 @@ __device__ __forceinline__ float3 sample_irr_atlas(const uint2* __restrict__ t, 
     return f3(mix2(a0.x, b0.x, c0.x, d0.x), mix2(a0.y, b0.y, c0.y, d0.y), mix2(a1.x, b1.x, c1.x, d1.x));
 }
 
-// sample_irradiance, gi_common.glsl:188-320 (LINEAR_BLENDING undefined => sqrt-space blend)
+// Per-atlas constants of texture_coord_from_direction hoisted out of the 8-probe loop (reciprocals instead of the
+// reference's divisions, float reciprocal for the probe's column / row: exact for probe indices below 2^22).
+struct AtlasGeom { float inv_w, inv_h, side, pb, inv_ppr; int ppr, W, H; };
+__device__ __forceinline__ AtlasGeom atlas_geom(int tex_w, int tex_h, int side)
+{
+    AtlasGeom a;
+    a.W = tex_w; a.H = tex_h;
+    a.inv_w = __fdividef(1.0f, (float)tex_w);
+    a.inv_h = __fdividef(1.0f, (float)tex_h);
+    a.side  = (float)side;
+    a.pb    = (float)side + 2.0f;
+    a.ppr   = (tex_w - 2) / (side + 2);
+    a.inv_ppr = __fdividef(1.0f, (float)a.ppr);
+    return a;
+}
+__device__ __forceinline__ float3 normalize_fast(float3 a) { return a * rsqrtf(dot(a, a)); }
+__device__ __forceinline__ float2 oct_encode_fast(float3 v)
+{
+    const float inv = __fdividef(1.0f, fabsf(v.x) + fabsf(v.y) + fabsf(v.z));
+    float2      r   = make_float2(v.x * inv, v.y * inv);
+    if (v.z < 0.0f) r = make_float2((1.0f - fabsf(r.y)) * sign_not_zero(r.x), (1.0f - fabsf(r.x)) * sign_not_zero(r.y));
+    return r;
+}
+// dir must be normalised (oct_encode is scale invariant, so the reference's normalize(dir) is a no-op up to rounding)
+__device__ __forceinline__ float2 texture_coord_fast(float3 dir, int probe_index, const AtlasGeom& a)
+{
+    const float2 o   = oct_encode_fast(dir);
+    const int    row = (int)(((float)probe_index + 0.5f) * a.inv_ppr), col = probe_index - row * a.ppr;
+    const float  tlx = (float)col * a.pb + 2.0f, tly = (float)row * a.pb + 2.0f;
+    return make_float2((tlx + (o.x + 1.0f) * 0.5f * a.side) * a.inv_w, (tly + (o.y + 1.0f) * 0.5f * a.side) * a.inv_h);
+}
+
+// sample_irradiance, gi_common.glsl:188-320 (LINEAR_BLENDING undefined => sqrt-space blend).  A tolerance-checked colour
+// stage: reciprocal square roots / approximate reciprocals replace the IEEE sqrt + divide sequences (the IEEE forms made
+// K21 instruction-bound at 1.19 ms per 4K frame), the per-atlas constants are hoisted, and the probe loop is unrolled UNR
+// times so the 8 atlas fetches of independent probes are in flight together.
+template <int UNR = 1>
 __device__ inline float3 sample_irradiance(const hr_ddgi_uniforms& d, const AtlasDev& at, float3 P, float3 N, float3 Wo)
 {
     const float3 start = f3(d.grid_start_position[0], d.grid_start_position[1], d.grid_start_position[2]);
     const float3 step  = f3(d.grid_step[0], d.grid_step[1], d.grid_step[2]);
+    const float3 istep = f3(__fdividef(1.0f, step.x), __fdividef(1.0f, step.y), __fdividef(1.0f, step.z));
     int base[3];
-    base[0] = min(max((int)((P.x - start.x) / step.x), 0), d.probe_counts[0] - 1);
+    base[0] = min(max((int)((P.x - start.x) / step.x), 0), d.probe_counts[0] - 1); // exact divisions: they pick the probe cell
     base[1] = min(max((int)((P.y - start.y) / step.y), 0), d.probe_counts[1] - 1);
     base[2] = min(max((int)((P.z - start.z) / step.z), 0), d.probe_counts[2] - 1);
     const float3 base_pos = f3(step.x * (float)base[0] + start.x, step.y * (float)base[1] + start.y, step.z * (float)base[2] + start.z);
-    const float3 alpha    = f3(__saturatef((P.x - base_pos.x) / step.x), __saturatef((P.y - base_pos.y) / step.y), __saturatef((P.z - base_pos.z) / step.z));
+    const float3 alpha    = f3(__saturatef((P.x - base_pos.x) * istep.x), __saturatef((P.y - base_pos.y) * istep.y), __saturatef((P.z - base_pos.z) * istep.z));
+    const AtlasGeom gd = atlas_geom(d.depth_texture_width, d.depth_texture_height, d.depth_probe_side_length);
+    const AtlasGeom gi_ = atlas_geom(d.irradiance_texture_width, d.irradiance_texture_height, d.irradiance_probe_side_length);
+    const float3 bias_v = (N + Wo * 3.0f) * d.normal_bias;
+    const float3 Nn     = normalize_fast(N);
     float3 sum_irr = f3(0, 0, 0);
     float  sum_w   = 0.0f;
-#pragma unroll 1
+#pragma unroll UNR
     for (int i = 0; i < 8; ++i)
     {
         const int off0 = i & 1, off1 = (i >> 1) & 1, off2 = (i >> 2) & 1;
         const int g0 = min(base[0] + off0, d.probe_counts[0] - 1), g1 = min(base[1] + off1, d.probe_counts[1] - 1), g2 = min(base[2] + off2, d.probe_counts[2] - 1);
         const int p  = g0 + g1 * d.probe_counts[0] + g2 * d.probe_counts[0] * d.probe_counts[1];
         const float3 probe_pos      = f3(step.x * (float)g0 + start.x, step.y * (float)g1 + start.y, step.z * (float)g2 + start.z);
-        const float3 probe_to_point = (P - probe_pos) + (N + Wo * 3.0f) * d.normal_bias;
-        const float3 dir            = normalize(probe_to_point * -1.0f);
+        const float3 probe_to_point = (P - probe_pos) + bias_v;
+        const float  ptp2           = dot(probe_to_point, probe_to_point);
+        const float  inv_len        = rsqrtf(ptp2);
         const float3 tri            = f3(off0 ? alpha.x : 1.0f - alpha.x, off1 ? alpha.y : 1.0f - alpha.y, off2 ? alpha.z : 1.0f - alpha.z);
         float weight = 1.0f;
         {
-            const float3 tdir = normalize(probe_pos - P);
+            const float3 tdir = normalize_fast(probe_pos - P);
             const float  t    = fmaxf(0.0001f, (dot(tdir, N) + 1.0f) * 0.5f);
             weight *= t * t + 0.2f;
         }
         if (d.visibility_test == 1)
         {
-            const float2 tc   = texture_coord_from_direction(dir * -1.0f, p, d.depth_texture_width, d.depth_texture_height, d.depth_probe_side_length);
-            const float  dist = length(probe_to_point);
-            const float2 t2   = sample_depth_atlas(at.depth, d.depth_texture_width, d.depth_texture_height, tc);
+            // texture_coord_from_direction(-dir) with dir = normalize(-probe_to_point)
+            const float2 tc   = texture_coord_fast(probe_to_point * inv_len, p, gd);
+            const float  dist = ptp2 * inv_len;
+            const float2 t2   = sample_depth_atlas(at.depth, gd.W, gd.H, tc);
             const float  mean = t2.x, variance = fabsf(t2.x * t2.x - t2.y);
             const float  dm   = fmaxf(dist - mean, 0.0f);
-            float        cheb = variance / (variance + dm * dm);
+            float        cheb = __fdividef(variance, variance + dm * dm);
             cheb              = fmaxf(cheb * cheb * cheb, 0.0f);
             weight *= (dist <= mean) ? 1.0f : cheb;
         }
         weight = fmaxf(0.000001f, weight);
-        const float2 tc = texture_coord_from_direction(N, p, d.irradiance_texture_width, d.irradiance_texture_height, d.irradiance_probe_side_length);
-        const float3 pi = sample_irr_atlas(at.irr, d.irradiance_texture_width, d.irradiance_texture_height, tc);
+        const float2 tc = texture_coord_fast(Nn, p, gi_);
+        const float3 pi = sample_irr_atlas(at.irr, gi_.W, gi_.H, tc);
         if (weight < 0.2f) weight *= weight * weight * (1.0f / (0.2f * 0.2f));
         weight *= tri.x * tri.y * tri.z;
-        sum_irr = sum_irr + f3(sqrtf(pi.x), sqrtf(pi.y), sqrtf(pi.z)) * weight;
+        sum_irr = sum_irr + f3(pi.x * rsqrtf(fmaxf(pi.x, 1e-30f)), pi.y * rsqrtf(fmaxf(pi.y, 1e-30f)), pi.z * rsqrtf(fmaxf(pi.z, 1e-30f))) * weight;
         sum_w += weight;
     }
-    float3 net = f3(sum_irr.x / sum_w, sum_irr.y / sum_w, sum_irr.z / sum_w);
+    const float inv_w = __fdividef(1.0f, sum_w);
+    float3      net   = sum_irr * inv_w;
     if (!(net.x == net.x)) net.x = 0.5f;
     if (!(net.y == net.y)) net.y = 0.5f;
     if (!(net.z == net.z)) net.z = 0.5f;

@@ -229,12 +229,13 @@ __device__ __forceinline__ V3 importance_sample_ggx(float ex, float ey, V3 N, fl
 struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int row0, row1; };
 
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
-__global__ void __launch_bounds__(256) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
+// 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
+__global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
                                                                 ReflTraceParams P, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk,
                                                                 uint2* __restrict__ out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7), y = P.row0 + blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
+    const int x = blockIdx.x * 16 + warp * 8 + (lane & 7), y = P.row0 + blockIdx.y * 4 + (lane >> 3);
     if (x >= g.W || y >= g.H || y >= P.row1) return;
     const size_t idx   = (size_t)y * g.W + x;
     const float  depth = __ldg(g.depth + idx);
@@ -320,6 +321,6 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    dim3         grid((g.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_reflections_ray_trace<<<grid, 256, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    dim3         grid((g.W + 15) / 16, (row1 - row0 + 3) / 4);
+    k_reflections_ray_trace<<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
 }
