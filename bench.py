@@ -179,6 +179,8 @@ def main():
         ctx.lib.hr_debug_set(2, int(os.environ["HR_TRACE_IMPL"]))
     if os.environ.get("HR_FORCE_SHARED_RT"):  # single GPU: run the cooperative (multi-GPU) ray-trace kernel, for overhead A/B
         ctx.lib.hr_debug_set(4, int(os.environ["HR_FORCE_SHARED_RT"]))
+    if os.environ.get("HR_ATROUS_ROWS"):  # 1 (default) row-interleaved tiles for a-trous steps 4 and 8, 0 dense tiles
+        ctx.lib.hr_debug_set(5, int(os.environ["HR_ATROUS_ROWS"]))
     if os.environ.get("HR_BVH_QUALITY"):  # 0 Karras radix tree, 1 PLOC (default); must be set before the scene build
         ctx.lib.hr_debug_set(3, int(os.environ["HR_BVH_QUALITY"]))
     ctx.set_bluenoise(*pyhr.blue_noise())

@@ -14,6 +14,7 @@ extern int         g_hr_atrous_impl;
 extern int         g_hr_trace_impl;
 extern int         g_hr_bvh_quality;
 extern int         g_hr_force_shared_rt;
+extern int         g_hr_atrous_rows;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -147,6 +148,7 @@ int hr_debug_set(int key, int value)
     if (key == 2) { g_hr_trace_impl = value; return HR_OK; }
     if (key == 3) { g_hr_bvh_quality = value; return HR_OK; }
     if (key == 4) { g_hr_force_shared_rt = value; return HR_OK; }
+    if (key == 5) { g_hr_atrous_rows = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 

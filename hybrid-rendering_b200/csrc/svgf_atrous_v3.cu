@@ -172,6 +172,178 @@ __global__ void __launch_bounds__(256) k_atrous_v3(GBufLevelDev g, const uint32_
     }
 }
 
+// ---- row-interleaved tiles for the wide steps ---------------------------------------------------------------------------
+// With the dense 64x16 tile a step-8 iteration stages (64+16) x (16+16) texels for 1024 outputs (2.5x; 85 us vs 55 us for
+// step 1).  The taps of row y only touch rows y and y +- STEP, so a CTA that filters the 16 rows {Y0 + phase + STEP*j}
+// (one residue class of the row index) needs just 18 staged rows: (64+16) x 18 = 1.4x.  Rows stay contiguous in x, so
+// global accesses are as coalesced as before.  compute_variance_center works at unit pixel spacing whatever the step:
+// the variance of the rows y-1 / y+1 (centre columns only) is staged into two extra single-plane buffers.
+template <int STEP>
+__global__ void __launch_bounds__(256) k_atrous_v3s(GBufLevelDev g, const uint32_t* __restrict__ in, const uint8_t* __restrict__ tile_flags, V3Params P,
+                                                     uint32_t* __restrict__ out)
+{
+    extern __shared__ float smem_f[];
+    constexpr int PADL = STEP;                 // STEP is even here
+    constexpr int RW   = TW3 + 2 * STEP;       // even
+    constexpr int RH   = TH3 + 2;
+    constexpr int PL   = RW * RH;
+    constexpr int TROWS = (TH3 * STEP) / 8;    // 8-row tile rows spanned by the CTA's 16*STEP image rows
+    float* s_nx = smem_f;
+    float* s_ny = s_nx + PL;
+    float* s_nz = s_ny + PL;
+    float* s_zs = s_nz + PL;
+    float* s_vi = s_zs + PL;
+    float* s_va = s_vi + PL;
+    float* s_vadj = s_va + PL;                 // [2][TH3][RW]: variance of rows y-1 (0) and y+1 (1)
+    __shared__ uint8_t s_tfl[TROWS][8];
+    __shared__ int     s_any;
+
+    const int W = P.W, H = P.H;
+    const int x0 = blockIdx.x * TW3;
+    const int blk = blockIdx.y / STEP, phase = blockIdx.y - blk * STEP;
+    const int Y0 = P.row0 + blk * (TH3 * STEP); // multiple of 8 (row0 is)
+    const int TWt = (W + 7) >> 3, THt = (H + 7) >> 3;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (threadIdx.x < TROWS * 8)
+    {
+        const int  tx = (x0 >> 3) + (threadIdx.x & 7), ty = (Y0 >> 3) + (threadIdx.x >> 3);
+        const bool f  = tx < TWt && ty < THt && tile_flags[(size_t)ty * TWt + tx] != 0;
+        s_tfl[threadIdx.x >> 3][threadIdx.x & 7] = f ? 1 : 0;
+        if (f) s_any = 1;
+    }
+    __syncthreads();
+
+    if (s_any)
+    {
+        const uint32_t* gb2w = reinterpret_cast<const uint32_t*>(g.gb2);
+        const uint32_t* gb3w = reinterpret_cast<const uint32_t*>(g.gb3);
+        for (int i = threadIdx.x; i < PL; i += 256)
+        {
+            const int rx = i % RW, ry = i / RW;
+            const int px = x0 - PADL + rx, py = Y0 + phase + STEP * (ry - 1);
+            float nx = 0.0f, ny = 0.0f, nz = 0.0f, zs = 0.0f, vi = 0.0f, va = 0.0f;
+            if (px >= 0 && py >= 0 && px < W && py < H)
+            {
+                const size_t pi = (size_t)py * W + px;
+                const float2 e  = h2_to_f2(__ldg(gb2w + 2 * pi));
+                const float2 zz = h2_to_f2(__ldg(gb3w + 2 * pi + 1));
+                const float2 iv = h2_to_f2(__ldg(in + pi));
+                const float3 n  = octohedral_to_direction(e.x, e.y);
+                nx = n.x; ny = n.y; nz = n.z;
+                zs = zz.y * P.c_sigma;
+                vi = iv.x; va = iv.y;
+            }
+            s_nx[i] = nx; s_ny[i] = ny; s_nz[i] = nz; s_zs[i] = zs; s_vi[i] = vi; s_va[i] = va;
+        }
+        // variance of the rows above / below each filtered row, columns x0-1 .. x0+TW3 (region columns PADL-1 .. PADL+TW3)
+        constexpr int VC = TW3 + 2;
+        for (int i = threadIdx.x; i < 2 * TH3 * VC; i += 256)
+        {
+            const int a = i / (TH3 * VC), r = i - a * (TH3 * VC), j = r / VC, c = r - j * VC;
+            const int px = x0 - 1 + c, py = Y0 + phase + STEP * j + (a ? 1 : -1);
+            float     va = 0.0f;
+            if (px >= 0 && py >= 0 && px < W && py < H) va = h2_to_f2(__ldg(in + (size_t)py * W + px)).y;
+            s_vadj[(a * TH3 + j) * RW + PADL - 1 + c] = va;
+        }
+    }
+    __syncthreads();
+
+    const int lx2 = threadIdx.x & 31, lyb = threadIdx.x >> 5; // 32 pixel pairs x 8 rows, 2 rows per thread
+    const int x = x0 + 2 * lx2;
+    const float2 neg1 = make_float2(-1.0f, -1.0f), nl2e = make_float2(-1.44269504f, -1.44269504f);
+    const float  LK1 = -0.5849625007f, LK2 = -1.1699250014f; // log2(2/3), log2(4/9): kernel weights folded into the exponent
+#pragma unroll
+    for (int k = 0; k < TH3 / 8; k++)
+    {
+        const int ly = lyb + 8 * k, y = Y0 + phase + STEP * ly;
+        if (x >= W || y >= H || y >= P.row1) continue;
+        const size_t idx  = (size_t)y * W + x;
+        const bool   has1 = x + 1 < W;
+        if (!s_tfl[(phase + STEP * ly) >> 3][lx2 >> 2])
+        {
+            out[idx] = 0u;
+            if (has1) out[idx + 1] = 0u;
+            continue;
+        }
+        const int ci = (ly + 1) * RW + 2 * lx2 + PADL;
+        PairCell  c;
+        c.nx = ld_pair(s_nx, ci, true); c.ny = ld_pair(s_ny, ci, true); c.nz = ld_pair(s_nz, ci, true);
+        c.zs = ld_pair(s_zs, ci, true); c.vis = ld_pair(s_vi, ci, true); c.var = ld_pair(s_va, ci, true);
+        float2 vbar;
+        {
+            const float* up = s_vadj + (0 * TH3 + ly) * RW + 2 * lx2 + PADL;
+            const float* dn = s_vadj + (1 * TH3 + ly) * RW + 2 * lx2 + PADL;
+            const float  a0 = up[-1], d0 = up[2];
+            const float2 m0 = *reinterpret_cast<const float2*>(up);
+            const float  a1 = s_va[ci - 1], d1 = s_va[ci + 2];
+            const float  a2 = dn[-1], d2 = dn[2];
+            const float2 m2 = *reinterpret_cast<const float2*>(dn);
+            vbar.x = 0.25f * c.var.x + 0.125f * (a1 + c.var.y + m0.x + m2.x) + 0.0625f * (a0 + m0.y + a2 + m2.y);
+            vbar.y = 0.25f * c.var.y + 0.125f * (c.var.x + d1 + m0.y + m2.y) + 0.0625f * (m0.x + d0 + m2.x + d2);
+        }
+        const float2 cphi = make_float2(P.c_phi0 * rsqrtf(fmaxf(1e-10f + vbar.x, 1e-30f)), P.c_phi0 * rsqrtf(fmaxf(1e-10f + vbar.y, 1e-30f)));
+        float2 sumw = make_float2(1.0f, 1.0f), s0 = c.vis, s1 = c.var;
+#pragma unroll
+        for (int yy = -1; yy <= 1; yy++)
+#pragma unroll
+            for (int xx = -1; xx <= 1; xx++)
+            {
+                if (xx == 0 && yy == 0) continue;
+                const float lk = (xx != 0 && yy != 0) ? LK2 : LK1;
+                const int   si = ci + yy * RW + xx * STEP;
+                PairCell    s;
+                s.nx = ld_pair(s_nx, si, true); s.ny = ld_pair(s_ny, si, true); s.nz = ld_pair(s_nz, si, true);
+                s.zs = ld_pair(s_zs, si, true); s.vis = ld_pair(s_vi, si, true); s.var = ld_pair(s_va, si, true);
+                const float2 dz = __ffma2_rn(s.zs, neg1, c.zs);
+                float2       wZ;
+                wZ.x = fast_exp2(-fabsf(dz.x));
+                wZ.y = fast_exp2(-fabsf(dz.y));
+                const float2 dl = __ffma2_rn(s.vis, neg1, c.vis);
+                float2       ea;
+                ea.x = fmaf(fabsf(dl.x), cphi.x, lk);
+                ea.y = fmaf(fabsf(dl.y), cphi.y, lk);
+                ea   = __ffma2_rn(wZ, nl2e, ea);
+                float2 e;
+                e.x = fast_exp2(ea.x);
+                e.y = fast_exp2(ea.y);
+                float2 nd = __fmul2_rn(c.nz, s.nz);
+                nd        = __ffma2_rn(c.ny, s.ny, nd);
+                nd        = __ffma2_rn(c.nx, s.nx, nd);
+                nd.x      = fmaxf(nd.x, 0.0f);
+                nd.y      = fmaxf(nd.y, 0.0f);
+                float2 p = __fmul2_rn(nd, nd);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                p        = __fmul2_rn(p, p);
+                const float2 wk = __fmul2_rn(e, p);
+                sumw = __fadd2_rn(sumw, wk);
+                s0   = __ffma2_rn(wk, s.vis, s0);
+                s1   = __ffma2_rn(__fmul2_rn(wk, wk), s.var, s1);
+            }
+        const float2 inv = make_float2(fast_rcp(sumw.x), fast_rcp(sumw.y));
+        float2       o0 = __fmul2_rn(s0, inv), o1 = __fmul2_rn(__fmul2_rn(s1, inv), inv);
+        if (P.power != 0.0f) { o0.x = pow_pos(o0.x, P.power); o0.y = pow_pos(o0.y, P.power); }
+        const uint32_t r0 = c.zs.x < 0.0f ? f2_to_h2(c.vis.x, c.var.x) : f2_to_h2(o0.x, o1.x);
+        const uint32_t r1 = c.zs.y < 0.0f ? f2_to_h2(c.vis.y, c.var.y) : f2_to_h2(o0.y, o1.y);
+        if (has1) *reinterpret_cast<uint2*>(out + idx) = make_uint2(r0, r1);
+        else out[idx] = r0;
+    }
+}
+
+template <int STEP>
+void launch_v3s(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, const V3Params& P, uint32_t* out, cudaStream_t st)
+{
+    constexpr int RW = TW3 + 2 * STEP, RH = TH3 + 2;
+    const size_t  smem = ((size_t)RW * RH * 6 + (size_t)2 * TH3 * RW) * sizeof(float);
+    static bool   configured = false;
+    if (!configured) { cudaFuncSetAttribute(k_atrous_v3s<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    const int rows = P.row1 - P.row0, blocks = (rows + TH3 * STEP - 1) / (TH3 * STEP);
+    dim3      grid((P.W + TW3 - 1) / TW3, blocks * STEP);
+    k_atrous_v3s<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
+}
+
 template <int STEP>
 void launch_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, const V3Params& P, uint32_t* out, cudaStream_t st)
 {
@@ -187,6 +359,9 @@ void launch_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, con
 
 } // namespace
 
+// 1 (default): steps 4 and 8 use the row-interleaved tiles (k_atrous_v3s); 0: dense tiles for every step.  hr_debug_set key 5.
+int g_hr_atrous_rows = 1;
+
 // returns false when this variant does not support the configuration (caller falls back to the scalar kernels)
 bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tile_flags, int radius, int step, float phi_vis, float phi_n, float sigma_z,
                               float power, uint32_t* out, int row0, int row1, cudaStream_t st)
@@ -197,8 +372,8 @@ bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const u
     {
         case 1: launch_v3<1>(g, in, tile_flags, P, out, st); break;
         case 2: launch_v3<2>(g, in, tile_flags, P, out, st); break;
-        case 4: launch_v3<4>(g, in, tile_flags, P, out, st); break;
-        default: launch_v3<8>(g, in, tile_flags, P, out, st); break;
+        case 4: if (g_hr_atrous_rows) launch_v3s<4>(g, in, tile_flags, P, out, st); else launch_v3<4>(g, in, tile_flags, P, out, st); break;
+        default: if (g_hr_atrous_rows) launch_v3s<8>(g, in, tile_flags, P, out, st); else launch_v3<8>(g, in, tile_flags, P, out, st); break;
     }
     return true;
 }
