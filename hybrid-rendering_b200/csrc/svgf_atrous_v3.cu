@@ -33,6 +33,29 @@ __device__ __forceinline__ float2 ld_pair(const float* __restrict__ plane, int i
 
 struct PairCell { float2 nx, ny, nz, zs, vis, var; };
 
+// Stage the texel pair (px, px+1) of row py (px even) into the six planes at region index ri (even): decoded normal,
+// scaled linear depth, visibility, variance; zeros outside the image (zero normal = weight 0, the reference's `inside`).
+__device__ __forceinline__ void stage_pair(const GBufLevelDev& g, const uint32_t* __restrict__ in, float c_sigma, int px, int py, int W, int H, int ri, float* s_nx,
+                                           float* s_ny, float* s_nz, float* s_zs, float* s_vi, float* s_va)
+{
+    float2 nx = make_float2(0.0f, 0.0f), ny = nx, nz = nx, zs = nx, vi = nx, va = nx;
+    if (px >= 0 && py >= 0 && px < W && py < H)
+    {
+        const size_t pi = (size_t)py * W + px;
+        const uint4  a  = __ldg(reinterpret_cast<const uint4*>(g.gb2 + pi)); // two RGBA16F texels: .x / .z hold the oct normals
+        const uint4  b  = __ldg(reinterpret_cast<const uint4*>(g.gb3 + pi)); // .y / .w hold (mesh id, linear z)
+        const uint2  c  = __ldg(reinterpret_cast<const uint2*>(in + pi));    // two RG16F texels (visibility, variance)
+        const float2 e0 = h2_to_f2(a.x), e1 = h2_to_f2(a.z);
+        const float3 n0 = octohedral_to_direction(e0.x, e0.y), n1 = octohedral_to_direction(e1.x, e1.y);
+        const float2 i0 = h2_to_f2(c.x), i1 = h2_to_f2(c.y);
+        nx = make_float2(n0.x, n1.x); ny = make_float2(n0.y, n1.y); nz = make_float2(n0.z, n1.z);
+        zs = make_float2(h2_to_f2(b.y).y * c_sigma, h2_to_f2(b.w).y * c_sigma);
+        vi = make_float2(i0.x, i1.x); va = make_float2(i0.y, i1.y);
+    }
+    *reinterpret_cast<float2*>(s_nx + ri) = nx; *reinterpret_cast<float2*>(s_ny + ri) = ny; *reinterpret_cast<float2*>(s_nz + ri) = nz;
+    *reinterpret_cast<float2*>(s_zs + ri) = zs; *reinterpret_cast<float2*>(s_vi + ri) = vi; *reinterpret_cast<float2*>(s_va + ri) = va;
+}
+
 template <int STEP>
 __global__ void __launch_bounds__(256) k_atrous_v3(GBufLevelDev g, const uint32_t* __restrict__ in, const uint8_t* __restrict__ tile_flags, V3Params P,
                                                     uint32_t* __restrict__ out)
@@ -65,25 +88,13 @@ __global__ void __launch_bounds__(256) k_atrous_v3(GBufLevelDev g, const uint32_
 
     if (tf != 0)
     {
-        const uint32_t* gb2w = reinterpret_cast<const uint32_t*>(g.gb2);
-        const uint32_t* gb3w = reinterpret_cast<const uint32_t*>(g.gb3);
-        for (int i = threadIdx.x; i < PL; i += 256)
+        // staged two texels at a time: the region starts on an even column and W is even, so a pair is either inside or
+        // outside the image and its G-buffer words are one aligned 16-byte load each (half the load / store instructions)
+        for (int i = threadIdx.x; i < (RW / 2) * RH; i += 256)
         {
-            const int rx = i % RW, ry = i / RW;
+            const int rx = 2 * (i % (RW / 2)), ry = i / (RW / 2);
             const int px = x0 - PADL + rx, py = y0 - STEP + ry;
-            float nx = 0.0f, ny = 0.0f, nz = 0.0f, zs = 0.0f, vi = 0.0f, va = 0.0f;
-            if (px >= 0 && py >= 0 && px < W && py < H)
-            {
-                const size_t pi = (size_t)py * W + px;
-                const float2 e  = h2_to_f2(__ldg(gb2w + 2 * pi));
-                const float2 zz = h2_to_f2(__ldg(gb3w + 2 * pi + 1));
-                const float2 iv = h2_to_f2(__ldg(in + pi));
-                const float3 n  = octohedral_to_direction(e.x, e.y);
-                nx = n.x; ny = n.y; nz = n.z;
-                zs = zz.y * P.c_sigma;
-                vi = iv.x; va = iv.y;
-            }
-            s_nx[i] = nx; s_ny[i] = ny; s_nz[i] = nz; s_zs[i] = zs; s_vi[i] = vi; s_va[i] = va;
+            stage_pair(g, in, P.c_sigma, px, py, W, H, ry * RW + rx, s_nx, s_ny, s_nz, s_zs, s_vi, s_va);
         }
     }
     __syncthreads();
@@ -216,35 +227,25 @@ __global__ void __launch_bounds__(256) k_atrous_v3s(GBufLevelDev g, const uint32
 
     if (s_any)
     {
-        const uint32_t* gb2w = reinterpret_cast<const uint32_t*>(g.gb2);
-        const uint32_t* gb3w = reinterpret_cast<const uint32_t*>(g.gb3);
-        for (int i = threadIdx.x; i < PL; i += 256)
+        for (int i = threadIdx.x; i < (RW / 2) * RH; i += 256)
         {
-            const int rx = i % RW, ry = i / RW;
+            const int rx = 2 * (i % (RW / 2)), ry = i / (RW / 2);
             const int px = x0 - PADL + rx, py = Y0 + phase + STEP * (ry - 1);
-            float nx = 0.0f, ny = 0.0f, nz = 0.0f, zs = 0.0f, vi = 0.0f, va = 0.0f;
+            stage_pair(g, in, P.c_sigma, px, py, W, H, ry * RW + rx, s_nx, s_ny, s_nz, s_zs, s_vi, s_va);
+        }
+        // variance of the rows above / below each filtered row, texel pairs covering columns x0-2 .. x0+TW3+1
+        constexpr int VP = TW3 / 2 + 2;
+        for (int i = threadIdx.x; i < 2 * TH3 * VP; i += 256)
+        {
+            const int a = i / (TH3 * VP), r = i - a * (TH3 * VP), j = r / VP, c = 2 * (r - j * VP);
+            const int px = x0 - 2 + c, py = Y0 + phase + STEP * j + (a ? 1 : -1);
+            float2    va = make_float2(0.0f, 0.0f);
             if (px >= 0 && py >= 0 && px < W && py < H)
             {
-                const size_t pi = (size_t)py * W + px;
-                const float2 e  = h2_to_f2(__ldg(gb2w + 2 * pi));
-                const float2 zz = h2_to_f2(__ldg(gb3w + 2 * pi + 1));
-                const float2 iv = h2_to_f2(__ldg(in + pi));
-                const float3 n  = octohedral_to_direction(e.x, e.y);
-                nx = n.x; ny = n.y; nz = n.z;
-                zs = zz.y * P.c_sigma;
-                vi = iv.x; va = iv.y;
+                const uint2 w = __ldg(reinterpret_cast<const uint2*>(in + (size_t)py * W + px));
+                va = make_float2(h2_to_f2(w.x).y, h2_to_f2(w.y).y);
             }
-            s_nx[i] = nx; s_ny[i] = ny; s_nz[i] = nz; s_zs[i] = zs; s_vi[i] = vi; s_va[i] = va;
-        }
-        // variance of the rows above / below each filtered row, columns x0-1 .. x0+TW3 (region columns PADL-1 .. PADL+TW3)
-        constexpr int VC = TW3 + 2;
-        for (int i = threadIdx.x; i < 2 * TH3 * VC; i += 256)
-        {
-            const int a = i / (TH3 * VC), r = i - a * (TH3 * VC), j = r / VC, c = r - j * VC;
-            const int px = x0 - 1 + c, py = Y0 + phase + STEP * j + (a ? 1 : -1);
-            float     va = 0.0f;
-            if (px >= 0 && py >= 0 && px < W && py < H) va = h2_to_f2(__ldg(in + (size_t)py * W + px)).y;
-            s_vadj[(a * TH3 + j) * RW + PADL - 1 + c] = va;
+            *reinterpret_cast<float2*>(s_vadj + (a * TH3 + j) * RW + PADL - 2 + c) = va;
         }
     }
     __syncthreads();
