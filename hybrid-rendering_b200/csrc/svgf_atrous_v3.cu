@@ -360,7 +360,9 @@ void launch_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, con
 
 } // namespace
 
-// 1 (default): steps 4 and 8 use the row-interleaved tiles (k_atrous_v3s); 0: dense tiles for every step.  hr_debug_set key 5.
+// 1 (default): step 8 uses the row-interleaved tiles (k_atrous_v3s); 2: steps 4 and 8; 0: dense tiles for every step
+// (hr_debug_set key 5).  Measured at 4K: step 8 dense 70.1 us -> interleaved 63.3 us; step 4 dense 55.5 us -> interleaved
+// 60.6 us (the two extra variance rows per filtered row cost more than the 8 halo rows they save).
 int g_hr_atrous_rows = 1;
 
 // returns false when this variant does not support the configuration (caller falls back to the scalar kernels)
@@ -373,7 +375,7 @@ bool launch_shadows_atrous_v3(const GBufLevelDev& g, const uint32_t* in, const u
     {
         case 1: launch_v3<1>(g, in, tile_flags, P, out, st); break;
         case 2: launch_v3<2>(g, in, tile_flags, P, out, st); break;
-        case 4: if (g_hr_atrous_rows) launch_v3s<4>(g, in, tile_flags, P, out, st); else launch_v3<4>(g, in, tile_flags, P, out, st); break;
+        case 4: if (g_hr_atrous_rows == 2) launch_v3s<4>(g, in, tile_flags, P, out, st); else launch_v3<4>(g, in, tile_flags, P, out, st); break;
         default: if (g_hr_atrous_rows) launch_v3s<8>(g, in, tile_flags, P, out, st); else launch_v3<8>(g, in, tile_flags, P, out, st); break;
     }
     return true;

@@ -241,9 +241,9 @@ def test_atrous_tiled_equals_naive_and_oracle_1080p():
     osh = O.ShadowsOracle(W, H, 0)
     f, prev_g = None, O.zero_gbuf_mips(W, H)
     outs = {}
-    for impl in (1, 0, 3, 13):  # 13 = packed kernel (3) with dense tiles for every step (hr_debug_set(5, 0))
+    for impl in (1, 0, 3, 13, 23):  # 13 / 23 = packed kernel (3) with dense tiles for every step / interleaved rows for steps 4 and 8
         c.lib.hr_debug_set(1, impl % 10)
-        c.lib.hr_debug_set(5, 0 if impl == 13 else 1)
+        c.lib.hr_debug_set(5, {13: 0, 23: 2}.get(impl, 1))
         sh.reset_history()
         f = None
         c.gbuffer_upload(0, pyhr.GBufferHost(W, H))
@@ -262,7 +262,7 @@ def test_atrous_tiled_equals_naive_and_oracle_1080p():
     c.lib.hr_debug_set(5, 1)
     assert np.array_equal(sh.download(0), osh.mask)
     # row-interleaved tiles (steps 4, 8) only change which CTA filters which row: same arithmetic per pixel, same bits
-    assert np.array_equal(outs[3].view(np.uint32) if outs[3].dtype == np.float32 else outs[3], outs[13].view(np.uint32) if outs[13].dtype == np.float32 else outs[13])
+    assert np.array_equal(outs[3], outs[13]) and np.array_equal(outs[3], outs[23])
     ref = O.h2f(osh.final)
     assert rmse(outs[1], outs[0]) <= 2e-4 and np.abs(outs[1] - outs[0]).max() <= 2e-3
     assert rmse(outs[3], outs[0]) <= 2e-4 and np.abs(outs[3] - outs[0]).max() <= 2e-3  # packed fp32x2 kernel
