@@ -77,6 +77,10 @@ struct GBuffer {
     GBuffer(CommonResources* c) : common(c) { check(c->ctx, hr_gbuffer_create(c->ctx, (int)c->width, (int)c->height), "hr_gbuffer_create"); }
     // GBuffer::render (g_buffer.cpp:39-189) replaced by: upload the CPU-written G-buffer of this frame into slot[ping_pong]
     void render(const hr_gbuffer_desc* host_mip0, void* stream) { check(common->ctx, hr_gbuffer_upload(common->ctx, common->ping_pong ? 1 : 0, host_mip0, stream), "hr_gbuffer_upload"); }
+    // streaming host frames: stage_next() starts the PCIe copy of the NEXT frame on the library's upload
+    // stream, render_staged() swaps the staged surface into this frame's slot on `stream` (no copy) and builds the mips
+    void stage_next(const hr_gbuffer_desc* host_mip0) { check(common->ctx, hr_gbuffer_stage_upload(common->ctx, host_mip0), "hr_gbuffer_stage_upload"); }
+    void render_staged(void* stream) { check(common->ctx, hr_gbuffer_commit_staged(common->ctx, common->ping_pong ? 1 : 0, stream), "hr_gbuffer_commit_staged"); }
     void bind_device(const hr_gbuffer_desc* dev_mip0, void* stream) { check(common->ctx, hr_gbuffer_bind_device(common->ctx, common->ping_pong ? 1 : 0, dev_mip0, stream), "hr_gbuffer_bind_device"); }
 };
 
