@@ -11,7 +11,7 @@
 //     texel from the GPU that owns its row (HistPeers) — the exchange is fused into the kernel and moves exactly the
 //     texels the reprojection touches (a few boundary rows for a static camera).  Ordering is a per-pass frame tick:
 //     after its last history write of frame N a rank stores N into every peer's tick array (st.release.sys); before
-//     the reprojection of frame N+1 a one-warp kernel spins (ld.acquire.sys, 2 s time-out) until every peer's tick
+//     the reprojection of frame N+1 a one-warp kernel spins (ld.acquire.sys, 10 s time-out) until every peer's tick
 //     is >= N.  History images are double buffered by frame parity, so that wait also covers the write-after-read hazard.
 //   * the pass's FINAL OUTPUT (optional, hr_shard_set_gather; on by default): one NCCL group of per-band broadcasts (an
 //     all-gather with unequal counts: 2160 rows = 270 tiles do not divide evenly by 8) on a side stream, so every rank
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) k_rt_push(MaskPtrs masks, CostPtrs costs,
     }
 }
 
-// One warp.  Lanes spin until every peer's ray-trace tick reached `rt_tick` and its history tick `hist_tick` (2 s time-out),
+// One warp.  Lanes spin until every peer's ray-trace tick reached `rt_tick` and its history tick `hist_tick` (10 s time-out),
 // then the warp computes next frame's partition: bounds[k] = first mask row whose cost prefix reaches k/world of the total.
 // Every rank computes the same table from the same (complete) cost table.
 __global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, int hist_tick, int* err, const uint32_t* __restrict__ cost, int MH, int world, int self,
@@ -216,7 +216,7 @@ __global__ void k_rt_wait_partition(const int* __restrict__ ticks, int rt_tick, 
             if (hist_tick > 0) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(h) : "l"(ticks + lane) : "memory");
             if (v >= rt_tick && h >= hist_tick) break;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 2000000000ull) { *err = 1 + lane; break; }
+            if (t1 - t0 > 10000000000ull) { *err = 1 + lane; break; }
             __nanosleep(100);
         }
     }
@@ -276,7 +276,7 @@ __global__ void k_peer_wait(const int* __restrict__ ticks, int world, int self, 
         asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(ticks + r) : "memory");
         if (v >= tick) break;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 2000000000ull) { *err = 1 + r; break; } // a peer died or the ranks render different frame counts: do not hang the GPU
+        if (t1 - t0 > 10000000000ull) { *err = 1 + r; break; } // a peer died or the ranks render different frame counts: do not hang the GPU
         __nanosleep(200);
     }
 }

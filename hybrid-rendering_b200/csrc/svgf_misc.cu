@@ -104,6 +104,33 @@ __global__ void k_build_mip(int W, int H, const uint2* __restrict__ gb2, const u
     if (gb1 && o1) o1[d] = gb1[s];
 }
 
+// Levels 1 and 2 in one launch: level 2 is a NEAREST blit of level 1, i.e. of level 0 at the composed coordinates
+// (min(2*min(2X+1, w1-1)+1, W-1), ...), so it can be read straight from level 0 by the threads (x < w2, y < h2).
+__global__ void k_build_mips12(int W, int H, const uint2* __restrict__ gb2, const uint2* __restrict__ gb3, const float* __restrict__ depth,
+                               const uint32_t* __restrict__ gb1, uint2* __restrict__ o2a, uint2* __restrict__ o3a, float* __restrict__ oda, uint32_t* __restrict__ o1a,
+                               uint2* __restrict__ o2b, uint2* __restrict__ o3b, float* __restrict__ odb, uint32_t* __restrict__ o1b)
+{
+    const int w1 = max(W / 2, 1), h1 = max(H / 2, 1), w2 = max(w1 / 2, 1), h2 = max(h1 / 2, 1);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w1 || y >= h1) return;
+    {
+        const size_t s = (size_t)min(2 * y + 1, H - 1) * W + min(2 * x + 1, W - 1), d = (size_t)y * w1 + x;
+        o2a[d] = gb2[s];
+        o3a[d] = gb3[s];
+        oda[d] = depth[s];
+        if (gb1 && o1a) o1a[d] = gb1[s];
+    }
+    if (x < w2 && y < h2)
+    {
+        const int    x1 = min(2 * x + 1, w1 - 1), y1 = min(2 * y + 1, h1 - 1);
+        const size_t s = (size_t)min(2 * y1 + 1, H - 1) * W + min(2 * x1 + 1, W - 1), d = (size_t)y * w2 + x;
+        o2b[d] = gb2[s];
+        o3b[d] = gb3[s];
+        odb[d] = depth[s];
+        if (gb1 && o1b) o1b[d] = gb1[s];
+    }
+}
+
 } // namespace
 
 void launch_ao_blur_v1(const GBufLevelDev& g, const __half* in, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, __half* out,
@@ -126,6 +153,16 @@ void launch_upsample_scalar_v1(const GBufLevelDev& g0, const GBufLevelDev& gm, c
 
 int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st)
 {
+    if (HR_MAX_MIPS == 3)
+    {
+        const int w1 = W / 2 > 0 ? W / 2 : 1, h1 = H / 2 > 0 ? H / 2 : 1;
+        dim3      b(32, 8), g((w1 + 31) / 32, (h1 + 7) / 8);
+        k_build_mips12<<<g, b, 0, st>>>(W, H, (const uint2*)s.gb2[0], (const uint2*)s.gb3[0], s.depth[0], (const uint32_t*)s.gb1[0], (uint2*)s.gb2[1], (uint2*)s.gb3[1],
+                                        s.depth[1], (uint32_t*)s.gb1[1], (uint2*)s.gb2[2], (uint2*)s.gb3[2], s.depth[2], (uint32_t*)s.gb1[2]);
+        ctx->launches++;
+        HR_CHECK_LAUNCH(ctx);
+        return HR_OK;
+    }
     int w = W, h = H;
     for (int m = 1; m < HR_MAX_MIPS; m++)
     {
