@@ -234,10 +234,7 @@ __global__ void __launch_bounds__(256) k_refl_atrous(GBufLevelDev g, const uint2
                                                       uint2* __restrict__ out)
 {
     extern __shared__ float4 smem4[];
-    constexpr int TWD = 32, THT = 16;
-    constexpr int PADL = STEP + (STEP & 1);            // even left pad: staged texel pairs start on an even image column
-    constexpr int RW   = (TWD + PADL + STEP + 1) & ~1; // even row pitch
-    constexpr int RH   = THT + 2 * STEP;
+    constexpr int TWD = 32, THT = 16, RW = TWD + 2 * STEP, RH = THT + 2 * STEP;
     float4*       s_nz = smem4;
     float4*       s_c  = smem4 + RW * RH;
     __shared__ uint32_t s_tf;
@@ -251,65 +248,24 @@ __global__ void __launch_bounds__(256) k_refl_atrous(GBufLevelDev g, const uint2
         const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
         if (threadIdx.x == 0) s_tf = b;
     }
-    // the two pixels of this thread: depth / roughness words requested before the staging loop (overlapping round trips)
-    float    own_depth[THT / 8];
-    uint32_t own_g3[THT / 8];
-#pragma unroll
-    for (int k = 0; k < THT / 8; k++)
-    {
-        const int x = x0 + (int)(threadIdx.x & 31), y = y0 + (int)(threadIdx.x >> 5) + 8 * k;
-        own_depth[k] = 1.0f;
-        own_g3[k]    = 0u;
-        if (x < W && y < H && y < P.row1)
-        {
-            const size_t idx = (size_t)y * W + x;
-            own_depth[k] = __ldg(g.depth + idx);
-            own_g3[k]    = __ldg(reinterpret_cast<const uint32_t*>(g.gb3 + idx));
-        }
-    }
     __syncthreads();
     const uint32_t tf = s_tf;
-    if ((W & 1) == 0)
-    { // texel pairs: one aligned 16-byte load per G-buffer image and for the colour image (W even: a pair is inside or outside)
-        for (int i = threadIdx.x; i < (RW / 2) * RH; i += 256)
+    for (int i = threadIdx.x; i < RW * RH; i += 256)
+    {
+        const int rx = i % RW, ry = i / RW, px = x0 - STEP + rx, py = y0 - STEP + ry;
+        float4    nz = make_float4(0.0f, 0.0f, 0.0f, 0.0f), c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (px >= 0 && py >= 0 && px < W && py < H)
         {
-            const int rx = 2 * (i % (RW / 2)), ry = i / (RW / 2), px = x0 - PADL + rx, py = y0 - STEP + ry;
-            float4    nz0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nz1 = nz0, c0 = nz0, c1 = nz0;
-            if (px >= 0 && py >= 0 && px < W && py < H)
-            {
-                const size_t pi = (size_t)py * W + px;
-                const uint4  a  = __ldg(reinterpret_cast<const uint4*>(g.gb2 + pi));
-                const uint4  b  = __ldg(reinterpret_cast<const uint4*>(g.gb3 + pi));
-                const uint4  c  = __ldg(reinterpret_cast<const uint4*>(in + pi));
-                const float2 e0 = h2_to_f2(a.x), e1 = h2_to_f2(a.z);
-                const float3 n0 = octohedral_to_direction(e0.x, e0.y), n1 = octohedral_to_direction(e1.x, e1.y);
-                nz0 = make_float4(n0.x, n0.y, n0.z, h2_to_f2(b.y).y);
-                nz1 = make_float4(n1.x, n1.y, n1.z, h2_to_f2(b.w).y);
-                c0  = h4_to_f4(make_uint2(c.x, c.y));
-                c1  = h4_to_f4(make_uint2(c.z, c.w));
-            }
-            const int ri = ry * RW + rx;
-            s_nz[ri] = nz0; s_nz[ri + 1] = nz1;
-            s_c[ri]  = c0;  s_c[ri + 1]  = c1;
+            const size_t pi = (size_t)py * W + px;
+            const float2 e  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb2 + pi)));
+            const float2 zz = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb3 + pi) + 1));
+            const float3 n  = octohedral_to_direction(e.x, e.y);
+            nz = make_float4(n.x, n.y, n.z, zz.y);
+            c  = h4_to_f4(__ldg(in + pi));
         }
+        s_nz[i] = nz;
+        s_c[i]  = c;
     }
-    else
-        for (int i = threadIdx.x; i < RW * RH; i += 256)
-        {
-            const int rx = i % RW, ry = i / RW, px = x0 - PADL + rx, py = y0 - STEP + ry;
-            float4    nz = make_float4(0.0f, 0.0f, 0.0f, 0.0f), c = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (px >= 0 && py >= 0 && px < W && py < H)
-            {
-                const size_t pi = (size_t)py * W + px;
-                const float2 e  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb2 + pi)));
-                const float2 zz = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb3 + pi) + 1));
-                const float3 n  = octohedral_to_direction(e.x, e.y);
-                nz = make_float4(n.x, n.y, n.z, zz.y);
-                c  = h4_to_f4(__ldg(in + pi));
-            }
-            s_nz[i] = nz;
-            s_c[i]  = c;
-        }
     __syncthreads();
     const int   lx = threadIdx.x & 31, lyb = threadIdx.x >> 5;
     const float c_sigma = -1.44269504f / P.sigma_depth;
@@ -319,11 +275,12 @@ __global__ void __launch_bounds__(256) k_refl_atrous(GBufLevelDev g, const uint2
         const int ly = lyb + 8 * k, x = x0 + lx, y = y0 + ly;
         if (x >= W || y >= H || y >= P.row1) continue;
         const size_t idx = (size_t)y * W + x;
-        const int    ci  = (ly + STEP) * RW + lx + PADL;
+        const int    ci  = (ly + STEP) * RW + lx + STEP;
         const float4 cc  = s_c[ci];
         if (!((tf >> ((ly >> 3) * 4 + (lx >> 3))) & 1u)) { out[idx] = pack_h4(cc.x, cc.y, cc.z, cc.w); continue; } // copy tiles
-        if (own_depth[k] == 1.0f) { out[idx] = make_uint2(0u, 0u); continue; }
-        const float roughness = h2_to_f2(own_g3[k]).x;
+        const float depth = __ldg(g.depth + idx);
+        if (depth == 1.0f) { out[idx] = make_uint2(0u, 0u); continue; }
+        const float roughness = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(g.gb3 + idx))).x;
         if (roughness < 0.05f || (P.approximate_with_ddgi == 1 && roughness > 0.75f)) { out[idx] = pack_h4(cc.x, cc.y, cc.z, cc.w); continue; }
         const float4 cn = s_nz[ci];
         const float  cl = luminance(cc.x, cc.y, cc.z);
@@ -391,7 +348,7 @@ __global__ void __launch_bounds__(256) k_upsample_vec4(GBufLevelDev g0, GBufLeve
 template <int STEP>
 void launch_atrous_t(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const ReflAtrousParams& P, uint2* out, cudaStream_t st)
 {
-    constexpr int PADL = STEP + (STEP & 1), RW = (32 + PADL + STEP + 1) & ~1, RH = 16 + 2 * STEP;
+    constexpr int RW = 32 + 2 * STEP, RH = 16 + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * 2 * sizeof(float4);
     static bool   configured = false;
     if (!configured) { cudaFuncSetAttribute(k_refl_atrous<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
