@@ -280,6 +280,19 @@ int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st
 int hr_bvh_build(hr_scene* sc, cudaStream_t st);
 BvhDev hr_bvh_view(const hr_scene* sc);
 
+// Function attributes (opt-in shared memory sizes) are per device: launchers keep one flag per device, not per process, so
+// a process that drives several GPUs configures each of them.  Returns true the first time it is called for the current
+// device with this flag array.
+inline bool hr_once_per_device(bool (&done)[64])
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 
 void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
                               uint32_t* mask, int row0, int row1, cudaStream_t st);

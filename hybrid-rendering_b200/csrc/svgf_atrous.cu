@@ -319,12 +319,8 @@ void launch_chain(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 {
     constexpr int RW = CH_W + 2 * STEP, RH = CH_H + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * (sizeof(float4) + sizeof(float2));
-    static bool   configured = false;
-    if (!configured)
-    {
-        cudaFuncSetAttribute(k_atrous_chain<STEP, PHI32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static bool   configured[64] = {};
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_atrous_chain<STEP, PHI32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((P.W + CH_W - 1) / CH_W, (P.row1 - P.row0 + CH_H - 1) / CH_H);
     k_atrous_chain<STEP, PHI32><<<grid, 256, smem, st>>>(g, in, tf, P, out);
 }
@@ -334,12 +330,8 @@ void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 {
     constexpr int RW = TILE_W + 2 * STEP, RH = TILE_H + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * (sizeof(float4) + sizeof(float2));
-    static bool   configured = false;
-    if (!configured)
-    {
-        cudaFuncSetAttribute(k_atrous_tiled<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static bool   configured[64] = {};
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_atrous_tiled<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.row1 - P.row0 + TILE_H - 1) / TILE_H);
     k_atrous_tiled<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
 }

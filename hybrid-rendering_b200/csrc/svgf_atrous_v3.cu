@@ -338,8 +338,8 @@ void launch_v3s(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, co
 {
     constexpr int RW = TW3 + 2 * STEP, RH = TH3 + 2;
     const size_t  smem = ((size_t)RW * RH * 6 + (size_t)2 * TH3 * RW) * sizeof(float);
-    static bool   configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_atrous_v3s<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    static bool   configured[64] = {};
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_atrous_v3s<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int rows = P.row1 - P.row0, blocks = (rows + TH3 * STEP - 1) / (TH3 * STEP);
     dim3      grid((P.W + TW3 - 1) / TW3, blocks * STEP);
     k_atrous_v3s<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
@@ -352,8 +352,8 @@ void launch_v3(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, con
     constexpr int RW   = (TW3 + PADL + STEP + 1) & ~1;
     constexpr int RH   = TH3 + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * 6 * sizeof(float);
-    static bool   configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_atrous_v3<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    static bool   configured[64] = {};
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_atrous_v3<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((P.W + TW3 - 1) / TW3, (P.row1 - P.row0 + TH3 - 1) / TH3);
     k_atrous_v3<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
 }

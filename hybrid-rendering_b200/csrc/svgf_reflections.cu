@@ -350,8 +350,8 @@ void launch_atrous_t(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, 
 {
     constexpr int RW = 32 + 2 * STEP, RH = 16 + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * 2 * sizeof(float4);
-    static bool   configured = false;
-    if (!configured) { cudaFuncSetAttribute(k_refl_atrous<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    static bool   configured[64] = {};
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_refl_atrous<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((P.W + 31) / 32, (P.row1 - P.row0 + 15) / 16);
     k_refl_atrous<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
 }

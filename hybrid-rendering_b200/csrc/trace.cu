@@ -328,20 +328,23 @@ template <int MODE>
 static void launch_pt(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float p0, float p1, const uint8_t* sobol, const uint8_t* sr, uint32_t* mask,
                       int mrow0, int mrow1, cudaStream_t st)
 {
-    static unsigned int* counter[2] = { nullptr, nullptr }; // one work counter per kernel flavour (shadows / AO may overlap on different streams)
-    static int           ctas       = 0;
-    if (!counter[MODE])
+    // per device (a process may drive several GPUs) and per kernel flavour (shadows / AO may overlap on different streams)
+    static unsigned int* counter[64] = {};
+    static int           ctas[64]    = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!counter[dev])
     {
-        cudaMalloc(&counter[MODE], sizeof(unsigned int));
+        cudaMalloc(&counter[dev], sizeof(unsigned int));
         cudaFuncSetAttribute(k_ray_trace_mask_pt<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPtSmem);
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
+        int sms = 148, per_sm = 1;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ray_trace_mask_pt<MODE>, PT_WARPS * 32, kPtSmem);
-        ctas = sms * (per_sm > 0 ? per_sm : 1);
+        ctas[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
-    cudaMemsetAsync(counter[MODE], 0, sizeof(unsigned int), st);
-    k_ray_trace_mask_pt<MODE><<<ctas, PT_WARPS * 32, kPtSmem, st>>>(g, bvh, fc, p0, p1, sobol, sr, mask, mrow0, mrow1, counter[MODE]);
+    cudaMemsetAsync(counter[dev], 0, sizeof(unsigned int), st);
+    k_ray_trace_mask_pt<MODE><<<ctas[dev], PT_WARPS * 32, kPtSmem, st>>>(g, bvh, fc, p0, p1, sobol, sr, mask, mrow0, mrow1, counter[dev]);
 }
 
 void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
