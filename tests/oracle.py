@@ -129,6 +129,16 @@ def zero_gbuf_mips(W, H, n_mips=3):
     return GBufMips(pyhr.GBufferHost(W, H), n_mips)
 
 
+def _coop_mask(o):
+    """keep only the mask rows of this rank's ray-trace share, trash the rest, then let the exchange complete the image"""
+    a, b = o.rt_share
+    rng = np.random.default_rng(a * 31 + b)
+    for sl in (slice(0, a), slice(b, o.mask.shape[0])):
+        if o.mask[sl].size:
+            o.mask[sl] = rng.integers(0, 2**32, size=o.mask[sl].shape, dtype=np.uint64).astype(np.uint32)
+    o.mask[:] = o.mask_exchange(o.mask, a, b)
+
+
 class ShadowsOracle:
     def __init__(self, W0, H0, scale=0):
         self.W0, self.H0, self.scale = W0, H0, scale
@@ -151,6 +161,9 @@ class ShadowsOracle:
         P.radius, P.filter_iterations, P.feedback_iteration, P.denoise = 1, 4, 1, 1
         self.final = None
         self.band = None  # (b0, b1): emulate a sharded rank — rows a rank would not compute are overwritten with garbage
+        # cooperative ray trace emulation: this rank traces mask rows [rt_share[0], rt_share[1]) only and
+        # mask_exchange(mask, a, b) must return the complete mask (what k_rt_push + the frame ticks do between GPUs)
+        self.rt_share, self.mask_exchange = None, None
 
     def _poison(self, arr, halo, div=1, shift=0):
         """Sharding emulation (tests/test_sharding_cpu.py): keep rows [b0-halo, b1+halo) of a stage output, trash the rest."""
@@ -175,7 +188,10 @@ class ShadowsOracle:
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
         L.orc_shadows_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.bias, p(sobol), p(sr), p(self.mask))
-        self._poison(self.mask, 32, div=4)
+        if self.rt_share is not None:
+            _coop_mask(self)
+        else:
+            self._poison(self.mask, 32, div=4)
         self.final = self.mask
         if not P.denoise:
             return
@@ -236,7 +252,10 @@ class AOOracle:
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
         L.orc_ao_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, p(sobol), p(sr), p(self.mask))
-        self._poison(self.mask, 32, div=4)
+        if getattr(self, "rt_share", None) is not None:
+            _coop_mask(self)
+        else:
+            self._poison(self.mask, 32, div=4)
         self.final = self.mask
         if not P.denoise:
             return

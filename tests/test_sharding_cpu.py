@@ -5,6 +5,11 @@ Each rank runs the CPU oracle but trashes, after every stage, the rows a sharded
 (oracle._poison with the same halos the CUDA host code uses: ray trace +-32, temporal / a-trous +-16, AO vertical blur
 +-8); the bands are then all-gathered with torch.distributed (gloo) exactly like hr_shard_exchange does with NCCL.
 If a halo were too small, garbage would leak into a band and the comparison with the unsharded oracle would fail.
+
+test_cooperative_trace_and_distributed_history_gloo restates the production multi-GPU plan the same way: the
+ray trace is split into arbitrary, frame-varying shares of mask rows that are exchanged into a complete mask (no halo
+re-trace), the denoise stages keep their band +- halo, and each rank keeps the temporal history of its own band only and
+fetches the peers' rows before the reprojection.
 """
 import os
 import sys
@@ -89,6 +94,106 @@ def _worker(rank, world, port, q):
         q.put("ok")
     finally:
         dist.destroy_process_group()
+
+
+def _coop_bounds(mh, world, frame):
+    """a frame-dependent, deliberately uneven split of the mask rows (stands in for the cost-balanced partition): every rank
+    computes the same table from the same inputs, shares are >= 1 row and unrelated to the denoise bands"""
+    rng = np.random.default_rng(1000 + frame)
+    cuts = np.sort(rng.choice(np.arange(1, mh), size=world - 1, replace=False))
+    return [0] + [int(c) for c in cuts] + [mh]
+
+
+def _worker_coop(rank, world, port, q):
+    """Cooperative ray trace + distributed history (the production multi-GPU plan): each rank traces an arbitrary share of
+    the mask rows, the shares are exchanged so every rank holds the complete mask, the denoise stages run on band +- halo,
+    and the temporal history of a rank is valid on its own band only — the rows a reprojection needs are fetched from
+    their owners before the temporal stage (the GPU kernel pulls them texel by texel; here: one gather)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+        tri, _ = sc.world_triangles()
+        osc = O.Scene(tri, brute=True)
+        bn = pyhr.blue_noise()
+        ref_sh, ref_ao = O.ShadowsOracle(W, H, 0), O.AOOracle(W, H, 1)
+        sh, ao = O.ShadowsOracle(W, H, 0), O.AOOracle(W, H, 1)
+        sh.band = shard_rows(sh.H, rank, world)
+        ao.band = shard_rows(ao.H, rank, world)
+        state = {"bounds": None}
+
+        def exchange(mask, a, b):
+            out = mask.copy()
+            bd = state["bounds"]
+            for r in range(world):
+                t = torch.from_numpy(np.ascontiguousarray(mask[bd[r]:bd[r + 1]]).view(np.uint8).copy())
+                dist.broadcast(t, src=r)
+                out[bd[r]:bd[r + 1]] = t.numpy().view(np.uint32).reshape(out[bd[r]:bd[r + 1]].shape)
+            return out
+
+        sh.mask_exchange = ao.mask_exchange = exchange
+        f, prev = None, O.zero_gbuf_mips(W, H)
+        for i in range(5):
+            dx = 0.0 if i < 2 else 0.08 * (i - 1)
+            dy = 0.0 if i < 2 else 0.3 * (i - 1)  # vertical motion: history taps cross the band borders
+            f = pyhr.make_frame((dx, 14 + dy, 34), (dx, 3 - dy, 0), W, H, prev=f, num_frames=i)
+            cur = O.GBufMips(pyhr.write_gbuffer(sc, f, W, H))
+            ref_sh.render(osc, cur, prev, f, bn)
+            ref_ao.render(osc, cur, prev, f, bn)
+            pp = f.ping_pong
+            # history is distributed: before the reprojection, rows owned by the peers are fetched from them
+            if i > 0:
+                sh.prev_image[:] = _gather_bands(dist, sh.prev_image, sh.H, rank, world)
+                sh.moments[1 - pp][:] = _gather_bands(dist, sh.moments[1 - pp], sh.H, rank, world)
+                ao.color[1 - pp][:] = _gather_bands(dist, ao.color[1 - pp], ao.H, rank, world)
+                ao.length[1 - pp][:] = _gather_bands(dist, ao.length[1 - pp], ao.H, rank, world)
+            for o in (sh, ao):
+                state["bounds"] = _coop_bounds(o.mask.shape[0], world, i)
+                o.rt_share = (state["bounds"][rank], state["bounds"][rank + 1])
+                o.render(osc, cur, prev, f, bn)
+            prev = cur
+            if not (np.array_equal(sh.mask, ref_sh.mask) and np.array_equal(ao.mask, ref_ao.mask)):
+                q.put(f"rank {rank} frame {i}: exchanged ray mask is not the complete mask")
+                return
+            # own band only: trash everything else in the history this rank keeps
+            for o, arrs in ((sh, (sh.prev_image, sh.moments[pp])), (ao, (ao.color[pp], ao.length[pp]))):
+                for a in arrs:
+                    o._poison(a, 0)
+            b0, b1 = sh.band
+            a0, a1 = ao.band
+            checks = (("shadows final", sh.final[b0:b1], ref_sh.final[b0:b1]), ("prev_image", sh.prev_image[b0:b1], ref_sh.prev_image[b0:b1]),
+                      ("moments", sh.moments[pp][b0:b1], ref_sh.moments[pp][b0:b1]), ("ao colour", ao.color[pp][a0:a1], ref_ao.color[pp][a0:a1]),
+                      ("ao length", ao.length[pp][a0:a1], ref_ao.length[pp][a0:a1]),
+                      ("ao final", ao.final[a0 << 1:(ao.final.shape[0] if a1 >= ao.H else a1 << 1)], ref_ao.final[a0 << 1:(ao.final.shape[0] if a1 >= ao.H else a1 << 1)]))
+            for name, a, b in checks:
+                if not np.array_equal(a, b):
+                    q.put(f"rank {rank} frame {i}: {name} (own band) differs from the unsharded result")
+                    return
+        q.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_world(worker, world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world + (17 if worker is _worker_coop else 0)
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = [q.get(timeout=600) for _ in range(world)]
+    for p_ in procs:
+        p_.join(60)
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_cooperative_trace_and_distributed_history_gloo(world):
+    assert _run_world(_worker_coop, world) == ["ok"] * world
 
 
 @pytest.mark.parametrize("world", [2, 3])
