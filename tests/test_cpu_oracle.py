@@ -4,6 +4,7 @@ The reference ships no tests / golden vectors for this path (SURVEY.md §4, §8c
 tests/golden/ are outputs of this oracle (script: tests/golden/make_golden.py) and pin it against regressions.
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -132,6 +133,20 @@ def test_golden_vectors():
             assert d.max() <= 1e-3, name
         else:
             assert np.array_equal(a, b), name
+
+
+def test_golden_sequence_256x144():
+    """The larger fixture (state after the 12-frame static + pan sequence, the one tests/test_gpu_golden.py compares the CUDA path
+    with) is reproduced by the oracle: integer images bit for bit, fp16 images within one ulp of libm noise."""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import seq12_oracle
+    g = np.load(os.path.join(GOLDEN, "shadows_ao_256x144_seq12.npz"))
+    sh, ao = seq12_oracle()
+    for name, arr in (("sh_mask", sh.mask), ("sh_tiles", sh.tile_flags), ("ao_mask", ao.mask), ("ao_tiles", ao.tile_flags)):
+        assert np.array_equal(arr, g[name]), name
+    for name, arr in (("sh_temporal", sh.temporal), ("sh_moments", sh.cur_moments), ("sh_atrous", sh.atrous_out), ("sh_prev_image", sh.prev_image),
+                      ("sh_final", sh.final), ("ao_temporal", ao.temporal), ("ao_length", ao.cur_length), ("ao_blur", ao.blur[1]), ("ao_final", ao.final)):
+        assert np.abs(O.h2f(np.asarray(arr)) - O.h2f(g[name])).max() <= 1e-3, name
 
 
 def test_mask_bit_order_and_tile_partition():
