@@ -149,6 +149,22 @@ def test_golden_sequence_256x144():
         assert np.abs(O.h2f(np.asarray(arr)) - O.h2f(g[name])).max() <= 1e-3, name
 
 
+def test_golden_ddgi_reflections_192x112():
+    """DDGI + reflections fixture (tests/test_gpu_golden.py compares the CUDA path with it): reproduced by the oracle; exact where
+    the values are decisions (ray lengths, tile flags, history length), within fp16 / libm noise elsewhere."""
+    sys.path.insert(0, GOLDEN)
+    from make_golden import gi_oracle
+    g = np.load(os.path.join(GOLDEN, "ddgi_reflections_192x112_seq5.npz"))
+    odd, orf = gi_oracle()
+    assert np.array_equal(orf.tile_flags, g["refl_tiles"])
+    assert np.array_equal(O.h2f(orf.rt)[..., 3], O.h2f(g["refl_rt"])[..., 3])
+    assert np.array_equal(O.h2f(orf.cur_moments)[..., 2], O.h2f(g["refl_moments"])[..., 2])
+    for name, arr in (("ddgi_sample", odd.sample), ("refl_rt", orf.rt), ("refl_temporal", orf.cur_temporal), ("refl_moments", orf.cur_moments),
+                      ("refl_atrous", orf.atrous_out), ("refl_final", orf.final)):
+        a, b = O.h2f(np.asarray(arr)), O.h2f(g[name])
+        assert (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max() <= 2e-3, name
+
+
 def test_mask_bit_order_and_tile_partition():
     sh, ao = small_sequence(frames=2)
     W, H = 64, 48

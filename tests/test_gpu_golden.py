@@ -61,3 +61,46 @@ def test_sequence_matches_committed_golden():
         ao.destroy()
     finally:
         ctx.close()
+
+
+def close(a, b, name, r=1e-3, m=6e-3):
+    """rmse and max-abs bounds relative to max(1, |reference|), as in tests/test_gpu_gi_refl.py"""
+    assert a.shape == b.shape, name
+    d = np.abs(a - b) / np.maximum(1.0, np.abs(b))
+    e = float(np.sqrt(np.mean(d.astype(np.float64) ** 2)))
+    assert e <= r, f"{name}: rmse {e}"
+    assert d.max() <= m, f"{name}: max abs {d.max()}"
+
+
+def test_ddgi_reflections_sequence_matches_committed_golden():
+    """DDGI (K18-K21) + half-res reflections (K12, K14-K17) after 3 static + 2 panning frames against
+    tests/golden/ddgi_reflections_192x112_seq5.npz (screen-space images; ray lengths, tile flags and history length exact)."""
+    from make_golden import GI_H, GI_W, gi_frames, gi_params
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "ddgi_reflections_192x112_seq5.npz"))
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ctx = pyhr.Context(0)
+    try:
+        ctx.set_bluenoise(*pyhr.blue_noise())
+        ctx.build_scene(sc)
+        ctx.gbuffer_create(GI_W, GI_H)
+        dd, rf = pyhr.DDGIPass(ctx, GI_W, GI_H, 0), pyhr.ReflectionsPass(ctx, GI_W, GI_H, 1)
+        gi_params(dd.params, rf.params)
+        for i, f, rot in gi_frames():
+            ctx.gbuffer_upload(f.ping_pong, pyhr.write_gbuffer(sc, f, GI_W, GI_H))
+            dd.render(f, rot)
+            rf.render(f, dd)
+        close(f16(dd.download(4)), O.h2f(g["ddgi_sample"]), "ddgi sample")
+        rt_c, rt_o = f16(rf.download(0)), O.h2f(g["refl_rt"])
+        assert np.array_equal(rt_c[..., 3], rt_o[..., 3]), "reflection ray length (hit / miss / t) not exact against the golden fixture"
+        close(rt_c[..., :3], rt_o[..., :3], "reflections ray trace", 1e-3, 0.02)
+        assert np.array_equal(rf.download(6), g["refl_tiles"]), "reflections tile classification differs from the golden fixture"
+        close(f16(rf.download(1)), O.h2f(g["refl_temporal"]), "reflections temporal")
+        mo_c, mo_o = f16(rf.download(4)), O.h2f(g["refl_moments"])
+        assert np.array_equal(mo_c[..., 2], mo_o[..., 2]), "reflections history length differs from the golden fixture"
+        close(mo_c, mo_o, "reflections moments")
+        close(f16(rf.download(2)), O.h2f(g["refl_atrous"]), "reflections a-trous")
+        close(f16(rf.download(100)), O.h2f(g["refl_final"]), "reflections final")
+        rf.destroy()
+        dd.destroy()
+    finally:
+        ctx.close()
