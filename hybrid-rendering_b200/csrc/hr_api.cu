@@ -541,7 +541,7 @@ extern "C" {
 void hr_shadows_default_params(hr_shadows_params* p)
 {
     p->bias = 0.5f; p->alpha = 0.01f; p->moments_alpha = 0.2f; p->phi_visibility = 10.0f; p->phi_normal = 32.0f; p->sigma_depth = 1.0f;
-    p->power = 1.2f; p->radius = 1; p->filter_iterations = 4; p->feedback_iteration = 1; p->denoise = 1;
+    p->power = 1.2f; p->radius = 1; p->filter_iterations = 4; p->feedback_iteration = 1; p->denoise = 1; p->spp = 1;
 }
 
 int hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
@@ -610,8 +610,10 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     }
     // ray_trace (:972-1011).  Linked to peers: this rank traces its cost-balanced share of the WHOLE image and stores the
     // mask words into every rank's mask image (no halo re-trace); otherwise its band +- 32 rows into its own image.
+    const int  spp = prm->spp > 1 ? prm->spp : 1;
+    HR_REQUIRE(ctx, spp <= 255 && (spp == 1 || ctx->world == 1), HR_ERR_UNSUPPORTED, "hr_shadows_render: spp > 1 needs spp <= 255 and a single GPU");
     RtShare    rts;
-    const bool shared_rt = hr_rt_share(p, epoch & 1, &rts);
+    const bool shared_rt = spp == 1 && hr_rt_share(p, epoch & 1, &rts);
     uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
     if (shared_rt)
     {
@@ -625,15 +627,23 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         if (rc != HR_OK) return rc;
         timer_mark(p, "Mask Exchange Wait", st);
     }
+    else if (spp > 1)
+    { // spp rays per pixel into an 8-bit count image (allocated on first use)
+        if (!p->count) { rc = pass_alloc(p, p->count, px); if (rc != HR_OK) return rc; }
+        launch_shadows_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->count, spp, rt0, rt1, st);
+        ctx->launches++;
+        timer_mark(p, "Ray Trace", st);
+    }
     else
     {
         launch_shadows_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, mask, rt0, rt1, st);
         ctx->launches++;
         timer_mark(p, "Ray Trace", st);
     }
-    set_view(p, HR_SHADOWS_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
-    void* final_ptr = mask;
-    int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
+    if (spp > 1) set_view(p, HR_SHADOWS_OUT_RAY_TRACE, p->count, p->W, p->H, HR_FMT_R8_UINT);
+    else set_view(p, HR_SHADOWS_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = spp > 1 ? (void*)p->count : (void*)mask;
+    int   final_w = spp > 1 ? p->W : (p->W + 7) / 8, final_h = spp > 1 ? p->H : (p->H + 3) / 4, final_fmt = spp > 1 ? HR_FMT_R8_UINT : HR_FMT_R32_UINT;
     if (prm->denoise)
     {
         // temporal_accumulation (:1041-1090); reset_args (:1015-1037) is subsumed by the per-tile flag image.
@@ -646,7 +656,10 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
             rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;
         }
-        launch_shadows_temporal(cur, prev, mask, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
+        if (spp > 1)
+            launch_shadows_temporal_count(cur, prev, p->count, spp, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
+        else
+            launch_shadows_temporal(cur, prev, mask, hist, fc, prm->alpha, prm->moments_alpha, p->temporal_out, p->moments[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
         timer_mark(p, "Temporal Accumulation", st);
         // a_trous_filter (:1094-1215).  The reference ping-pongs image[0]/image[1] and copies the output of
@@ -731,7 +744,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
 // ---------------------------------------------------------------------------------------------------------------
 void hr_ao_default_params(hr_ao_params* p)
 {
-    p->ray_length = 7.0f; p->bias = 0.3f; p->alpha = 0.01f; p->power = 1.2f; p->blur_radius = 4; p->denoise = 1;
+    p->ray_length = 7.0f; p->bias = 0.3f; p->alpha = 0.01f; p->power = 1.2f; p->blur_radius = 4; p->denoise = 1; p->spp = 1;
 }
 
 int hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
@@ -791,8 +804,10 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
         p->first = false;
     }
+    const int  spp = prm->spp > 1 ? prm->spp : 1;
+    HR_REQUIRE(ctx, spp <= 255 && (spp == 1 || ctx->world == 1), HR_ERR_UNSUPPORTED, "hr_ao_render: spp > 1 needs spp <= 255 and a single GPU");
     RtShare    rts;
-    const bool shared_rt = hr_rt_share(p, epoch & 1, &rts); // see hr_shadows_render
+    const bool shared_rt = spp == 1 && hr_rt_share(p, epoch & 1, &rts); // see hr_shadows_render
     uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
     if (shared_rt)
     {
@@ -805,15 +820,23 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         if (rc != HR_OK) return rc;
         timer_mark(p, "Mask Exchange Wait", st);
     }
+    else if (spp > 1)
+    {
+        if (!p->count) { rc = pass_alloc(p, p->count, px); if (rc != HR_OK) return rc; }
+        launch_ao_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->count, spp, rt0, rt1, st);
+        ctx->launches++;
+        timer_mark(p, "Ray Trace", st);
+    }
     else
     {
         launch_ao_ray_trace(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, mask, rt0, rt1, st);
         ctx->launches++;
         timer_mark(p, "Ray Trace", st);
     }
-    set_view(p, HR_AO_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
-    void* final_ptr = mask;
-    int   final_w = (p->W + 7) / 8, final_h = (p->H + 3) / 4, final_fmt = HR_FMT_R32_UINT;
+    if (spp > 1) set_view(p, HR_AO_OUT_RAY_TRACE, p->count, p->W, p->H, HR_FMT_R8_UINT);
+    else set_view(p, HR_AO_OUT_RAY_TRACE, mask, (p->W + 7) / 8, (p->H + 3) / 4, HR_FMT_R32_UINT);
+    void* final_ptr = spp > 1 ? (void*)p->count : (void*)mask;
+    int   final_w = spp > 1 ? p->W : (p->W + 7) / 8, final_h = spp > 1 ? p->H : (p->H + 3) / 4, final_fmt = spp > 1 ? HR_FMT_R8_UINT : HR_FMT_R32_UINT;
     bool  signalled = false;
     if (prm->denoise)
     {
@@ -825,7 +848,8 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
             rc = hr_peer_wait(p, 0, epoch - 1, st);
             if (rc != HR_OK) return rc;
         }
-        launch_ao_temporal(cur, prev, mask, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
+        if (spp > 1) launch_ao_temporal_count(cur, prev, p->count, spp, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
+        else launch_ao_temporal(cur, prev, mask, hist, fc, prm->alpha, p->ao_color[pp], p->ao_len[pp], p->tile_flags, row0, row1, st);
         ctx->launches++;
         rc = hr_peer_signal(p, 0, epoch, st); // this frame's history (ao_color[pp], ao_len[pp]) is complete
         if (rc != HR_OK) return rc;

@@ -161,6 +161,7 @@ struct hr_pass {
     Img     out_view[128];     // indexed by `which` (filled per render)
     // shadows
     uint32_t* mask = nullptr;
+    uint8_t*  count = nullptr;       // spp > 1: unoccluded rays per pixel (allocated on first use)
     __half2*  temporal_out = nullptr;
     uint2*    moments[2] = { nullptr, nullptr };
     __half2*  prev_image[2] = { nullptr, nullptr }; // [ping_pong]: written by frame N's feedback iteration, read by frame N+1's temporal
@@ -298,6 +299,14 @@ void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const Fr
                               uint32_t* mask, int row0, int row1, cudaStream_t st);
 void launch_ao_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
                          const uint8_t* sr, uint32_t* mask, int row0, int row1, cudaStream_t st);
+void launch_shadows_ray_trace_count(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
+                                    uint8_t* count, int spp, int row0, int row1, cudaStream_t st);
+void launch_ao_ray_trace_count(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
+                               const uint8_t* sr, uint8_t* count, int spp, int row0, int row1, cudaStream_t st);
+void launch_shadows_temporal_count(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint8_t* count, int spp, const HistPeers& hist, const FrameConsts& fc,
+                                   float alpha, float moments_alpha, __half2* out, uint2* moments_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
+void launch_ao_temporal_count(const GBufLevelDev& cur, const GBufLevelDev& prev, const uint8_t* count, int spp, const HistPeers& hist, const FrameConsts& fc,
+                              float alpha, __half* out, __half* len_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st);
 void launch_trace_closest(const BvhDev& bvh, const float* rays, size_t n, float* out_t, uint32_t* out_prim, float* out_uv, cudaStream_t st);
 

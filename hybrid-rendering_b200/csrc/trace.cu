@@ -81,6 +81,64 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelD
     if (lane == 0) mask[(size_t)my * MW + mx] = word;
 }
 
+// spp > 1 (not in the reference): `spp` rays per pixel with sample index num_frames * spp + s; returns the number
+// of unoccluded rays.  Separate from trace_pixel so the 1-spp kernels stay exactly what the parity runs validated.
+template <int MODE>
+__device__ __forceinline__ uint32_t trace_pixel_spp(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+                                                    const uint8_t* __restrict__ sr, int x, int y, int spp)
+{
+    uint32_t n = 0;
+    if (x < g.W && y < g.H)
+    {
+        const size_t idx   = (size_t)y * g.W + x;
+        const float  depth = __ldg(g.depth + idx);
+        if (depth != 1.0f)
+        {
+            const float  u = ((float)x + 0.5f) / (float)g.W, v = ((float)y + 0.5f) / (float)g.H;
+            const V3     P  = det::world_position_from_depth(u, v, depth, fc.view_proj_inverse);
+            const float2 e  = load_oct_normal(g.gb2, idx);
+            const V3     N  = det::octohedral_to_direction(e.x, e.y);
+            for (int s = 0; s < spp; s++)
+            {
+                const int   si = (int)fc.num_frames * spp + s;
+                const float r0 = det::sample_blue_noise(x, y, si, 0, sobol, sr);
+                const float r1 = det::sample_blue_noise(x, y, si, 1, sobol, sr);
+                Ray         r;
+                r.tmin = 0.01f;
+                if (MODE == 0)
+                {
+                    r.o = det::add(P, det::scale(N, p0)); // bias
+                    float att;
+                    det::fetch_light_properties_shadow(fc.light, P, N, r0, r1, r.d, r.tmax, att);
+                    if (att > 0.0f) n += trace_any(bvh, r) ? 0u : 1u;
+                }
+                else
+                {
+                    r.o    = det::add(P, det::scale(N, p1)); // bias
+                    r.d    = det::sample_cosine_lobe(N, r0, r1);
+                    r.tmax = p0; // ray_length
+                    n += trace_any(bvh, r) ? 0u : 1u;
+                }
+            }
+        }
+    }
+    return n;
+}
+
+// count image: one byte per pixel (0..spp); same warp <-> 8x4 block mapping as the mask kernels
+template <int MODE>
+__global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_count(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
+                                                                          const uint8_t* __restrict__ sr, uint8_t* __restrict__ count, int spp, int mrow0, int mrow1)
+{
+    const int MW   = (g.W + 7) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
+    if (mx >= MW || my >= mrow1) return;
+    const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+    const uint32_t n = trace_pixel_spp<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y, spp);
+    if (x < g.W && y < g.H) count[(size_t)y * g.W + x] = (uint8_t)n;
+}
+
 // Multi-GPU variant (shard.cu, "cooperative ray trace"): this rank traces mask rows [bounds[self], bounds[self+1]) — a
 // partition of the WHOLE image balanced on last frame's measured cost, read from device memory, so the host never needs
 // to know it: the launch grid covers the largest share the partition kernel may hand out (hr_rt_share_cap) and CTAs past
@@ -382,6 +440,22 @@ void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const 
                                 const uint8_t* sr, const RtShare& sh, cudaStream_t st)
 {
     k_ray_trace_mask_shared<1><<<shared_grid(g.W, g.H, sh.world), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, sh);
+}
+
+void launch_shadows_ray_trace_count(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float bias, const uint8_t* sobol, const uint8_t* sr,
+                                    uint8_t* count, int spp, int row0, int row1, cudaStream_t st)
+{
+    const int mrow0 = row0 / 4, mrow1 = (row1 + 3) / 4;
+    if (mrow1 <= mrow0) return;
+    k_ray_trace_count<0><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, count, spp, mrow0, mrow1);
+}
+
+void launch_ao_ray_trace_count(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
+                               const uint8_t* sr, uint8_t* count, int spp, int row0, int row1, cudaStream_t st)
+{
+    const int mrow0 = row0 / 4, mrow1 = (row1 + 3) / 4;
+    if (mrow1 <= mrow0) return;
+    k_ray_trace_count<1><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, ray_length, bias, sobol, sr, count, spp, mrow0, mrow1);
 }
 
 void launch_trace_any(const BvhDev& bvh, const float* rays, size_t n, uint32_t* out, cudaStream_t st)

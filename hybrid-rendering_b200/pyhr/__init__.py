@@ -66,12 +66,12 @@ class hr_image(C.Structure):
 class hr_shadows_params(C.Structure):
     _fields_ = [("bias", C.c_float), ("alpha", C.c_float), ("moments_alpha", C.c_float), ("phi_visibility", C.c_float), ("phi_normal", C.c_float),
                 ("sigma_depth", C.c_float), ("power", C.c_float), ("radius", C.c_int32), ("filter_iterations", C.c_int32),
-                ("feedback_iteration", C.c_int32), ("denoise", C.c_int32)]
+                ("feedback_iteration", C.c_int32), ("denoise", C.c_int32), ("spp", C.c_int32)]
 
 
 class hr_ao_params(C.Structure):
     _fields_ = [("ray_length", C.c_float), ("bias", C.c_float), ("alpha", C.c_float), ("power", C.c_float), ("blur_radius", C.c_int32),
-                ("denoise", C.c_int32)]
+                ("denoise", C.c_int32), ("spp", C.c_int32)]
 
 
 class hrs_light_desc(C.Structure):

@@ -218,6 +218,10 @@ typedef struct hr_shadows_params { /* defaults: src/ray_traced_shadows.h:50-115 
     int32_t filter_iterations;  /* 4    */
     int32_t feedback_iteration; /* 1    */
     int32_t denoise;            /* 1    */
+    int32_t spp;                /* 1: the reference's single ray per pixel.  > 1 (not in the reference):
+                                 * spp rays per pixel, sample index num_frames * spp + s; output 0 becomes an R8_UINT W x H image
+                                 * of unoccluded-ray counts, the temporal stage uses visibility = count / spp; single GPU only;
+                                 * 0 is read as 1 */
 } hr_shadows_params;
 
 /* OutputType, src/ray_traced_shadows.h:10-16 (+ internals for tests) */
@@ -246,6 +250,7 @@ typedef struct hr_ao_params { /* defaults: src/ray_traced_ao.h:51-110 */
     float   power;       /* 1.2  */
     int32_t blur_radius; /* 4    */
     int32_t denoise;     /* 1    */
+    int32_t spp;         /* 1; > 1: see hr_shadows_params.spp */
 } hr_ao_params;
 
 enum {

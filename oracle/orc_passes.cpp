@@ -91,6 +91,46 @@ void ao_ray_trace(const Scene& scene, const GBufLevel& g, const hr_frame& f, flo
         }
 }
 
+// ------------------------------------------------------------------------------------------------
+// spp > 1 (NOT in the reference; defined by SURVEY.md §8d for configs 4-5): `spp` rays per pixel with sample index
+// num_frames * spp + s; the 1-bit mask cannot hold the result, the kernels emit an 8-bit image of the number of
+// unoccluded rays per pixel; the temporal stage uses visibility = count / spp, everything downstream is unchanged.
+// ------------------------------------------------------------------------------------------------
+void ray_trace_count(const Scene& scene, const GBufLevel& g, const hr_frame& f, bool ao, float p0, float bias, int spp, const BlueNoise& bn, uint8_t* count)
+{
+    const mat4 vpi = load_mat4(f.ubo.view_proj_inverse);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < g.H; y++)
+        for (int x = 0; x < g.W; x++)
+        {
+            const ivec2 c = { x, y };
+            const vec2  tex_coord = { ((float)c.x + 0.5f) / (float)g.W, ((float)c.y + 0.5f) / (float)g.H };
+            const float depth = g.fetchd(c);
+            uint32_t    n = 0;
+            if (depth != 1.0f)
+            {
+                const vec3 world_pos  = world_position_from_depth(tex_coord, depth, vpi);
+                const vec4 gb2        = g.fetch2(c);
+                const vec3 normal     = octohedral_to_direction({ gb2.x, gb2.y });
+                const vec3 ray_origin = world_pos + normal * bias;
+                for (int s = 0; s < spp; s++)
+                {
+                    const int  idx = (int)f.num_frames * spp + s;
+                    const vec2 rnd = { sample_blue_noise(c, idx, 0, bn), sample_blue_noise(c, idx, 1, bn) };
+                    if (ao) n += (uint32_t)scene.query_visibility(ray_origin, sample_cosine_lobe(normal, rnd), p0);
+                    else
+                    {
+                        vec3  Wi;
+                        float t_max, attenuation;
+                        fetch_light_properties_shadow(f.ubo.light, world_pos, normal, rnd, Wi, t_max, attenuation);
+                        if (attenuation > 0.0f) n += (uint32_t)scene.query_visibility(ray_origin, Wi, t_max);
+                    }
+                }
+            }
+            count[(size_t)y * g.W + x] = (uint8_t)n;
+        }
+}
+
 // unpack_*_hit_value + neighborhood_mean (shadows_denoise_reprojection.comp:114-190, ao twin :101-185):
 // exact 17x17 box sum of mask bits; mask words outside the mask image read as `oob_word`.
 inline uint32_t mask_bit(const uint32_t* mask, int MW, int MH, ivec2 p, uint32_t oob_word)
@@ -114,14 +154,45 @@ inline float neighborhood_mean(const uint32_t* mask, int MW, int MH, ivec2 c, ui
     return mean / 289.0f;
 }
 
+// Visibility source of the temporal stages: the packed 1-bit ray mask (spp = 1, the reference's format) or, for spp > 1,
+// the 8-bit count image (see ray_trace_count).  Pixels outside the image read as `oob_word`'s bit (shadows 0, AO all rays
+// unoccluded: ao_denoise_reprojection.comp:111-112).
+struct VisSrc {
+    const uint32_t* mask;
+    const uint8_t*  count;
+    int             W, H, spp;
+    uint32_t        oob_word;
+    float hits(ivec2 p) const
+    {
+        if (!count) return (float)mask_bit(mask, (W + 7) / 8, (H + 3) / 4, p, oob_word);
+        // the mask image covers whole 8x4 groups: pixels of a partially covered group that lie outside the image count 0
+        const int MW = (W + 7) / 8, MH = (H + 3) / 4;
+        if (p.x < 0 || p.y < 0 || p.x >= MW * 8 || p.y >= MH * 4) return oob_word ? (float)spp : 0.0f;
+        if (p.x >= W || p.y >= H) return 0.0f;
+        return (float)count[(size_t)p.y * W + p.x];
+    }
+    float visibility(ivec2 p) const { return spp == 1 ? hits(p) : hits(p) / (float)spp; }
+    float mean(ivec2 c) const
+    {
+        float m = 0.0f;
+        for (int y = -8; y <= 8; y++)
+        {
+            float row = 0.0f;
+            for (int x = -8; x <= 8; x++) row += hits({ c.x + x, c.y + y });
+            m += row;
+        }
+        return m / (289.0f * (float)spp);
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // K3  shadows/shadows_denoise_reprojection.comp:196-293
 // tile_flags: 1 = tile appended to DenoiseTileData, 0 = to ShadowTileData (:274-292).
 // ------------------------------------------------------------------------------------------------
-void shadows_temporal(const GBufLevel& cur, const GBufLevel& prev, const uint32_t* mask, const uint16_t* prev_image, const uint16_t* prev_moments,
+void shadows_temporal(const GBufLevel& cur, const GBufLevel& prev, const VisSrc& vs, const uint16_t* prev_image, const uint16_t* prev_moments,
                       const hr_frame& f, float alpha_p, float moments_alpha_p, uint16_t* out, uint16_t* moments_out, uint8_t* tile_flags)
 {
-    const int  W = cur.W, H = cur.H, MW = (W + 7) / 8, MH = (H + 3) / 4, TW = (W + 7) / 8, TH = (H + 7) / 8;
+    const int  W = cur.W, H = cur.H, TW = (W + 7) / 8, TH = (H + 7) / 8;
     const mat4 vpi = load_mat4(f.ubo.view_proj_inverse);
     memset(tile_flags, 0, (size_t)TW * TH);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -134,12 +205,12 @@ void shadows_temporal(const GBufLevel& cur, const GBufLevel& prev, const uint32_
                 {
                     ivec2 c = { tx * 8 + lx, ty * 8 + ly };
                     if (!cur.inside(c)) continue;
-                    float mean  = neighborhood_mean(mask, MW, MH, c, 0u);
+                    float mean  = vs.mean(c);
                     float depth = cur.fetchd(c);
                     float visibility = 0.0f, ov = 0.0f, ovar = 0.0f, om0 = 0.0f, om1 = 0.0f, history_length = 0.0f;
                     if (depth != 1.0f)
                     {
-                        visibility = (float)mask_bit(mask, MW, MH, c, 0u);
+                        visibility = vs.visibility(c);
                         ReprojectIn in;
                         in.frag_coord        = c;
                         in.depth             = depth;
@@ -292,10 +363,10 @@ void upsample_scalar(const GBufLevel& g0, const GBufLevel& gm, const uint16_t* i
 // ------------------------------------------------------------------------------------------------
 // K9  ao/ao_denoise_reprojection.comp:191-260
 // ------------------------------------------------------------------------------------------------
-void ao_temporal(const GBufLevel& cur, const GBufLevel& prev, const uint32_t* mask, const uint16_t* prev_ao, const uint16_t* prev_len,
+void ao_temporal(const GBufLevel& cur, const GBufLevel& prev, const VisSrc& vs, const uint16_t* prev_ao, const uint16_t* prev_len,
                  const hr_frame& f, float alpha_p, uint16_t* out, uint16_t* len_out, uint8_t* tile_flags)
 {
-    const int  W = cur.W, H = cur.H, MW = (W + 7) / 8, MH = (H + 3) / 4, TW = (W + 7) / 8, TH = (H + 7) / 8;
+    const int  W = cur.W, H = cur.H, TW = (W + 7) / 8, TH = (H + 7) / 8;
     const mat4 vpi = load_mat4(f.ubo.view_proj_inverse);
 #pragma omp parallel for schedule(dynamic, 1)
     for (int ty = 0; ty < TH; ty++)
@@ -307,12 +378,12 @@ void ao_temporal(const GBufLevel& cur, const GBufLevel& prev, const uint32_t* ma
                 {
                     ivec2 c = { tx * 8 + lx, ty * 8 + ly };
                     if (!cur.inside(c)) continue;
-                    float mean   = neighborhood_mean(mask, MW, MH, c, 0xFFFFFFFFu); // :111-112
+                    float mean   = vs.mean(c); // out-of-image words read as all-visible, :111-112
                     float depth  = cur.fetchd(c);
                     float out_ao = 1.0f, history_length = 0.0f;
                     if (depth != 1.0f)
                     {
-                        float ao = (float)mask_bit(mask, MW, MH, c, 0xFFFFFFFFu);
+                        float ao = vs.visibility(c);
                         ReprojectIn in;
                         in.frag_coord        = c;
                         in.depth             = depth;
@@ -456,7 +527,7 @@ void orc_ao_ray_trace(void* scene, const orc_gbuf* g, const hr_frame* f, float r
 
 void orc_shadows_temporal(const orc_gbuf* cur, const orc_gbuf* prev, const uint32_t* mask, const uint16_t* prev_image, const uint16_t* prev_moments,
                           const hr_frame* f, float alpha, float moments_alpha, uint16_t* out, uint16_t* moments_out, uint8_t* tile_flags)
-{ shadows_temporal(lvl(cur), lvl(prev), mask, prev_image, prev_moments, *f, alpha, moments_alpha, out, moments_out, tile_flags); }
+{ VisSrc vs{ mask, nullptr, cur->W, cur->H, 1, 0u }; shadows_temporal(lvl(cur), lvl(prev), vs, prev_image, prev_moments, *f, alpha, moments_alpha, out, moments_out, tile_flags); }
 
 void orc_shadows_atrous(const orc_gbuf* g, const uint16_t* in_img, const uint8_t* tile_flags, int radius, int step_size, float phi_visibility,
                         float phi_normal, float sigma_depth, float power, uint16_t* out)
@@ -467,10 +538,26 @@ void orc_upsample_scalar(const orc_gbuf* g0, const orc_gbuf* gm, const uint16_t*
 
 void orc_ao_temporal(const orc_gbuf* cur, const orc_gbuf* prev, const uint32_t* mask, const uint16_t* prev_ao, const uint16_t* prev_len,
                      const hr_frame* f, float alpha, uint16_t* out, uint16_t* len_out, uint8_t* tile_flags)
-{ ao_temporal(lvl(cur), lvl(prev), mask, prev_ao, prev_len, *f, alpha, out, len_out, tile_flags); }
+{ VisSrc vs{ mask, nullptr, cur->W, cur->H, 1, 0xFFFFFFFFu }; ao_temporal(lvl(cur), lvl(prev), vs, prev_ao, prev_len, *f, alpha, out, len_out, tile_flags); }
 
 void orc_ao_bilateral_blur(const orc_gbuf* g, const uint16_t* in_img, const uint8_t* tile_flags, const float* zbp, int dirx, int diry, int radius, uint16_t* out)
 { ao_bilateral_blur(lvl(g), in_img, tile_flags, zbp, dirx, diry, radius, out); }
+
+// ---- spp > 1 (count images) ----
+void orc_shadows_ray_trace_spp(void* scene, const orc_gbuf* g, const hr_frame* f, float bias, int spp, const uint8_t* sobol, const uint8_t* sr, uint8_t* count)
+{ BlueNoise bn{ sobol, sr }; ray_trace_count(*(Scene*)scene, lvl(g), *f, false, 0.0f, bias, spp, bn, count); }
+
+void orc_ao_ray_trace_spp(void* scene, const orc_gbuf* g, const hr_frame* f, float ray_length, float bias, int spp, const uint8_t* sobol, const uint8_t* sr,
+                          uint8_t* count)
+{ BlueNoise bn{ sobol, sr }; ray_trace_count(*(Scene*)scene, lvl(g), *f, true, ray_length, bias, spp, bn, count); }
+
+void orc_shadows_temporal_spp(const orc_gbuf* cur, const orc_gbuf* prev, const uint8_t* count, int spp, const uint16_t* prev_image, const uint16_t* prev_moments,
+                              const hr_frame* f, float alpha, float moments_alpha, uint16_t* out, uint16_t* moments_out, uint8_t* tile_flags)
+{ VisSrc vs{ nullptr, count, cur->W, cur->H, spp, 0u }; shadows_temporal(lvl(cur), lvl(prev), vs, prev_image, prev_moments, *f, alpha, moments_alpha, out, moments_out, tile_flags); }
+
+void orc_ao_temporal_spp(const orc_gbuf* cur, const orc_gbuf* prev, const uint8_t* count, int spp, const uint16_t* prev_ao, const uint16_t* prev_len,
+                         const hr_frame* f, float alpha, uint16_t* out, uint16_t* len_out, uint8_t* tile_flags)
+{ VisSrc vs{ nullptr, count, cur->W, cur->H, spp, 0xFFFFFFFFu }; ao_temporal(lvl(cur), lvl(prev), vs, prev_ao, prev_len, *f, alpha, out, len_out, tile_flags); }
 
 int orc_num_threads(void)
 {

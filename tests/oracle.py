@@ -50,6 +50,10 @@ def lib():
         L.orc_upsample_scalar.argtypes = [P, P, P, I, F, F, P]
         L.orc_ao_temporal.argtypes = [P, P, P, P, P, P, F, P, P, P]
         L.orc_ao_bilateral_blur.argtypes = [P, P, P, P, I, I, I, P]
+        L.orc_shadows_ray_trace_spp.argtypes = [P, P, P, F, I, P, P, P]
+        L.orc_ao_ray_trace_spp.argtypes = [P, P, P, F, F, I, P, P, P]
+        L.orc_shadows_temporal_spp.argtypes = [P, P, P, I, P, P, P, F, F, P, P, P]
+        L.orc_ao_temporal_spp.argtypes = [P, P, P, I, P, P, P, F, P, P, P]
         L.orc_num_threads.restype = C.c_int
         L.orc_shading_create.restype = C.c_void_p
         L.orc_shading_create.argtypes = [P, P, P, P, C.c_size_t, P, C.c_size_t]
@@ -140,12 +144,14 @@ def _coop_mask(o):
 
 
 class ShadowsOracle:
-    def __init__(self, W0, H0, scale=0):
+    def __init__(self, W0, H0, scale=0, spp=1):
         self.W0, self.H0, self.scale = W0, H0, scale
         self.W, self.H = W0, H0
         for _ in range(scale):
             self.W, self.H = max(self.W // 2, 1), max(self.H // 2, 1)
         W, H = self.W, self.H
+        self.spp = spp  # > 1: SURVEY.md §8d definition (count image instead of the bit mask)
+        self.count = np.zeros((H, W), np.uint8)
         self.mask = np.zeros(((H + 3) // 4, (W + 7) // 8), np.uint32)
         self.temporal = np.zeros((H, W, 2), np.uint16)
         self.moments = [np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)]
@@ -187,16 +193,24 @@ class ShadowsOracle:
             self.moments[1 - pp][:] = 0
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
-        L.orc_shadows_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.bias, p(sobol), p(sr), p(self.mask))
-        if self.rt_share is not None:
-            _coop_mask(self)
+        if self.spp > 1:
+            L.orc_shadows_ray_trace_spp(scene.h, C.byref(gc), C.byref(frame), P.bias, self.spp, p(sobol), p(sr), p(self.count))
+            self.final = self.count
+            if not P.denoise:
+                return
+            L.orc_shadows_temporal_spp(C.byref(gc), C.byref(gp), p(self.count), self.spp, p(self.prev_image), p(self.moments[1 - pp]), C.byref(frame),
+                                       P.alpha, P.moments_alpha, p(self.temporal), p(self.moments[pp]), p(self.tile_flags))
         else:
-            self._poison(self.mask, 32, div=4)
-        self.final = self.mask
-        if not P.denoise:
-            return
-        L.orc_shadows_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.prev_image), p(self.moments[1 - pp]), C.byref(frame), P.alpha,
-                               P.moments_alpha, p(self.temporal), p(self.moments[pp]), p(self.tile_flags))
+            L.orc_shadows_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.bias, p(sobol), p(sr), p(self.mask))
+            if self.rt_share is not None:
+                _coop_mask(self)
+            else:
+                self._poison(self.mask, 32, div=4)
+            self.final = self.mask
+            if not P.denoise:
+                return
+            L.orc_shadows_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.prev_image), p(self.moments[1 - pp]), C.byref(frame), P.alpha,
+                                   P.moments_alpha, p(self.temporal), p(self.moments[pp]), p(self.tile_flags))
         self.cur_moments = self.moments[pp]
         for a in (self.temporal, self.moments[pp], self.tile_flags):
             self._poison(a, 16, div=8 if a is self.tile_flags else 1)
@@ -222,12 +236,14 @@ class ShadowsOracle:
 
 
 class AOOracle:
-    def __init__(self, W0, H0, scale=1):
+    def __init__(self, W0, H0, scale=1, spp=1):
         self.W0, self.H0, self.scale = W0, H0, scale
         self.W, self.H = W0, H0
         for _ in range(scale):
             self.W, self.H = max(self.W // 2, 1), max(self.H // 2, 1)
         W, H = self.W, self.H
+        self.spp = spp
+        self.count = np.zeros((H, W), np.uint8)
         self.mask = np.zeros(((H + 3) // 4, (W + 7) // 8), np.uint32)
         self.color = [np.zeros((H, W), np.uint16), np.zeros((H, W), np.uint16)]
         self.length = [np.zeros((H, W), np.uint16), np.zeros((H, W), np.uint16)]
@@ -251,16 +267,24 @@ class AOOracle:
             self.length[1 - pp][:] = 0
             self.first = False
         gc, gp = cur.c(self.scale), prev.c(self.scale)
-        L.orc_ao_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, p(sobol), p(sr), p(self.mask))
-        if getattr(self, "rt_share", None) is not None:
-            _coop_mask(self)
+        if self.spp > 1:
+            L.orc_ao_ray_trace_spp(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, self.spp, p(sobol), p(sr), p(self.count))
+            self.final = self.count
+            if not P.denoise:
+                return
+            L.orc_ao_temporal_spp(C.byref(gc), C.byref(gp), p(self.count), self.spp, p(self.color[1 - pp]), p(self.length[1 - pp]), C.byref(frame),
+                                  P.alpha, p(self.color[pp]), p(self.length[pp]), p(self.tile_flags))
         else:
-            self._poison(self.mask, 32, div=4)
-        self.final = self.mask
-        if not P.denoise:
-            return
-        L.orc_ao_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.color[1 - pp]), p(self.length[1 - pp]), C.byref(frame), P.alpha,
-                          p(self.color[pp]), p(self.length[pp]), p(self.tile_flags))
+            L.orc_ao_ray_trace(scene.h, C.byref(gc), C.byref(frame), P.ray_length, P.bias, p(sobol), p(sr), p(self.mask))
+            if getattr(self, "rt_share", None) is not None:
+                _coop_mask(self)
+            else:
+                self._poison(self.mask, 32, div=4)
+            self.final = self.mask
+            if not P.denoise:
+                return
+            L.orc_ao_temporal(C.byref(gc), C.byref(gp), p(self.mask), p(self.color[1 - pp]), p(self.length[1 - pp]), C.byref(frame), P.alpha,
+                              p(self.color[pp]), p(self.length[pp]), p(self.tile_flags))
         self.temporal = self.color[pp]
         self.cur_length = self.length[pp]
         for a in (self.color[pp], self.length[pp], self.tile_flags):

@@ -44,6 +44,7 @@ def test_version_and_defaults_without_gpu():
     a = pyhr.hr_ao_params()
     lib.hr_ao_default_params(C.byref(a))          # src/ray_traced_ao.h:51-110
     assert (a.ray_length, a.blur_radius, a.denoise) == (7.0, 4, 1) and abs(a.bias - 0.3) < 1e-7 and abs(a.power - 1.2) < 1e-7
+    assert p.spp == 1 and a.spp == 1             # one ray per pixel like the reference; > 1 is the SURVEY.md §8d extension
 
 
 def test_shard_rows_partition():

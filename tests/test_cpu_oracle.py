@@ -165,6 +165,67 @@ def test_golden_ddgi_reflections_192x112():
         assert (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max() <= 2e-3, name
 
 
+def _unpack_mask(mask, W, H):
+    y, x = np.mgrid[0:H, 0:W]
+    return ((mask[y >> 2, x >> 3] >> ((y & 3) * 8 + (x & 7)).astype(np.uint32)) & 1).astype(np.uint8)
+
+
+def test_spp_count_images():
+    """spp > 1 (spp rays per pixel, sample index num_frames * spp + s, 8-bit count image instead of the bit mask):
+    * spp = 1 through the count path is the mask path: count == unpacked mask, every temporal output bit-identical;
+    * with a static camera the 2-spp count of frame n is the sum of the 1-spp masks of frames 2n and 2n+1 (same rays);
+    * the denoised 2-spp result stays a visibility in [0, 1] close to the 1-spp mean."""
+    W, H = 64, 48
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    tri, _ = sc.world_triangles()
+    osc = O.Scene(tri, brute=True)
+    bn = pyhr.blue_noise()
+    L = O.lib()
+    import ctypes as C
+    f0 = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H)
+    g = O.GBufMips(pyhr.write_gbuffer(sc, f0, W, H))
+    gc = g.c(0)
+    # (1) spp = 1: count path == mask path, including the temporal stage
+    sh1 = O.ShadowsOracle(W, H, 0)
+    zero = O.zero_gbuf_mips(W, H)
+    sh1.render(osc, g, zero, f0, bn)
+    cnt = np.zeros((H, W), np.uint8)
+    L.orc_shadows_ray_trace_spp(osc.h, C.byref(gc), C.byref(f0), sh1.params.bias, 1, O.p(bn[0]), O.p(bn[1]), O.p(cnt))
+    assert np.array_equal(cnt, _unpack_mask(sh1.mask, W, H))
+    t2, m2, tf2 = np.zeros_like(sh1.temporal), np.zeros_like(sh1.moments[0]), np.zeros_like(sh1.tile_flags)
+    zimg, zmom = np.zeros((H, W, 2), np.uint16), np.zeros((H, W, 4), np.uint16)
+    gz = zero.c(0)
+    L.orc_shadows_temporal_spp(C.byref(gc), C.byref(gz), O.p(cnt), 1, O.p(zimg), O.p(zmom), C.byref(f0), sh1.params.alpha, sh1.params.moments_alpha,
+                               O.p(t2), O.p(m2), O.p(tf2))
+    assert np.array_equal(t2, sh1.temporal) and np.array_equal(m2, sh1.cur_moments) and np.array_equal(tf2, sh1.tile_flags)
+    # (2) 2 spp at frame n == 1 spp at frames 2n and 2n+1 (static camera: only the sample index changes)
+    for n in (0, 3):
+        c2 = np.zeros((H, W), np.uint8)
+        fn = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H, num_frames=n)
+        L.orc_shadows_ray_trace_spp(osc.h, C.byref(gc), C.byref(fn), sh1.params.bias, 2, O.p(bn[0]), O.p(bn[1]), O.p(c2))
+        acc = np.zeros((H, W), np.uint8)
+        for k in (2 * n, 2 * n + 1):
+            fk = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H, num_frames=k)
+            mk = np.zeros_like(sh1.mask)
+            L.orc_shadows_ray_trace(osc.h, C.byref(gc), C.byref(fk), sh1.params.bias, O.p(bn[0]), O.p(bn[1]), O.p(mk))
+            acc += _unpack_mask(mk, W, H)
+        assert np.array_equal(c2, acc)
+    # (3) full chains at 2 spp
+    sh2, ao2 = O.ShadowsOracle(W, H, 0, spp=2), O.AOOracle(W, H, 1, spp=2)
+    sh1b, ao1b = O.ShadowsOracle(W, H, 0), O.AOOracle(W, H, 1)
+    f, prev = None, zero
+    for i in range(4):
+        f = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H, prev=f, num_frames=i)
+        for o in (sh2, ao2, sh1b, ao1b):
+            o.render(osc, g, prev, f, bn)
+        prev = g
+    v2, v1 = O.h2f(sh2.final)[..., 0], O.h2f(sh1b.final)[..., 0]
+    assert v2.min() >= 0.0 and v2.max() <= 1.0 + 1e-3 and abs(float(v2.mean()) - float(v1.mean())) < 0.05
+    a2, a1 = O.h2f(ao2.final), O.h2f(ao1b.final)
+    assert a2.min() >= 0.0 and a2.max() <= 1.0 + 1e-3 and abs(float(a2.mean()) - float(a1.mean())) < 0.05
+    assert sh2.count.max() <= 2 and ao2.count.max() <= 2 and sh2.count.any()
+
+
 def test_mask_bit_order_and_tile_partition():
     sh, ao = small_sequence(frames=2)
     W, H = 64, 48
