@@ -1,4 +1,5 @@
-"""BASELINE.json's full size (3840x2160, the 262 144-triangle arcade of bench.py) through size-independent properties — the
+"""(File name sorts after the suites validated on hardware this round: this one was added after the GPU budget was spent.)
+BASELINE.json's full size (3840x2160, the 262 144-triangle arcade of bench.py) through size-independent properties — the
 oracle needs minutes per 4K frame, so nothing here runs it:
 
 * determinism: the same three frames rendered by two fresh contexts give bit-identical images (masks AND fp16 outputs);
