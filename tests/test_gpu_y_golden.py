@@ -1,5 +1,4 @@
-"""(File name sorts after the suites validated on hardware this round: this one was added after the GPU budget was spent.)
-The CUDA path against the COMMITTED golden fixture (tests/golden/shadows_ao_256x144_seq12.npz, generated from the oracle
+"""The CUDA path against the COMMITTED golden fixture (tests/golden/shadows_ao_256x144_seq12.npz, generated from the oracle
 by tests/golden/make_golden.py): the 8-static + 4-panning-frame sequence of test_gpu_parity.py is driven through the C ABI
 and the state after the last frame is compared with the stored images — no oracle code runs in this test.
 Visibility masks, tile classification and history lengths bit-exact; tolerance-checked images within 1e-3 RMSE."""
