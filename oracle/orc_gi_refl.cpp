@@ -7,6 +7,7 @@
 // Environment = constant colour (sky cubemaps / IBL prefilter / BRDF LUT are release-zip assets: the IBL specular
 // term of reflections_ray_trace.rchit:97-104 is therefore 0).  Parity unpinned.
 #include "orc_shading.h"
+#include <array>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -125,32 +126,37 @@ void ddgi_probe_update(const DDGIUniforms& d, const uint16_t* radiance, const ui
                 }
 }
 
-// K20  gi_border_update.glsl:151-175; the g_offsets tables (:35-143) follow one pattern, generated here:
-//   top/bottom rows mirror x, left/right columns mirror y, corners copy the opposite interior corner.
+// K20  gi_border_update.glsl:151-175.  The g_offsets tables (:35-143) follow one pattern — top / bottom rows mirror x, left /
+// right columns mirror y, corners copy the opposite interior corner — generated here in the reference's order and checked
+// entry by entry against the reference's two literal tables (tests/test_ref_constants.py, tests/golden/ref_constants.json).
+// Entry = (src.x, src.y, dst.x, dst.y) relative to the probe's gutter origin.
+static std::vector<std::array<int, 4>> border_offsets(int S)
+{
+    std::vector<std::array<int, 4>> t;
+    for (int i = 1; i <= S; i++) t.push_back({ S + 1 - i, 1, i, 0 });
+    for (int i = 1; i <= S; i++) t.push_back({ S + 1 - i, S, i, S + 1 });
+    for (int i = 1; i <= S; i++) t.push_back({ 1, S + 1 - i, 0, i });
+    for (int i = 1; i <= S; i++) t.push_back({ S, S + 1 - i, S + 1, i });
+    t.push_back({ S, S, 0, 0 });
+    t.push_back({ 1, S, S + 1, 0 });
+    t.push_back({ S, 1, 0, S + 1 });
+    t.push_back({ 1, 1, S + 1, S + 1 });
+    return t;
+}
+
 void ddgi_border_update(const DDGIUniforms& d, bool depth, uint16_t* atlas)
 {
     const int S = depth ? d.depth_probe_side_length : d.irradiance_probe_side_length;
     const int TWd = depth ? d.depth_texture_width : d.irradiance_texture_width;
     const int C = depth ? 2 : 4;
     const int px = d.probe_counts[0] * d.probe_counts[1], pz = d.probe_counts[2];
-    auto copy = [&](int bx, int by, int sx, int sy, int dx, int dy) {
-        memcpy(atlas + C * ((size_t)(by + dy) * TWd + bx + dx), atlas + C * ((size_t)(by + sy) * TWd + bx + sx), C * 2);
-    };
+    const auto offs = border_offsets(S);
     for (int wy = 0; wy < pz; wy++)
         for (int wx = 0; wx < px; wx++)
         {
             const int bx = wx * (S + 2) + 1, by = wy * (S + 2) + 1; // :169
-            for (int i = 1; i <= S; i++)
-            {
-                copy(bx, by, S + 1 - i, 1, i, 0);
-                copy(bx, by, S + 1 - i, S, i, S + 1);
-                copy(bx, by, 1, S + 1 - i, 0, i);
-                copy(bx, by, S, S + 1 - i, S + 1, i);
-            }
-            copy(bx, by, S, S, 0, 0);
-            copy(bx, by, 1, S, S + 1, 0);
-            copy(bx, by, S, 1, 0, S + 1);
-            copy(bx, by, 1, 1, S + 1, S + 1);
+            for (const auto& o : offs) // copy_texel :151-161
+                memcpy(atlas + C * ((size_t)(by + o[3]) * TWd + bx + o[2]), atlas + C * ((size_t)(by + o[1]) * TWd + bx + o[0]), C * 2);
         }
 }
 
@@ -218,8 +224,8 @@ void reflections_ray_trace(const ShadingScene& ss, const GBufLevel& g, const hr_
             float ray_length = -1.0f;
             bool  trace = false;
             vec3  dir   = { 0, 0, 1 };
-            if (roughness < 0.05f) { dir = reflect(-Wo, N); trace = true; }
-            else if (roughness > 0.75f && rp.approximate_with_ddgi == 1)
+            if (roughness < orc_const::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD) { dir = reflect(-Wo, N); trace = true; }
+            else if (roughness > orc_const::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD && rp.approximate_with_ddgi == 1)
             {
                 vec3 R = reflect(-Wo, N);
                 color  = sample_irradiance(*d, P, R, Wo, irr, dep) * rp.rough_ddgi_intensity;
@@ -326,9 +332,9 @@ void reflections_temporal(const GBufLevel& cur, const GBufLevel& prev, const uin
                     }
                     store4(moments_out, W, c.x, c.y, omom[0], omom[1], omom[2], omom[3]);
                     store4(out, W, c.x, c.y, orad[0], orad[1], orad[2], orad[3]);
-                    if (depth != 1.0f && roughness >= 0.05f)
+                    if (depth != 1.0f && roughness >= orc_const::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD)
                     {
-                        if (approximate_with_ddgi == 1) { if (roughness <= 0.75f) should = true; }
+                        if (approximate_with_ddgi == 1) { if (roughness <= orc_const::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD) should = true; }
                         else should = true;
                     }
                 }
@@ -342,8 +348,8 @@ void reflections_atrous(const GBufLevel& g, const uint16_t* in_img, const uint8_
 {
     const int   W = g.W, H = g.H, TW = (W + 7) / 8;
     const ImgH  in = { W, H, 4, in_img };
-    const float kernel_weights[3] = { 1.0f, 2.0f / 3.0f, 1.0f / 6.0f };
-    const float vk[2][2] = { { 1.0f / 4.0f, 1.0f / 8.0f }, { 1.0f / 8.0f, 1.0f / 16.0f } };
+    const float* kernel_weights = orc_const::ATROUS_KERNEL_WEIGHTS;
+    const auto& vk = orc_const::ATROUS_VARIANCE_KERNEL;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++)
@@ -359,8 +365,8 @@ void reflections_atrous(const GBufLevel& g, const uint16_t* in_img, const uint8_
             vec3  current_normal = octohedral_to_direction({ c2.x, c2.y });
             float center_depth = c3.w, depth = g.fetchd(ipos), roughness = c3.x;
             if (depth == 1.0f) { store4(out, W, x, y, 0, 0, 0, 0); continue; }
-            if (roughness < 0.05f || (approximate_with_ddgi == 1 && roughness > 0.75f)) { store4(out, W, x, y, cc[0], cc[1], cc[2], cc[3]); continue; }
-            const float phi_c = phi_color * sqrtf(fmaxf(0.0f, 1e-10f + var));
+            if (roughness < orc_const::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD || (approximate_with_ddgi == 1 && roughness > orc_const::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD)) { store4(out, W, x, y, cc[0], cc[1], cc[2], cc[3]); continue; }
+            const float phi_c = phi_color * sqrtf(fmaxf(0.0f, orc_const::ATROUS_EPS_VARIANCE + var));
             float sum_w = 1.0f, sc[4] = { cc[0], cc[1], cc[2], cc[3] };
             for (int yy = -radius; yy <= radius; yy++)
                 for (int xx = -radius; xx <= radius; xx++)
@@ -456,6 +462,39 @@ void orc_ddgi_probe_update(const DDGIUniforms* d, const uint16_t* radiance, cons
 { ddgi_probe_update(*d, radiance, dirdepth, depth ? atlas_dep(d, prev) : atlas_irr(d, prev), first_frame, depth != 0, out); }
 
 void orc_ddgi_border_update(const DDGIUniforms* d, int depth, uint16_t* atlas) { ddgi_border_update(*d, depth != 0, atlas); }
+// the generated g_offsets table for probe side S: 4*S + 4 entries of (src.x, src.y, dst.x, dst.y); returns the entry count
+int orc_border_offsets(int S, int32_t* out4)
+{
+    const auto t = border_offsets(S);
+    if (out4) for (size_t i = 0; i < t.size(); i++) for (int k = 0; k < 4; k++) out4[4 * i + k] = t[i][k];
+    return (int)t.size();
+}
+// named constant of orc_constants.h by name (tests compare them with the values parsed from the reference's sources)
+int orc_get_constant(const char* name, double* out, int cap)
+{
+    namespace oc = orc_const;
+    struct E { const char* n; int cnt; double v[6]; };
+    const E table[] = {
+        { "M_PI", 1, { oc::M_PI_REF } }, { "EPSILON", 1, { oc::EPSILON } },
+        { "MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD", 1, { oc::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD } },
+        { "DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD", 1, { oc::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD } },
+        { "NORMAL_DISTANCE", 1, { oc::NORMAL_DISTANCE } }, { "PLANE_DISTANCE", 1, { oc::PLANE_DISTANCE } }, { "MIN_ROUGHNESS", 1, { oc::MIN_ROUGHNESS } },
+        { "atrous_eps_variance", 1, { oc::ATROUS_EPS_VARIANCE } },
+        { "atrous_kernel_weights", 3, { oc::ATROUS_KERNEL_WEIGHTS[0], oc::ATROUS_KERNEL_WEIGHTS[1], oc::ATROUS_KERNEL_WEIGHTS[2] } },
+        { "atrous_variance_kernel", 4, { oc::ATROUS_VARIANCE_KERNEL[0][0], oc::ATROUS_VARIANCE_KERNEL[0][1], oc::ATROUS_VARIANCE_KERNEL[1][0], oc::ATROUS_VARIANCE_KERNEL[1][1] } },
+        { "rng.star_multiplier", 1, { (double)oc::RNG_STAR_MULTIPLIER } }, { "rng.rotl_a", 1, { (double)oc::RNG_ROTL_A } }, { "rng.shift_b", 1, { (double)oc::RNG_SHIFT_B } },
+        { "rng.rotl_c", 1, { (double)oc::RNG_ROTL_C } },
+        { "rng.hash", 6, { (double)oc::RNG_HASH_XOR0, (double)oc::RNG_HASH_SHR0, (double)oc::RNG_HASH_MUL0, (double)oc::RNG_HASH_SHR1, (double)oc::RNG_HASH_MUL1, (double)oc::RNG_HASH_SHR2 } },
+        { "rng.seed_shift", 1, { (double)oc::RNG_SEED_SHIFT } }, { "rng.float_bits", 2, { (double)oc::RNG_FLOAT_ONE, (double)oc::RNG_FLOAT_SHIFT } },
+    };
+    for (const E& e : table)
+        if (!strcmp(e.n, name))
+        {
+            for (int i = 0; i < e.cnt && i < cap; i++) out[i] = e.v[i];
+            return e.cnt;
+        }
+    return 0;
+}
 
 void orc_ddgi_sample_probe_grid(const orc_gbuf* g, const hr_frame* f, const DDGIUniforms* d, const uint16_t* irr, const uint16_t* dep, float gi_intensity, uint16_t* out)
 { ddgi_sample_probe_grid(lvl(g), *f, *d, atlas_irr(d, irr), atlas_dep(d, dep), gi_intensity, out); }

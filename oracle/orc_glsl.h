@@ -6,6 +6,7 @@
 // run here (Vulkan RT + GLSL); this restatement follows the shader source.
 #pragma once
 #include "../include/hr_api.h"
+#include "orc_constants.h"
 #include "orc_math.h"
 #include <algorithm>
 #include <vector>
@@ -49,7 +50,7 @@ inline mat4 load_mat4(const float* m) { mat4 r; memcpy(r.m, m, 64); return r; }
 // ------------------------------------------------------------------------------------------------
 // common.glsl
 // ------------------------------------------------------------------------------------------------
-static constexpr float M_PI_F = 3.14159265359f; // common.glsl:16
+static constexpr float M_PI_F = orc_const::M_PI_REF; // common.glsl:16
 
 // common.glsl:143-146
 inline float luminance(vec3 rgb) { return fmaxf(dot(rgb, vec3{ 0.299f, 0.587f, 0.114f }), 0.0001f); }
@@ -216,8 +217,8 @@ inline float compute_edge_stopping_weight(float center_depth, float sample_depth
 // ------------------------------------------------------------------------------------------------
 // reprojection.glsl
 // ------------------------------------------------------------------------------------------------
-static constexpr float NORMAL_DISTANCE = 0.1f; // :6
-static constexpr float PLANE_DISTANCE  = 5.0f; // :7
+static constexpr float NORMAL_DISTANCE = orc_const::NORMAL_DISTANCE; // :6
+static constexpr float PLANE_DISTANCE  = orc_const::PLANE_DISTANCE; // :7
 
 inline bool plane_distance_disocclusion_check(vec3 current_pos, vec3 history_pos, vec3 current_normal) // :11-17
 {

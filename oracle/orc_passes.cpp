@@ -261,8 +261,8 @@ void shadows_atrous(const GBufLevel& g, const uint16_t* in_img, const uint8_t* t
 {
     const int   W = g.W, H = g.H, TW = (W + 7) / 8;
     const ImgH  in = { W, H, 2, in_img };
-    const float kernel_weights[3] = { 1.0f, 2.0f / 3.0f, 1.0f / 6.0f };
-    const float vk[2][2] = { { 1.0f / 4.0f, 1.0f / 8.0f }, { 1.0f / 8.0f, 1.0f / 16.0f } };
+    const float* kernel_weights = orc_const::ATROUS_KERNEL_WEIGHTS;
+    const auto& vk = orc_const::ATROUS_VARIANCE_KERNEL;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++)
@@ -287,7 +287,7 @@ void shadows_atrous(const GBufLevel& g, const uint16_t* in_img, const uint8_t* t
                 store_h(out, W, 2, ipos, 1, cv1);
                 continue;
             }
-            const float phi_vis = phi_visibility * sqrtf(fmaxf(0.0f, 1e-10f + var));
+            const float phi_vis = phi_visibility * sqrtf(fmaxf(0.0f, orc_const::ATROUS_EPS_VARIANCE + var));
             float       sum_w = 1.0f, s0 = cv0, s1 = cv1;
             for (int yy = -radius; yy <= radius; yy++)
                 for (int xx = -radius; xx <= radius; xx++)

@@ -17,32 +17,32 @@ struct RNG { uint32_t sx, sy; };
 inline uint32_t rng_rotl(uint32_t x, uint32_t k) { return (x << k) | (x >> (32 - k)); }
 inline uint32_t rng_next(RNG& r)
 {
-    uint32_t result = r.sx * 0x9e3779bbu;
+    uint32_t result = r.sx * orc_const::RNG_STAR_MULTIPLIER;
     r.sy ^= r.sx;
-    r.sx = rng_rotl(r.sx, 26) ^ r.sy ^ (r.sy << 9);
-    r.sy = rng_rotl(r.sy, 13);
+    r.sx = rng_rotl(r.sx, orc_const::RNG_ROTL_A) ^ r.sy ^ (r.sy << orc_const::RNG_SHIFT_B);
+    r.sy = rng_rotl(r.sy, orc_const::RNG_ROTL_C);
     return result;
 }
 inline uint32_t rng_hash(uint32_t seed)
 {
-    seed = (seed ^ 61u) ^ (seed >> 16);
-    seed *= 9u;
-    seed = seed ^ (seed >> 4);
-    seed *= 0x27d4eb2du;
-    seed = seed ^ (seed >> 15);
+    seed = (seed ^ orc_const::RNG_HASH_XOR0) ^ (seed >> orc_const::RNG_HASH_SHR0);
+    seed *= orc_const::RNG_HASH_MUL0;
+    seed = seed ^ (seed >> orc_const::RNG_HASH_SHR1);
+    seed *= orc_const::RNG_HASH_MUL1;
+    seed = seed ^ (seed >> orc_const::RNG_HASH_SHR2);
     return seed;
 }
 inline RNG rng_init(uint32_t idx, uint32_t idy, uint32_t frame_index)
 {
     RNG r;
-    r.sx = rng_hash((idx << 16) | idy);
+    r.sx = rng_hash((idx << orc_const::RNG_SEED_SHIFT) | idy);
     r.sy = rng_hash(frame_index);
     rng_next(r);
     return r;
 }
 inline float next_float(RNG& r)
 {
-    uint32_t u = 0x3f800000u | (rng_next(r) >> 9);
+    uint32_t u = orc_const::RNG_FLOAT_ONE | (rng_next(r) >> orc_const::RNG_FLOAT_SHIFT);
     float    f;
     memcpy(&f, &u, 4);
     return f - 1.0f;
@@ -71,13 +71,13 @@ inline Surface fetch_surface(const ShadingScene& ss, const Hit& h)
     s.N = normalize((vec3{ n[0], n[1], n[2] } * b0 + vec3{ n[3], n[4], n[5] } * b1) + vec3{ n[6], n[7], n[8] } * b2);
     const hr_material& m = ss.materials[ss.prim_mat[h.prim]];
     s.albedo    = { m.albedo[0], m.albedo[1], m.albedo[2] };
-    s.roughness = fmaxf(m.roughness, 0.1f); // MIN_ROUGHNESS, scene_descriptor_set.glsl:202
+    s.roughness = fmaxf(m.roughness, orc_const::MIN_ROUGHNESS); // MIN_ROUGHNESS, scene_descriptor_set.glsl:202
     s.metallic  = m.metallic;
     return s;
 }
 
 // ---- brdf.glsl:36-142 ------------------------------------------------------------------------------------------------
-static constexpr float EPSILON_F = 0.0001f;
+static constexpr float EPSILON_F = orc_const::EPSILON;
 inline float D_ggx(float ndoth, float alpha)
 {
     float a2 = alpha * alpha, denom = (ndoth * ndoth) * (a2 - 1.0f) + 1.0f;
