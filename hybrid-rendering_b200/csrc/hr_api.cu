@@ -28,9 +28,10 @@ void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
     if (ctx) ctx->last_error = buf;
 }
 
-static FrameConsts make_consts(const hr_frame* f)
+static FrameConsts make_consts(const hr_frame* f, const hr_pass* p)
 {
     FrameConsts c;
+    c.ray_ctr = p ? p->ray_ctr : nullptr;
     memcpy(c.view_proj_inverse, f->ubo.view_proj_inverse, 64);
     memcpy(c.prev_view_proj, f->ubo.prev_view_proj, 64);
     memcpy(c.cam_pos, f->ubo.cam_pos, 16);
@@ -518,8 +519,24 @@ static int pass_common_create(hr_ctx* ctx, int width, int height, int scale, int
     for (int m = 0; m < scale; m++) { w = w / 2 > 0 ? w / 2 : 1; h = h / 2 > 0 ? h / 2 : 1; } // = swapchain / 2^scale, ray_traced_shadows.cpp:78-83
     p->W = w;
     p->H = h;
+    const size_t ctr_bytes = sizeof(unsigned long long) * 2 * HR_RAY_CTR_SLOTS * HR_RAY_CTR_STRIDE;
+    if (cudaMalloc((void**)&p->ray_ctr, ctr_bytes) != cudaSuccess) { delete p; hr_set_error(ctx, "pass create: out of memory"); return HR_ERR_OUT_OF_MEMORY; }
+    cudaMemset(p->ray_ctr, 0, ctr_bytes);
+    p->allocs.push_back(p->ray_ctr);
     *out = p;
     return HR_OK;
+}
+
+// Recompute halos of a sharded rank, derived from the parameters (rows beyond the owned band, multiples of 8 so tile and mask
+// alignment are kept).  An a-trous iteration at step 2^i with the given radius reads rows y +- radius * 2^i, so n iterations
+// erode sum(radius << i) rows (+1: the upsample stage reads one coarse row beyond the band); the temporal stage's 17x17
+// statistics read the ray-trace output 8 rows beyond its own rows.
+static int round_up8(int v) { return (v + 7) & ~7; }
+static int atrous_halo_rows(int radius, int iterations)
+{
+    long h = 0;
+    for (int i = 0; i < iterations; i++) h += (long)radius << i;
+    return round_up8((int)(h > (1 << 20) ? (1 << 20) : h) + 1);
 }
 
 static int check_render_ready(hr_pass* p, const hr_frame* f, const void* params, bool needs_scene)
@@ -566,6 +583,11 @@ int hr_shadows_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** o
     if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; }
     void* hist[7] = { p->prev_image[0], p->prev_image[1], p->moments[0], p->moments[1], p->mask_pp[0], p->mask_pp[1], p->rt_cost_all };
     hr_peer_register(p, hist, 7);
+    for (int i = 0; i < 2; i++)
+    {
+        p->hist_view[HR_SHADOWS_OUT_PREV_IMAGE][i] = { p->prev_image[i], p->W, p->H, HR_FMT_RG16F };
+        p->hist_view[HR_SHADOWS_OUT_MOMENTS][i]    = { p->moments[i], p->W, p->H, HR_FMT_RGBA16F };
+    }
     return HR_OK;
 }
 
@@ -579,15 +601,19 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
                "hr_shadows_render: filter_iterations must be 0..8 and radius 1..2");
     cudaStream_t       st  = (cudaStream_t)stream;
     const int          pp  = f->ping_pong;
-    const FrameConsts  fc  = make_consts(f);
+    const FrameConsts  fc  = make_consts(f, p);
     const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
     const size_t       px = (size_t)p->W * p->H;
-    // row-band sharding (shard.cu): owned band [b0,b1); ray trace on band+-32, temporal / a-trous on band+-16:
-    // 17x17 mean needs mask rows +-8 beyond the temporal rows; 4 a-trous iterations at steps 1,2,4,8 erode +-15 rows.
+    // row-band sharding (shard.cu): owned band [b0,b1); temporal / a-trous on band +- the rows the a-trous chain erodes (16 for
+    // the default 4 iterations at radius 1: 1+2+4+8 = 15), ray trace 8 rows further (17x17 mean of the temporal stage).
+    const int spp = prm->spp > 1 ? prm->spp : 1;
+    HR_REQUIRE(ctx, spp <= 255, HR_ERR_UNSUPPORTED, "hr_shadows_render: spp must be <= 255");
+    const int halo = ctx->world > 1 && prm->denoise ? atrous_halo_rows(prm->radius, prm->filter_iterations) : 0;
     int b0, b1, rt0, rt1, row0, row1;
     hr_band(ctx, p->H, &b0, &b1);
-    hr_extend(b0, b1, ctx->world > 1 ? 32 : 0, p->H, &rt0, &rt1);
-    hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
+    hr_extend(b0, b1, ctx->world > 1 && prm->denoise ? halo + 8 : 0, p->H, &rt0, &rt1);
+    hr_extend(b0, b1, halo, p->H, &row0, &row1);
+    p->last_rows[0] = row0; p->last_rows[1] = row1;
     timer_begin(p, st);
 
     if (ctx->world > 1 && ctx->nccl_comm && !p->peers_linked)
@@ -596,6 +622,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         if (rc != HR_OK) return rc;
     }
     const int  epoch      = ++p->epoch;
+    p->n_renders++;
     const bool no_history = p->first;
     bool       signalled  = false;
     hr_wait_exchange(p, st); // last frame's gather of the final output (side stream) reads images this frame rewrites
@@ -610,8 +637,6 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     }
     // ray_trace (:972-1011).  Linked to peers: this rank traces its cost-balanced share of the WHOLE image and stores the
     // mask words into every rank's mask image (no halo re-trace); otherwise its band +- 32 rows into its own image.
-    const int  spp = prm->spp > 1 ? prm->spp : 1;
-    HR_REQUIRE(ctx, spp <= 255 && (spp == 1 || ctx->world == 1), HR_ERR_UNSUPPORTED, "hr_shadows_render: spp > 1 needs spp <= 255 and a single GPU");
     RtShare    rts;
     const bool shared_rt = spp == 1 && hr_rt_share(p, epoch & 1, &rts);
     uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
@@ -768,6 +793,11 @@ int hr_ao_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out)
     if (rc != HR_OK) { hr_pass_destroy(p); *out = nullptr; return rc; }
     void* hist[7] = { p->ao_color[0], p->ao_color[1], p->ao_len[0], p->ao_len[1], p->mask_pp[0], p->mask_pp[1], p->rt_cost_all };
     hr_peer_register(p, hist, 7);
+    for (int i = 0; i < 2; i++)
+    {
+        p->hist_view[HR_AO_OUT_TEMPORAL_ACCUMULATION][i] = { p->ao_color[i], p->W, p->H, HR_FMT_R16F };
+        p->hist_view[HR_AO_OUT_HISTORY_LENGTH][i]        = { p->ao_len[i], p->W, p->H, HR_FMT_R16F };
+    }
     return HR_OK;
 }
 
@@ -780,15 +810,21 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     HR_REQUIRE(ctx, prm->blur_radius >= 1 && prm->blur_radius <= 16, HR_ERR_INVALID_ARG, "hr_ao_render: blur_radius must be 1..16");
     cudaStream_t       st  = (cudaStream_t)stream;
     const int          pp  = f->ping_pong;
-    const FrameConsts  fc  = make_consts(f);
+    const FrameConsts  fc  = make_consts(f, p);
     const GBufLevelDev cur = level_view(ctx, pp, p->scale), prev = level_view(ctx, !pp, p->scale);
     const size_t       px = (size_t)p->W * p->H;
-    // row-band sharding: ray trace band+-32, temporal + horizontal blur band+-16, vertical blur (needs +-4 rows) band+-8
+    // row-band sharding: the vertical blur runs on band +- 8 (the upsample reads one coarse row beyond the band) and reads
+    // +- blur_radius rows of the horizontal pass, which is pointwise in y over the temporal output; the temporal stage's
+    // 17x17 mean reads the ray mask 8 rows further
+    const int spp = prm->spp > 1 ? prm->spp : 1;
+    HR_REQUIRE(ctx, spp <= 255, HR_ERR_UNSUPPORTED, "hr_ao_render: spp must be <= 255");
+    const int halo = ctx->world > 1 && prm->denoise ? 8 + round_up8(prm->blur_radius) : 0;
     int b0, b1, rt0, rt1, row0, row1, v0, v1;
     hr_band(ctx, p->H, &b0, &b1);
-    hr_extend(b0, b1, ctx->world > 1 ? 32 : 0, p->H, &rt0, &rt1);
-    hr_extend(b0, b1, ctx->world > 1 ? 16 : 0, p->H, &row0, &row1);
-    hr_extend(b0, b1, ctx->world > 1 ? 8 : 0, p->H, &v0, &v1);
+    hr_extend(b0, b1, ctx->world > 1 && prm->denoise ? halo + 8 : 0, p->H, &rt0, &rt1);
+    hr_extend(b0, b1, halo, p->H, &row0, &row1);
+    hr_extend(b0, b1, ctx->world > 1 && prm->denoise ? 8 : 0, p->H, &v0, &v1);
+    p->last_rows[0] = row0; p->last_rows[1] = row1;
     timer_begin(p, st);
     if (ctx->world > 1 && ctx->nccl_comm && !p->peers_linked)
     {
@@ -796,6 +832,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         if (rc != HR_OK) return rc;
     }
     const int  epoch      = ++p->epoch;
+    p->n_renders++;
     const bool no_history = p->first;
     hr_wait_exchange(p, st);
     if (p->first)
@@ -804,8 +841,6 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
         HR_CUDA(ctx, cudaMemsetAsync(p->ao_color[!pp], 0, px * sizeof(__half), st));
         p->first = false;
     }
-    const int  spp = prm->spp > 1 ? prm->spp : 1;
-    HR_REQUIRE(ctx, spp <= 255 && (spp == 1 || ctx->world == 1), HR_ERR_UNSUPPORTED, "hr_ao_render: spp > 1 needs spp <= 255 and a single GPU");
     RtShare    rts;
     const bool shared_rt = spp == 1 && hr_rt_share(p, epoch & 1, &rts); // see hr_shadows_render
     uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;
@@ -961,6 +996,18 @@ int hr_pass_download(hr_pass* p, int which, void* dst, size_t bytes, void* strea
 // facility): overwrite one of the pass's images, e.g. the history surfaces saved with hr_pass_download.
 int hr_pass_upload(hr_pass* p, int which, const void* src, size_t bytes, void* stream)
 {
+    if (p && p->epoch == 0 && which >= 0 && which < 8 && p->hist_view[which][0].p)
+    { // cold start (a fresh process restoring a checkpoint before its first render): the next render reads the history of
+      // parity !ping_pong, which is not known yet — restore both parities and skip that render's first-frame clear
+        hr_ctx*             ctx  = p->ctx;
+        const hr_pass::Img& v    = p->hist_view[which][0];
+        const size_t        need = (size_t)v.w * v.h * texel_size(v.fmt);
+        HR_REQUIRE(ctx, src && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_upload: byte count mismatch");
+        for (int i = 0; i < 2; i++) HR_CUDA(ctx, cudaMemcpyAsync(p->hist_view[which][i].p, src, need, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        HR_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+        p->first = false;
+        return HR_OK;
+    }
     hr_image img;
     int      rc = hr_pass_output(p, which, &img);
     if (rc != HR_OK) return rc;
@@ -974,6 +1021,62 @@ int hr_pass_upload(hr_pass* p, int which, const void* src, size_t bytes, void* s
 }
 
 int hr_pass_reset_history(hr_pass* p) { if (!p) return HR_ERR_INVALID_ARG; p->first = true; return HR_OK; }
+
+int hr_pass_get_stats(hr_pass* p, hr_pass_stats* out, void* stream)
+{
+    hr_ctx* ctx = p ? p->ctx : nullptr;
+    HR_REQUIRE(ctx, p && out, HR_ERR_INVALID_ARG, "hr_pass_get_stats: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    memset(out, 0, sizeof(*out));
+    unsigned long long* d = nullptr;
+    HR_CUDA(ctx, cudaMalloc((void**)&d, 4 * sizeof(unsigned long long)));
+    HR_CUDA(ctx, cudaMemsetAsync(d, 0, 4 * sizeof(unsigned long long), st));
+    launch_drain_ray_counters(p->ray_ctr, d, st);
+    const int r0 = p->last_rows[0], r1 = p->last_rows[1], TW = (p->W + 7) / 8;
+    const int t0 = r0 / 8, t1 = (r1 + 7) / 8;
+    if (p->tile_flags && r1 > r0) launch_tile_stats(p->tile_flags, TW, t0, t1, d + 2, st);
+    unsigned long long h[4] = {};
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    HR_CUDA(ctx, e);
+    out->rays_primary   = h[0];
+    out->rays_secondary = h[1];
+    out->renders        = p->n_renders;
+    p->n_renders        = 0;
+    if (p->tile_flags && r1 > r0)
+    {
+        out->tiles_total   = (uint64_t)(t1 - t0) * TW;
+        out->tiles_denoise = h[2];
+        out->pixels_total  = (uint64_t)(r1 - r0) * p->W;
+    }
+    return HR_OK;
+}
+
+int hr_pass_output_checksum(hr_pass* p, int which, int row0, int row1, uint64_t* out, void* stream)
+{
+    hr_image img;
+    int      rc = hr_pass_output(p, which, &img);
+    if (rc != HR_OK) return rc;
+    hr_ctx* ctx = p->ctx;
+    HR_REQUIRE(ctx, out != nullptr, HR_ERR_INVALID_ARG, "hr_pass_output_checksum: null argument");
+    if (row1 <= 0) { row0 = 0; row1 = img.height; }
+    HR_REQUIRE(ctx, row0 >= 0 && row1 >= row0 && row1 <= img.height, HR_ERR_INVALID_ARG, "hr_pass_output_checksum: bad row range");
+    cudaStream_t st = (cudaStream_t)stream;
+    hr_wait_exchange(p, st);
+    const size_t row_bytes = (size_t)img.width * texel_size(img.format);
+    unsigned long long* d = nullptr;
+    HR_CUDA(ctx, cudaMalloc((void**)&d, sizeof(unsigned long long)));
+    HR_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), st));
+    launch_checksum(img.data, row_bytes * row0, row_bytes * row1, d, st);
+    unsigned long long h = 0;
+    cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    HR_CUDA(ctx, e);
+    *out = h;
+    return HR_OK;
+}
 
 int hr_pass_destroy(hr_pass* p)
 {
@@ -1038,6 +1141,7 @@ int hr_shard_rows(int height, int rank, int world, int* row_begin, int* row_end)
 int hr_shard_config(hr_ctx* ctx, int rank, int world)
 {
     HR_REQUIRE(ctx, ctx && world >= 1 && rank >= 0 && rank < world, HR_ERR_INVALID_ARG, "hr_shard_config: bad rank/world");
+    HR_REQUIRE(ctx, world <= HR_MAX_RANKS, HR_ERR_UNSUPPORTED, "hr_shard_config: at most 8 ranks (the GPUs of one box)");
     ctx->rank  = rank;
     ctx->world = world;
     return HR_OK;

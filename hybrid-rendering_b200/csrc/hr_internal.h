@@ -48,7 +48,10 @@ struct FrameConsts {           // what kernels need from hr_frame (passed by val
     float    z_buffer_params[4];
     float    camera_delta[3];
     uint32_t num_frames;
+    unsigned long long* ray_ctr; // per-pass ray counters (hr_pass_get_stats): [kind][HR_RAY_CTR_SLOTS] spread over 32-byte slots; may be null
 };
+#define HR_RAY_CTR_SLOTS 32
+#define HR_RAY_CTR_STRIDE 4 // unsigned long longs between slots (32 bytes: one sector each)
 
 // ---- objects ----------------------------------------------------------------------------------------
 #define HR_MAX_RANKS 8
@@ -159,6 +162,7 @@ struct hr_pass {
     struct Img { void* p = nullptr; int w = 0, h = 0, fmt = 0; };
     Img     img[16];
     Img     out_view[128];     // indexed by `which` (filled per render)
+    Img     hist_view[8][2];   // history surfaces by `which` (< 8) and frame parity, known from creation: hr_pass_upload before the first render
     // shadows
     uint32_t* mask = nullptr;
     uint8_t*  count = nullptr;       // spp > 1: unoccluded rays per pixel (allocated on first use)
@@ -212,6 +216,9 @@ struct hr_pass {
     int*        peer_ticks[HR_MAX_RANKS] = {};       // the peers' tick arrays (we write slot [self])
     int*        sync_error = nullptr;                // set by the wait kernel on time-out
     int         epoch = 0;                           // renders of this pass so far
+    unsigned long long* ray_ctr = nullptr;           // [2 kinds][HR_RAY_CTR_SLOTS * HR_RAY_CTR_STRIDE]: primary / secondary rays traced since the last hr_pass_get_stats
+    uint64_t    n_renders = 0;                       // renders since the last hr_pass_get_stats
+    int         last_rows[2] = { 0, 0 };             // rows [r0, r1) the last render's denoise stages covered (tile statistics)
     StageTimer timer;
     std::vector<void*> allocs;
 };
@@ -219,7 +226,7 @@ struct hr_pass {
 // rt_shade.cu / ddgi_update.cu / svgf_reflections.cu
 void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const void* irr_prev, const void* depth_prev, const hr_light& light, const float* rot16,
                            uint32_t num_frames, uint32_t infinite_bounces, float gi_intensity, const float* sky3, int probe0, int probe1, void* radiance,
-                           void* dirdepth, cudaStream_t st);
+                           void* dirdepth, unsigned long long* ray_ctr, cudaStream_t st);
 void launch_ddgi_probe_update(const hr_ddgi_uniforms& d, const void* radiance, const void* dirdepth, const void* prev_irr, const void* prev_depth, void* out_irr,
                               void* out_depth, int first_frame, int probe0, int probe1, cudaStream_t st);
 void launch_ddgi_sample_probe_grid(const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms& d, const void* irr, const void* depth, float gi_intensity,
@@ -277,6 +284,10 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
 void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
+// stats.cu (measurement helpers, not on the frame path)
+void launch_tile_stats(const uint8_t* flags, int TW, int t0, int t1, unsigned long long* d_out, cudaStream_t st);
+void launch_drain_ray_counters(unsigned long long* ctr, unsigned long long* d_out, cudaStream_t st);
+void launch_checksum(const void* base, size_t byte0, size_t byte1, unsigned long long* d_out, cudaStream_t st);
 int hr_launch_build_mips(hr_ctx* ctx, GBufSlot& s, int W, int H, cudaStream_t st);
 int hr_bvh_build(hr_scene* sc, cudaStream_t st);
 BvhDev hr_bvh_view(const hr_scene* sc);

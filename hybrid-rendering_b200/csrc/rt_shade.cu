@@ -91,7 +91,7 @@ __device__ __forceinline__ void fetch_light_properties_hard(const hr_light& L, V
 
 // direct_lighting, lighting.glsl:117-196
 __device__ float3 direct_lighting(const BvhDev& bvh, const hr_light& light, V3 Wo, V3 N, V3 P, float3 F0, float3 diffuse_color, float roughness, bool sky_light,
-                                  float r0, float r1, float3 sky)
+                                  float r0, float r1, float3 sky, unsigned long long* ray_ctr)
 {
     using namespace gi;
     float3 Lo = f3(0, 0, 0);
@@ -108,6 +108,7 @@ __device__ float3 direct_lighting(const BvhDev& bvh, const hr_light& light, V3 W
         {
             sr.d    = Wi;
             sr.tmax = t_max;
+            count_rays(ray_ctr, 1, 1u);
             att *= trace_any(bvh, sr) ? 0.0f : 1.0f;
         }
         const float3 brdf = evaluate_uber_brdf(diffuse_color, roughness, N, F0, Wo, Wh, Wi);
@@ -119,6 +120,7 @@ __device__ float3 direct_lighting(const BvhDev& bvh, const hr_light& light, V3 W
         const V3 Wh = det::normalize(det::add(Wo, Wi));
         sr.d    = Wi;
         sr.tmax = 10000.0f;
+        count_rays(ray_ctr, 1, 1u);
         const float  vis  = trace_any(bvh, sr) ? 0.0f : 1.0f;
         const float3 brdf = evaluate_uber_brdf(diffuse_color, roughness, N, F0, Wo, Wh, Wi);
         Lo = Lo + brdf * (sky * vis);
@@ -139,14 +141,15 @@ __device__ float3 indirect_diffuse(const hr_ddgi_uniforms& d, const gi::AtlasDev
 }
 
 __device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& sd, const hr_light& light, const Ray& r, uint32_t prim, float u, float v, bool sky_light,
-                                            float r0, float r1, float3 sky, bool gi_on, const hr_ddgi_uniforms& d, const gi::AtlasDev& at, float gi_intensity)
+                                            float r0, float r1, float3 sky, bool gi_on, const hr_ddgi_uniforms& d, const gi::AtlasDev& at, float gi_intensity,
+                                            unsigned long long* ray_ctr)
 {
     using namespace gi;
     const Surface s  = fetch_surface(sd, prim, u, v);
     const V3      Wo = det::scale(r.d, -1.0f);
     const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;             // mix(0.04, albedo, metallic)
     const float3  cd = (s.albedo * (f3(1, 1, 1) - F0)) * (1.0f - s.metallic) + f3(0, 0, 0) * s.metallic; // mix(albedo*(1-F0), 0, metallic)
-    float3        Lo = direct_lighting(bvh, light, Wo, s.N, s.P, F0, cd, s.roughness, sky_light, r0, r1, sky);
+    float3        Lo = direct_lighting(bvh, light, Wo, s.N, s.P, F0, cd, s.roughness, sky_light, r0, r1, sky, ray_ctr);
     if (gi_on) Lo = Lo + indirect_diffuse(d, at, Wo, s.N, s.P, F0, cd, s.roughness, s.metallic, gi_intensity);
     return Lo;
 }
@@ -170,7 +173,7 @@ __device__ __forceinline__ V3 spherical_fibonacci(float i, float n)
     return det::mk(cs * st, sn * st, ct);
 }
 
-struct GiTraceParams { float rot[16]; uint32_t num_frames, infinite_bounces; float gi_intensity; float sky[3]; int probe0, probe1; };
+struct GiTraceParams { float rot[16]; uint32_t num_frames, infinite_bounces; float gi_intensity; float sky[3]; int probe0, probe1; unsigned long long* ray_ctr; };
 
 // K18: one block per probe, one thread per ray (blockDim = rays_per_probe rounded up to 32, looped if > 256)
 __global__ void __launch_bounds__(256) k_ddgi_ray_trace(BvhDev bvh, ShadeDev sd, hr_ddgi_uniforms d, gi::AtlasDev at, hr_light light, GiTraceParams P,
@@ -195,10 +198,11 @@ __global__ void __launch_bounds__(256) k_ddgi_ray_trace(BvhDev bvh, ShadeDev sd,
         float    t, u, v, hit_distance = 10000.0f;
         uint32_t prim;
         float3   L;
+        count_rays(P.ray_ctr, 0, 1u);
         if (trace_closest(bvh, r, t, prim, u, v))
         {
             const float r0 = gi::next_float(rng), r1 = gi::next_float(rng);
-            L              = shade_hit(bvh, sd, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity);
+            L              = shade_hit(bvh, sd, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity, P.ray_ctr);
             hit_distance   = 0.001f + t;
         }
         else L = sky;
@@ -274,9 +278,10 @@ __global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, Bv
     {
         float    t, hu, hv;
         uint32_t prim;
+        count_rays(fc.ray_ctr, 0, 1u);
         if (trace_closest(bvh, r, t, prim, hu, hv))
         {
-            color      = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity);
+            color      = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr);
             ray_length = 0.001f + t;
         }
         else color = sky;
@@ -298,7 +303,7 @@ ShadeDev shade_view(const hr_scene* sc)
 
 void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const void* irr_prev, const void* depth_prev, const hr_light& light, const float* rot16,
                            uint32_t num_frames, uint32_t infinite_bounces, float gi_intensity, const float* sky3, int probe0, int probe1, void* radiance,
-                           void* dirdepth, cudaStream_t st)
+                           void* dirdepth, unsigned long long* ray_ctr, cudaStream_t st)
 {
     if (probe1 <= probe0) return;
     GiTraceParams P;
@@ -306,6 +311,7 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
     P.num_frames = num_frames; P.infinite_bounces = infinite_bounces; P.gi_intensity = gi_intensity;
     P.sky[0] = sky3[0]; P.sky[1] = sky3[1]; P.sky[2] = sky3[2];
     P.probe0 = probe0; P.probe1 = probe1;
+    P.ray_ctr = ray_ctr;
     gi::AtlasDev at { (const uint2*)irr_prev, (const uint32_t*)depth_prev };
     int threads = d.rays_per_probe < 256 ? ((d.rays_per_probe + 31) / 32) * 32 : 256;
     k_ddgi_ray_trace<<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth);

@@ -505,6 +505,7 @@ int hr_shard_unique_id(void* out_128_bytes)
 int hr_shard_init(hr_ctx* ctx, int rank, int world, const void* unique_id_128_bytes)
 {
     HR_REQUIRE(ctx, ctx && world >= 1 && rank >= 0 && rank < world, HR_ERR_INVALID_ARG, "hr_shard_init: bad rank/world");
+    HR_REQUIRE(ctx, world <= HR_MAX_RANKS, HR_ERR_UNSUPPORTED, "hr_shard_init: at most 8 ranks — one process per GPU of ONE box (peer history uses CUDA IPC mappings)");
     ctx->rank  = rank;
     ctx->world = world;
     if (world == 1) return HR_OK;

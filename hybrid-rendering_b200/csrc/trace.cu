@@ -27,9 +27,10 @@ __device__ __forceinline__ float2 load_oct_normal(const uint2* gb2, size_t idx)
 // one pixel of K1 (MODE 0) / K7 (MODE 1): 1 = the ray reached the light / left the AO radius unoccluded
 template <int MODE>
 __device__ __forceinline__ uint32_t trace_pixel(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float p0, float p1, const uint8_t* __restrict__ sobol,
-                                                const uint8_t* __restrict__ sr, int x, int y)
+                                                const uint8_t* __restrict__ sr, int x, int y, bool& traced)
 {
     uint32_t result = 0;
+    traced          = false;
     if (x < g.W && y < g.H)
     {
         const size_t idx   = (size_t)y * g.W + x;
@@ -49,13 +50,14 @@ __device__ __forceinline__ uint32_t trace_pixel(const GBufLevelDev& g, const Bvh
                 r.o = det::add(P, det::scale(N, p0)); // bias
                 float att;
                 det::fetch_light_properties_shadow(fc.light, P, N, r0, r1, r.d, r.tmax, att);
-                if (att > 0.0f) result = trace_any(bvh, r) ? 0u : 1u;
+                if (att > 0.0f) { traced = true; result = trace_any(bvh, r) ? 0u : 1u; }
             }
             else
             {
                 r.o    = det::add(P, det::scale(N, p1)); // bias
                 r.d    = det::sample_cosine_lobe(N, r0, r1);
                 r.tmax = p0; // ray_length
+                traced = true;
                 result = trace_any(bvh, r) ? 0u : 1u;
             }
         }
@@ -76,18 +78,21 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelD
     const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
     if (mx >= MW || my >= mrow1) return; // whole warp exits together
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+    bool           traced;
+    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y, traced);
     const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
     if (lane == 0) mask[(size_t)my * MW + mx] = word;
+    count_rays(fc.ray_ctr, 0, traced ? 1u : 0u);
 }
 
 // spp > 1 (not in the reference): `spp` rays per pixel with sample index num_frames * spp + s; returns the number
 // of unoccluded rays.  Separate from trace_pixel so the 1-spp kernels stay exactly what the parity runs validated.
 template <int MODE>
 __device__ __forceinline__ uint32_t trace_pixel_spp(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float p0, float p1, const uint8_t* __restrict__ sobol,
-                                                    const uint8_t* __restrict__ sr, int x, int y, int spp)
+                                                    const uint8_t* __restrict__ sr, int x, int y, int spp, uint32_t& n_traced)
 {
     uint32_t n = 0;
+    n_traced   = 0;
     if (x < g.W && y < g.H)
     {
         const size_t idx   = (size_t)y * g.W + x;
@@ -110,13 +115,14 @@ __device__ __forceinline__ uint32_t trace_pixel_spp(const GBufLevelDev& g, const
                     r.o = det::add(P, det::scale(N, p0)); // bias
                     float att;
                     det::fetch_light_properties_shadow(fc.light, P, N, r0, r1, r.d, r.tmax, att);
-                    if (att > 0.0f) n += trace_any(bvh, r) ? 0u : 1u;
+                    if (att > 0.0f) { n_traced++; n += trace_any(bvh, r) ? 0u : 1u; }
                 }
                 else
                 {
                     r.o    = det::add(P, det::scale(N, p1)); // bias
                     r.d    = det::sample_cosine_lobe(N, r0, r1);
                     r.tmax = p0; // ray_length
+                    n_traced++;
                     n += trace_any(bvh, r) ? 0u : 1u;
                 }
             }
@@ -135,8 +141,10 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_count(GBufLevel
     const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
     if (mx >= MW || my >= mrow1) return;
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-    const uint32_t n = trace_pixel_spp<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y, spp);
+    uint32_t       n_traced;
+    const uint32_t n = trace_pixel_spp<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y, spp, n_traced);
     if (x < g.W && y < g.H) count[(size_t)y * g.W + x] = (uint8_t)n;
+    count_rays(fc.ray_ctr, 0, n_traced);
 }
 
 // Multi-GPU variant (shard.cu, "cooperative ray trace"): this rank traces mask rows [bounds[self], bounds[self+1]) — a
@@ -157,13 +165,15 @@ __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_shared(GBu
     const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
     if (mx >= MW || my >= mrow1) return; // whole warp exits together
     const int      x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
-    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y);
+    bool           traced;
+    const uint32_t result = trace_pixel<MODE>(g, bvh, fc, p0, p1, sobol, sr, x, y, traced);
     const uint32_t word   = __ballot_sync(0xFFFFFFFFu, result != 0);
     if (lane == 0)
     {
         sh.mask_local[(size_t)my * MW + mx] = word;
         atomicAdd(sh.cost_acc + my, (uint32_t)((clock64() - t0) >> 6) + 1u);
     }
+    count_rays(fc.ray_ctr, 0, traced ? 1u : 0u);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -253,6 +263,7 @@ __global__ void __launch_bounds__(PT_WARPS * 32) k_ray_trace_mask_pt(GBufLevelDe
             count += __popc(b);
         }
         __syncwarp();
+        count_rays(fc.ray_ctr, 0, lane == 0 ? (uint32_t)count : 0u);
         // ---- traversal with dynamic refill -----------------------------------------------------------------------------
         int       head  = 0;
         bool      valid = false;

@@ -31,6 +31,18 @@ __device__ __forceinline__ bool ray_triangle(const float4 A, const float4 B, con
     return t > r.tmin && t < r.tmax;
 }
 
+// Rays traced (SURVEY.md §8d "rays per frame", reported by hr_pass_get_stats): the calling threads — whatever subset of the
+// warp is active — add `n` each; one atomic per warp lands in one of HR_RAY_CTR_SLOTS counters picked by the block index
+// (fire-and-forget RED, no return value needed).  kind 0 = primary rays, 1 = secondary (shadow / sky-light) rays.
+__device__ __forceinline__ void count_rays(unsigned long long* ctr, int kind, uint32_t n)
+{
+    if (!ctr) return;
+    const unsigned am   = __activemask();
+    const uint32_t tot  = __reduce_add_sync(am, n); // REDUX: any subset of lanes
+    if ((threadIdx.x & 31) == __ffs(am) - 1 && tot)
+        atomicAdd(ctr + ((size_t)kind * HR_RAY_CTR_SLOTS + ((blockIdx.x + blockIdx.y * 7u) & (HR_RAY_CTR_SLOTS - 1))) * HR_RAY_CTR_STRIDE, (unsigned long long)tot);
+}
+
 #define STACK_SIZE 64
 #define SENTINEL 0x7FFFFFFF
 

@@ -74,6 +74,11 @@ class hr_ao_params(C.Structure):
                 ("denoise", C.c_int32), ("spp", C.c_int32)]
 
 
+class hr_pass_stats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_secondary", C.c_uint64), ("tiles_total", C.c_uint64), ("tiles_denoise", C.c_uint64),
+                ("pixels_total", C.c_uint64), ("renders", C.c_uint64)]
+
+
 class hrs_light_desc(C.Structure):
     _fields_ = [("type", C.c_int32), ("rot_y_deg", C.c_float), ("rot_x_deg", C.c_float), ("position", C.c_float * 3), ("radius", C.c_float),
                 ("intensity", C.c_float), ("color", C.c_float * 3), ("cone_inner_deg", C.c_float), ("cone_outer_deg", C.c_float)]
@@ -90,7 +95,7 @@ ABI_SYMBOLS = [
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
-    "hr_reflections_render",
+    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum",
 ]
 
 _product = None
@@ -419,6 +424,18 @@ class Pass:
 
     def reset_history(self):
         self.lib.hr_pass_reset_history(self.h)
+
+    def stats(self, stream=0):
+        """work done since the previous call (rays) / by the last render (tiles): hr_pass_get_stats"""
+        s = hr_pass_stats()
+        self.ctx.check(self.lib.hr_pass_get_stats(self.h, C.byref(s), C.c_void_p(stream)), "hr_pass_get_stats")
+        return s
+
+    def checksum(self, which=100, row0=0, row1=0, stream=0):
+        """device-side order-independent checksum of an output image (rows [row0,row1), default whole image)"""
+        v = C.c_uint64()
+        self.ctx.check(self.lib.hr_pass_output_checksum(self.h, which, row0, row1, C.byref(v), C.c_void_p(stream)), "hr_pass_output_checksum")
+        return int(v.value)
 
     def destroy(self):
         if self.h:

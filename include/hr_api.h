@@ -129,8 +129,10 @@ typedef struct hr_instance {
     uint32_t material_idx;
 } hr_instance;
 
-/* Builds the device LBVH (Morton sort + Karras hierarchy + bottom-up fit) over all instances'
- * world-space triangles.  Host pointers in; synchronises the context's build stream before returning. */
+/* Builds the device BVH over all instances' world-space triangles: 63-bit Morton codes + radix sort, then PLOC
+ * agglomerative clustering (default) or the Karras radix tree + bottom-up fit (hr_debug_set key 3), collapsed into
+ * <= 4-triangle leaves and packed into 64-byte two-child nodes.  Host pointers in; synchronises the context's build
+ * stream before returning.  Fails with HR_ERR_UNSUPPORTED when the tree is deeper than the traversal stack (64). */
 HR_API int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, const uint32_t* indices, size_t n_indices,
                           const hr_instance* instances, size_t n_instances, const hr_material* materials, size_t n_materials,
                           hr_scene** out);
@@ -392,14 +394,32 @@ HR_API int hr_debug_set(int key, int value);
 /* Number of kernels this library launched since the context was created (bench.py gpu_launches). */
 HR_API uint64_t hr_ctx_launch_count(hr_ctx* ctx);
 
+/* Work actually done by a pass (bench.py: roofline on processed bytes, Mrays/s on counted rays).
+ * Ray counts accumulate on the device since the previous hr_pass_get_stats call (warp-aggregated atomics inside the trace
+ * kernels); the tile counts describe the last render: 8x8 tiles of the rows this rank's denoise stages covered, and how many
+ * of them were on the denoise list (the others take the reference's copy / zero-fill path).  Synchronises `stream`. */
+typedef struct hr_pass_stats {
+    uint64_t rays_primary;   /* K1/K7: pixels that traced a ray; K12: reflection rays; K18: probe rays                     */
+    uint64_t rays_secondary; /* shadow / sky-light rays of the hit shading (K12, K18)                                      */
+    uint64_t tiles_total;    /* 8x8 tiles in the rows covered by the last render's denoise stages                          */
+    uint64_t tiles_denoise;  /* of those, tiles on the denoise list (tile flag = 1)                                        */
+    uint64_t pixels_total;   /* pixels in those rows                                                                       */
+    uint64_t renders;        /* renders since the previous call                                                           */
+} hr_pass_stats;
+HR_API int hr_pass_get_stats(hr_pass* pass, hr_pass_stats* out, void* stream);
+/* Order-independent 64-bit checksum of an output image computed on the device (sum over texels of a 64-bit mix of
+ * (index, value)); rows [row0,row1) only, row1 <= 0 = whole image.  bench.py uses it to show that an N-GPU frame equals the
+ * single-GPU frame without moving the images.  Synchronises `stream`. */
+HR_API int hr_pass_output_checksum(hr_pass* pass, int which, int row0, int row1, uint64_t* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Screen-space row-band sharding across GPUs (new).  rank owns pass rows
  * [row_begin, row_end) aligned to 8; the other rows are skipped by every stage except a halo.
  * ---------------------------------------------------------------------------------------------- */
-HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world); /* band assignment only; the caller exchanges bands itself */
+HR_API int hr_shard_config(hr_ctx* ctx, int rank, int world); /* band assignment only (world <= 8); the caller exchanges bands itself */
 /* NCCL-backed sharding: rank 0 obtains a 128-byte ncclUniqueId, every rank calls hr_shard_init with it (one process per
- * GPU).  After every hr_*_render the ranks exchange their bands of the final output and of the temporal history with one
- * NCCL group on the caller's stream, so each rank holds the complete, single-GPU-identical images. */
+ * GPU of ONE box, world <= 8: the peer mappings are CUDA IPC).  The temporal history stays distributed (see below); the
+ * only per-frame collective is the optional all-gather of each pass's final output on the library's side stream. */
 HR_API int hr_shard_unique_id(void* out_128_bytes);
 HR_API int hr_shard_init(hr_ctx* ctx, int rank, int world, const void* unique_id_128_bytes);
 HR_API int hr_shard_shutdown(hr_ctx* ctx);

@@ -205,7 +205,7 @@ class ShadowsOracle:
             if self.rt_share is not None:
                 _coop_mask(self)
             else:
-                self._poison(self.mask, 32, div=4)
+                self._poison(self.mask, 24, div=4)
             self.final = self.mask
             if not P.denoise:
                 return
@@ -279,7 +279,7 @@ class AOOracle:
             if getattr(self, "rt_share", None) is not None:
                 _coop_mask(self)
             else:
-                self._poison(self.mask, 32, div=4)
+                self._poison(self.mask, 24, div=4)
             self.final = self.mask
             if not P.denoise:
                 return
