@@ -443,6 +443,25 @@ int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev, vo
     return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, (cudaStream_t)stream);
 }
 
+int hr_gbuffer_render(hr_ctx* ctx, int slot, const hr_frame* frame, int row0, int row1, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && frame && (slot == 0 || slot == 1), HR_ERR_INVALID_ARG, "hr_gbuffer_render: bad argument");
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_render: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, ctx->scene && ctx->scene->d_materials, HR_ERR_NOT_READY, "hr_gbuffer_render: no current scene with materials (hr_scene_build)");
+    if (row1 <= 0) { row0 = 0; row1 = ctx->gb_h; }
+    HR_REQUIRE(ctx, row0 >= 0 && row1 > row0 && row1 <= ctx->gb_h && row0 % 8 == 0 && (row1 % 8 == 0 || row1 == ctx->gb_h), HR_ERR_INVALID_ARG,
+               "hr_gbuffer_render: rows must be multiples of 8 (or end at the image height)");
+    GBufSlot& s = ctx->slot[slot];
+    s.gb1[0]   = ctx->owned_mip0[slot][0]; // library-owned storage (the slot may have been bound zero-copy before)
+    s.gb2[0]   = ctx->owned_mip0[slot][1];
+    s.gb3[0]   = ctx->owned_mip0[slot][2];
+    s.depth[0] = (float*)ctx->owned_mip0[slot][3];
+    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, row0, row1, s.gb1[0], s.gb2[0], s.gb3[0], s.depth[0], ctx->gbuf_ray_ctr, (cudaStream_t)stream);
+    ctx->launches++;
+    HR_CHECK_LAUNCH(ctx);
+    return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, (cudaStream_t)stream);
+}
+
 int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* dst, size_t bytes)
 {
     HR_REQUIRE(ctx, ctx && dst && (slot == 0 || slot == 1) && mip >= 0 && mip < HR_MAX_MIPS && which >= 0 && which <= 3, HR_ERR_INVALID_ARG,

@@ -107,6 +107,7 @@ struct hr_ctx {
     uint64_t     launches  = 0;
     int          sm_count  = 148;
     cudaStream_t build_stream = nullptr;
+    unsigned long long* gbuf_ray_ctr = nullptr; // primary rays of hr_gbuffer_render (same slot layout as hr_pass::ray_ctr)
 };
 
 struct hr_scene {
@@ -284,6 +285,8 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
 void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
+void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, void* gb1, void* gb2, void* gb3, float* depth,
+                           unsigned long long* ray_ctr, cudaStream_t st); // gbuffer.cu
 // stats.cu (measurement helpers, not on the frame path)
 void launch_tile_stats(const uint8_t* flags, int TW, int t0, int t1, unsigned long long* d_out, cudaStream_t st);
 void launch_drain_ray_counters(unsigned long long* ctr, unsigned long long* d_out, cudaStream_t st);

@@ -191,6 +191,14 @@ HR_API int hr_gbuffer_commit_staged(hr_ctx* ctx, int slot, void* stream);
 HR_API int hr_gbuffer_copy_from_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev_mip0, void* stream);
 /* Zero-copy: bind caller-owned device mip-0 images as slot; the library only builds mips 1.. from them. */
 HR_API int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* dev_mip0, void* stream);
+/* G-buffer producer on the device: replaces the reference's raster G-buffer pass (src/g_buffer.cpp:100-263,
+ * src/shaders/g_buffer.{vert,frag}) with a primary-visibility ray cast over the current scene's BVH — depth, octahedral
+ * normal, motion vector from frame->ubo.prev_view_proj, curvature from the 2x2-quad normal differences, mesh id, linear z,
+ * albedo / metallic — into the library-owned storage of `slot`, then the NEAREST mip chain.  A headless frame then needs
+ * only the 496-byte hr_frame from the host instead of a 24 B/pixel upload.  rows [row0, row1) (multiples of 8, or the image
+ * height; row1 <= 0 = the whole image) let a sharded rank produce just the rows it consumes.  Async on `stream`.  The CPU
+ * statement oracle/orc_gbuffer.cpp produces the same bits. */
+HR_API int hr_gbuffer_render(hr_ctx* ctx, int slot, const hr_frame* frame, int row0, int row1, void* stream);
 /* Read back one mip of a slot (tests). which: 1,2,3 = gb1..3, 0 = depth. Synchronous. */
 HR_API int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* host_dst, size_t bytes);
 

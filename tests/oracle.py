@@ -69,6 +69,7 @@ def lib():
         L.orc_upsample_vec4.argtypes = [P, P, P, P]
         L.orc_rng_sequence.restype = U
         L.orc_rng_sequence.argtypes = [U, U, U, P, I]
+        L.orc_gbuffer_render.argtypes = [P, P, P, I, I, P, P, P, P]
         _lib = L
     return _lib
 
@@ -324,6 +325,15 @@ class ShadingScene:
             lib().orc_shading_destroy(self.h)
         except Exception:
             pass
+
+
+def gbuffer_render(ss: "ShadingScene", frame, W, H, out=None):
+    """oracle statement of the device G-buffer producer (oracle/orc_gbuffer.cpp) -> pyhr.GBufferHost"""
+    g = out if out is not None else pyhr.GBufferHost(W, H)
+    _, inst = ss.synth.world_triangles()
+    inst = np.ascontiguousarray(inst, np.uint32)
+    lib().orc_gbuffer_render(ss.h, p(inst), C.byref(frame), W, H, p(g.gb1), p(g.gb2), p(g.gb3), p(g.depth))
+    return g
 
 
 def ddgi_uniforms_from(params, bounds_min, bounds_max):
