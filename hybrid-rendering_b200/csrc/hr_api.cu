@@ -978,7 +978,7 @@ int hr_pass_download_async(hr_pass* p, int which, void* dst, size_t bytes, void*
     const size_t need = (size_t)img.width * img.height * texel_size(img.format);
     HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download_async: byte count mismatch");
     hr_wait_exchange(p, (cudaStream_t)stream);
-    HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    HR_CUDA(ctx, cudaMemcpyAsync(dst, img.data, need, cudaMemcpyDefault, (cudaStream_t)stream));
     return HR_OK;
 }
 
@@ -993,7 +993,7 @@ int hr_pass_download_rows_async(hr_pass* p, int which, int row0, int row1, void*
     const size_t row_bytes = (size_t)img.width * texel_size(img.format), need = row_bytes * (size_t)(row1 - row0);
     HR_REQUIRE(ctx, dst && bytes == need, HR_ERR_INVALID_ARG, "hr_pass_download_rows_async: byte count mismatch");
     hr_wait_exchange(p, (cudaStream_t)stream);
-    if (need) HR_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(img.data) + row_bytes * row0, need, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    if (need) HR_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(img.data) + row_bytes * row0, need, cudaMemcpyDefault, (cudaStream_t)stream));
     return HR_OK;
 }
 

@@ -379,7 +379,8 @@ HR_API int hr_reflections_render(hr_pass* pass, const hr_frame* frame, const hr_
 HR_API int hr_pass_output(hr_pass* pass, int which, hr_image* out);
 /* Synchronous device->host copy of an output on `stream` (waits for it). bytes must equal w*h*texel. */
 HR_API int hr_pass_download(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
-/* Same copy enqueued on `stream` without the host synchronisation (pinned host_dst; the caller synchronises). */
+/* Same copy enqueued on `stream` without the host synchronisation (pinned host_dst, or a device pointer: the copy kind is
+ * inferred, so a caller may stage the image on the device and run the PCIe copy on its own stream; the caller synchronises). */
 HR_API int hr_pass_download_async(hr_pass* pass, int which, void* host_dst, size_t bytes, void* stream);
 /* Rows [row0,row1) only — e.g. a rank's own band (hr_shard_rows, scaled to the image) of an output left distributed. */
 HR_API int hr_pass_download_rows_async(hr_pass* pass, int which, int row0, int row1, void* host_dst, size_t bytes, void* stream);

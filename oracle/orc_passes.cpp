@@ -559,6 +559,14 @@ void orc_ao_temporal_spp(const orc_gbuf* cur, const orc_gbuf* prev, const uint8_
                          const hr_frame* f, float alpha, uint16_t* out, uint16_t* len_out, uint8_t* tile_flags)
 { VisSrc vs{ nullptr, count, cur->W, cur->H, spp, 0xFFFFFFFFu }; ao_temporal(lvl(cur), lvl(prev), vs, prev_ao, prev_len, *f, alpha, out, len_out, tile_flags); }
 
+// bench.py sets the thread count explicitly (launchers such as torchrun export OMP_NUM_THREADS=1)
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+
 int orc_num_threads(void)
 {
     int n = 1;

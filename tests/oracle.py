@@ -55,6 +55,7 @@ def lib():
         L.orc_shadows_temporal_spp.argtypes = [P, P, P, I, P, P, P, F, F, P, P, P]
         L.orc_ao_temporal_spp.argtypes = [P, P, P, I, P, P, P, F, P, P, P]
         L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_shading_create.restype = C.c_void_p
         L.orc_shading_create.argtypes = [P, P, P, P, C.c_size_t, P, C.c_size_t]
         L.orc_shading_destroy.argtypes = [P]
