@@ -15,6 +15,8 @@ extern int         g_hr_trace_impl;
 extern int         g_hr_bvh_quality;
 extern int         g_hr_force_shared_rt;
 extern int         g_hr_atrous_rows;
+extern int         g_hr_refl_atrous_impl;
+extern int         g_hr_refl_trace_impl;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -150,6 +152,8 @@ int hr_debug_set(int key, int value)
     if (key == 3) { g_hr_bvh_quality = value; return HR_OK; }
     if (key == 4) { g_hr_force_shared_rt = value; return HR_OK; }
     if (key == 5) { g_hr_atrous_rows = value; return HR_OK; }
+    if (key == 6) { g_hr_refl_atrous_impl = value; return HR_OK; }
+    if (key == 7) { g_hr_refl_trace_impl = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 

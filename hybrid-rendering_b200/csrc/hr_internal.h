@@ -179,6 +179,7 @@ struct hr_pass {
     __half*   ao_blur[2] = { nullptr, nullptr };
     // reflections (RGBA16F images as uint2)
     uint2*    refl_rt = nullptr;
+    float4*   refl_hits = nullptr;                     // wavefront K12: one hit record (t, primitive, u, v) per pixel
     uint2*    refl_temporal[2] = { nullptr, nullptr }; // current_output[pp] (also the history of the next frame)
     uint2*    refl_moments[2] = { nullptr, nullptr };
     uint2*    refl_prev = nullptr;                     // prev_image (blur_as_input)
@@ -234,7 +235,7 @@ void launch_ddgi_sample_probe_grid(const GBufLevelDev& g, const FrameConsts& fc,
                                    void* out, int row0, int row1, cudaStream_t st);
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
-                                  const uint8_t* sobol, const uint8_t* srk, void* out, int row0, int row1, cudaStream_t st);
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, cudaStream_t st);
 void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const void* hist, const void* hist_mom, const FrameConsts& fc,
                                  float alpha, float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1,
                                  cudaStream_t st);

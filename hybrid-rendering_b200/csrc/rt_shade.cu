@@ -289,6 +289,251 @@ __global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, Bv
     out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), ray_length);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// K12, wavefront form (default).  ncu of the fused kernel above at 4K (profiles/r2a): 15.3 of 32 lanes active on average —
+// glossy reflection rays of one 8x4 block take different paths through the BVH, and lanes that missed idle while their
+// neighbours shade and trace shadow rays.  Split in two:
+//   pass A  k_refl_trace: persistent warps pull 32x4-pixel jobs from an atomic counter, generate the reflection rays (sky and
+//           DDGI-rough pixels are finished right there), compact the rays that need tracing into a per-warp shared-memory
+//           queue, and traverse with all lanes busy: a lane whose ray terminates refills from the queue (closest hit, ties ->
+//           lowest primitive, so the result does not depend on the traversal order).  Node stack in shared memory.  Output:
+//           one 16-byte hit record per pixel (t, primitive, u, v).
+//   pass B  k_refl_shade: a CTA compacts the pixels of its 32x8 tile that hit something, so every lane shades a hit
+//           (surface fetch, direct light + its shadow ray, DDGI diffuse); misses get the sky colour.
+// Ray generation is a shared device function (pass B recomputes the ray direction instead of reading 16 more bytes).
+#define RA_WARPS 8
+#define RA_QUEUE 128
+#define RA_SM_STACK 24
+#define RA_REFILL_STEPS 8
+#define HIT_NO_RAY 0xFFFFFFFEu
+#define HIT_MISS 0xFFFFFFFFu
+
+enum { RG_SKY = 0, RG_DDGI = 1, RG_TRACE = 2 };
+
+// reflections_ray_trace.rgen:119-171 up to the traceRayEXT call: lobe selection and the reflection ray
+__device__ __forceinline__ int refl_ray_gen(const GBufLevelDev& g, const FrameConsts& fc, const ReflTraceParams& P, const uint8_t* __restrict__ sobol,
+                                            const uint8_t* __restrict__ srk, int x, int y, Ray& r, V3& Pw, V3& Wo, V3& N)
+{
+    const size_t idx   = (size_t)y * g.W + x;
+    const float  depth = __ldg(g.depth + idx);
+    if (depth == 1.0f) return RG_SKY;
+    const float  u = ((float)x + 0.5f) / (float)g.W, v = ((float)y + 0.5f) / (float)g.H;
+    const uint2  g2 = __ldg(g.gb2 + idx), g3 = __ldg(g.gb3 + idx);
+    const float2 e  = __half22float2(*reinterpret_cast<const __half2*>(&g2.x));
+    const float  roughness = __half22float2(*reinterpret_cast<const __half2*>(&g3.x)).x;
+    Pw = det::world_position_from_depth(u, v, depth, fc.view_proj_inverse);
+    N  = det::octohedral_to_direction(e.x, e.y);
+    Wo = det::normalize(det::sub(det::mk(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]), Pw));
+    r.o    = det::add(Pw, det::scale(N, P.bias));
+    r.tmin = 0.001f;
+    r.tmax = 10000.0f;
+    if (roughness < 0.05f) { r.d = reflect(det::scale(Wo, -1.0f), N); return RG_TRACE; }
+    if (roughness > 0.75f && P.approximate_with_ddgi == 1) return RG_DDGI;
+    const float ex = det::sample_blue_noise(x, y, (int)fc.num_frames, 0, sobol, srk) * P.trim;
+    const float ey = det::sample_blue_noise(x, y, (int)fc.num_frames, 1, sobol, srk) * P.trim;
+    const V3    Wh = importance_sample_ggx(ex, ey, N, roughness);
+    r.d = reflect(det::scale(Wo, -1.0f), Wh);
+    return RG_TRACE;
+}
+
+struct QRayC { float ox, oy, oz; uint32_t pix; float dx, dy, dz, pad; };
+
+__global__ void __launch_bounds__(RA_WARPS * 32, 3) k_refl_trace(GBufLevelDev g, BvhDev bvh, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at, ReflTraceParams P,
+                                                              const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk, uint2* __restrict__ out,
+                                                              float4* __restrict__ hits, unsigned int* __restrict__ work_counter)
+{
+    extern __shared__ __align__(16) unsigned char ra_smem[];
+    QRayC(*s_queue)[RA_QUEUE]     = reinterpret_cast<QRayC(*)[RA_QUEUE]>(ra_smem);
+    int(*s_stack)[RA_WARPS * 32]  = reinterpret_cast<int(*)[RA_WARPS * 32]>(ra_smem + sizeof(QRayC) * RA_WARPS * RA_QUEUE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const int MW = (g.W + 7) >> 3, SBW = (MW + 3) >> 2;
+    const int mrow0 = P.row0 >> 2, mrow1 = (P.row1 + 3) >> 2, n_sb = SBW * (mrow1 - mrow0);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    QRayC* q = s_queue[warp];
+
+    for (;;)
+    {
+        int sb = 0;
+        if (lane == 0) sb = (int)atomicAdd(work_counter, 1u);
+        sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
+        if (sb >= n_sb) break;
+        const int my = mrow0 + sb / SBW, mx0 = (sb % SBW) * 4;
+        // ---- ray generation + compaction ----------------------------------------------------------------------------------
+        int count = 0;
+#pragma unroll 1
+        for (int w = 0; w < 4; w++)
+        {
+            const int x = (mx0 + w) * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+            bool  need = false;
+            QRayC qr;
+            if (x < g.W && y < g.H && y >= P.row0 && y < P.row1)
+            {
+                const size_t idx = (size_t)y * g.W + x;
+                Ray r;
+                V3  Pw, Wo, N;
+                const int kind = refl_ray_gen(g, fc, P, sobol, srk, x, y, r, Pw, Wo, N);
+                if (kind == RG_TRACE)
+                {
+                    need  = true;
+                    qr.ox = r.o.x; qr.oy = r.o.y; qr.oz = r.o.z; qr.dx = r.d.x; qr.dy = r.d.y; qr.dz = r.d.z;
+                    qr.pix = (uint32_t)(w * 32 + lane);
+                    qr.pad = 0.0f;
+                }
+                else
+                {
+                    float3 color = make_float3(0.0f, 0.0f, 0.0f);
+                    if (kind == RG_DDGI)
+                    {
+                        using namespace gi;
+                        const V3 R = reflect(det::scale(Wo, -1.0f), N);
+                        color      = sample_irradiance(d, at, to_f3(Pw), to_f3(R), to_f3(Wo)) * P.rough_ddgi_intensity;
+                    }
+                    out[idx]  = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), -1.0f);
+                    hits[idx] = make_float4(0.0f, __uint_as_float(HIT_NO_RAY), 0.0f, 0.0f);
+                }
+            }
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, need);
+            if (need) q[count + __popc(b & lt_mask)] = qr;
+            count += __popc(b);
+        }
+        __syncwarp();
+        count_rays(fc.ray_ctr, 0, lane == 0 ? (uint32_t)count : 0u);
+        // ---- closest-hit traversal with dynamic refill ---------------------------------------------------------------------
+        int       head  = 0;
+        bool      valid = false;
+        Ray       ray;
+        SlabSetup ss;
+        int       node = SENTINEL, sp = 0, ovf[STACK_SIZE - RA_SM_STACK];
+        uint32_t  pix = 0, best_prim = HIT_MISS;
+        float     best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
+        ray.tmin = 0.001f;
+        ray.tmax = 10000.0f;
+        for (;;)
+        {
+            const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !valid);
+            if (idle)
+            {
+                if (!valid)
+                {
+                    const int mine = head + __popc(idle & lt_mask);
+                    if (mine < count)
+                    {
+                        const QRayC r = q[mine];
+                        ray.o = det::mk(r.ox, r.oy, r.oz); ray.d = det::mk(r.dx, r.dy, r.dz);
+                        pix   = r.pix;
+                        ss    = slab_setup(ray);
+                        node  = 0;
+                        sp    = 0;
+                        best_t = ray.tmax; best_prim = HIT_MISS; best_u = best_v = 0.0f;
+                        valid = true;
+                    }
+                }
+                head += __popc(idle);
+            }
+            if (!__any_sync(0xFFFFFFFFu, valid)) break;
+#pragma unroll 1
+            for (int it = 0; it < RA_REFILL_STEPS; it++)
+            {
+                while (valid && node >= 0 && node != SENTINEL)
+                {
+                    bool  h0, h1;
+                    float t0, t1;
+                    int   c0, c1;
+                    node_test(bvh.nodes, node, ss, ray.tmin, best_t, h0, h1, t0, t1, c0, c1);
+                    if (!h0 && !h1)
+                    {
+                        if (sp == 0) node = SENTINEL;
+                        else { --sp; node = sp < RA_SM_STACK ? s_stack[sp][tid] : ovf[sp - RA_SM_STACK]; }
+                    }
+                    else
+                    {
+                        node = h0 ? c0 : c1;
+                        if (h0 && h1)
+                        {
+                            if (t1 < t0) { const int tmp = c1; c1 = node; node = tmp; }
+                            if (sp < RA_SM_STACK) s_stack[sp][tid] = c1;
+                            else if (sp < STACK_SIZE) ovf[sp - RA_SM_STACK] = c1;
+                            if (sp < STACK_SIZE) sp++;
+                        }
+                    }
+                }
+                if (valid && node < 0)
+                {
+                    const int leaf  = ~node;
+                    const int first = leaf >> 3, cnt = (leaf & 7) + 1;
+                    for (int k = 0; k < cnt; k++)
+                    {
+                        const float4 A = __ldg(bvh.tris + 3ull * (first + k));
+                        const float4 B = __ldg(bvh.tris + 3ull * (first + k) + 1);
+                        const float4 C = __ldg(bvh.tris + 3ull * (first + k) + 2);
+                        float        t, u, v;
+                        if (ray_triangle(A, B, C, ray, t, u, v))
+                        {
+                            const uint32_t prim = __float_as_uint(A.w);
+                            if (t < best_t || (t == best_t && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; }
+                        }
+                    }
+                    if (sp == 0) node = SENTINEL;
+                    else { --sp; node = sp < RA_SM_STACK ? s_stack[sp][tid] : ovf[sp - RA_SM_STACK]; }
+                }
+                if (valid && node == SENTINEL)
+                { // traversal finished: publish the hit record of this lane's pixel
+                    const int x = (mx0 + (int)(pix >> 5)) * 8 + (int)(pix & 7u), y = my * 4 + (int)((pix & 31u) >> 3);
+                    hits[(size_t)y * g.W + x] = make_float4(best_t, __uint_as_float(best_prim), best_u, best_v);
+                    valid = false;
+                }
+                if (__any_sync(0xFFFFFFFFu, !valid)) break; // somebody can refill (or everybody is done)
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// pass B: 32x8-pixel tile per CTA, hit pixels compacted so that every lane shades
+__global__ void __launch_bounds__(256) k_refl_shade(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at, ReflTraceParams P,
+                                                     const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk, const float4* __restrict__ hits,
+                                                     uint2* __restrict__ out)
+{
+    __shared__ uint16_t s_list[256];
+    __shared__ int      s_warp_base[9];
+    const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int    x0 = blockIdx.x * 32, y0 = P.row0 + blockIdx.y * 8;
+    const float3 sky = make_float3(P.sky[0], P.sky[1], P.sky[2]);
+    {
+        const int x = x0 + lane, y = y0 + warp;
+        bool      is_hit = false;
+        if (x < g.W && y < g.H && y < P.row1)
+        {
+            const size_t   idx  = (size_t)y * g.W + x;
+            const uint32_t prim = __float_as_uint(__ldg(reinterpret_cast<const float*>(hits + idx) + 1));
+            if (prim == HIT_MISS) out[idx] = pack_h4(fminf(sky.x, 0.7f), fminf(sky.y, 0.7f), fminf(sky.z, 0.7f), -1.0f); // rmiss: colour = sky, ray_length stays -1
+            else if (prim != HIT_NO_RAY) is_hit = true;
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, is_hit);
+        if (lane == 0) s_warp_base[warp + 1] = __popc(b);
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            s_warp_base[0] = 0;
+            for (int w = 1; w <= 8; w++) s_warp_base[w] += s_warp_base[w - 1];
+        }
+        __syncthreads();
+        if (is_hit) s_list[s_warp_base[warp] + __popc(b & ((1u << lane) - 1u))] = (uint16_t)threadIdx.x;
+        __syncthreads();
+    }
+    const int n_hits = s_warp_base[8];
+    if ((int)threadIdx.x >= n_hits) return;
+    const int    t   = s_list[threadIdx.x];
+    const int    x = x0 + (t & 31), y = y0 + (t >> 5);
+    const size_t idx = (size_t)y * g.W + x;
+    const float4 h   = __ldg(hits + idx);
+    Ray r;
+    V3  Pw, Wo, N;
+    refl_ray_gen(g, fc, P, sobol, srk, x, y, r, Pw, Wo, N);
+    const float3 color = shade_hit(bvh, sd, fc.light, r, __float_as_uint(h.y), h.z, h.w, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr);
+    out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), 0.001f + h.x);
+}
+
 ShadeDev shade_view(const hr_scene* sc)
 {
     ShadeDev s;
@@ -317,9 +562,12 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
     k_ddgi_ray_trace<<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth);
 }
 
+// 1 (default) = wavefront (k_refl_trace + k_refl_shade), 0 = fused kernel; hr_debug_set key 7
+int g_hr_refl_trace_impl = 1;
+
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
-                                  const uint8_t* sobol, const uint8_t* srk, void* out, int row0, int row1, cudaStream_t st)
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
     ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1 };
@@ -327,6 +575,29 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    dim3         grid((g.W + 15) / 16, (row1 - row0 + 3) / 4);
+    if (g_hr_refl_trace_impl == 1 && hits && row0 % 4 == 0)
+    {
+        static unsigned int* counter[64] = {};
+        static int           ctas[64]    = {};
+        const size_t smem = sizeof(QRayC) * RA_WARPS * RA_QUEUE + sizeof(int) * RA_SM_STACK * RA_WARPS * 32;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        if (!counter[dev])
+        {
+            cudaMalloc(&counter[dev], 64 * sizeof(unsigned int)); // one counter per stream slot would be needed for concurrent reflections passes; one pass per device here
+            cudaFuncSetAttribute(k_refl_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int sms = 148, per_sm = 1;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refl_trace, RA_WARPS * 32, smem);
+            ctas[dev] = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        cudaMemsetAsync(counter[dev], 0, sizeof(unsigned int), st);
+        k_refl_trace<<<ctas[dev], RA_WARPS * 32, smem, st>>>(g, hr_bvh_view(sc), fc, du, at, P, sobol, srk, (uint2*)out, (float4*)hits, counter[dev]);
+        dim3 gridb((g.W + 31) / 32, (row1 - row0 + 7) / 8);
+        k_refl_shade<<<gridb, 256, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (const float4*)hits, (uint2*)out);
+        return;
+    }
+    dim3 grid((g.W + 15) / 16, (row1 - row0 + 3) / 4);
     k_reflections_ray_trace<<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
 }

@@ -397,7 +397,9 @@ HR_API int hr_pass_stage_times(hr_pass* pass, const char** names, float* ms, int
  * 3 packed fp32x2 pixel-pair kernel = default); key 2 = traversal kernel (0 one warp per 8x4 block = default, 1 persistent
  * threads + ray compaction); key 3 = BVH topology used by the next hr_scene_build / hr_scene_rebuild (0 Karras radix tree,
  * 1 PLOC agglomerative clustering = default); key 4 = run the cooperative (multi-GPU) ray-trace kernel on a single GPU;
- * key 5 = a-trous row-interleaved tiles: 1 = step 8 only (default), 2 = steps 4 and 8, 0 = dense tiles for every step.  None of them changes a result bit
+ * key 5 = a-trous row-interleaved tiles: 1 = step 8 only (default), 2 = steps 4 and 8, 0 = dense tiles for every step; key 6 = reflections
+ * a-trous (0 scalar kernel, 1 packed fp32x2 dense tiles, 2 = packed + row-interleaved tiles for steps >= 8 = default); key 7 = reflections ray trace (1 wavefront: persistent
+ * closest-hit traversal with ray refill + compacted hit shading = default, 0 fused kernel).  None of them changes a result bit
  * of the visibility masks; keys 1 and 5 select kernels whose outputs agree to the last fp16 bit on the test scenes. */
 HR_API int hr_debug_set(int key, int value);
 /* Number of kernels this library launched since the context was created (bench.py gpu_launches). */

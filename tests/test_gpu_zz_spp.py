@@ -68,7 +68,7 @@ def test_spp_counts_exact_and_denoise_within_tolerance(spp):
         ctx.close()
 
 
-def test_spp_rejected_when_sharded():
+def _disabled_spp_rejected_when_sharded():  # sharded spp > 1 is supported since round 2 (band-local count images)
     ctx = pyhr.Context(0)
     try:
         sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
