@@ -474,6 +474,8 @@ def main():
         f = next_frame()
         if single_tri:
             ctx.gbuffer_upload(f.ping_pong, g_host, stream)
+        elif world > 1 and cfg["passes"] == ["reflections"] and cfg.get("refl_scale", 1) == 0:
+            ctx.gbuffer_render_sharded(f.ping_pong, f, 64, stream)  # only the rows this rank's stages read (band +- 64, its ray-trace chunks)
         else:
             ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream)
         rig.render(f, stream)

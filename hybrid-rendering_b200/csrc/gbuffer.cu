@@ -24,6 +24,7 @@ struct GbufScene {
 struct GbufParams {
     float vpi[16], vp[16], pvp[16];
     int   W, H, row0, row1;
+    int   chunk_first, chunk_stride; // chunk_stride > 1: the 8-row chunks c = chunk_first + i * chunk_stride of the whole image (rows ignored)
 };
 
 __device__ __forceinline__ float4 mul_m4(const float* M, V3 p)
@@ -48,8 +49,10 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
                                                         float* __restrict__ depth, unsigned long long* ray_ctr)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = (blockIdx.x * 2 + warp) * 8 + (lane & 7), y = P.row0 + blockIdx.y * 4 + (lane >> 3);
-    const bool in_img = x < P.W && y < P.H && y < P.row1;
+    const int x = (blockIdx.x * 2 + warp) * 8 + (lane & 7);
+    const int y = (P.chunk_stride > 1 ? 8 * (P.chunk_first + ((int)blockIdx.y >> 1) * P.chunk_stride) + 4 * ((int)blockIdx.y & 1) : P.row0 + (int)blockIdx.y * 4) + (lane >> 3);
+    const int y_end = P.chunk_stride > 1 ? P.H : P.row1;
+    const bool in_img = x < P.W && y < P.H && y < y_end;
     V3       N   = det::mk(0.0f, 0.0f, 0.0f);
     uint32_t mid = 0xFFFFFFFFu;
     uint32_t g2x = 0u, g2y = 0u, g3x = 0u, g3w_mid = 0u, g1 = 0u;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
     // lanes (lane & ~1, lane | 1) in x and (lane & ~8, lane | 8) in y; a partner outside the image is the pixel itself.
     const uint32_t full = 0xFFFFFFFFu;
     const int      lx0 = lane & ~1, lx1 = lane | 1, ly0 = lane & ~8, ly1 = lane | 8;
-    const bool     x1_in = (x | 1) < P.W, y1_in = (y | 1) < P.H && (y | 1) < P.row1; // row1 is a multiple of 4 or H
+    const bool     x1_in = (x | 1) < P.W, y1_in = (y | 1) < P.H && (y | 1) < y_end; // row1 is a multiple of 4 or H
     V3 ax, bx, ay, by;
     ax.x = __shfl_sync(full, N.x, lx0); ax.y = __shfl_sync(full, N.y, lx0); ax.z = __shfl_sync(full, N.z, lx0);
     bx.x = __shfl_sync(full, N.x, lx1); bx.y = __shfl_sync(full, N.y, lx1); bx.z = __shfl_sync(full, N.z, lx1);
@@ -133,16 +136,18 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
 
 } // namespace
 
-void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, void* gb1, void* gb2, void* gb3, float* depth,
-                           unsigned long long* ray_ctr, cudaStream_t st)
+void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, int chunk_first, int chunk_stride, void* gb1, void* gb2, void* gb3,
+                           float* depth, unsigned long long* ray_ctr, cudaStream_t st)
 {
-    if (row1 <= row0) return;
+    const int n_chunks_mine = chunk_stride > 1 ? (((H + 7) / 8) - chunk_first + chunk_stride - 1) / chunk_stride : 0;
+    if (chunk_stride > 1 ? n_chunks_mine <= 0 : row1 <= row0) return;
     GbufScene gs { sc->d_vnormals, sc->d_prim_inst, sc->d_prim_mat, sc->d_materials };
     GbufParams P;
     memcpy(P.vpi, f->ubo.view_proj_inverse, 64);
     memcpy(P.vp, f->ubo.view_proj, 64);
     memcpy(P.pvp, f->ubo.prev_view_proj, 64);
     P.W = W; P.H = H; P.row0 = row0; P.row1 = row1;
-    dim3 grid((W + 15) / 16, (row1 - row0 + 3) / 4);
+    P.chunk_first = chunk_first; P.chunk_stride = chunk_stride;
+    dim3 grid((W + 15) / 16, chunk_stride > 1 ? 2 * n_chunks_mine : (row1 - row0 + 3) / 4);
     k_gbuffer_render<<<grid, 64, 0, st>>>(hr_bvh_view(sc), gs, P, (uint32_t*)gb1, (uint2*)gb2, (uint2*)gb3, depth, ray_ctr);
 }

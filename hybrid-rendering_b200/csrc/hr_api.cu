@@ -30,6 +30,8 @@ void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
     if (ctx) ctx->last_error = buf;
 }
 
+static int round_up8(int v) { return (v + 7) & ~7; }
+
 static FrameConsts make_consts(const hr_frame* f, const hr_pass* p)
 {
     FrameConsts c;
@@ -460,8 +462,31 @@ int hr_gbuffer_render(hr_ctx* ctx, int slot, const hr_frame* frame, int row0, in
     s.gb2[0]   = ctx->owned_mip0[slot][1];
     s.gb3[0]   = ctx->owned_mip0[slot][2];
     s.depth[0] = (float*)ctx->owned_mip0[slot][3];
-    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, row0, row1, s.gb1[0], s.gb2[0], s.gb3[0], s.depth[0], ctx->gbuf_ray_ctr, (cudaStream_t)stream);
+    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, row0, row1, 0, 1, s.gb1[0], s.gb2[0], s.gb3[0], s.depth[0], ctx->gbuf_ray_ctr, (cudaStream_t)stream);
     ctx->launches++;
+    HR_CHECK_LAUNCH(ctx);
+    return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, (cudaStream_t)stream);
+}
+
+// The rows a sharded rank's FULL-RESOLUTION passes consume: its band +- halo_rows (denoise stages) and the 8-row chunks it traces
+// in the interleaved cooperative ray trace (shard.cu).  Single GPU: the whole image.
+int hr_gbuffer_render_sharded(hr_ctx* ctx, int slot, const hr_frame* frame, int halo_rows, void* stream)
+{
+    HR_REQUIRE(ctx, ctx && frame && (slot == 0 || slot == 1) && halo_rows >= 0, HR_ERR_INVALID_ARG, "hr_gbuffer_render_sharded: bad argument");
+    if (ctx->world <= 1) return hr_gbuffer_render(ctx, slot, frame, 0, 0, stream);
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_render_sharded: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, ctx->scene && ctx->scene->d_materials, HR_ERR_NOT_READY, "hr_gbuffer_render_sharded: no current scene with materials (hr_scene_build)");
+    GBufSlot& s = ctx->slot[slot];
+    s.gb1[0]   = ctx->owned_mip0[slot][0];
+    s.gb2[0]   = ctx->owned_mip0[slot][1];
+    s.gb3[0]   = ctx->owned_mip0[slot][2];
+    s.depth[0] = (float*)ctx->owned_mip0[slot][3];
+    int b0, b1, r0, r1;
+    hr_band(ctx, ctx->gb_h, &b0, &b1);
+    hr_extend(b0, b1, round_up8(halo_rows), ctx->gb_h, &r0, &r1);
+    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, r0, r1, 0, 1, s.gb1[0], s.gb2[0], s.gb3[0], s.depth[0], ctx->gbuf_ray_ctr, (cudaStream_t)stream);
+    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, 0, 0, ctx->rank, ctx->world, s.gb1[0], s.gb2[0], s.gb3[0], s.depth[0], ctx->gbuf_ray_ctr, (cudaStream_t)stream);
+    ctx->launches += 2;
     HR_CHECK_LAUNCH(ctx);
     return hr_launch_build_mips(ctx, s, ctx->gb_w, ctx->gb_h, (cudaStream_t)stream);
 }
@@ -554,7 +579,6 @@ static int pass_common_create(hr_ctx* ctx, int width, int height, int scale, int
 // alignment are kept).  An a-trous iteration at step 2^i with the given radius reads rows y +- radius * 2^i, so n iterations
 // erode sum(radius << i) rows (+1: the upsample stage reads one coarse row beyond the band); the temporal stage's 17x17
 // statistics read the ray-trace output 8 rows beyond its own rows.
-static int round_up8(int v) { return (v + 7) & ~7; }
 static int atrous_halo_rows(int radius, int iterations)
 {
     long h = 0;

@@ -179,6 +179,7 @@ struct hr_pass {
     __half*   ao_blur[2] = { nullptr, nullptr };
     // reflections (RGBA16F images as uint2)
     uint2*    refl_rt = nullptr;
+    uint2*    refl_rt_pp[2] = { nullptr, nullptr };   // ray-trace output by frame parity when the ranks trace cooperatively (refl_rt_pp[0] == refl_rt)
     float4*   refl_hits = nullptr;                     // wavefront K12: one hit record (t, primitive, u, v) per pixel
     uint2*    refl_temporal[2] = { nullptr, nullptr }; // current_output[pp] (also the history of the next frame)
     uint2*    refl_moments[2] = { nullptr, nullptr };
@@ -235,10 +236,10 @@ void launch_ddgi_sample_probe_grid(const GBufLevelDev& g, const FrameConsts& fc,
                                    void* out, int row0, int row1, cudaStream_t st);
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
-                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, cudaStream_t st);
-void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const void* hist, const void* hist_mom, const FrameConsts& fc,
-                                 float alpha, float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1,
-                                 cudaStream_t st);
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, int chunk_first, int chunk_stride,
+                                  cudaStream_t st); // chunk_stride > 1: only the 8-row chunks c = chunk_first + i * chunk_stride (rows are ignored)
+void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const HistPeers& hist, const FrameConsts& fc, float alpha,
+                                 float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
 int  launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
                                float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st);
 void launch_upsample_vec4(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st);
@@ -271,6 +272,10 @@ void launch_shadows_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, c
                                      const RtShare& sh, cudaStream_t st);
 void launch_ao_ray_trace_shared(const GBufLevelDev& g, const BvhDev& bvh, const FrameConsts& fc, float ray_length, float bias, const uint8_t* sobol,
                                 const uint8_t* sr, const RtShare& sh, cudaStream_t st);
+// Interleaved cooperative ray trace of the reflections pass (shard.cu): rank r traces the 8-row chunks c with c % world == r of the
+// WHOLE image into its own image and copies every chunk to the ranks whose denoise stages read it (rows [need0[q], need1[q]));
+// the last block publishes the ray-trace tick.
+int hr_refl_push_chunks(hr_pass* p, int parity, int tick, const int* need0, const int* need1, cudaStream_t st);
 // Rows of an image of height H owned by this context's rank (all rows when world == 1).
 void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1);
 // [b0 - halo, b1 + halo) clamped to [0, H); halo must be a multiple of 8 so tile alignment is kept.
@@ -286,8 +291,8 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
 void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
-void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, void* gb1, void* gb2, void* gb3, float* depth,
-                           unsigned long long* ray_ctr, cudaStream_t st); // gbuffer.cu
+void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, int chunk_first, int chunk_stride, void* gb1, void* gb2, void* gb3,
+                           float* depth, unsigned long long* ray_ctr, cudaStream_t st); // gbuffer.cu
 // stats.cu (measurement helpers, not on the frame path)
 void launch_tile_stats(const uint8_t* flags, int TW, int t0, int t1, unsigned long long* d_out, cudaStream_t st);
 void launch_drain_ray_counters(unsigned long long* ctr, unsigned long long* d_out, cudaStream_t st);

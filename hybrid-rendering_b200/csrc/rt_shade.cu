@@ -230,7 +230,8 @@ __device__ __forceinline__ V3 importance_sample_ggx(float ex, float ey, V3 N, fl
     return det::normalize(det::add(det::add(det::scale(tangent, H.x), det::scale(bitangent, H.y)), det::scale(N, H.z)));
 }
 
-struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int row0, row1; };
+struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int row0, row1;
+                         int chunk_first, chunk_stride; }; // chunk_stride > 1: the 8-row chunks c = chunk_first + i * chunk_stride of the whole image
 
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
 // 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
@@ -347,7 +348,9 @@ __global__ void __launch_bounds__(RA_WARPS * 32, 3) k_refl_trace(GBufLevelDev g,
     int(*s_stack)[RA_WARPS * 32]  = reinterpret_cast<int(*)[RA_WARPS * 32]>(ra_smem + sizeof(QRayC) * RA_WARPS * RA_QUEUE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int MW = (g.W + 7) >> 3, SBW = (MW + 3) >> 2;
-    const int mrow0 = P.row0 >> 2, mrow1 = (P.row1 + 3) >> 2, n_sb = SBW * (mrow1 - mrow0);
+    const int mrow0 = P.row0 >> 2, mrow1 = (P.row1 + 3) >> 2;
+    const int n_chunks_mine = P.chunk_stride > 1 ? (((g.H + 7) >> 3) - P.chunk_first + P.chunk_stride - 1) / P.chunk_stride : 0;
+    const int n_sb = P.chunk_stride > 1 ? SBW * 2 * n_chunks_mine : SBW * (mrow1 - mrow0);
     const uint32_t lt_mask = (1u << lane) - 1u;
     QRayC* q = s_queue[warp];
 
@@ -357,7 +360,8 @@ __global__ void __launch_bounds__(RA_WARPS * 32, 3) k_refl_trace(GBufLevelDev g,
         if (lane == 0) sb = (int)atomicAdd(work_counter, 1u);
         sb = __shfl_sync(0xFFFFFFFFu, sb, 0);
         if (sb >= n_sb) break;
-        const int my = mrow0 + sb / SBW, mx0 = (sb % SBW) * 4;
+        const int jr = sb / SBW, mx0 = (sb % SBW) * 4; // job row: a mask row (4 pixel rows) of the row range, or of this rank's chunk list
+        const int my = P.chunk_stride > 1 ? 2 * (P.chunk_first + (jr >> 1) * P.chunk_stride) + (jr & 1) : mrow0 + jr;
         // ---- ray generation + compaction ----------------------------------------------------------------------------------
         int count = 0;
 #pragma unroll 1
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(RA_WARPS * 32, 3) k_refl_trace(GBufLevelDev g,
             const int x = (mx0 + w) * 8 + (lane & 7), y = my * 4 + (lane >> 3);
             bool  need = false;
             QRayC qr;
-            if (x < g.W && y < g.H && y >= P.row0 && y < P.row1)
+            if (x < g.W && y < g.H && (P.chunk_stride > 1 || (y >= P.row0 && y < P.row1)))
             {
                 const size_t idx = (size_t)y * g.W + x;
                 Ray r;
@@ -497,12 +501,13 @@ __global__ void __launch_bounds__(256) k_refl_shade(GBufLevelDev g, BvhDev bvh, 
     __shared__ uint16_t s_list[256];
     __shared__ int      s_warp_base[9];
     const int    lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int    x0 = blockIdx.x * 32, y0 = P.row0 + blockIdx.y * 8;
+    const int    x0 = blockIdx.x * 32, y0 = P.chunk_stride > 1 ? 8 * (P.chunk_first + (int)blockIdx.y * P.chunk_stride) : P.row0 + blockIdx.y * 8;
+    const int    y_end = P.chunk_stride > 1 ? g.H : P.row1;
     const float3 sky = make_float3(P.sky[0], P.sky[1], P.sky[2]);
     {
         const int x = x0 + lane, y = y0 + warp;
         bool      is_hit = false;
-        if (x < g.W && y < g.H && y < P.row1)
+        if (x < g.W && y < g.H && y < y_end)
         {
             const size_t   idx  = (size_t)y * g.W + x;
             const uint32_t prim = __float_as_uint(__ldg(reinterpret_cast<const float*>(hits + idx) + 1));
@@ -567,15 +572,17 @@ int g_hr_refl_trace_impl = 1;
 
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
-                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, cudaStream_t st)
+                                  const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, int chunk_first, int chunk_stride,
+                                  cudaStream_t st)
 {
-    if (row1 <= row0) return;
-    ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1 };
+    const int n_chunks_mine = chunk_stride > 1 ? (((g.H + 7) / 8) - chunk_first + chunk_stride - 1) / chunk_stride : 0;
+    if (chunk_stride > 1 ? n_chunks_mine <= 0 : row1 <= row0) return;
+    ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1, chunk_first, chunk_stride };
     hr_ddgi_uniforms du;
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    if (g_hr_refl_trace_impl == 1 && hits && row0 % 4 == 0)
+    if ((g_hr_refl_trace_impl == 1 || chunk_stride > 1) && hits && row0 % 4 == 0)
     {
         static unsigned int* counter[64] = {};
         static int           ctas[64]    = {};
@@ -594,7 +601,7 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
         }
         cudaMemsetAsync(counter[dev], 0, sizeof(unsigned int), st);
         k_refl_trace<<<ctas[dev], RA_WARPS * 32, smem, st>>>(g, hr_bvh_view(sc), fc, du, at, P, sobol, srk, (uint2*)out, (float4*)hits, counter[dev]);
-        dim3 gridb((g.W + 31) / 32, (row1 - row0 + 7) / 8);
+        dim3 gridb((g.W + 31) / 32, chunk_stride > 1 ? n_chunks_mine : (row1 - row0 + 7) / 8);
         k_refl_shade<<<gridb, 256, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (const float4*)hits, (uint2*)out);
         return;
     }

@@ -281,6 +281,43 @@ __global__ void k_peer_wait(const int* __restrict__ ticks, int world, int self, 
     }
 }
 
+// Reflections (interleaved cooperative ray trace): block b copies this rank's chunk c = self + b * world (8 image rows of RGBA16F
+// texels) to every rank whose denoise stages read those rows; the last block to finish publishes the ray-trace tick.
+struct RowPtrs { uint2* p[HR_MAX_RANKS]; };
+struct NeedRows { int r0[HR_MAX_RANKS], r1[HR_MAX_RANKS]; };
+__global__ void __launch_bounds__(256) k_rt_push_chunks(RowPtrs imgs, NeedRows need, TickPtrs ticks, int* __restrict__ ctl, int world, int self, int W, int H, int tick)
+{
+    const int c = self + (int)blockIdx.x * world, r0 = c * 8, r1 = min(r0 + 8, H);
+    if (r0 < H)
+        for (int q = 0; q < world; q++)
+        {
+            if (q == self) continue;
+            const int a = max(r0, need.r0[q]), b = min(r1, need.r1[q]);
+            if (b <= a) continue;
+            const size_t first = (size_t)a * W, n = (size_t)(b - a) * W; // W is even: 16-byte pairs
+            const uint4* s4 = reinterpret_cast<const uint4*>(imgs.p[self] + first);
+            uint4*       d4 = reinterpret_cast<uint4*>(imgs.p[q] + first);
+            for (size_t i = threadIdx.x; i < n / 2; i += blockDim.x) d4[i] = s4[i];
+        }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0)
+    {
+        const int done = atomicAdd(ctl + HR_MAX_RANKS + 2, 1);
+        s_last         = done == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) ctl[HR_MAX_RANKS + 2] = 0;
+    const int r = threadIdx.x;
+    if (r < world && r != self && ticks.p[r])
+    {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(ticks.p[r] + 1 * HR_MAX_RANKS + self), "r"(tick) : "memory");
+    }
+}
+
 int peer_alloc_ticks(hr_pass* p)
 {
     hr_ctx* ctx = p->ctx;
@@ -415,6 +452,25 @@ int hr_peer_signal(hr_pass* p, int which, int tick, cudaStream_t st)
     for (int r = 0; r < p->ctx->world; r++) t.p[r] = p->peer_ticks[r];
     k_peer_signal<<<1, 32, 0, st>>>(t, p->ctx->world, p->ctx->rank, which, tick);
     p->ctx->launches++;
+    return HR_OK;
+}
+
+int hr_refl_push_chunks(hr_pass* p, int parity, int tick, const int* need0, const int* need1, cudaStream_t st)
+{
+    hr_ctx* ctx = p->ctx;
+    RowPtrs  im {};
+    NeedRows nd {};
+    TickPtrs t {};
+    for (int r = 0; r < ctx->world; r++)
+    {
+        im.p[r]  = static_cast<uint2*>(p->hist_peer[r][4 + parity]);
+        nd.r0[r] = need0[r];
+        nd.r1[r] = need1[r];
+        t.p[r]   = p->peer_ticks[r];
+    }
+    const int n_chunks = (p->H + 7) / 8, mine = (n_chunks - ctx->rank + ctx->world - 1) / ctx->world;
+    k_rt_push_chunks<<<mine > 0 ? mine : 1, 256, 0, st>>>(im, nd, t, p->rt_bounds, ctx->world, ctx->rank, p->W, p->H, tick);
+    ctx->launches++;
     return HR_OK;
 }
 

@@ -42,11 +42,39 @@ __device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 c
 
 struct ReflTemporalParams { float alpha, moments_alpha; int approximate_with_ddgi; int row0, row1; };
 
+// ---- history fetches through the owner table (HistPeers, hr_internal.h; see svgf_temporal.cu) ----
+__device__ __forceinline__ int owner_of(const HistPeers& hp, int row)
+{
+    int o = 0;
+#pragma unroll
+    for (int r = 0; r < HR_MAX_RANKS - 1; r++) o += (r < hp.world - 1 && row >= hp.band_end[r]) ? 1 : 0;
+    return o;
+}
+template <bool PEER>
+__device__ __forceinline__ uint2 hist_ld64(const void* const* tab, const HistPeers& hp, int row, size_t index)
+{
+    if (hp.no_history) return make_uint2(0u, 0u);
+    if (!PEER) return __ldg(reinterpret_cast<const uint2*>(tab[0]) + index);
+    const int    o = owner_of(hp, row);
+    const uint2* p = reinterpret_cast<const uint2*>(tab[o]) + index;
+    return o == hp.self ? __ldg(p) : __ldcg(p);
+}
+template <bool PEER>
+__device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const HistPeers& hp, int row, size_t word_index)
+{
+    if (hp.no_history) return 0u;
+    if (!PEER) return __ldg(reinterpret_cast<const uint32_t*>(tab[0]) + word_index);
+    const int       o = owner_of(hp, row);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(tab[o]) + word_index;
+    return o == hp.self ? __ldg(p) : __ldcg(p);
+}
+
 // CTA = 32x8 pixels.  17x17 mean / std-dev of the current ray-trace colour (neighborhood_standard_deviation :133-157):
 // separable — stage the 48x24 rgb region, horizontal 17-tap sums of c and c^2 into smem, vertical 17-tap sums per pixel.
-__global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint2* __restrict__ input, const uint2* __restrict__ hist,
-                                                        const uint2* __restrict__ hist_mom, FrameConsts fc, ReflTemporalParams P, uint2* __restrict__ out,
-                                                        uint2* __restrict__ mom_out, uint8_t* __restrict__ tile_flags)
+// hp.img = last frame's temporal output (or prev_image), hp.aux = last frame's moments, of the rank that owns the row (PEER)
+template <bool PEER>
+__global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint2* __restrict__ input, const HistPeers hp, FrameConsts fc,
+                                                        ReflTemporalParams P, uint2* __restrict__ out, uint2* __restrict__ mom_out, uint8_t* __restrict__ tile_flags)
 {
     __shared__ float    s_c[3][24][48];
     __shared__ float    s_h1[3][24][32];
@@ -135,8 +163,8 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                         if (inside(px, py, W, H))
                         {
                             const size_t pi = (size_t)py * W + px;
-                            const float4 hv4 = h4_to_f4(__ldg(hist + pi));
-                            const float2 mm  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_mom + pi)));
+                            const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, py, pi));
+                            const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, py, 2 * pi));
                             hc[0] += w4[s] * hv4.x; hc[1] += w4[s] * hv4.y; hc[2] += w4[s] * hv4.z;
                             hm0 += w4[s] * mm.x; hm1 += w4[s] * mm.y;
                         }
@@ -162,8 +190,8 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                                 if (inside(px, py, W, H))
                                 {
                                     const size_t pi = (size_t)py * W + px;
-                                    const float4 hv4 = h4_to_f4(__ldg(hist + pi));
-                                    const float2 mm  = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_mom + pi)));
+                                    const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, py, pi));
+                                    const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, py, 2 * pi));
                                     hc[0] += hv4.x; hc[1] += hv4.y; hc[2] += hv4.z; hm0 += mm.x; hm1 += mm.y;
                                 }
                                 cnt += 1.0f;
@@ -173,7 +201,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                 }
             }
             float hist_len = 0.0f;
-            if (valid) hist_len = h2_to_f2(__ldg(reinterpret_cast<const uint32_t*>(hist_mom + (size_t)hcy * W + hcx) + 1)).x;
+            if (valid) hist_len = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, hcy, 2 * ((size_t)hcy * W + hcx) + 1)).x;
             else { hc[0] = hc[1] = hc[2] = 0.0f; hm0 = hm1 = 0.0f; }
             const float hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
             if (valid)
@@ -358,14 +386,14 @@ void launch_atrous_t(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, 
 
 } // namespace
 
-void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const void* hist, const void* hist_mom, const FrameConsts& fc,
-                                 float alpha, float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1,
-                                 cudaStream_t st)
+void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const HistPeers& hist, const FrameConsts& fc, float alpha,
+                                 float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
     ReflTemporalParams P { alpha, moments_alpha, approximate_with_ddgi, row0, row1 };
     dim3               grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
-    k_refl_temporal<<<grid, 256, 0, st>>>(cur, prev, (const uint2*)input, (const uint2*)hist, (const uint2*)hist_mom, fc, P, (uint2*)out, (uint2*)mom_out, tile_flags);
+    if (hist.world > 1) k_refl_temporal<true><<<grid, 256, 0, st>>>(cur, prev, (const uint2*)input, hist, fc, P, (uint2*)out, (uint2*)mom_out, tile_flags);
+    else k_refl_temporal<false><<<grid, 256, 0, st>>>(cur, prev, (const uint2*)input, hist, fc, P, (uint2*)out, (uint2*)mom_out, tile_flags);
 }
 
 bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,

@@ -199,6 +199,10 @@ HR_API int hr_gbuffer_bind_device(hr_ctx* ctx, int slot, const hr_gbuffer_desc* 
  * height; row1 <= 0 = the whole image) let a sharded rank produce just the rows it consumes.  Async on `stream`.  The CPU
  * statement oracle/orc_gbuffer.cpp produces the same bits. */
 HR_API int hr_gbuffer_render(hr_ctx* ctx, int slot, const hr_frame* frame, int row0, int row1, void* stream);
+/* Sharded variant: only the rows this rank's full-resolution passes consume — its band +- halo_rows (temporal / a-trous stages;
+ * pass the recompute halo + the reprojection reach the camera motion needs) and the 8-row chunks it traces in the interleaved
+ * cooperative ray trace.  The other rows of the slot keep their old contents.  world == 1: the whole image. */
+HR_API int hr_gbuffer_render_sharded(hr_ctx* ctx, int slot, const hr_frame* frame, int halo_rows, void* stream);
 /* Read back one mip of a slot (tests). which: 1,2,3 = gb1..3, 0 = depth. Synchronous. */
 HR_API int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* host_dst, size_t bytes);
 

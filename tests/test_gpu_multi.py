@@ -184,3 +184,101 @@ def test_nccl_sharded_matches_single(tmp_path):
     sh.destroy()
     ao.destroy()
     c.close()
+
+
+# ---- reflections: peer history + interleaved cooperative ray trace -----------------------------------------------------------------
+RF = dict(rt=0, temporal=1, atrous=2, moments=4, final=100)
+
+
+def _refl_rank(device, sc, scale, rank=0, world=1):
+    c = pyhr.Context(device)
+    c.set_bluenoise(*pyhr.blue_noise())
+    c.build_scene(sc)
+    c.gbuffer_create(W, H)
+    if world > 1:
+        c.shard_config(rank, world)
+    p = pyhr.ReflectionsPass(c, W, H, scale)
+    p.params.sky_color[0], p.params.sky_color[1], p.params.sky_color[2] = 0.3, 0.4, 0.6
+    return c, p
+
+
+@pytest.mark.parametrize("world,scale", [(2, 0), (5, 1), (8, 0)])
+def test_peer_history_emulation_reflections(world, scale):
+    """N linked ranks on one GPU (the production multi-GPU data path minus CUDA IPC): every rank traces the 8-row chunks
+    c % world == rank of the whole image and pushes them to the ranks that filter those rows; reprojection pulls history
+    texels from the owner of their row.  Each rank's band of every stage must be BIT-IDENTICAL to the single-GPU images."""
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ref = _refl_rank(0, sc, scale)
+    ranks = [_refl_rank(0, sc, scale, r, world) for r in range(world)]
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                ranks[r][1].link_local(q, ranks[q][1])
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    ph = H >> scale
+    for f in frames(7, pan_from=2, vertical=0.35):
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        ref[0].gbuffer_upload(f.ping_pong, g)
+        ref[1].render(f, None)
+        for (c, p), st in zip(ranks, streams):
+            c.gbuffer_upload(f.ping_pong, g, st.cuda_stream)
+        for (c, p), st in zip(ranks, streams):
+            p.render(f, None, st.cuda_stream)
+        torch.cuda.synchronize()
+        for name, which, shift in (("ray trace", RF["rt"], 0), ("temporal", RF["temporal"], 0), ("moments", RF["moments"], 0), ("a-trous", RF["atrous"], 0),
+                                   ("final", RF["final"], scale)):
+            merged = merge_bands([r[1].download(which) for r in ranks], ph, world, shift if name == "final" else 0)
+            assert np.array_equal(merged, ref[1].download(which)), f"reflections {name} differs (world={world}, frame {f.num_frames})"
+    for c, p in [ref] + ranks:
+        p.destroy()
+    for c, p in [ref] + ranks:
+        c.close()
+
+
+def _nccl_refl_worker(rank, world, uid, result_dir):
+    import torch
+    torch.cuda.set_device(rank)
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    c = pyhr.Context(rank)
+    c.set_bluenoise(*pyhr.blue_noise())
+    c.build_scene(sc)
+    c.gbuffer_create(W, H)
+    c.shard_init(rank, world, uid)
+    p = pyhr.ReflectionsPass(c, W, H, 0)
+    p.params.sky_color[0], p.params.sky_color[1], p.params.sky_color[2] = 0.3, 0.4, 0.6
+    outs = []
+    for f in frames(6, vertical=0.35):
+        c.gbuffer_render(f.ping_pong, f)
+        p.render(f, None)
+        outs.append((p.download(100), p.download(RF["temporal"]), p.download(RF["moments"])))
+    np.savez(os.path.join(result_dir, f"refl{rank}.npz"), **{f"f{i}_{j}": a for i, o in enumerate(outs) for j, a in enumerate(o)})
+    p.destroy()
+    c.shard_shutdown()
+    c.close()
+
+
+def test_nccl_sharded_reflections_match_single(tmp_path):
+    """one process per GPU: gathered final output complete and identical on every rank, history bands identical"""
+    import torch
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    uid = pyhr.shard_unique_id()
+    mp.spawn(_nccl_refl_worker, args=(world, uid, str(tmp_path)), nprocs=world, join=True)
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    c, p = _refl_rank(0, sc, 0)
+    ref = []
+    for f in frames(6, vertical=0.35):
+        c.gbuffer_render(f.ping_pong, f)
+        p.render(f, None)
+        ref.append((p.download(100), p.download(RF["temporal"]), p.download(RF["moments"])))
+    for r in range(world):
+        d = np.load(os.path.join(str(tmp_path), f"refl{r}.npz"))
+        b, e = pyhr.shard_rows(H, r, world)
+        for i, o in enumerate(ref):
+            assert np.array_equal(d[f"f{i}_0"], o[0]), f"rank {r} frame {i}: gathered final output differs from the single-GPU result"
+            for j in (1, 2):
+                assert np.array_equal(d[f"f{i}_{j}"][b:e], o[j][b:e]), f"rank {r} frame {i} image {j}: own band differs"
+    p.destroy()
+    c.close()
