@@ -69,16 +69,19 @@ __device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const Hist
     return o == hp.self ? __ldg(p) : __ldcg(p);
 }
 
-// CTA = 32x8 pixels.  17x17 mean / std-dev of the current ray-trace colour (neighborhood_standard_deviation :133-157):
-// separable — stage the 48x24 rgb region, horizontal 17-tap sums of c and c^2 into smem, vertical 17-tap sums per pixel.
+// CTA = 32x8 pixels.  17x17 mean / std-dev of the current ray-trace colour (neighborhood_standard_deviation :133-157; the
+// reference does 289 fetches per pixel): separable, each direction as a SLIDING window — stage the 48x24 rgb region; 144 threads
+// each walk half a staged row of one channel keeping the running 17-tap sums of c and c^2 (17 + 15 * 2 loads instead of
+// 16 * 17); 192 threads each walk one column of one of the six horizontal sums (17 + 7 * 2 loads instead of 8 * 17); every
+// pixel then reads its six window sums.  ncu (r2a) had this kernel at 1 733 instructions per pixel, 72 % issue-active.
 // hp.img = last frame's temporal output (or prev_image), hp.aux = last frame's moments, of the rank that owns the row (PEER)
 template <bool PEER>
 __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint2* __restrict__ input, const HistPeers hp, FrameConsts fc,
                                                         ReflTemporalParams P, uint2* __restrict__ out, uint2* __restrict__ mom_out, uint8_t* __restrict__ tile_flags)
 {
-    __shared__ float    s_c[3][24][48];
-    __shared__ float    s_h1[3][24][32];
-    __shared__ float    s_h2[3][24][32];
+    __shared__ float    s_c[3][24][49];  // row pitch 49: the 144 row walkers of a phase hit 32 different banks
+    __shared__ float    s_h[6][24][32];  // horizontal window sums: [ch] = sum c, [3 + ch] = sum c^2
+    __shared__ float    s_v[6][8][32];   // 17x17 window sums per pixel of the tile
     __shared__ uint32_t s_flags;
     const int W = cur.W, H = cur.H;
     const int x0 = blockIdx.x * 32, y0 = P.row0 + blockIdx.y * 8;
@@ -97,18 +100,38 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
         s_c[0][ry][rx] = r; s_c[1][ry][rx] = g; s_c[2][ry][rx] = b;
     }
     __syncthreads();
+    if (threadIdx.x < 144)
+    { // horizontal: task = (half, channel, row); outputs 16 columns
+        const int    row = threadIdx.x % 24, ch = (threadIdx.x / 24) % 3, base = (threadIdx.x / 72) * 16;
+        const float* v = &s_c[ch][row][base];
+        float        a = 0.0f, b = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 3; k++)
-    {
-        const int ry = ly + 8 * k;
+        for (int t = 0; t < 17; t++) { const float c = v[t]; a += c; b = fmaf(c, c, b); }
+        s_h[ch][row][base]     = a;
+        s_h[3 + ch][row][base] = b;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++)
+        for (int i = 1; i < 16; i++)
         {
-            float a = 0.0f, b = 0.0f;
+            const float cin = v[16 + i], cout = v[i - 1];
+            a += cin - cout;
+            b = fmaf(cin, cin, fmaf(-cout, cout, b));
+            s_h[ch][row][base + i]     = a;
+            s_h[3 + ch][row][base + i] = b;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 192)
+    { // vertical: task = (quantity, column); outputs 8 rows
+        const int    q = threadIdx.x >> 5, col = threadIdx.x & 31;
+        float        a = 0.0f;
 #pragma unroll
-            for (int t = 0; t < 17; t++) { const float v = s_c[ch][ry][lx + t]; a += v; b = fmaf(v, v, b); }
-            s_h1[ch][ry][lx] = a;
-            s_h2[ch][ry][lx] = b;
+        for (int r = 0; r < 17; r++) a += s_h[q][r][col];
+        s_v[q][0][col] = a;
+#pragma unroll
+        for (int i = 1; i < 8; i++)
+        {
+            a += s_h[q][16 + i][col] - s_h[q][i - 1][col];
+            s_v[q][i][col] = a;
         }
     }
     __syncthreads();
@@ -174,7 +197,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                 if (any)
                 {
                     valid = sumw >= 0.01f;
-                    const float inv = valid ? 1.0f / sumw : 0.0f;
+                    const float inv = valid ? fast_rcp(sumw) : 0.0f;
                     hc[0] *= inv; hc[1] *= inv; hc[2] *= inv; hm0 *= inv; hm1 *= inv;
                 }
                 if (!valid)
@@ -197,7 +220,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                                 cnt += 1.0f;
                             }
                         }
-                    if (cnt > 0.0f) { valid = true; const float inv = 1.0f / cnt; hc[0] *= inv; hc[1] *= inv; hc[2] *= inv; hm0 *= inv; hm1 *= inv; }
+                    if (cnt > 0.0f) { valid = true; const float inv = fast_rcp(cnt); hc[0] *= inv; hc[1] *= inv; hc[2] *= inv; hm0 *= inv; hm1 *= inv; }
                 }
             }
             float hist_len = 0.0f;
@@ -210,10 +233,8 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
 #pragma unroll
                 for (int ch = 0; ch < 3; ch++)
                 {
-                    float m1 = 0.0f, m2 = 0.0f;
-#pragma unroll
-                    for (int r = 0; r < 17; r++) { m1 += s_h1[ch][ly + r][lx]; m2 += s_h2[ch][ly + r][lx]; }
-                    const float mean = m1 / 289.0f, var = m2 / 289.0f - mean * mean, sd = sqrtf(fmaxf(var, 0.0f));
+                    const float m1 = s_v[ch][ly][lx], m2 = s_v[3 + ch][ly][lx];
+                    const float mean = m1 * (1.0f / 289.0f), var = m2 * (1.0f / 289.0f) - mean * mean, sd = sqrtf(fmaxf(var, 0.0f));
                     mn[ch] = mean - sd;
                     mx[ch] = mean + sd;
                 }
@@ -224,14 +245,15 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                     ctr[ch] = 0.5f * (mx[ch] + mn[ch]);
                     const float ext = 0.5f * (mx[ch] - mn[ch]) + 0.001f;
                     cv[ch] = hc[ch] - ctr[ch];
-                    mabs   = fmaxf(mabs, fabsf(cv[ch] / ext));
+                    mabs   = fmaxf(mabs, fabsf(cv[ch] * fast_rcp(ext)));
                 }
-                if (mabs > 1.0f) { hc[0] = ctr[0] + cv[0] / mabs; hc[1] = ctr[1] + cv[1] / mabs; hc[2] = ctr[2] + cv[2] / mabs; }
+                if (mabs > 1.0f) { const float im = fast_rcp(mabs); hc[0] = ctr[0] + cv[0] * im; hc[1] = ctr[1] + cv[1] * im; hc[2] = ctr[2] + cv[2] * im; }
             }
             const float cdl = sqrtf(fc.camera_delta[0] * fc.camera_delta[0] + fc.camera_delta[1] * fc.camera_delta[1] + fc.camera_delta[2] * fc.camera_delta[2]);
             const float maxacc = cdl > 0.0f ? 8.0f : hlen;
-            const float alpha  = valid ? fmaxf(P.alpha, 1.0f / maxacc) : 1.0f;
-            const float alpham = valid ? fmaxf(P.moments_alpha, 1.0f / maxacc) : 1.0f;
+            const float iacc   = fast_rcp(maxacc);
+            const float alpha  = valid ? fmaxf(P.alpha, iacc) : 1.0f;
+            const float alpham = valid ? fmaxf(P.moments_alpha, iacc) : 1.0f;
             const float lum = luminance(color[0], color[1], color[2]);
             const float mo0 = hm0 * (1.0f - alpham) + lum * alpham, mo1 = hm1 * (1.0f - alpham) + (lum * lum) * alpham;
             o[0] = hc[0] * (1.0f - alpha) + color[0] * alpha;

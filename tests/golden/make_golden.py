@@ -20,7 +20,7 @@ if __name__ == "__main__":
 
 
 # ---- 256x144, 8 static + 4 panning frames (the sequence of tests/test_gpu_parity.py::test_shadows_ao_static_then_pan):
-# the state after the last frame; tests/test_gpu_y_golden.py drives the same inputs through the C ABI and compares with it.
+# the state after the last frame; tests/test_gpu_golden.py drives the same inputs through the C ABI and compares with it.
 import oracle as O  # noqa: E402
 import pyhr  # noqa: E402
 

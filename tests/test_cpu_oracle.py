@@ -136,7 +136,7 @@ def test_golden_vectors():
 
 
 def test_golden_sequence_256x144():
-    """The larger fixture (state after the 12-frame static + pan sequence, the one tests/test_gpu_y_golden.py compares the CUDA path
+    """The larger fixture (state after the 12-frame static + pan sequence, the one tests/test_gpu_golden.py compares the CUDA path
     with) is reproduced by the oracle: integer images bit for bit, fp16 images within one ulp of libm noise."""
     sys.path.insert(0, GOLDEN)
     from make_golden import seq12_oracle
@@ -150,7 +150,7 @@ def test_golden_sequence_256x144():
 
 
 def test_golden_ddgi_reflections_192x112():
-    """DDGI + reflections fixture (tests/test_gpu_y_golden.py compares the CUDA path with it): reproduced by the oracle; exact where
+    """DDGI + reflections fixture (tests/test_gpu_golden.py compares the CUDA path with it): reproduced by the oracle; exact where
     the values are decisions (ray lengths, tile flags, history length), within fp16 / libm noise elsewhere."""
     sys.path.insert(0, GOLDEN)
     from make_golden import gi_oracle

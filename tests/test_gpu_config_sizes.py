@@ -1,0 +1,102 @@
+"""GPU parity at the BASELINE.json configuration sizes ("parity is only tested far below the BASELINE sizes").
+
+* config 2: 1920x1080, shadows (full-res) + AO (half-res), 262 144-triangle arcade — EVERY intermediate of both denoise chains
+  against the CPU oracle, static frames then a lateral pan (real motion vectors from the device G-buffer producer);
+* config 3: 3840x2160, reflections at full resolution + SVGF on the same scene — ray length exact, every stage within the
+  stated tolerance, on full 4K frames (the oracle's OpenMP loops need a many-core host: a few seconds per frame there).
+
+The G-buffer comes from hr_gbuffer_render; the oracle is fed its own statement of it (oracle/orc_gbuffer.cpp), and the two
+are first checked to be the same bits at these sizes.
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+import pyhr
+from test_gpu_parity import check_all, f16
+from test_gpu_gi_refl import close
+
+pytestmark = pytest.mark.gpu
+
+CAM = ((0.0, 9.0, -4.0), (2.0, 7.0, 60.0))
+TRIS = 262144
+
+
+def _frames(W, H, n, pan_from, light):
+    f = None
+    for i in range(n):
+        dx = 0.0 if i < pan_from else 0.05 * (i - pan_from + 1)
+        f = pyhr.make_frame((CAM[0][0] + dx, CAM[0][1], CAM[0][2]), (CAM[1][0] + dx, CAM[1][1], CAM[1][2]), W, H, prev=f, num_frames=i, light=light)
+        yield i, f
+
+
+def _same_gbuffer(ctx, f, ref, W, H):
+    for which, arr in ((0, ref.depth), (2, ref.gb2), (3, ref.gb3)):
+        assert np.array_equal(ctx.gbuffer_download(f.ping_pong, 0, which, W, H), arr), f"device G-buffer image {which} differs from the oracle's at {W}x{H}"
+
+
+def test_config2_1080p_shadows_ao_every_intermediate():
+    W, H = 1920, 1080
+    light = pyhr.default_light(rot_x_deg=25.0)
+    sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, TRIS)
+    ss = O.ShadingScene(sc, brute=False)
+    bn = pyhr.blue_noise()
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(*bn)
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    sh, ao = pyhr.Pass(ctx, "shadows", W, H, 0), pyhr.Pass(ctx, "ao", W, H, 1)
+    osh, oao = O.ShadowsOracle(W, H, 0), O.AOOracle(W, H, 1)
+    prev_g, stats = O.zero_gbuf_mips(W, H), []
+    for i, f in _frames(W, H, 5, 3, light):  # 3 static frames, 2 pan frames
+        ctx.gbuffer_render(f.ping_pong, f)
+        ref = O.gbuffer_render(ss, f, W, H)
+        _same_gbuffer(ctx, f, ref, W, H)
+        sh.render(f)
+        ao.render(f)
+        cur_g = O.GBufMips(ref)
+        osh.render(ss.scene, cur_g, prev_g, f, bn)
+        oao.render(ss.scene, cur_g, prev_g, f, bn)
+        prev_g = cur_g
+        check_all(i, sh, ao, osh, oao, stats)
+    assert len(stats) == 5
+    sh.destroy()
+    ao.destroy()
+    ctx.close()
+
+
+def test_config3_4k_reflections_full_res():
+    W, H = 3840, 2160
+    light = pyhr.default_light(rot_x_deg=25.0)
+    sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, TRIS)
+    ss = O.ShadingScene(sc, brute=False)
+    bn = pyhr.blue_noise()
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(*bn)
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    rf = pyhr.ReflectionsPass(ctx, W, H, 0)
+    rf.params.sky_color[0], rf.params.sky_color[1], rf.params.sky_color[2] = 0.3, 0.4, 0.6
+    orf = O.ReflectionsOracle(W, H, 0, rf.params)
+    prev_g = O.zero_gbuf_mips(W, H)
+    for i, f in _frames(W, H, 3, 2, light):  # 2 static frames, 1 pan frame
+        ctx.gbuffer_render(f.ping_pong, f)
+        ref = O.gbuffer_render(ss, f, W, H)
+        if i == 0:
+            _same_gbuffer(ctx, f, ref, W, H)
+        rf.render(f, None)
+        cur_g = O.GBufMips(ref)
+        orf.render(ss, cur_g, prev_g, f, bn, None)
+        prev_g = cur_g
+        rt_c, rt_o = f16(rf.download(0)), O.h2f(orf.rt)
+        assert np.array_equal(rt_c[..., 3], rt_o[..., 3]), f"frame {i}: reflection ray length (hit / miss / t) not exact at 4K"
+        close(rt_c[..., :3], rt_o[..., :3], f"frame {i} reflections ray trace", 1e-3, 0.02)
+        assert np.array_equal(rf.download(6), orf.tile_flags), f"frame {i}: tile classification"
+        close(f16(rf.download(1)), O.h2f(orf.cur_temporal), f"frame {i} temporal")
+        mo_c, mo_o = f16(rf.download(4)), O.h2f(orf.cur_moments)
+        assert np.array_equal(mo_c[..., 2], mo_o[..., 2]), f"frame {i}: history length"
+        close(mo_c, mo_o, f"frame {i} moments")
+        close(f16(rf.download(2)), O.h2f(orf.atrous_out), f"frame {i} a-trous")
+        close(f16(rf.download(100)), O.h2f(orf.final), f"frame {i} final")
+    rf.destroy()
+    ctx.close()

@@ -94,7 +94,6 @@ def test_4k_properties(inputs, first_run):
     assert a["sh_mask"].any() and a["ao_mask"].any()
 
 
-@pytest.mark.xfail(strict=False, reason="check fixed after its first hardware run (the test fed frame 0's G-buffer); not re-run, GPU budget was at 0")
 def test_4k_static_camera_history(inputs, first_run):
     """static camera: history accepted everywhere => history length = frames rendered; the filter averages."""
     sc, frames, g = inputs
