@@ -134,6 +134,7 @@ int hr_shutdown(hr_ctx* ctx)
     if (ctx->ev_storage_free) cudaEventDestroy(ctx->ev_storage_free);
     cudaFree(ctx->d_sobol);
     cudaFree(ctx->d_scr_rank);
+    cudaFree(ctx->d_brdf_lut);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->nccl_comm) hr_shard_shutdown(ctx);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);

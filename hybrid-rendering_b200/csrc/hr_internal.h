@@ -107,6 +107,7 @@ struct hr_ctx {
     uint64_t     launches  = 0;
     int          sm_count  = 148;
     cudaStream_t build_stream = nullptr;
+    uint32_t*    d_brdf_lut = nullptr;  // 512 x 512 RG16F split-sum LUT (hr_brdf_lut_set); null: the IBL specular terms are 0
     unsigned long long* gbuf_ray_ctr = nullptr; // primary rays of hr_gbuffer_render (same slot layout as hr_pass::ray_ctr)
 };
 
@@ -142,7 +143,7 @@ struct hr_scene {
     hr_scene_info info {};
 };
 
-enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4 };
+enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4, PASS_DEFERRED = 5 };
 
 struct StageTimer { // one Rec per profiled render; hr_pass_stage_times averages and recycles them
     struct Rec { std::vector<std::string> names; std::vector<cudaEvent_t> ev; };
@@ -198,6 +199,7 @@ struct hr_pass {
     uint2*    ddgi_irr[2] = { nullptr, nullptr };
     uint32_t* ddgi_depth[2] = { nullptr, nullptr };
     uint2*    ddgi_sample = nullptr;
+    uint2*    deferred_out = nullptr;                  // deferred shading combine: RGBA16F (Lo, 1)
     std::vector<void*> ddgi_grid_allocs;
     // asynchronous band exchange (shard.cu): ev_ready = pass kernels done on the caller's stream, ev_done = exchange done on
     // ctx->comm_stream.  Whoever next touches an exchanged image (next frame's temporal stage, hr_pass_output/download)
@@ -237,7 +239,7 @@ void launch_ddgi_sample_probe_grid(const GBufLevelDev& g, const FrameConsts& fc,
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
                                   const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, int chunk_first, int chunk_stride,
-                                  cudaStream_t st); // chunk_stride > 1: only the 8-row chunks c = chunk_first + i * chunk_stride (rows are ignored)
+                                  int spp, const void* brdf_lut, float ibl_intensity, cudaStream_t st); // chunk_stride > 1: only the 8-row chunks c = chunk_first + i * chunk_stride (rows are ignored)
 void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const HistPeers& hist, const FrameConsts& fc, float alpha,
                                  float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
 int  launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
@@ -293,6 +295,8 @@ void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 // ---- kernel launchers (defined in the .cu files) -----------------------------------------------------
 void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, int row0, int row1, int chunk_first, int chunk_stride, void* gb1, void* gb2, void* gb3,
                            float* depth, unsigned long long* ray_ctr, cudaStream_t st); // gbuffer.cu
+void launch_deferred(const GBufLevelDev& g, const FrameConsts& fc, const void* shadow, int shadow_channels, const void* ao, const void* reflections, const void* gi,
+                     const float* env3, const void* brdf_lut, void* out, int row0, int row1, cudaStream_t st); // deferred.cu
 // stats.cu (measurement helpers, not on the frame path)
 void launch_tile_stats(const uint8_t* flags, int TW, int t0, int t1, unsigned long long* d_out, cudaStream_t st);
 void launch_drain_ray_counters(unsigned long long* ctr, unsigned long long* d_out, cudaStream_t st);

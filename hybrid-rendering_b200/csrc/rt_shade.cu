@@ -140,9 +140,23 @@ __device__ float3 indirect_diffuse(const hr_ddgi_uniforms& d, const gi::AtlasDev
     return (kD * diffuse_color) * irr * gi_intensity;
 }
 
+// IBL specular, reflections_ray_trace.rchit:97-104: prefiltered * (F * brdf.x + brdf.y) * intensity; brdf = bilinear CLAMP_TO_EDGE fetch of
+// the 512 x 512 RG16F LUT at (max(N.Wo, 0), roughness); the prefiltered environment is the constant sky colour
+struct IblDev { const uint32_t* lut; float intensity; };
+__device__ __forceinline__ float2 brdf_lut_fetch(const uint32_t* __restrict__ lut, float u, float v)
+{
+    const float x = u * 512.0f - 0.5f, y = v * 512.0f - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y), fx = x - fx0, fy = y - fy0;
+    const int   x0 = min(max((int)fx0, 0), 511), x1 = min(max((int)fx0 + 1, 0), 511), y0 = min(max((int)fy0, 0), 511), y1 = min(max((int)fy0 + 1, 0), 511);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(lut + y0 * 512 + x0)), b = __half22float2(*reinterpret_cast<const __half2*>(lut + y0 * 512 + x1));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(lut + y1 * 512 + x0)), e = __half22float2(*reinterpret_cast<const __half2*>(lut + y1 * 512 + x1));
+    return make_float2((a.x * (1.0f - fx) + b.x * fx) * (1.0f - fy) + (c.x * (1.0f - fx) + e.x * fx) * fy,
+                       (a.y * (1.0f - fx) + b.y * fx) * (1.0f - fy) + (c.y * (1.0f - fx) + e.y * fx) * fy);
+}
+
 __device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& sd, const hr_light& light, const Ray& r, uint32_t prim, float u, float v, bool sky_light,
                                             float r0, float r1, float3 sky, bool gi_on, const hr_ddgi_uniforms& d, const gi::AtlasDev& at, float gi_intensity,
-                                            unsigned long long* ray_ctr)
+                                            unsigned long long* ray_ctr, IblDev ibl = IblDev { nullptr, 0.0f })
 {
     using namespace gi;
     const Surface s  = fetch_surface(sd, prim, u, v);
@@ -150,7 +164,17 @@ __device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& s
     const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;             // mix(0.04, albedo, metallic)
     const float3  cd = (s.albedo * (f3(1, 1, 1) - F0)) * (1.0f - s.metallic) + f3(0, 0, 0) * s.metallic; // mix(albedo*(1-F0), 0, metallic)
     float3        Lo = direct_lighting(bvh, light, Wo, s.N, s.P, F0, cd, s.roughness, sky_light, r0, r1, sky, ray_ctr);
-    if (gi_on) Lo = Lo + indirect_diffuse(d, at, Wo, s.N, s.P, F0, cd, s.roughness, s.metallic, gi_intensity);
+    if (gi_on)
+    {
+        Lo = Lo + indirect_diffuse(d, at, Wo, s.N, s.P, F0, cd, s.roughness, s.metallic, gi_intensity);
+        if (ibl.lut)
+        {
+            const float  ct = fmaxf(det::dot(s.N, Wo), 0.0f), p5 = powf(fmaxf(1.0f - ct, 0.0f), 5.0f), omr = 1.0f - s.roughness;
+            const float3 F  = F0 + (f3(fmaxf(omr, F0.x), fmaxf(omr, F0.y), fmaxf(omr, F0.z)) - F0) * p5;
+            const float2 b  = brdf_lut_fetch(ibl.lut, ct, s.roughness);
+            Lo = Lo + (sky * (F * b.x + f3(b.y, b.y, b.y))) * ibl.intensity;
+        }
+    }
     return Lo;
 }
 
@@ -231,7 +255,7 @@ __device__ __forceinline__ V3 importance_sample_ggx(float ex, float ey, V3 N, fl
 }
 
 struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int row0, row1;
-                         int chunk_first, chunk_stride; }; // chunk_stride > 1: the 8-row chunks c = chunk_first + i * chunk_stride of the whole image
+                         int chunk_first, chunk_stride; int spp; IblDev ibl; }; // chunk_stride > 1: the 8-row chunks c = chunk_first + i * chunk_stride of the whole image
 
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
 // 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
@@ -259,35 +283,46 @@ __global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, Bv
     r.tmax = 10000.0f;
     float3 color = make_float3(0, 0, 0);
     float  ray_length = -1.0f;
-    bool   trace = false;
-    if (roughness < 0.05f) { r.d = reflect(det::scale(Wo, -1.0f), N); trace = true; }
-    else if (roughness > 0.75f && P.approximate_with_ddgi == 1)
+    // spp > 1: the GGX lobe draws spp directions, the clamped radiance is averaged, ray_length = first sample's
+    const int  spp = P.spp > 1 ? P.spp : 1;
+    const bool ggx = !(roughness < 0.05f) && !(roughness > 0.75f && P.approximate_with_ddgi == 1);
+    const int  n_s = ggx ? spp : 1;
+    float3     acc = make_float3(0, 0, 0);
+    for (int s = 0; s < n_s; s++)
     {
-        const V3 R = reflect(det::scale(Wo, -1.0f), N);
-        using namespace gi;
-        color = sample_irradiance(d, at, to_f3(Pw), to_f3(R), to_f3(Wo)) * P.rough_ddgi_intensity;
-    }
-    else
-    {
-        const float ex = det::sample_blue_noise(x, y, (int)fc.num_frames, 0, sobol, srk) * P.trim;
-        const float ey = det::sample_blue_noise(x, y, (int)fc.num_frames, 1, sobol, srk) * P.trim;
-        const V3    Wh = importance_sample_ggx(ex, ey, N, roughness);
-        r.d   = reflect(det::scale(Wo, -1.0f), Wh);
-        trace = true;
-    }
-    if (trace)
-    {
-        float    t, hu, hv;
-        uint32_t prim;
-        count_rays(fc.ray_ctr, 0, 1u);
-        if (trace_closest(bvh, r, t, prim, hu, hv))
+        bool trace = false;
+        if (roughness < 0.05f) { r.d = reflect(det::scale(Wo, -1.0f), N); trace = true; }
+        else if (roughness > 0.75f && P.approximate_with_ddgi == 1)
         {
-            color      = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr);
-            ray_length = 0.001f + t;
+            const V3 R = reflect(det::scale(Wo, -1.0f), N);
+            using namespace gi;
+            color = sample_irradiance(d, at, to_f3(Pw), to_f3(R), to_f3(Wo)) * P.rough_ddgi_intensity;
         }
-        else color = sky;
+        else
+        {
+            const int   si = (int)fc.num_frames * spp + s;
+            const float ex = det::sample_blue_noise(x, y, si, 0, sobol, srk) * P.trim;
+            const float ey = det::sample_blue_noise(x, y, si, 1, sobol, srk) * P.trim;
+            const V3    Wh = importance_sample_ggx(ex, ey, N, roughness);
+            r.d   = reflect(det::scale(Wo, -1.0f), Wh);
+            trace = true;
+        }
+        if (trace)
+        {
+            float    t, hu, hv;
+            uint32_t prim;
+            count_rays(fc.ray_ctr, 0, 1u);
+            if (trace_closest(bvh, r, t, prim, hu, hv))
+            {
+                color = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr, P.ibl);
+                if (s == 0) ray_length = 0.001f + t;
+            }
+            else color = sky;
+        }
+        acc = make_float3(acc.x + fminf(color.x, 0.7f), acc.y + fminf(color.y, 0.7f), acc.z + fminf(color.z, 0.7f));
     }
-    out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), ray_length);
+    const float inv_n = 1.0f / (float)n_s;
+    out[idx] = pack_h4(acc.x * inv_n, acc.y * inv_n, acc.z * inv_n, ray_length);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -535,7 +570,7 @@ __global__ void __launch_bounds__(256) k_refl_shade(GBufLevelDev g, BvhDev bvh, 
     Ray r;
     V3  Pw, Wo, N;
     refl_ray_gen(g, fc, P, sobol, srk, x, y, r, Pw, Wo, N);
-    const float3 color = shade_hit(bvh, sd, fc.light, r, __float_as_uint(h.y), h.z, h.w, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr);
+    const float3 color = shade_hit(bvh, sd, fc.light, r, __float_as_uint(h.y), h.z, h.w, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr, P.ibl);
     out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), 0.001f + h.x);
 }
 
@@ -573,16 +608,17 @@ int g_hr_refl_trace_impl = 1;
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
                                   const uint8_t* sobol, const uint8_t* srk, void* out, void* hits, int row0, int row1, int chunk_first, int chunk_stride,
-                                  cudaStream_t st)
+                                  int spp, const void* brdf_lut, float ibl_intensity, cudaStream_t st)
 {
     const int n_chunks_mine = chunk_stride > 1 ? (((g.H + 7) / 8) - chunk_first + chunk_stride - 1) / chunk_stride : 0;
     if (chunk_stride > 1 ? n_chunks_mine <= 0 : row1 <= row0) return;
-    ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1, chunk_first, chunk_stride };
+    ReflTraceParams P { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] }, row0, row1, chunk_first, chunk_stride, spp,
+                        IblDev { (const uint32_t*)brdf_lut, ibl_intensity } };
     hr_ddgi_uniforms du;
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    if ((g_hr_refl_trace_impl == 1 || chunk_stride > 1) && hits && row0 % 4 == 0)
+    if ((g_hr_refl_trace_impl == 1 || chunk_stride > 1) && hits && row0 % 4 == 0 && spp <= 1) // spp > 1 runs on the fused kernel
     {
         static unsigned int* counter[64] = {};
         static int           ctas[64]    = {};

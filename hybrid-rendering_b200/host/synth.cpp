@@ -682,4 +682,46 @@ void hrs_blue_noise(uint32_t seed, uint8_t* sobol, uint8_t* sr)
     for (int i = 0; i < 128 * 128 * 4; i++) sr[i] = (uint8_t)(rng.next() & 0xFF);
 }
 
+// Stand-in for textures/brdf_lut.bin (release-zip asset): the usual split-sum environment-BRDF integral (Karis 2013) over a
+// Hammersley / GGX-importance-sampled hemisphere; texel (i, j): N.V = (i + .5) / 512, roughness = (j + .5) / 512; RG16F.
+void hrs_brdf_lut(int samples, uint16_t* out_512x512x2)
+{
+    const int N = 512;
+    if (samples < 16) samples = 16;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int j = 0; j < N; j++)
+        for (int i = 0; i < N; i++)
+        {
+            const float ndv = ((float)i + 0.5f) / N, rough = ((float)j + 0.5f) / N;
+            const float vx = std::sqrt(1.0f - ndv * ndv), vz = ndv;
+            const float a = rough * rough, k = a / 2.0f;
+            float A = 0.0f, B = 0.0f;
+            for (int s = 0; s < samples; s++)
+            {
+                uint32_t bits = (uint32_t)s;
+                bits = (bits << 16) | (bits >> 16);
+                bits = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+                bits = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+                bits = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+                bits = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+                const float e1 = (float)s / (float)samples, e2 = (float)bits * 2.3283064365386963e-10f;
+                const float phi = 6.28318530718f * e1, ct = std::sqrt((1.0f - e2) / (1.0f + (a * a - 1.0f) * e2)), st = std::sqrt(1.0f - ct * ct);
+                const float hx = std::cos(phi) * st, hy = std::sin(phi) * st, hz = ct;
+                const float vdh = vx * hx + vz * hz;
+                const float lz  = 2.0f * vdh * hz - vz;
+                (void)hy;
+                const float ndl = std::max(lz, 0.0f), ndh = std::max(hz, 0.0f), vh = std::max(vdh, 0.0f);
+                if (ndl > 0.0f)
+                {
+                    const float g = (ndv / (ndv * (1.0f - k) + k)) * (ndl / (ndl * (1.0f - k) + k));
+                    const float gv = g * vh / std::max(ndh * ndv, 1e-6f), fc = std::pow(1.0f - vh, 5.0f);
+                    A += (1.0f - fc) * gv;
+                    B += fc * gv;
+                }
+            }
+            out_512x512x2[2 * ((size_t)j * N + i)]     = f2h(A / samples);
+            out_512x512x2[2 * ((size_t)j * N + i) + 1] = f2h(B / samples);
+        }
+}
+
 } // extern "C"

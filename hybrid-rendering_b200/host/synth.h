@@ -61,6 +61,9 @@ HR_API void hrs_write_gbuffer(const hrs_scene* visible, const hr_frame* frame, i
  * 8-bit Sobol' points dims 0..3 from the Joe-Kuo direction numbers; seeded-PRNG scramble/rank tile. */
 HR_API void hrs_blue_noise(uint32_t seed, uint8_t* sobol_256x4, uint8_t* scrambling_ranking_128x128x4);
 
+/* synthetic stand-in for textures/brdf_lut.bin: 512 x 512 RG16F split-sum LUT */
+HR_API void hrs_brdf_lut(int samples, uint16_t* out_512x512x2);
+
 #ifdef __cplusplus
 }
 #endif

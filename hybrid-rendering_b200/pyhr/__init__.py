@@ -95,7 +95,7 @@ ABI_SYMBOLS = [
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
-    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded",
+    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render",
 ]
 
 _product = None
@@ -295,6 +295,11 @@ class Context:
             self.lib.hr_shutdown(self.h)
             self.h = None
 
+    def set_brdf_lut(self, lut):
+        lut = np.ascontiguousarray(lut, np.uint16)
+        assert lut.shape == (512, 512, 2)
+        self.check(self.lib.hr_brdf_lut_set(self.h, _ptr(lut)), "hr_brdf_lut_set")
+
     def set_bluenoise(self, sobol, sr):
         self.check(self.lib.hr_bluenoise_set(self.h, _ptr(np.ascontiguousarray(sobol)), _ptr(np.ascontiguousarray(sr))), "hr_bluenoise_set")
 
@@ -468,7 +473,20 @@ class hr_reflections_params(C.Structure):
     _fields_ = [("bias", C.c_float), ("trim", C.c_float), ("sample_gi", C.c_int32), ("approximate_with_ddgi", C.c_int32), ("gi_intensity", C.c_float),
                 ("rough_ddgi_intensity", C.c_float), ("ibl_indirect_specular_intensity", C.c_float), ("alpha", C.c_float), ("moments_alpha", C.c_float),
                 ("blur_as_input", C.c_int32), ("phi_color", C.c_float), ("phi_normal", C.c_float), ("sigma_depth", C.c_float), ("radius", C.c_int32),
-                ("filter_iterations", C.c_int32), ("feedback_iteration", C.c_int32), ("denoise", C.c_int32), ("sky_color", C.c_float * 3)]
+                ("filter_iterations", C.c_int32), ("feedback_iteration", C.c_int32), ("denoise", C.c_int32), ("sky_color", C.c_float * 3), ("spp", C.c_int32)]
+
+
+class hr_deferred_params(C.Structure):
+    _fields_ = [("env_color", C.c_float * 3)]
+
+
+def brdf_lut(samples=128):
+    """synthetic stand-in for textures/brdf_lut.bin: 512 x 512 RG16F split-sum LUT (host/synth.cpp::hrs_brdf_lut)"""
+    a = np.empty((512, 512, 2), np.uint16)
+    L = load_synth()
+    L.hrs_brdf_lut.argtypes = [C.c_int, C.c_void_p]
+    L.hrs_brdf_lut(samples, _ptr(a))
+    return a
 
 
 def rotation_matrix(angle, axis):
@@ -515,3 +533,18 @@ class ReflectionsPass(Pass):
     def render(self, frame: hr_frame, ddgi: DDGIPass = None, stream=0):
         self.ctx.check(self.lib.hr_reflections_render(self.h, C.byref(frame), C.byref(self.params), ddgi.h if ddgi is not None else None, C.c_void_p(stream)),
                        "hr_reflections_render")
+
+
+class DeferredPass(Pass):
+    """deferred shading combine (hr_deferred_*): consumes the four pass outputs + G-buffer"""
+
+    def __init__(self, ctx: Context, W, H):
+        self.ctx, self.kind, self.lib = ctx, "deferred", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_deferred_create(ctx.h, W, H, C.byref(h)), "hr_deferred_create")
+        self.h = h
+        self.params = hr_deferred_params()
+
+    def render(self, frame: hr_frame, shadows=None, ao=None, reflections=None, ddgi=None, stream=0):
+        hs = [x.h if x is not None else None for x in (shadows, ao, reflections, ddgi)]
+        self.ctx.check(self.lib.hr_deferred_render(self.h, C.byref(frame), C.byref(self.params), hs[0], hs[1], hs[2], hs[3], C.c_void_p(stream)), "hr_deferred_render")

@@ -96,6 +96,12 @@ HR_API int         hr_version(void);
  * sobol: 256 x RGBA8 (sobol_256_4d.png); scrambling_ranking: 128 x 128 x RGBA8 (…_1spp.png). Host pointers. */
 HR_API int hr_bluenoise_set(hr_ctx* ctx, const uint8_t* sobol_256x4, const uint8_t* scrambling_ranking_128x128x4);
 
+/* Split-sum BRDF LUT (dw::BRDFIntegrateLUT: textures/brdf_lut.bin, 512 x 512 RG16F, extras/brdf_preintegrate_lut.cpp:8-31; bound
+ * with the bilinear CLAMP_TO_EDGE sampler, src/common.cpp:814-816).  Host pointer to 512 * 512 * 2 halves.  Until it is set the IBL
+ * specular terms (reflections_ray_trace.rchit:97-104, deferred.frag:167-170) are 0.  The sky / prefiltered environment cubemaps
+ * are replaced by the constant colour passed in the pass parameters (sky_color). */
+HR_API int hr_brdf_lut_set(hr_ctx* ctx, const uint16_t* rg16f_512x512);
+
 /* ------------------------------------------------------------------------------------------------
  * Scene  (replaces dw::RayTracedScene + driver BLAS/TLAS build,
  *         external/dwSampleFramework/extras/ray_traced_scene.cpp:196-248, src/mesh.cpp:169-231)
@@ -359,6 +365,9 @@ typedef struct hr_reflections_params { /* defaults: src/ray_traced_reflections.h
     int32_t feedback_iteration;    /* 1    */
     int32_t denoise;               /* 1    */
     float   sky_color[3];          /* miss colour (skybox cubemap replaced by a constant) */
+    int32_t spp;                   /* 1: the reference's single ray per pixel.  > 1 (not in the reference): the GGX
+                                    * lobe draws spp directions (sample index num_frames * spp + s) and stores the mean of the clamped
+                                    * radiance; the ray length is the first sample's; 0 is read as 1 */
 } hr_reflections_params;
 
 enum {
@@ -375,6 +384,19 @@ HR_API void hr_reflections_default_params(hr_reflections_params* p);
 HR_API int  hr_reflections_create(hr_ctx* ctx, int width, int height, int scale, hr_pass** out); /* ray_traced_reflections.cpp:67-103 */
 /* render(cmd_buf, DDGI*), ray_traced_reflections.cpp:107-123; ddgi may be NULL (then sample_gi / approximate_with_ddgi are off). */
 HR_API int hr_reflections_render(hr_pass* pass, const hr_frame* frame, const hr_reflections_params* params, hr_pass* ddgi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Deferred shading combine  (src/deferred_shading.{h,cpp}; shaders/deferred.frag:146-205)
+ * Lo = direct_lighting * shadows.r + indirect_lighting(DDGI irradiance, reflections, BRDF LUT) * AO  ->  RGBA16F (Lo, 1), full res.
+ * Any of the four passes may be NULL (the reference's push constants shadow / ao / reflections / gi = 0: visibility 1, AO 1, the
+ * environment colour as prefiltered reflection / irradiance).  Reads GB1 (albedo, metallic): bind or render it.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_deferred_params {
+    float env_color[3]; /* constant environment: evaluate_sh9_irradiance / prefiltered cubemap value */
+} hr_deferred_params;
+HR_API int hr_deferred_create(hr_ctx* ctx, int width, int height, hr_pass** out);
+HR_API int hr_deferred_render(hr_pass* pass, const hr_frame* frame, const hr_deferred_params* params, hr_pass* shadows, hr_pass* ao, hr_pass* reflections, hr_pass* ddgi,
+                              void* stream); /* output: hr_pass_output(pass, HR_..._OUT_FINAL = 100) */
 
 /* ------------------------------------------------------------------------------------------------
  * Common pass functions

@@ -197,7 +197,8 @@ inline vec3 importance_sample_ggx(vec2 E, vec3 N, float roughness)
     return normalize((tangent * H.x + bitangent * H.y) + N * H.z);
 }
 
-struct ReflParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; };
+struct ReflParams { float bias, trim; int sample_gi, approximate_with_ddgi; float gi_intensity, rough_ddgi_intensity; float sky[3]; int spp = 1;
+                    BrdfLut lut; float ibl_intensity = 0.0f; };
 
 // K12  reflections_ray_trace.rgen:119-171 + rchit:117-150 + rmiss:26-30
 void reflections_ray_trace(const ShadingScene& ss, const GBufLevel& g, const hr_frame& f, const ReflParams& rp, const BlueNoise& bn, const DDGIUniforms* d,
@@ -224,6 +225,16 @@ void reflections_ray_trace(const ShadingScene& ss, const GBufLevel& g, const hr_
             float ray_length = -1.0f;
             bool  trace = false;
             vec3  dir   = { 0, 0, 1 };
+            // spp > 1 (not in the reference): the GGX lobe draws `spp` directions with sample index num_frames * spp + s
+            // and averages the clamped radiance; ray_length is the first sample's (it only steers the virtual-point reprojection)
+            const int  spp  = rp.spp > 1 ? rp.spp : 1;
+            const bool ggx  = !(roughness < orc_const::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD) &&
+                              !(roughness > orc_const::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD && rp.approximate_with_ddgi == 1);
+            const int  n_s  = ggx ? spp : 1;
+            vec3       acc  = { 0, 0, 0 };
+            for (int smp = 0; smp < n_s; smp++)
+            {
+            trace = false;
             if (roughness < orc_const::MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD) { dir = reflect(-Wo, N); trace = true; }
             else if (roughness > orc_const::DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD && rp.approximate_with_ddgi == 1)
             {
@@ -232,7 +243,8 @@ void reflections_ray_trace(const ShadingScene& ss, const GBufLevel& g, const hr_
             }
             else
             {
-                vec2 Xi = { sample_blue_noise(c, (int)f.num_frames, 0, bn) * rp.trim, sample_blue_noise(c, (int)f.num_frames, 1, bn) * rp.trim };
+                const int si = (int)f.num_frames * spp + smp;
+                vec2 Xi = { sample_blue_noise(c, si, 0, bn) * rp.trim, sample_blue_noise(c, si, 1, bn) * rp.trim };
                 vec3 Wh = importance_sample_ggx(Xi, N, roughness);
                 dir     = reflect(-Wo, Wh);
                 trace   = true;
@@ -247,13 +259,21 @@ void reflections_ray_trace(const ShadingScene& ss, const GBufLevel& g, const hr_
                     vec3    F0 = mix3(vec3{ 0.04f, 0.04f, 0.04f }, s.albedo, s.metallic);
                     vec3    cd = mix3(s.albedo * (vec3{ 1, 1, 1 } - F0), vec3{ 0, 0, 0 }, s.metallic);
                     vec3    Lo = direct_lighting(*ss.scene, f.ubo.light, wo, s.N, s.P, F0, cd, s.roughness, false, { 0, 0 }, sky);
-                    if (rp.sample_gi == 1) Lo = Lo + indirect_diffuse(*d, irr, dep, wo, s.N, s.P, F0, cd, s.roughness, s.metallic, rp.gi_intensity);
-                    color      = Lo;
-                    ray_length = 0.001f + h.t;
+                    if (rp.sample_gi == 1)
+                    { // indirect_lighting, rchit:87-111: kD * diffuse + specular
+                        Lo = Lo + indirect_diffuse(*d, irr, dep, wo, s.N, s.P, F0, cd, s.roughness, s.metallic, rp.gi_intensity);
+                        const float ndv = fmaxf(dot(s.N, wo), 0.0f);
+                        Lo = Lo + ibl_specular(rp.lut, sky, fresnel_schlick_roughness(ndv, F0, s.roughness), ndv, s.roughness, rp.ibl_intensity);
+                    }
+                    color = Lo;
+                    if (smp == 0) ray_length = 0.001f + h.t;
                 }
-                else { color = sky; ray_length = -1.0f; }
+                else { color = sky; if (smp == 0) ray_length = -1.0f; }
             }
-            store4(out, g.W, x, y, fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), ray_length);
+            acc = acc + vec3{ fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f) };
+            }
+            color = acc * (1.0f / (float)n_s);
+            store4(out, g.W, x, y, color.x, color.y, color.z, ray_length);
         }
 }
 
@@ -506,6 +526,20 @@ void orc_reflections_ray_trace(void* ss, const orc_gbuf* g, const hr_frame* f, f
     ReflParams rp { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] } };
     BlueNoise  bn { sobol, sr };
     ImgH       ii = d ? atlas_irr(d, irr) : ImgH {}, dd = d ? atlas_dep(d, dep) : ImgH {};
+    reflections_ray_trace(*(ShadingScene*)ss, lvl(g), *f, rp, bn, d, ii, dd, out);
+}
+
+// extended form: spp > 1 and / or the IBL specular term (brdf_lut = 512 x 512 RG16F or NULL)
+void orc_reflections_ray_trace_spp(void* ss, const orc_gbuf* g, const hr_frame* f, float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity,
+                                   float rough_ddgi_intensity, const float* sky3, int spp, const uint8_t* sobol, const uint8_t* sr, const DDGIUniforms* d,
+                                   const uint16_t* irr, const uint16_t* dep, uint16_t* out, const uint16_t* brdf_lut, float ibl_intensity)
+{
+    ReflParams rp { bias, trim, sample_gi, approximate_with_ddgi, gi_intensity, rough_ddgi_intensity, { sky3[0], sky3[1], sky3[2] } };
+    rp.spp = spp;
+    rp.lut.rg = brdf_lut;
+    rp.ibl_intensity = ibl_intensity;
+    BlueNoise bn { sobol, sr };
+    ImgH      ii = d ? atlas_irr(d, irr) : ImgH {}, dd = d ? atlas_dep(d, dep) : ImgH {};
     reflections_ray_trace(*(ShadingScene*)ss, lvl(g), *f, rp, bn, d, ii, dd, out);
 }
 

@@ -286,8 +286,27 @@ inline vec3 sample_irradiance(const DDGIUniforms& d, vec3 P, vec3 N, vec3 Wo, co
     return net * (0.5f * M_PI_F);
 }
 
+// IBL specular of reflections_ray_trace.rchit:97-104 (IBL_INDIRECT_SPECULAR) / deferred.frag:167-170:
+//   prefiltered_color * (F * brdf.x + brdf.y) * intensity, brdf = texture(s_BRDF, (max(N.Wo, 0), roughness)) with the bilinear
+//   CLAMP_TO_EDGE sampler (vk.cpp:3453-3471, common.cpp:814-816) on the 512 x 512 RG16F LUT (brdf_preintegrate_lut.cpp:8-31).
+// The prefiltered environment cubemap is a constant colour here (asset absent), so every mip returns it.
+struct BrdfLut { const uint16_t* rg = nullptr; int N = 512; };
+inline vec3 ibl_specular(const BrdfLut& lut, vec3 prefiltered, vec3 F, float n_dot_v, float roughness, float intensity)
+{
+    if (!lut.rg) return { 0, 0, 0 };
+    ImgH  img { lut.N, lut.N, 2, lut.rg };
+    float b[2];
+    bilinear(img, { n_dot_v, roughness }, 2, b);
+    return (prefiltered * (F * b[0] + vec3{ b[1], b[1], b[1] })) * intensity;
+}
+inline vec3 fresnel_schlick_roughness(float cos_theta, vec3 F0, float roughness) // reflections_ray_trace.rchit:80-83, deferred.frag:146-149
+{
+    float p5 = powf(fmaxf(1.0f - cos_theta, 0.0f), 5.0f), omr = 1.0f - roughness;
+    return F0 + (vec3{ fmaxf(omr, F0.x), fmaxf(omr, F0.y), fmaxf(omr, F0.z) } - F0) * p5;
+}
+
 // fresnel_schlick_roughness + indirect diffuse term shared by both rchit shaders
-// (reflections_ray_trace.rchit:80-111 with specular = 0: no IBL assets; gi_ray_trace.rchit:74-93)
+// (reflections_ray_trace.rchit:80-111; gi_ray_trace.rchit:74-93)
 inline vec3 indirect_diffuse(const DDGIUniforms& d, const ImgH& irr, const ImgH& dep, vec3 Wo, vec3 N, vec3 P, vec3 F0, vec3 diffuse_color, float roughness,
                              float metallic, float gi_intensity)
 {

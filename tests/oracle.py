@@ -65,6 +65,8 @@ def lib():
         L.orc_ddgi_border_update.argtypes = [P, I, P]
         L.orc_ddgi_sample_probe_grid.argtypes = [P, P, P, P, P, F, P]
         L.orc_reflections_ray_trace.argtypes = [P, P, P, F, F, I, I, F, F, P, P, P, P, P, P, P]
+        L.orc_reflections_ray_trace_spp.argtypes = [P, P, P, F, F, I, I, F, F, P, I, P, P, P, P, P, P, P, F]
+        L.orc_deferred.argtypes = [P, P, P, I, P, P, P, P, P, P]
         L.orc_reflections_temporal.argtypes = [P, P, P, P, P, P, F, F, I, P, P, P]
         L.orc_reflections_atrous.argtypes = [P, P, P, I, I, F, F, F, I, P]
         L.orc_upsample_vec4.argtypes = [P, P, P, P]
@@ -427,8 +429,14 @@ class ReflectionsOracle:
         up = C.byref(ddgi.u) if have_gi else None
         irr = p(ddgi.cur_irr) if have_gi else None
         dep = p(ddgi.cur_dep) if have_gi else None
-        L.orc_reflections_ray_trace(ss.h, C.byref(gc), C.byref(frame), P.bias, P.trim, sample_gi, approx, P.gi_intensity, P.rough_ddgi_intensity, p(sky), p(sobol), p(sr),
-                                    up, irr, dep, p(self.rt))
+        spp = max(1, int(getattr(P, "spp", 1)))
+        lut = getattr(self, "brdf_lut", None)  # 512 x 512 x 2 uint16 (RG16F) or None: IBL specular term of the hit shading
+        if spp > 1 or lut is not None:
+            L.orc_reflections_ray_trace_spp(ss.h, C.byref(gc), C.byref(frame), P.bias, P.trim, sample_gi, approx, P.gi_intensity, P.rough_ddgi_intensity, p(sky), spp,
+                                            p(sobol), p(sr), up, irr, dep, p(self.rt), p(lut) if lut is not None else None, P.ibl_indirect_specular_intensity)
+        else:
+            L.orc_reflections_ray_trace(ss.h, C.byref(gc), C.byref(frame), P.bias, P.trim, sample_gi, approx, P.gi_intensity, P.rough_ddgi_intensity, p(sky), p(sobol), p(sr),
+                                        up, irr, dep, p(self.rt))
         self.final = self.rt
         self.first = False
         if not P.denoise:
@@ -450,3 +458,20 @@ class ReflectionsOracle:
             g0 = cur.c(0)
             L.orc_upsample_vec4(C.byref(g0), C.byref(gc), p(src), p(self.upsample))
             self.final = self.upsample
+
+
+class orc_gbuf_full(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("gb1", C.c_void_p), ("gb2", C.c_void_p), ("gb3", C.c_void_p), ("depth", C.c_void_p)]
+
+
+def deferred(g: "pyhr.GBufferHost", frame, shadow=None, ao=None, reflections=None, gi=None, env=(0.0, 0.0, 0.0), brdf_lut=None):
+    """oracle statement of the deferred shading combine (oracle/orc_deferred.cpp); inputs are full-resolution uint16 (half) images"""
+    gf = orc_gbuf_full(g.W, g.H, p(g.gb1), p(g.gb2), p(g.gb3), p(g.depth))
+    out = np.zeros((g.H, g.W, 4), np.uint16)
+    envv = np.array(env, np.float32)
+    ch = 0 if shadow is None else (shadow.shape[2] if shadow.ndim == 3 else 1)
+    arrs = [np.ascontiguousarray(a) if a is not None else None for a in (shadow, ao, reflections, gi)]
+    lib().orc_deferred(C.byref(gf), C.byref(frame), p(arrs[0]) if arrs[0] is not None else None, ch, p(arrs[1]) if arrs[1] is not None else None,
+                       p(arrs[2]) if arrs[2] is not None else None, p(arrs[3]) if arrs[3] is not None else None, p(envv),
+                       p(brdf_lut) if brdf_lut is not None else None, p(out))
+    return out

@@ -107,3 +107,39 @@ def test_spp_sharded_emulation_matches_single():
     for c, sh in [ref] + ranks:
         sh.destroy()
         c.close()
+
+
+@pytest.mark.parametrize("spp", [2, 4])
+def test_reflections_spp_matches_oracle(spp):
+    """reflections with spp > 1: GGX lobe averaged over spp directions; ray length of sample 0 exact, colours and the
+    denoised chain within the 1-spp tolerances."""
+    from test_gpu_gi_refl import close, f16
+    W, H = 192, 112
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ss = O.ShadingScene(sc, brute=sc.n_tris <= 4096)
+    bn = pyhr.blue_noise()
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(*bn)
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    rf = pyhr.ReflectionsPass(ctx, W, H, 0)
+    rf.params.spp = spp
+    rf.params.sky_color[0], rf.params.sky_color[1], rf.params.sky_color[2] = 0.3, 0.4, 0.6
+    orf = O.ReflectionsOracle(W, H, 0, rf.params)
+    f, prev_g = None, O.zero_gbuf_mips(W, H)
+    for i in range(3):
+        f = pyhr.make_frame((0.05 * i, 14.0, 34.0), (0.0, 3.0, 0.0), W, H, prev=f, num_frames=i)
+        g = pyhr.write_gbuffer(sc, f, W, H)
+        ctx.gbuffer_upload(f.ping_pong, g)
+        cur_g = O.GBufMips(g)
+        rf.render(f, None)
+        orf.render(ss, cur_g, prev_g, f, bn, None)
+        prev_g = cur_g
+        rt_c, rt_o = f16(rf.download(0)), O.h2f(orf.rt)
+        assert np.array_equal(rt_c[..., 3], rt_o[..., 3]), f"frame {i}: ray length of sample 0 not exact"
+        close(rt_c[..., :3], rt_o[..., :3], f"frame {i} ray trace", 1e-3, 0.02)
+        close(f16(rf.download(100)), O.h2f(orf.final), f"frame {i} final")
+    s = rf.stats()
+    assert s.rays_primary > W * H  # more than one ray per traced GGX pixel
+    rf.destroy()
+    ctx.close()
