@@ -355,7 +355,7 @@ def main():
         sc = gsc = pyhr.SynthScene(pyhr.SCENE_ARCADE, cfg["tris"])
         cam, tgt = CAM_POS, CAM_TGT
     ctx = pyhr.Context(local_rank)
-    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7)):
+    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7), ("HR_REFL_ATROUS_MINB", 8)):
         if os.environ.get(env):
             ctx.lib.hr_debug_set(key, int(os.environ[env]))
     ctx.set_bluenoise(*pyhr.blue_noise())
@@ -470,21 +470,37 @@ def main():
                 host.copy_(dev, non_blocking=True)
             ev_copied.record(s_copy)
 
+    pipelined = world == 1 and not single_tri  # the next frame's G-buffer ray cast runs on the library's side stream under this frame's passes
+
     def step_e2e():
-        f = next_frame()
-        if single_tri:
-            ctx.gbuffer_upload(f.ping_pong, g_host, stream)
-        elif world > 1 and cfg["passes"] == ["reflections"] and cfg.get("refl_scale", 1) == 0:
-            ctx.gbuffer_render_sharded(f.ping_pong, f, 64, stream)  # only the rows this rank's stages read (band +- 64, its ray-trace chunks)
+        if pipelined:
+            f = state["staged"]
+            ctx.gbuffer_commit_staged(f.ping_pong, stream)
+            state["staged"] = next_frame()
+            ctx.gbuffer_stage_render(state["staged"])
         else:
-            ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream)
+            f = next_frame()
+            if single_tri:
+                ctx.gbuffer_upload(f.ping_pong, g_host, stream)
+            elif cfg["passes"] == ["reflections"] and cfg.get("refl_scale", 1) == 0:
+                ctx.gbuffer_render_sharded(f.ping_pong, f, 64, stream)  # only the rows this rank's stages read (band +- 64, its ray-trace chunks)
+            else:
+                ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream)
         rig.render(f, stream)
         read_back()
+
+    if pipelined:
+        state["staged"] = next_frame()
+        ctx.gbuffer_stage_render(state["staged"])
 
     gather(False)  # e2e: every rank reads its own band back to its host
     for _ in range(3):
         step_e2e()
     r_e2e = timed(step_e2e, args.steps, finish=lambda: cur.wait_event(ev_copied))  # the last frame's PCIe copy is inside the timed region
+    if pipelined:  # retire the frame staged by the last step (never rendered: it pays back the one staged before the clock started)
+        ctx.gbuffer_commit_staged(state["staged"].ping_pong, stream)
+        state["f"] = state["staged"]
+        torch.cuda.synchronize()
     h2d_bytes = int(g_host.nbytes()) if single_tri else C.sizeof(pyhr.hr_frame)
 
     extras = {}
@@ -648,7 +664,7 @@ def main():
             "clocks": r_val["clocks"], "gpu_launches": int(r_val["launches"]),
             "e2e": {"value": args.steps / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "mode": ("host G-buffer upload (the analytic plane is not in the BVH)" if single_tri else
-                             "host hr_frame -> hr_gbuffer_render on the device -> passes -> outputs staged and copied to pinned host memory on a copy stream"),
+                             "host hr_frame -> G-buffer ray cast on the device (pipelined one frame ahead on a side stream when N = 1) -> passes -> outputs staged and copied to pinned host memory on a copy stream"),
                     "host_gbuffer_value": extras.get("e2e_host_gbuffer", {}).get("value"), "host_gbuffer_h2d_bytes_per_step": extras.get("e2e_host_gbuffer", {}).get("h2d_bytes_per_step")},
             "roofline": roof, "stages_ms": r_val["stages"], "mrays_per_s": rays, "scene_build_ms": build_ms,
             "rank_busy_ms": [{"stage_sum": round(float(b[0]), 4), "ray_trace": round(float(b[1]), 4), "waits": round(float(b[2]), 4)} for b in busy_all],

@@ -17,6 +17,7 @@ extern int         g_hr_force_shared_rt;
 extern int         g_hr_atrous_rows;
 extern int         g_hr_refl_atrous_impl;
 extern int         g_hr_refl_trace_impl;
+extern int         g_hr_refl_atrous_minb;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -157,6 +158,7 @@ int hr_debug_set(int key, int value)
     if (key == 5) { g_hr_atrous_rows = value; return HR_OK; }
     if (key == 6) { g_hr_refl_atrous_impl = value; return HR_OK; }
     if (key == 7) { g_hr_refl_trace_impl = value; return HR_OK; }
+    if (key == 8) { g_hr_refl_atrous_minb = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 
@@ -412,6 +414,38 @@ int hr_gbuffer_stage_upload(hr_ctx* ctx, const hr_gbuffer_desc* host)
     HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[1], host->gb2, px * 8, cudaMemcpyHostToDevice, ctx->upload_stream));
     HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[2], host->gb3, px * 8, cudaMemcpyHostToDevice, ctx->upload_stream));
     HR_CUDA(ctx, cudaMemcpyAsync(ctx->staging_mip0[3], host->depth, px * 4, cudaMemcpyHostToDevice, ctx->upload_stream));
+    HR_CUDA(ctx, cudaEventRecord(ctx->ev_staged, ctx->upload_stream));
+    ctx->staged_pending = true;
+    return HR_OK;
+}
+
+// Pipelined device G-buffer: render the NEXT frame's G-buffer into the staging surface on the library's side stream while the
+// caller's stream still runs this frame's passes (which read both G-buffer slots); hr_gbuffer_commit_staged swaps it in.
+int hr_gbuffer_stage_render(hr_ctx* ctx, const hr_frame* frame)
+{
+    HR_REQUIRE(ctx, ctx && frame, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_render: bad argument");
+    HR_REQUIRE(ctx, ctx->gb_w > 0, HR_ERR_NOT_READY, "hr_gbuffer_stage_render: call hr_gbuffer_create first");
+    HR_REQUIRE(ctx, ctx->scene && ctx->scene->d_materials, HR_ERR_NOT_READY, "hr_gbuffer_stage_render: no current scene with materials (hr_scene_build)");
+    HR_REQUIRE(ctx, !ctx->staged_pending, HR_ERR_INVALID_ARG, "hr_gbuffer_stage_render: a staged frame is already waiting for hr_gbuffer_commit_staged");
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->gb_w * ctx->gb_h;
+    if (!ctx->upload_stream)
+    {
+        HR_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_staged, cudaEventDisableTiming));
+        HR_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_storage_free, cudaEventDisableTiming));
+        const size_t bytes[4] = { px * 4, px * 8, px * 8, px * 4 };
+        for (int k = 0; k < 4; k++)
+        {
+            HR_CUDA(ctx, cudaMalloc(&ctx->staging_mip0[k], bytes[k]));
+            HR_CUDA(ctx, cudaMemset(ctx->staging_mip0[k], 0, bytes[k]));
+        }
+    }
+    if (ctx->storage_free_recorded) HR_CUDA(ctx, cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_storage_free, 0));
+    launch_gbuffer_render(ctx->scene, frame, ctx->gb_w, ctx->gb_h, 0, ctx->gb_h, 0, 1, ctx->staging_mip0[0], ctx->staging_mip0[1], ctx->staging_mip0[2],
+                          (float*)ctx->staging_mip0[3], ctx->gbuf_ray_ctr, ctx->upload_stream);
+    ctx->launches++;
+    HR_CHECK_LAUNCH(ctx);
     HR_CUDA(ctx, cudaEventRecord(ctx->ev_staged, ctx->upload_stream));
     ctx->staged_pending = true;
     return HR_OK;

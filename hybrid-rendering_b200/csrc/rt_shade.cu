@@ -259,13 +259,17 @@ struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi;
 
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
 // 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
-__global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
+// MULTI = false: exactly the reference's one ray per pixel (straight-line code); true: the spp > 1 extension (sample loop)
+template <bool MULTI>
+__global__ void __launch_bounds__(64, MULTI ? 8 : 14) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
                                                                 ReflTraceParams P, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk,
                                                                 uint2* __restrict__ out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = blockIdx.x * 16 + warp * 8 + (lane & 7), y = P.row0 + blockIdx.y * 4 + (lane >> 3);
-    if (x >= g.W || y >= g.H || y >= P.row1) return;
+    // rows: [row0, row1) or, when the ranks trace cooperatively, the 8-row chunks c = chunk_first + i * chunk_stride of the whole image
+    const int x = blockIdx.x * 16 + warp * 8 + (lane & 7);
+    const int y = (P.chunk_stride > 1 ? 8 * (P.chunk_first + ((int)blockIdx.y >> 1) * P.chunk_stride) + 4 * ((int)blockIdx.y & 1) : P.row0 + (int)blockIdx.y * 4) + (lane >> 3);
+    if (x >= g.W || y >= g.H || (P.chunk_stride <= 1 && y >= P.row1)) return;
     const size_t idx   = (size_t)y * g.W + x;
     const float  depth = __ldg(g.depth + idx);
     if (depth == 1.0f) { out[idx] = pack_h4(0.0f, 0.0f, 0.0f, -1.0f); return; }
@@ -284,10 +288,11 @@ __global__ void __launch_bounds__(64) k_reflections_ray_trace(GBufLevelDev g, Bv
     float3 color = make_float3(0, 0, 0);
     float  ray_length = -1.0f;
     // spp > 1: the GGX lobe draws spp directions, the clamped radiance is averaged, ray_length = first sample's
-    const int  spp = P.spp > 1 ? P.spp : 1;
+    const int  spp = MULTI ? (P.spp > 1 ? P.spp : 1) : 1;
     const bool ggx = !(roughness < 0.05f) && !(roughness > 0.75f && P.approximate_with_ddgi == 1);
-    const int  n_s = ggx ? spp : 1;
+    const int  n_s = MULTI ? (ggx ? spp : 1) : 1;
     float3     acc = make_float3(0, 0, 0);
+#pragma unroll 1
     for (int s = 0; s < n_s; s++)
     {
         bool trace = false;
@@ -602,8 +607,12 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
     k_ddgi_ray_trace<<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth);
 }
 
-// 1 (default) = wavefront (k_refl_trace + k_refl_shade), 0 = fused kernel; hr_debug_set key 7
-int g_hr_refl_trace_impl = 1;
+// 0 (default) = fused kernel (one warp per 8x4 block: ray generation, closest hit, hit shading incl. its shadow ray);
+// 1 = wavefront (k_refl_trace + k_refl_shade).  Measured at 4K (profiles/r2c): fused 2.45 ms, wavefront 1.85 + 1.27 ms — the
+// refill keeps lanes supplied with rays, but lane-level divergence inside the while-while traversal (15.4 of 32 lanes active in
+// both forms) is what costs, and the 56 KB queue / stack footprint per CTA takes L1 away from the BVH (hit rate 40 % vs 64 %).
+// hr_debug_set key 7.
+int g_hr_refl_trace_impl = 0;
 
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
@@ -618,7 +627,7 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    if ((g_hr_refl_trace_impl == 1 || chunk_stride > 1) && hits && row0 % 4 == 0 && spp <= 1) // spp > 1 runs on the fused kernel
+    if (g_hr_refl_trace_impl == 1 && hits && row0 % 4 == 0 && spp <= 1) // spp > 1 runs on the fused kernel
     {
         static unsigned int* counter[64] = {};
         static int           ctas[64]    = {};
@@ -641,6 +650,7 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
         k_refl_shade<<<gridb, 256, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (const float4*)hits, (uint2*)out);
         return;
     }
-    dim3 grid((g.W + 15) / 16, (row1 - row0 + 3) / 4);
-    k_reflections_ray_trace<<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    dim3 grid((g.W + 15) / 16, chunk_stride > 1 ? 2 * n_chunks_mine : (row1 - row0 + 3) / 4);
+    if (spp > 1) k_reflections_ray_trace<true><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else k_reflections_ray_trace<false><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
 }

@@ -12,6 +12,8 @@
 #include "glsl_fast.cuh"
 #include "hr_internal.h"
 
+int g_hr_refl_atrous_minb = 4; // hr_debug_set key 8: registers tuned for 4 (default, measured: 110 us / iteration at 4K vs 141 us with 2), 3 or 2 CTAs per SM
+
 namespace {
 
 using namespace gf;
@@ -168,9 +170,9 @@ __device__ __forceinline__ void store_pair(uint2* __restrict__ out, size_t idx, 
     else out[idx] = r0;
 }
 
-// Dense tile: 64x16 pixels + STEP halo.
-template <int STEP>
-__global__ void __launch_bounds__(256) k_refl_atrous_v2(GBufLevelDev g, const uint2* __restrict__ in, const uint8_t* __restrict__ tile_flags, R2Params P, uint2* __restrict__ out)
+// Dense tile: 64x16 pixels + STEP halo.  MINB = minimum resident CTAs per SM the register allocation is tuned for (A/B: hr_debug_set 8).
+template <int STEP, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_refl_atrous_v2(GBufLevelDev g, const uint2* __restrict__ in, const uint8_t* __restrict__ tile_flags, R2Params P, uint2* __restrict__ out)
 {
     extern __shared__ float smem_f[];
     constexpr int PADL = STEP + (STEP & 1);            // even left pad => even region column for even image column
@@ -327,17 +329,24 @@ __global__ void __launch_bounds__(256) k_refl_atrous_v2s(GBufLevelDev g, const u
     }
 }
 
-template <int STEP>
-void launch_r2(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, cudaStream_t st)
+template <int STEP, int MINB>
+void launch_r2m(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, cudaStream_t st)
 {
     constexpr int PADL = STEP + (STEP & 1);
     constexpr int RW   = (TWR + PADL + STEP + 1) & ~1;
     constexpr int RH   = THR + 2 * STEP;
     const size_t  smem = (size_t)RW * RH * NPL * sizeof(float);
     static bool   configured[64] = {};
-    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_refl_atrous_v2<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_refl_atrous_v2<STEP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((P.W + TWR - 1) / TWR, (P.row1 - P.row0 + THR - 1) / THR);
-    k_refl_atrous_v2<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
+    k_refl_atrous_v2<STEP, MINB><<<grid, 256, smem, st>>>(g, in, tf, P, out);
+}
+template <int STEP>
+void launch_r2(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, cudaStream_t st)
+{
+    if (g_hr_refl_atrous_minb == 2) launch_r2m<STEP, 2>(g, in, tf, P, out, st);
+    else if (g_hr_refl_atrous_minb == 3) launch_r2m<STEP, 3>(g, in, tf, P, out, st);
+    else launch_r2m<STEP, 4>(g, in, tf, P, out, st);
 }
 
 template <int STEP>

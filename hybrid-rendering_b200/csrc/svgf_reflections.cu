@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                                                         ReflTemporalParams P, uint2* __restrict__ out, uint2* __restrict__ mom_out, uint8_t* __restrict__ tile_flags)
 {
     __shared__ float    s_c[3][24][49];  // row pitch 49: the 144 row walkers of a phase hit 32 different banks
-    __shared__ float    s_h[6][24][32];  // horizontal window sums: [ch] = sum c, [3 + ch] = sum c^2
+    __shared__ float    s_h[6][24][33];  // horizontal window sums: [ch] = sum c, [3 + ch] = sum c^2 (pitch 33: the row walkers store one column at a time)
     __shared__ float    s_v[6][8][32];   // 17x17 window sums per pixel of the tile
     __shared__ uint32_t s_flags;
     const int W = cur.W, H = cur.H;

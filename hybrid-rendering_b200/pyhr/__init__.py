@@ -95,7 +95,7 @@ ABI_SYMBOLS = [
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
-    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render",
+    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render",
 ]
 
 _product = None
@@ -340,6 +340,10 @@ class Context:
     def gbuffer_render(self, slot, frame, row0=0, row1=0, stream=0):
         """device G-buffer producer (hr_gbuffer_render): primary-visibility ray cast of the current scene into `slot`"""
         self.check(self.lib.hr_gbuffer_render(self.h, slot, C.byref(frame), row0, row1, C.c_void_p(stream)), "hr_gbuffer_render")
+
+    def gbuffer_stage_render(self, frame):
+        """start the NEXT frame's G-buffer ray cast on the library's side stream (hr_gbuffer_stage_render); commit with gbuffer_commit_staged"""
+        self.check(self.lib.hr_gbuffer_stage_render(self.h, C.byref(frame)), "hr_gbuffer_stage_render")
 
     def gbuffer_render_sharded(self, slot, frame, halo_rows=48, stream=0):
         self.check(self.lib.hr_gbuffer_render_sharded(self.h, slot, C.byref(frame), halo_rows, C.c_void_p(stream)), "hr_gbuffer_render_sharded")

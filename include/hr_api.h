@@ -209,6 +209,10 @@ HR_API int hr_gbuffer_render(hr_ctx* ctx, int slot, const hr_frame* frame, int r
  * pass the recompute halo + the reprojection reach the camera motion needs) and the 8-row chunks it traces in the interleaved
  * cooperative ray trace.  The other rows of the slot keep their old contents.  world == 1: the whole image. */
 HR_API int hr_gbuffer_render_sharded(hr_ctx* ctx, int slot, const hr_frame* frame, int halo_rows, void* stream);
+/* Pipelined variant: the ray cast for the NEXT frame runs on the library's side stream into a third surface while the caller's
+ * stream still renders the current frame (whose passes read both slots); hr_gbuffer_commit_staged(slot, stream) then swaps it in.
+ * Same protocol as hr_gbuffer_stage_upload: stage, commit, stage, commit ... */
+HR_API int hr_gbuffer_stage_render(hr_ctx* ctx, const hr_frame* frame);
 /* Read back one mip of a slot (tests). which: 1,2,3 = gb1..3, 0 = depth. Synchronous. */
 HR_API int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* host_dst, size_t bytes);
 
@@ -424,8 +428,8 @@ HR_API int hr_pass_stage_times(hr_pass* pass, const char** names, float* ms, int
  * threads + ray compaction); key 3 = BVH topology used by the next hr_scene_build / hr_scene_rebuild (0 Karras radix tree,
  * 1 PLOC agglomerative clustering = default); key 4 = run the cooperative (multi-GPU) ray-trace kernel on a single GPU;
  * key 5 = a-trous row-interleaved tiles: 1 = step 8 only (default), 2 = steps 4 and 8, 0 = dense tiles for every step; key 6 = reflections
- * a-trous (0 scalar kernel, 1 packed fp32x2 dense tiles, 2 = packed + row-interleaved tiles for steps >= 8 = default); key 7 = reflections ray trace (1 wavefront: persistent
- * closest-hit traversal with ray refill + compacted hit shading = default, 0 fused kernel).  None of them changes a result bit
+ * a-trous (0 scalar kernel, 1 packed fp32x2 dense tiles, 2 = packed + row-interleaved tiles for steps >= 8 = default); key 7 = reflections ray trace (0 fused kernel = default, 1 wavefront:
+ * persistent closest-hit traversal with ray refill + compacted hit shading); key 8 = reflections a-trous register tuning (CTAs / SM).  None of them changes a result bit
  * of the visibility masks; keys 1 and 5 select kernels whose outputs agree to the last fp16 bit on the test scenes. */
 HR_API int hr_debug_set(int key, int value);
 /* Number of kernels this library launched since the context was created (bench.py gpu_launches). */

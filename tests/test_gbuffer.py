@@ -136,3 +136,30 @@ def test_passes_on_the_device_gbuffer_match_the_oracle_on_the_same_gbuffer():
     sh.destroy()
     ao.destroy()
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_pipelined_stage_render_equals_direct_render():
+    """hr_gbuffer_stage_render (next frame's ray cast on the side stream) + hr_gbuffer_commit_staged == hr_gbuffer_render"""
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(*pyhr.blue_noise())
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    fr = _frames(4)
+    ctx.gbuffer_stage_render(fr[0])
+    for i, f in enumerate(fr):
+        ctx.gbuffer_commit_staged(f.ping_pong)
+        if i + 1 < len(fr):
+            ctx.gbuffer_stage_render(fr[i + 1])
+        got = [ctx.gbuffer_download(f.ping_pong, m, k, W, H) for m in (0, 1) for k in range(4)]
+        c2 = pyhr.Context(0)
+        c2.set_bluenoise(*pyhr.blue_noise())
+        c2.build_scene(sc)
+        c2.gbuffer_create(W, H)
+        c2.gbuffer_render(f.ping_pong, f)
+        ref = [c2.gbuffer_download(f.ping_pong, m, k, W, H) for m in (0, 1) for k in range(4)]
+        c2.close()
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b), f"frame {i}"
+    ctx.close()
