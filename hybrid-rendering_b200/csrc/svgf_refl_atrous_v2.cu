@@ -11,6 +11,8 @@
 // Tile classification (K13/K15): tiles whose flag is 0 are copied (reflections_denoise_copy_tiles.comp:35-38).
 #include "glsl_fast.cuh"
 #include "hr_internal.h"
+#include <cuda.h> // CUtensorMap (driver types only; cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint)
+#include <vector>
 
 int g_hr_refl_atrous_minb = 4; // hr_debug_set key 8: registers tuned for 4 (default, measured: 110 us / iteration at 4K vs 141 us with 2), 3 or 2 CTAs per SM
 
@@ -361,11 +363,270 @@ void launch_r2s(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const
     k_refl_atrous_v2s<STEP><<<grid, 256, smem, st>>>(g, in, tf, P, out);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// TMA-staged, persistent form of the dense-tile kernel (steps 1, 2, 4).
+//
+// ncu of k_refl_atrous_v2 at 4K (profiles/r2c): 55 M warp instructions per iteration (the scalar kernel: 85 M) but only 34-45 %
+// issue-active — the top stall is long_scoreboard: every CTA first waits for its own staging loads from DRAM (L2 hit rate
+// 16-25 %: the images are larger than L2), and 2-4 resident CTAs per SM are not enough to cover that.  Here the loads leave the
+// instruction stream: CTAs are persistent, tiles come from an atomic counter, and the three raw images of the NEXT tile (GB2, GB3,
+// input colour: tile + halo boxes of 8-byte texels) are fetched by the TMA engine (cp.async.bulk.tensor.2d, one elected
+// thread, completion on an mbarrier, out-of-image texels zero-filled by the hardware) while the CTA filters the CURRENT tile.
+// Per tile: wait for the mbarrier -> decode raw texel pairs from shared memory into the nine fp32 planes -> barrier -> issue
+// the TMA loads of the next active tile into the (now free) raw buffers -> filter from the planes -> barrier.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)), "l"(tm),
+                 "r"(smem_u32(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+
+template <int STEP>
+struct TmaGeom {
+    static constexpr int PADL = STEP + (STEP & 1);
+    static constexpr int RW   = (TWR + PADL + STEP + 1) & ~1;
+    static constexpr int RH   = THR + 2 * STEP;
+    static constexpr int PL   = RW * RH;
+    static constexpr int RAWB = (PL * 8 + 127) & ~127; // bytes of one raw image box, padded to the 128-byte TMA destination alignment
+    static constexpr int SMEM = 3 * RAWB + NPL * PL * 4 + TWR * THR; // + one class byte per pixel of the tile
+};
+
+template <int STEP>
+__global__ void __launch_bounds__(256, (STEP <= 1 ? 3 : 2))
+k_refl_atrous_tma(const __grid_constant__ CUtensorMap tm_gb2, const __grid_constant__ CUtensorMap tm_gb3, const __grid_constant__ CUtensorMap tm_in, GBufLevelDev g,
+                  const uint2* __restrict__ in, const uint8_t* __restrict__ tile_flags, R2Params P, uint2* __restrict__ out, int tiles_x, int n_tiles,
+                  unsigned int* __restrict__ counter)
+{
+    using G = TmaGeom<STEP>;
+    constexpr int PADL = G::PADL, RW = G::RW, RH = G::RH, PL = G::PL;
+    extern __shared__ __align__(128) unsigned char smem_b[];
+    unsigned char* raw0 = smem_b;
+    float*         planes = reinterpret_cast<float*>(smem_b + 3 * G::RAWB);
+    unsigned char* s_cls  = smem_b + 3 * G::RAWB + NPL * PL * 4; // per pixel of the tile: 0 sky, 1 pass-through, 2 filter (pixel_class)
+    __shared__ __align__(8) uint64_t s_mbar;
+    __shared__ int      s_tile[2];
+    __shared__ uint32_t s_flag[2];
+    const int W = P.W, H = P.H;
+    const int TWt = (W + 7) >> 3, THt = (H + 7) >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx2 = lane, lyb = warp; // 32 pixel pairs x 8 rows, 2 rows per thread
+
+    // warp 0: take the next tile from the counter and read its 8 x 2 tile flags
+    auto fetch_tile = [&](int slot) {
+        int t = 0;
+        if (lane == 0) t = (int)atomicAdd(counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        bool f = false;
+        if (t < n_tiles && lane < 16)
+        {
+            const int x0 = (t % tiles_x) * TWR, y0 = P.row0 + (t / tiles_x) * THR;
+            const int tx = (x0 >> 3) + (lane & 7), ty = (y0 >> 3) + (lane >> 3);
+            f = tx < TWt && ty < THt && tile_flags[(size_t)ty * TWt + tx] != 0;
+        }
+        const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
+        if (lane == 0) { s_tile[slot] = t < n_tiles ? t : -1; s_flag[slot] = b; }
+    };
+    auto issue_tma = [&](int t) { // one thread
+        const int x0 = (t % tiles_x) * TWR, y0 = P.row0 + (t / tiles_x) * THR;
+        mbar_arrive_expect_tx(&s_mbar, 3u * (uint32_t)(PL * 8));
+        tma_load_2d(raw0, &tm_gb2, &s_mbar, x0 - PADL, y0 - STEP);
+        tma_load_2d(raw0 + G::RAWB, &tm_gb3, &s_mbar, x0 - PADL, y0 - STEP);
+        tma_load_2d(raw0 + 2 * G::RAWB, &tm_in, &s_mbar, x0 - PADL, y0 - STEP);
+    };
+
+    if (threadIdx.x == 0) { mbar_init(&s_mbar, 1); fence_mbar_init(); }
+    if (warp == 0) fetch_tile(0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_tile[0] >= 0 && s_flag[0] != 0u) issue_tma(s_tile[0]);
+    uint32_t phase = 0;
+    int      slot  = 0;
+    for (;;)
+    {
+        const int      t  = s_tile[slot];
+        const uint32_t tf = s_flag[slot];
+        if (t < 0) break;
+        if (warp == 0) fetch_tile(slot ^ 1); // overlaps the wait below
+        const int x0 = (t % tiles_x) * TWR, y0 = P.row0 + (t / tiles_x) * THR;
+        if (tf != 0u)
+        {
+            {
+                const long long t_start = clock64();
+                while (!mbar_try_wait(&s_mbar, phase))
+                    if (clock64() - t_start > 4000000000ll) __trap(); // ~2 s: a lost TMA completion must fail loudly, never hang the GPU
+            }
+            phase ^= 1u;
+            // decode the raw boxes (two texels per step) into the nine planes; cells outside the image get a zero normal (weight 0)
+            const uint4* r2 = reinterpret_cast<const uint4*>(raw0);
+            const uint4* r3 = reinterpret_cast<const uint4*>(raw0 + G::RAWB);
+            const uint4* rc = reinterpret_cast<const uint4*>(raw0 + 2 * G::RAWB);
+            for (int i = threadIdx.x; i < (RW / 2) * RH; i += 256)
+            {
+                const int rx = 2 * (i % (RW / 2)), ry = i / (RW / 2);
+                const int px = x0 - PADL + rx, py = y0 - STEP + ry;
+                float2 nx = make_float2(0.0f, 0.0f), ny = nx, nz = nx, zs = nx, cr = nx, cg = nx, cb = nx, va = nx, lu = make_float2(0.0001f, 0.0001f);
+                float2 rough = make_float2(0.0f, 0.0f);
+                if (px >= 0 && py >= 0 && px < W && py < H)
+                {
+                    const uint4  a = r2[i], b = r3[i], c = rc[i];
+                    rough = make_float2(h2_to_f2(b.x).x, h2_to_f2(b.z).x);
+                    const float2 e0 = h2_to_f2(a.x), e1 = h2_to_f2(a.z);
+                    const float3 n0 = octohedral_to_direction(e0.x, e0.y), n1 = octohedral_to_direction(e1.x, e1.y);
+                    const float2 c0 = h2_to_f2(c.x), c1 = h2_to_f2(c.y), c2 = h2_to_f2(c.z), c3 = h2_to_f2(c.w);
+                    nx = make_float2(n0.x, n1.x); ny = make_float2(n0.y, n1.y); nz = make_float2(n0.z, n1.z);
+                    zs = make_float2(h2_to_f2(b.y).y * P.c_sigma, h2_to_f2(b.w).y * P.c_sigma);
+                    cr = make_float2(c0.x, c2.x); cg = make_float2(c0.y, c2.y); cb = make_float2(c1.x, c3.x); va = make_float2(c1.y, c3.y);
+                    lu = make_float2(lum3(c0.x, c0.y, c1.x), lum3(c2.x, c2.y, c3.x));
+                }
+                float* p = planes + ry * RW + rx;
+                *reinterpret_cast<float2*>(p) = nx; p += PL;
+                *reinterpret_cast<float2*>(p) = ny; p += PL;
+                *reinterpret_cast<float2*>(p) = nz; p += PL;
+                *reinterpret_cast<float2*>(p) = zs; p += PL;
+                *reinterpret_cast<float2*>(p) = cr; p += PL;
+                *reinterpret_cast<float2*>(p) = cg; p += PL;
+                *reinterpret_cast<float2*>(p) = cb; p += PL;
+                *reinterpret_cast<float2*>(p) = va; p += PL;
+                *reinterpret_cast<float2*>(p) = lu;
+                const int tx = rx - PADL, ty = ry - STEP;
+                if (tx >= 0 && tx < TWR && ty >= 0 && ty < THR)
+                { // the reference's early-outs (:119-128).  Sky = linear z < 0 (GB3.w = -1): identical to its depth == 1 test whenever the
+                  // sky pixels carry the G-buffer clear values (depth 1 and GB3 = (0,0,0,-1) are written together, g_buffer.cpp:72-96)
+                    const int c0 = zs.x < 0.0f ? 0 : ((rough.x < 0.05f || (P.approx == 1 && rough.x > 0.75f)) ? 1 : 2);
+                    const int c1 = zs.y < 0.0f ? 0 : ((rough.y < 0.05f || (P.approx == 1 && rough.y > 0.75f)) ? 1 : 2);
+                    *reinterpret_cast<uchar2*>(s_cls + ty * TWR + tx) = make_uchar2((unsigned char)c0, (unsigned char)c1);
+                }
+            }
+        }
+        __syncthreads(); // planes complete, raw boxes free, next tile's index / flags visible
+        if (threadIdx.x == 0)
+        {
+            const int tn = s_tile[slot ^ 1];
+            if (tn >= 0 && s_flag[slot ^ 1] != 0u) issue_tma(tn); // flies while this tile is filtered
+        }
+        const int x = x0 + 2 * lx2;
+#pragma unroll
+        for (int k = 0; k < THR / 8; k++)
+        {
+            const int ly = lyb + 8 * k, y = y0 + ly;
+            if (x >= W || y >= H || y >= P.row1) continue;
+            const size_t idx = (size_t)y * W + x;
+            if (tf == 0u)
+            { // copy tile (reflections_denoise_copy_tiles.comp:35-38)
+                *reinterpret_cast<uint4*>(out + idx) = __ldg(reinterpret_cast<const uint4*>(in + idx));
+                continue;
+            }
+            const int ci = (ly + STEP) * RW + 2 * lx2 + PADL;
+            int       k0 = 1, k1 = 1;
+            if ((tf >> ((ly >> 3) * 8 + (lx2 >> 2))) & 1u)
+            {
+                const uchar2 c = *reinterpret_cast<const uchar2*>(s_cls + ly * TWR + 2 * lx2);
+                k0 = c.x;
+                k1 = c.y;
+            }
+            float2 o_r = make_float2(0.f, 0.f), o_g = o_r, o_b = o_r, o_v = o_r, czs;
+            if (k0 == 2 || k1 == 2)
+            {
+                const float* s_va = planes + 7 * PL;
+                filter_pair<(STEP & 1) == 0>(planes, PL, ci, STEP * RW, STEP, s_va + ci - RW, s_va + ci + RW, P.c_phi0, o_r, o_g, o_b, o_v, czs);
+            }
+            store_pair(out, idx, true, k0, k1, planes, PL, ci, o_r, o_g, o_b, o_v);
+        }
+        __syncthreads(); // planes may be overwritten by the next tile's decode
+        slot ^= 1;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled tma_encoder()
+{
+    static PFN_encodeTiled fn     = nullptr;
+    static bool            looked = false;
+    if (!looked)
+    {
+        looked = true;
+        void*                            p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// tensor map of a W x H image of 8-byte texels with a (bw x bh) box; cached per (pointer, size, box)
+struct TmCacheEntry { const void* ptr; int W, H, bw, bh; CUtensorMap tm; };
+bool tensor_map_2d(const void* ptr, int W, int H, int bw, int bh, CUtensorMap* out)
+{
+    static std::vector<TmCacheEntry> cache;
+    for (const auto& e : cache)
+        if (e.ptr == ptr && e.W == W && e.H == H && e.bw == bw && e.bh == bh) { *out = e.tm; return true; }
+    PFN_encodeTiled enc = tma_encoder();
+    if (!enc) return false;
+    TmCacheEntry e { ptr, W, H, bw, bh, {} };
+    const cuuint64_t dims[2] = { (cuuint64_t)W, (cuuint64_t)H }, strides[1] = { (cuuint64_t)W * 8 };
+    const cuuint32_t box[2] = { (cuuint32_t)bw, (cuuint32_t)bh }, estr[2] = { 1, 1 };
+    if (enc(&e.tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    if (cache.size() > 256) cache.clear();
+    cache.push_back(e);
+    *out = e.tm;
+    return true;
+}
+
+template <int STEP>
+bool launch_r2_tma(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, cudaStream_t st)
+{
+    using G = TmaGeom<STEP>;
+    if ((((size_t)g.W * 8) & 15) != 0 || ((uintptr_t)g.gb2 & 15) || ((uintptr_t)g.gb3 & 15) || ((uintptr_t)in & 15)) return false;
+    CUtensorMap t2, t3, ti;
+    if (!tensor_map_2d(g.gb2, g.W, g.H, G::RW, G::RH, &t2) || !tensor_map_2d(g.gb3, g.W, g.H, G::RW, G::RH, &t3) || !tensor_map_2d(in, g.W, g.H, G::RW, G::RH, &ti)) return false;
+    static unsigned int* counter[64] = {};
+    static int           ctas[64]    = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (!counter[dev])
+    {
+        cudaMalloc(&counter[dev], 4 * sizeof(unsigned int));
+    }
+    static bool configured[64] = {};
+    if (hr_once_per_device(configured))
+    {
+        cudaFuncSetAttribute(k_refl_atrous_tma<STEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM);
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_refl_atrous_tma<STEP>, 256, G::SMEM);
+        ctas[dev] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int tiles_x = (P.W + TWR - 1) / TWR, tiles_y = (P.row1 - P.row0 + THR - 1) / THR, n_tiles = tiles_x * tiles_y;
+    // one counter word per STEP instantiation (iterations of different steps never overlap on a stream, passes on different streams might)
+    unsigned int* ctr = counter[dev] + (STEP == 1 ? 0 : STEP == 2 ? 1 : 2);
+    cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st);
+    const int grid = ctas[dev] < n_tiles ? ctas[dev] : n_tiles;
+    k_refl_atrous_tma<STEP><<<grid, 256, G::SMEM, st>>>(t2, t3, ti, g, in, tf, P, out, tiles_x, n_tiles, ctr);
+    return true;
+}
+
 } // namespace
 
 // hr_debug_set key 6: 0 = scalar kernel (svgf_reflections.cu), 1 = packed fp32x2 dense tiles for every step,
-// 2 (default) = packed, row-interleaved tiles for steps >= 8
-int g_hr_refl_atrous_impl = 2;
+// 2 = packed, row-interleaved tiles for steps >= 8, 3 (default) = 2 + TMA-staged persistent kernel for steps 1, 2, 4
+int g_hr_refl_atrous_impl = 3;
 
 // returns false when this variant does not support the configuration (the caller falls back to the scalar kernel)
 bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
@@ -376,12 +637,12 @@ bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const u
     R2Params P { g.W, g.H, 1.44269504f / sigma_depth, -1.44269504f / phi_color, approximate_with_ddgi, row0, row1 };
     const uint2* i2 = (const uint2*)in;
     uint2*       o2 = (uint2*)out;
-    const bool   il = g_hr_refl_atrous_impl == 2;
+    const bool   il = g_hr_refl_atrous_impl >= 2, tma = g_hr_refl_atrous_impl == 3;
     switch (step)
     {
-        case 1: launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
-        case 2: launch_r2<2>(g, i2, tile_flags, P, o2, st); break;
-        case 4: launch_r2<4>(g, i2, tile_flags, P, o2, st); break;
+        case 1: if (!(tma && launch_r2_tma<1>(g, i2, tile_flags, P, o2, st))) launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
+        case 2: if (!(tma && launch_r2_tma<2>(g, i2, tile_flags, P, o2, st))) launch_r2<2>(g, i2, tile_flags, P, o2, st); break;
+        case 4: if (!(tma && launch_r2_tma<4>(g, i2, tile_flags, P, o2, st))) launch_r2<4>(g, i2, tile_flags, P, o2, st); break;
         case 8: if (il) launch_r2s<8>(g, i2, tile_flags, P, o2, st); else launch_r2<8>(g, i2, tile_flags, P, o2, st); break;
         default: launch_r2s<16>(g, i2, tile_flags, P, o2, st); break;
     }

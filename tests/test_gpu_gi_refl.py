@@ -119,3 +119,34 @@ def test_reflections_arcade_all_lobes():
     """arcade scene: materials with roughness 0.02 (mirror), 0.2 / 0.5 (GGX) and 0.9 (DDGI lobe) are all present."""
     mean, hit_frac = run(pyhr.SCENE_ARCADE, 3, 1, True, light=pyhr.default_light(rot_x_deg=25.0), cam=((0.0, 9.0, -4.0), (2.0, 7.0, 60.0)), tris=20000)
     assert hit_frac > 0.2
+
+
+def test_reflections_atrous_variants_agree():
+    """K16 implementations (hr_debug_set key 6): 3 = TMA-staged persistent kernel (default), 2 = packed fp32x2 + row-interleaved wide
+    steps, 1 = packed dense tiles, 0 = scalar kernel.  Same staged values and the same arithmetic in 1-3 => bit-identical; the scalar
+    kernel differs by rounding only.  5 iterations (steps 1..16), odd tile counts, all lobes."""
+    Wt, Ht = 712, 392
+    sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, 20000)
+    light = pyhr.default_light(rot_x_deg=25.0)
+    outs = {}
+    for impl in (3, 2, 1, 0):
+        ctx = pyhr.Context(0)
+        ctx.lib.hr_debug_set(6, impl)
+        ctx.set_bluenoise(*pyhr.blue_noise())
+        ctx.build_scene(sc)
+        ctx.gbuffer_create(Wt, Ht)
+        rf = pyhr.ReflectionsPass(ctx, Wt, Ht, 0)
+        rf.params.filter_iterations = 5
+        rf.params.sky_color[0], rf.params.sky_color[1], rf.params.sky_color[2] = SKY
+        f = None
+        for i in range(3):
+            f = pyhr.make_frame((0.05 * i, 9.0, -4.0), (2.0, 7.0, 60.0), Wt, Ht, prev=f, num_frames=i, light=light)
+            ctx.gbuffer_render(f.ping_pong, f)
+            rf.render(f, None)
+        outs[impl] = (rf.download(2).copy(), rf.download(100).copy())
+        rf.destroy()
+        ctx.lib.hr_debug_set(6, 3)
+        ctx.close()
+    for impl in (2, 1):
+        assert np.array_equal(outs[3][0], outs[impl][0]) and np.array_equal(outs[3][1], outs[impl][1]), f"impl 3 vs {impl}"
+    close(f16(outs[3][1]), f16(outs[0][1]), "packed vs scalar a-trous", 2e-4, 4e-3)
