@@ -625,7 +625,10 @@ bool launch_r2_tma(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, co
 } // namespace
 
 // hr_debug_set key 6: 0 = scalar kernel (svgf_reflections.cu), 1 = packed fp32x2 dense tiles for every step,
-// 2 = packed, row-interleaved tiles for steps >= 8, 3 (default) = 2 + TMA-staged persistent kernel for steps 1, 2, 4
+// 2 = packed, row-interleaved tiles for steps >= 8, 3 (default) = 2 + TMA-staged persistent kernel for step 1,
+// 4 = 2 + TMA-staged persistent kernel for steps 1, 2 and 4.
+// Measured at 4K (profiles/r2e, us per iteration, steps 1 / 2 / 4): TMA 98 / 119 / 123, plain staging 108 / 101 / 122 — the TMA
+// kernel wins where its raw boxes + planes still allow 3 CTAs per SM (step 1: 74 KB) and loses where they allow 2 (82 / 104 KB).
 int g_hr_refl_atrous_impl = 3;
 
 // returns false when this variant does not support the configuration (the caller falls back to the scalar kernel)
@@ -637,10 +640,10 @@ bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const u
     R2Params P { g.W, g.H, 1.44269504f / sigma_depth, -1.44269504f / phi_color, approximate_with_ddgi, row0, row1 };
     const uint2* i2 = (const uint2*)in;
     uint2*       o2 = (uint2*)out;
-    const bool   il = g_hr_refl_atrous_impl >= 2, tma = g_hr_refl_atrous_impl == 3;
+    const bool   il = g_hr_refl_atrous_impl >= 2, tma1 = g_hr_refl_atrous_impl >= 3, tma = g_hr_refl_atrous_impl == 4;
     switch (step)
     {
-        case 1: if (!(tma && launch_r2_tma<1>(g, i2, tile_flags, P, o2, st))) launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
+        case 1: if (!(tma1 && launch_r2_tma<1>(g, i2, tile_flags, P, o2, st))) launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
         case 2: if (!(tma && launch_r2_tma<2>(g, i2, tile_flags, P, o2, st))) launch_r2<2>(g, i2, tile_flags, P, o2, st); break;
         case 4: if (!(tma && launch_r2_tma<4>(g, i2, tile_flags, P, o2, st))) launch_r2<4>(g, i2, tile_flags, P, o2, st); break;
         case 8: if (il) launch_r2s<8>(g, i2, tile_flags, P, o2, st); else launch_r2<8>(g, i2, tile_flags, P, o2, st); break;

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                 if (any)
                 {
                     valid = sumw >= 0.01f;
-                    if (valid) { const float inv = fast_rcp(sumw); hcol *= inv; hm0 *= inv; hm1 *= inv; }
+                    if (valid) { const float inv = fast_rcp(sumw); hcol = __fdiv_rn(hcol, sumw); hm0 *= inv; hm1 *= inv; } // colour: exact quotient (tile classification compares it with 0 / 1)
                     else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
                 }
                 if (!valid)
@@ -268,13 +268,13 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                                 cntv += 1.0f;
                             }
                         }
-                    if (cntv > 0.0f) { valid = true; const float inv = fast_rcp(cntv); hcol *= inv; hm0 *= inv; hm1 *= inv; }
+                    if (cntv > 0.0f) { valid = true; const float inv = fast_rcp(cntv); hcol = __fdiv_rn(hcol, cntv); hm0 *= inv; hm1 *= inv; }
                 }
             }
             if (!valid) { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; hist_len = 0.0f; }
             // ---- accumulate ----
             hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
-            const float ihlen = fast_rcp(hlen);
+            const float ihlen = __frcp_rn(hlen); // exact: alpha decides whether a saturated pixel lands on 1.0 or one ulp below (tile classification)
             if (valid)
             {
                 // neighborhood_mean: rows ly .. ly+16 of the per-row 17-wide counts (separable: 3 popcll per thread instead of 17)
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256, 4) k_temporal(GBufLevelDev cur, GBufLevel
                 m1 = hm1 * (1.0f - am) + (vis * vis) * am;
                 o1 = fmaxf(0.0f, m1 - m0 * m0);
             }
-            o0 = hcol * (1.0f - alpha) + vis * alpha;
+            o0 = __fadd_rn(__fmul_rn(hcol, __fsub_rn(1.0f, alpha)), __fmul_rn(vis, alpha)); // GLSL mix, never contracted: `o0 < 1` / `o0 > 0` classify the tile
         }
         if (MODE == 0)
         {
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(256, 4) k_temporal_count(GBufLevelDev cur, GBu
                 if (any)
                 {
                     valid = sumw >= 0.01f;
-                    if (valid) { const float inv = fast_rcp(sumw); hcol *= inv; hm0 *= inv; hm1 *= inv; }
+                    if (valid) { const float inv = fast_rcp(sumw); hcol = __fdiv_rn(hcol, sumw); hm0 *= inv; hm1 *= inv; } // colour: exact quotient (tile classification compares it with 0 / 1)
                     else { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; }
                 }
                 if (!valid)
@@ -483,13 +483,13 @@ __global__ void __launch_bounds__(256, 4) k_temporal_count(GBufLevelDev cur, GBu
                                 cntv += 1.0f;
                             }
                         }
-                    if (cntv > 0.0f) { valid = true; const float inv = fast_rcp(cntv); hcol *= inv; hm0 *= inv; hm1 *= inv; }
+                    if (cntv > 0.0f) { valid = true; const float inv = fast_rcp(cntv); hcol = __fdiv_rn(hcol, cntv); hm0 *= inv; hm1 *= inv; }
                 }
             }
             if (!valid) { hcol = 0.0f; hm0 = 0.0f; hm1 = 0.0f; hist_len = 0.0f; }
             // ---- accumulate ----
             hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
-            const float ihlen = fast_rcp(hlen);
+            const float ihlen = __frcp_rn(hlen); // exact: alpha decides whether a saturated pixel lands on 1.0 or one ulp below (tile classification)
             if (valid)
             {
                 // neighborhood_mean: rows ly .. ly+16 of the per-row 17-wide counts (separable: 3 popcll per thread instead of 17)
@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(256, 4) k_temporal_count(GBufLevelDev cur, GBu
                 m1 = hm1 * (1.0f - am) + (vis * vis) * am;
                 o1 = fmaxf(0.0f, m1 - m0 * m0);
             }
-            o0 = hcol * (1.0f - alpha) + vis * alpha;
+            o0 = __fadd_rn(__fmul_rn(hcol, __fsub_rn(1.0f, alpha)), __fmul_rn(vis, alpha)); // GLSL mix, never contracted: `o0 < 1` / `o0 > 0` classify the tile
         }
         if (MODE == 0)
         {

@@ -122,14 +122,14 @@ def test_reflections_arcade_all_lobes():
 
 
 def test_reflections_atrous_variants_agree():
-    """K16 implementations (hr_debug_set key 6): 3 = TMA-staged persistent kernel (default), 2 = packed fp32x2 + row-interleaved wide
+    """K16 implementations (hr_debug_set key 6): 4 / 3 = TMA-staged persistent kernel for steps 1-4 / step 1 (default), 2 = packed fp32x2 + row-interleaved wide
     steps, 1 = packed dense tiles, 0 = scalar kernel.  Same staged values and the same arithmetic in 1-3 => bit-identical; the scalar
     kernel differs by rounding only.  5 iterations (steps 1..16), odd tile counts, all lobes."""
     Wt, Ht = 712, 392
     sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, 20000)
     light = pyhr.default_light(rot_x_deg=25.0)
     outs = {}
-    for impl in (3, 2, 1, 0):
+    for impl in (4, 3, 2, 1, 0):
         ctx = pyhr.Context(0)
         ctx.lib.hr_debug_set(6, impl)
         ctx.set_bluenoise(*pyhr.blue_noise())
@@ -147,6 +147,6 @@ def test_reflections_atrous_variants_agree():
         rf.destroy()
         ctx.lib.hr_debug_set(6, 3)
         ctx.close()
-    for impl in (2, 1):
+    for impl in (4, 2, 1):
         assert np.array_equal(outs[3][0], outs[impl][0]) and np.array_equal(outs[3][1], outs[impl][1]), f"impl 3 vs {impl}"
     close(f16(outs[3][1]), f16(outs[0][1]), "packed vs scalar a-trous", 2e-4, 4e-3)
