@@ -48,6 +48,7 @@ __device__ __forceinline__ uint32_t unorm8(float v)
 __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc, GbufParams P, uint32_t* __restrict__ gb1, uint2* __restrict__ gb2, uint2* __restrict__ gb3,
                                                         float* __restrict__ depth, unsigned long long* ray_ctr)
 {
+    __shared__ int s_stack[2][STACK_SIZE]; // one packet-traversal stack per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = (blockIdx.x * 2 + warp) * 8 + (lane & 7);
     const int y = (P.chunk_stride > 1 ? 8 * (P.chunk_first + ((int)blockIdx.y >> 1) * P.chunk_stride) + 4 * ((int)blockIdx.y & 1) : P.row0 + (int)blockIdx.y * 4) + (lane >> 3);
@@ -57,21 +58,29 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
     uint32_t mid = 0xFFFFFFFFu;
     uint32_t g2x = 0u, g2y = 0u, g3x = 0u, g3w_mid = 0u, g1 = 0u;
     float    dz  = 1.0f, linz = -1.0f, fmid = 0.0f;
+    // primary rays of an 8x4 block are coherent: packet traversal (traverse.cuh), warp-uniform control flow.  Lanes outside the
+    // image carry a dummy ray and stay inactive.
+    Ray r;
+    V3  o = det::mk(0.0f, 0.0f, 0.0f);
+    r.o = o; r.d = det::mk(0.0f, 0.0f, 1.0f); r.tmin = 0.0f; r.tmax = 0.0f;
     if (in_img)
     {
         const float u = ((float)x + 0.5f) / (float)P.W, v = ((float)y + 0.5f) / (float)P.H;
-        const V3    o = det::world_position_from_depth(u, v, 0.0f, P.vpi), e = det::world_position_from_depth(u, v, 1.0f, P.vpi);
+        o = det::world_position_from_depth(u, v, 0.0f, P.vpi);
+        const V3    e   = det::world_position_from_depth(u, v, 1.0f, P.vpi);
         const V3    dv  = det::sub(e, o);
         const float len = det::length(dv);
-        Ray         r;
         r.o    = o;
         r.d    = det::scale(dv, 1.0f / len);
-        r.tmin = 0.0f;
         r.tmax = len;
-        float    t, hu, hv;
-        uint32_t prim;
         count_rays(ray_ctr, 0, 1u);
-        if (trace_closest(bvh, r, t, prim, hu, hv))
+    }
+    float    t, hu, hv;
+    uint32_t prim;
+    const bool hit = trace_closest_packet(bvh, r, in_img, s_stack[warp], t, prim, hu, hv);
+    if (in_img)
+    {
+        if (hit)
         {
             const V3     Pw = det::add(o, det::scale(r.d, t));
             const float4 c = mul_m4(P.vp, Pw), pc = mul_m4(P.pvp, Pw);

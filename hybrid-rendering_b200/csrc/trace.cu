@@ -69,6 +69,46 @@ __device__ __forceinline__ uint32_t trace_pixel(const GBufLevelDev& g, const Bvh
 // Small CTAs on purpose: ray costs are heavy-tailed and a CTA's slot (registers) is only recycled when its slowest warp
 // is done — with 8-warp CTAs the kernel ran its last ~20 % at a fraction of the occupancy.
 #define RT_CTA_WARPS 2
+// ray generation of K1 only (the traversal is done by the caller): returns whether the pixel traces a ray
+__device__ __forceinline__ bool shadow_ray_gen(const GBufLevelDev& g, const FrameConsts& fc, float bias, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ sr,
+                                               int x, int y, Ray& r)
+{
+    r.o = det::mk(0.0f, 0.0f, 0.0f); r.d = det::mk(0.0f, 0.0f, 1.0f); r.tmin = 0.01f; r.tmax = 0.0f;
+    if (x >= g.W || y >= g.H) return false;
+    const size_t idx   = (size_t)y * g.W + x;
+    const float  depth = __ldg(g.depth + idx);
+    if (depth == 1.0f) return false;
+    const float  u = ((float)x + 0.5f) / (float)g.W, v = ((float)y + 0.5f) / (float)g.H;
+    const V3     P  = det::world_position_from_depth(u, v, depth, fc.view_proj_inverse);
+    const float2 e  = load_oct_normal(g.gb2, idx);
+    const V3     N  = det::octohedral_to_direction(e.x, e.y);
+    const float  r0 = det::sample_blue_noise(x, y, (int)fc.num_frames, 0, sobol, sr);
+    const float  r1 = det::sample_blue_noise(x, y, (int)fc.num_frames, 1, sobol, sr);
+    r.o = det::add(P, det::scale(N, bias));
+    float att;
+    det::fetch_light_properties_shadow(fc.light, P, N, r0, r1, r.d, r.tmax, att);
+    return att > 0.0f;
+}
+
+// K1 with packet traversal (hr_debug_set key 9, default on): the soft-shadow rays of an 8x4 block are nearly parallel, so the
+// warp walks one path through the tree with a shared stack (traverse.cuh::trace_any_packet); the mask bits are identical.
+__global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask_packet(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float bias, const uint8_t* __restrict__ sobol,
+                                                                               const uint8_t* __restrict__ sr, uint32_t* __restrict__ mask, int mrow0, int mrow1)
+{
+    __shared__ int s_stack[RT_CTA_WARPS][STACK_SIZE];
+    const int MW   = (g.W + 7) >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mx = blockIdx.x * RT_CTA_WARPS + warp, my = mrow0 + blockIdx.y;
+    if (mx >= MW || my >= mrow1) return; // whole warp exits together
+    const int x = mx * 8 + (lane & 7), y = my * 4 + (lane >> 3);
+    Ray        r;
+    const bool traced   = shadow_ray_gen(g, fc, bias, sobol, sr, x, y, r);
+    const bool occluded = trace_any_packet(bvh, r, traced, s_stack[warp]);
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, traced && !occluded);
+    if (lane == 0) mask[(size_t)my * MW + mx] = word;
+    count_rays(fc.ray_ctr, 0, traced ? 1u : 0u);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(RT_CTA_WARPS * 32) k_ray_trace_mask(GBufLevelDev g, BvhDev bvh, FrameConsts fc, float p0, float p1, const uint8_t* __restrict__ sobol,
                                                          const uint8_t* __restrict__ sr, uint32_t* __restrict__ mask, int mrow0, int mrow1)
@@ -390,6 +430,8 @@ static inline dim3 mask_grid(int W, int mrow0, int mrow1) { return dim3(((W + 7)
 // Measured at 4K (profiles/README.md): shadows 585 us vs 712 us, AO 223 us vs 333 us — on this workload the 8x4 blocks are
 // almost uniformly active (coherent surfaces), so compaction buys little and the queue / refill bookkeeping costs more.
 int g_hr_trace_impl = 0;
+// hr_debug_set key 9: 1 (default) = packet traversal for the shadow rays of K1 (single-GPU / band-local path), 0 = per-lane traversal
+int g_hr_shadow_packet = 1;
 
 static const size_t kPtSmem = sizeof(QRay) * PT_WARPS * PT_QUEUE + sizeof(int) * SM_STACK * PT_WARPS * 32 + sizeof(uint32_t) * PT_WARPS * 4;
 
@@ -422,6 +464,7 @@ void launch_shadows_ray_trace(const GBufLevelDev& g, const BvhDev& bvh, const Fr
     const int mrow0 = row0 / 4, mrow1 = (row1 + 3) / 4;
     if (mrow1 <= mrow0) return;
     if (g_hr_trace_impl == 1) { launch_pt<0>(g, bvh, fc, bias, 0.0f, sobol, sr, mask, mrow0, mrow1, st); return; }
+    if (g_hr_shadow_packet) { k_ray_trace_mask_packet<<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, sobol, sr, mask, mrow0, mrow1); return; }
     k_ray_trace_mask<0><<<mask_grid(g.W, mrow0, mrow1), RT_CTA_WARPS * 32, 0, st>>>(g, bvh, fc, bias, 0.0f, sobol, sr, mask, mrow0, mrow1);
 }
 

@@ -188,4 +188,128 @@ static __device__ bool trace_closest(const BvhDev& bvh, const Ray& r, float& bes
 }
 
 
+// Packet traversal for COHERENT rays (primary visibility): the whole warp walks ONE path through the tree — a node is entered if
+// any lane's ray hits its box — with a single per-warp stack in shared memory.  Control flow is warp-uniform (no lane-level
+// divergence, node loads are one broadcast transaction); every lane still tests boxes and triangles against its own ray and its
+// own current best hit, so the result per lane is exactly trace_closest's (closest hit, ties -> lowest primitive; the set of
+// triangles a lane tests is a superset of what its own traversal would visit).  All 32 lanes must call it; `active` = lane has a ray.
+// warp_stack: STACK_SIZE ints of shared memory owned by this warp.
+static __device__ bool trace_closest_packet(const BvhDev& bvh, const Ray& r, bool active, int* __restrict__ warp_stack, float& best_t, uint32_t& best_prim,
+                                            float& best_u, float& best_v)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    int sp   = 0;
+    int node = 0;
+    best_t    = r.tmax;
+    best_prim = 0xFFFFFFFFu;
+    best_u = best_v = 0.0f;
+    const SlabSetup s = slab_setup(r);
+    if (!__any_sync(FULL, active)) return false;
+    for (;;)
+    {
+        if (node >= 0)
+        {
+            bool  h0, h1;
+            float t0, t1;
+            int   c0, c1;
+            node_test(bvh.nodes, node, s, r.tmin, best_t, h0, h1, t0, t1, c0, c1);
+            h0 = h0 && active;
+            h1 = h1 && active;
+            const uint32_t m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+            if (!(m0 | m1))
+            {
+                if (sp == 0) break;
+                node = warp_stack[--sp];
+            }
+            else if (m0 && m1)
+            {
+                // visit first the child most lanes would enter first; the other one goes on the stack
+                const uint32_t near1 = __ballot_sync(FULL, h1 && (!h0 || t1 < t0));
+                const bool     first1 = __popc(near1) > __popc((m0 | m1) & ~near1);
+                if (sp < STACK_SIZE) { if (lane == 0) warp_stack[sp] = first1 ? c0 : c1; sp++; }
+                __syncwarp();
+                node = first1 ? c1 : c0;
+            }
+            else node = m0 ? c0 : c1;
+        }
+        else
+        {
+            const int leaf  = ~node;
+            const int first = leaf >> 3, cnt = (leaf & 7) + 1;
+            for (int k = 0; k < cnt; k++)
+            {
+                const float4 A = __ldg(bvh.tris + 3ull * (first + k));
+                const float4 B = __ldg(bvh.tris + 3ull * (first + k) + 1);
+                const float4 C = __ldg(bvh.tris + 3ull * (first + k) + 2);
+                float        t, u, v;
+                if (active && ray_triangle(A, B, C, r, t, u, v))
+                {
+                    const uint32_t prim = __float_as_uint(A.w);
+                    if (t < best_t || (t == best_t && prim < best_prim)) { best_t = t; best_prim = prim; best_u = u; best_v = v; }
+                }
+            }
+            if (sp == 0) break;
+            node = warp_stack[--sp];
+        }
+    }
+    return best_prim != 0xFFFFFFFFu;
+}
+
+// Any-hit twin of trace_closest_packet for coherent occlusion rays (soft shadows of a small light: the rays of an 8x4 block are
+// nearly parallel).  A lane leaves the packet as soon as its ray is occluded; the warp stops when nobody is left or the
+// stack is empty.  Per-lane result = trace_any's (a ray is occluded iff some triangle intersects it in (tmin, tmax)).
+static __device__ bool trace_any_packet(const BvhDev& bvh, const Ray& r, bool active, int* __restrict__ warp_stack)
+{
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    int  sp = 0, node = 0;
+    bool alive = active, occluded = false;
+    const SlabSetup s = slab_setup(r);
+    if (!__any_sync(FULL, alive)) return false;
+    for (;;)
+    {
+        if (node >= 0)
+        {
+            bool  h0, h1;
+            float t0, t1;
+            int   c0, c1;
+            node_test(bvh.nodes, node, s, r.tmin, r.tmax, h0, h1, t0, t1, c0, c1);
+            h0 = h0 && alive;
+            h1 = h1 && alive;
+            const uint32_t m0 = __ballot_sync(FULL, h0), m1 = __ballot_sync(FULL, h1);
+            if (!(m0 | m1))
+            {
+                if (sp == 0) break;
+                node = warp_stack[--sp];
+            }
+            else if (m0 && m1)
+            {
+                const uint32_t near1 = __ballot_sync(FULL, h1 && (!h0 || t1 < t0));
+                const bool     first1 = __popc(near1) > __popc((m0 | m1) & ~near1);
+                if (sp < STACK_SIZE) { if (lane == 0) warp_stack[sp] = first1 ? c0 : c1; sp++; }
+                __syncwarp();
+                node = first1 ? c1 : c0;
+            }
+            else node = m0 ? c0 : c1;
+        }
+        else
+        {
+            const int leaf  = ~node;
+            const int first = leaf >> 3, cnt = (leaf & 7) + 1;
+            for (int k = 0; k < cnt; k++)
+            {
+                const float4 A = __ldg(bvh.tris + 3ull * (first + k));
+                const float4 B = __ldg(bvh.tris + 3ull * (first + k) + 1);
+                const float4 C = __ldg(bvh.tris + 3ull * (first + k) + 2);
+                float        t, u, v;
+                if (alive && ray_triangle(A, B, C, r, t, u, v)) { occluded = true; alive = false; }
+            }
+            if (sp == 0 || !__any_sync(FULL, alive)) break;
+            node = warp_stack[--sp];
+        }
+    }
+    return occluded;
+}
+
 } // namespace trv
