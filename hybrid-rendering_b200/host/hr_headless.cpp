@@ -1,10 +1,13 @@
 // hr_headless.cpp — headless frame loop in C++ on the host classes (the analogue of HybridRendering::update,
-// src/main.cpp:49-129): update_uniforms -> build_tlas -> GBuffer -> Shadows -> AO -> end_frame, no window / swapchain.
+// src/main.cpp:49-129): update_uniforms -> build_tlas -> GBuffer -> Shadows -> AO -> DDGI -> Reflections -> DeferredShading ->
+// end_frame, no window / swapchain / Vulkan: the G-buffer is ray cast on the device, the host only sends the per-frame constants.
 // Usage: hr_headless [width height frames tris]
 #include "hybrid_rendering.h"
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <vector>
 
@@ -18,46 +21,57 @@ int main(int argc, char** argv)
         std::vector<uint8_t> sobol(256 * 4), sr(128 * 128 * 4);
         hrs_blue_noise(1234, sobol.data(), sr.data());
         common.set_blue_noise(sobol.data(), sr.data());
+        std::vector<uint16_t> lut(512 * 512 * 2);
+        hrs_brdf_lut(64, lut.data());
+        hr::check(common.ctx, hr_brdf_lut_set(common.ctx, lut.data()), "hr_brdf_lut_set");
         hrs_scene* scene = hrs_scene_create(HRS_SCENE_ARCADE, tris, 7);
         common.load_scene(scene);
-        hr::GBuffer          g_buffer(&common);
-        hr::RayTracedShadows shadows(&common, &g_buffer, hr::RAY_TRACE_SCALE_FULL_RES);
-        hr::RayTracedAO      ao(&common, &g_buffer, hr::RAY_TRACE_SCALE_HALF_RES);
+        hr::GBuffer              g_buffer(&common);
+        hr::RayTracedShadows     shadows(&common, &g_buffer, hr::RAY_TRACE_SCALE_FULL_RES);
+        hr::RayTracedAO          ao(&common, &g_buffer, hr::RAY_TRACE_SCALE_HALF_RES);
+        hr::DDGI                 ddgi(&common, &g_buffer, hr::RAY_TRACE_SCALE_FULL_RES);
+        hr::RayTracedReflections reflections(&common, &g_buffer, hr::RAY_TRACE_SCALE_HALF_RES);
+        hr::DeferredShading      deferred(&common, &g_buffer);
+        ddgi.set_probe_distance(8.0f);
+        ddgi.set_normal_bias(0.5f);
+        const float sky[3] = { 0.3f, 0.4f, 0.6f };
+        for (int k = 0; k < 3; k++) ddgi.params.sky_color[k] = reflections.params.sky_color[k] = deferred.params.env_color[k] = sky[k];
 
-        const size_t px = (size_t)W * H;
-        uint8_t*  gb1;
-        uint16_t *gb2, *gb3;
-        float*    depth;
-        cudaMallocHost((void**)&gb1, px * 4);
-        cudaMallocHost((void**)&gb2, px * 8);
-        cudaMallocHost((void**)&gb3, px * 8);
-        cudaMallocHost((void**)&depth, px * 4);
         hrs_light_desc light;
         hrs_default_light(&light);
         light.rot_x_deg = 25.0f;
-        const float pos[3] = { 0.0f, 9.0f, -4.0f }, tgt[3] = { 2.0f, 7.0f, 60.0f };
+        const float tgt[3] = { 2.0f, 7.0f, 60.0f };
+        const float rot[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
         cudaStream_t st;
         cudaStreamCreate(&st);
-        hr_gbuffer_desc desc { W, H, gb1, gb2, gb3, depth };
         double gpu_ms = 0.0;
         for (int i = 0; i < frames; i++)
         {
+            const float pos[3] = { 0.02f * (float)i, 9.0f, -4.0f }; // slow lateral pan
             common.update_uniforms(pos, tgt, &light);
-            if (i < 2) hrs_write_gbuffer(scene, &common.frame, W, H, gb1, gb2, gb3, depth); // static camera: frames >= 1 share the G-buffer
-            hr_scene_rebuild(common.current_scene(), st);                                  // build_tlas every frame (main.cpp:74)
+            hr_scene_rebuild(common.current_scene(), st); // build_tlas every frame (main.cpp:74)
             auto t0 = std::chrono::steady_clock::now();
-            g_buffer.render(&desc, st);
+            g_buffer.render(st);
             shadows.render(st);
             ao.render(st);
+            ddgi.render(rot, st);
+            reflections.render(st, &ddgi);
+            deferred.render(st, shadows.handle(), ao.handle(), reflections.handle(), ddgi.handle());
             cudaStreamSynchronize(st);
             gpu_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             common.end_frame();
         }
-        hr_image s = shadows.output_ds(), a = ao.output_ds();
-        printf("frames=%d last frame %.3f ms (upload + shadows + ao); shadows out %dx%d fmt %d, ao out %dx%d fmt %d\n", frames, gpu_ms, s.width, s.height,
-               s.format, a.width, a.height, a.format);
+        hr_image o = deferred.output_ds();
+        std::vector<__half> px((size_t)o.width * o.height * 4);
+        cudaMemcpy(px.data(), o.data, px.size() * sizeof(__half), cudaMemcpyDeviceToHost);
+        double sum = 0.0;
+        bool   finite = true;
+        for (size_t k = 0; k < px.size(); k += 4)
+            for (int c = 0; c < 3; c++) { const float v = __half2float(px[k + c]); finite = finite && std::isfinite(v); sum += v; }
+        printf("frames=%d last frame %.3f ms (g-buffer + shadows + ao + ddgi + reflections + deferred); output %dx%d fmt %d mean %.5f finite %d\n", frames, gpu_ms, o.width,
+               o.height, o.format, sum / (3.0 * o.width * o.height), finite ? 1 : 0);
         hrs_scene_destroy(scene);
-        cudaFreeHost(gb1); cudaFreeHost(gb2); cudaFreeHost(gb3); cudaFreeHost(depth);
+        if (!finite || !(sum > 0.0)) return 2;
     }
     catch (const std::exception& e)
     {

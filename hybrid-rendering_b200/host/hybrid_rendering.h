@@ -5,6 +5,7 @@
 //   GBuffer         (src/g_buffer.h)               hr::GBuffer          (two device slots; output()/history() by ping_pong)
 //   RayTracedShadows(src/ray_traced_shadows.h)     hr::RayTracedShadows (ctor(common, gbuffer, scale); render(stream); output())
 //   RayTracedAO     (src/ray_traced_ao.h)          hr::RayTracedAO
+//   DDGI / RayTracedReflections / DeferredShading  hr::DDGI, hr::RayTracedReflections, hr::DeferredShading
 // Same method names and argument meaning; `dw::vk::CommandBuffer::Ptr` becomes a CUDA stream, descriptor sets become
 // hr_image views; construction errors throw std::runtime_error like the reference (common.cpp:350-353), render() does
 // not fail observably in the reference — here a failed launch throws as well.
@@ -81,6 +82,8 @@ struct GBuffer {
     // stream, render_staged() swaps the staged surface into this frame's slot on `stream` (no copy) and builds the mips
     void stage_next(const hr_gbuffer_desc* host_mip0) { check(common->ctx, hr_gbuffer_stage_upload(common->ctx, host_mip0), "hr_gbuffer_stage_upload"); }
     void render_staged(void* stream) { check(common->ctx, hr_gbuffer_commit_staged(common->ctx, common->ping_pong ? 1 : 0, stream), "hr_gbuffer_commit_staged"); }
+    // GBuffer::render (g_buffer.cpp:100-263) on the device: primary-visibility ray cast of the current scene for this frame's camera
+    void render(void* stream) { check(common->ctx, hr_gbuffer_render(common->ctx, common->ping_pong ? 1 : 0, &common->frame, 0, 0, stream), "hr_gbuffer_render"); }
     void bind_device(const hr_gbuffer_desc* dev_mip0, void* stream) { check(common->ctx, hr_gbuffer_bind_device(common->ctx, common->ping_pong ? 1 : 0, dev_mip0, stream), "hr_gbuffer_bind_device"); }
 };
 
@@ -167,6 +170,27 @@ private:
     CommonResources* m_common;
     hr_pass*         m_pass = nullptr;
     RayTraceScale    m_scale;
+};
+
+// DeferredShading (src/deferred_shading.h): render(cmd_buf, shadows, ao, reflections, ddgi) -> output image
+class DeferredShading {
+public:
+    DeferredShading(CommonResources* common, GBuffer* g_buffer) : m_common(common)
+    {
+        (void)g_buffer;
+        params.env_color[0] = params.env_color[1] = params.env_color[2] = 0.0f;
+        check(common->ctx, hr_deferred_create(common->ctx, (int)common->width, (int)common->height, &m_pass), "hr_deferred_create");
+    }
+    ~DeferredShading() { if (m_pass) hr_pass_destroy(m_pass); }
+    void     render(void* stream, hr_pass* shadows, hr_pass* ao, hr_pass* reflections, hr_pass* ddgi)
+    {
+        check(m_common->ctx, hr_deferred_render(m_pass, &m_common->frame, &params, shadows, ao, reflections, ddgi, stream), "hr_deferred_render");
+    }
+    hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, 100, &img), "hr_pass_output"); return img; }
+    hr_deferred_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
 };
 
 // RayTracedReflections (src/ray_traced_reflections.h): render(cmd_buf, DDGI*)
