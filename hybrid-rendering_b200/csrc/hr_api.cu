@@ -34,6 +34,18 @@ void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 
 static int round_up8(int v) { return (v + 7) & ~7; }
 
+// scrambling / ranking table a pass rendered with `spp` samples reads (hr_bluenoise_set_slot)
+static const uint8_t* bn_table(const hr_ctx* ctx, int spp)
+{
+    if (spp > 1 && (spp & (spp - 1)) == 0)
+    {
+        int slot = 0;
+        while ((1 << slot) < spp) slot++;
+        if (slot <= 8 && ctx->d_scr_rank_slot[slot]) return ctx->d_scr_rank_slot[slot];
+    }
+    return ctx->d_scr_rank;
+}
+
 static FrameConsts make_consts(const hr_frame* f, const hr_pass* p)
 {
     FrameConsts c;
@@ -137,6 +149,7 @@ int hr_shutdown(hr_ctx* ctx)
     cudaFree(ctx->d_sobol);
     cudaFree(ctx->d_scr_rank);
     cudaFree(ctx->d_brdf_lut);
+    for (int k = 1; k < 9; k++) cudaFree(ctx->d_scr_rank_slot[k]);
     if (ctx->build_stream) cudaStreamDestroy(ctx->build_stream);
     if (ctx->nccl_comm) hr_shard_shutdown(ctx);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -175,6 +188,20 @@ int hr_bluenoise_set(hr_ctx* ctx, const uint8_t* sobol, const uint8_t* sr)
     HR_CUDA(ctx, cudaMemcpy(ctx->d_sobol, sobol, 256 * 4, cudaMemcpyHostToDevice));
     HR_CUDA(ctx, cudaMemcpy(ctx->d_scr_rank, sr, 128 * 128 * 4, cudaMemcpyHostToDevice));
     ctx->bn_set = true;
+    ctx->d_scr_rank_slot[0] = ctx->d_scr_rank;
+    return HR_OK;
+}
+
+int hr_bluenoise_set_slot(hr_ctx* ctx, int slot, const uint8_t* sr)
+{
+    HR_REQUIRE(ctx, ctx && sr && slot >= 0 && slot <= 8, HR_ERR_INVALID_ARG, "hr_bluenoise_set_slot: slot must be 0..8 (1, 2, 4, ..., 256 spp)");
+    if (slot == 0)
+    {
+        if (!ctx->d_scr_rank) HR_CUDA(ctx, cudaMalloc(&ctx->d_scr_rank, 128 * 128 * 4));
+        ctx->d_scr_rank_slot[0] = ctx->d_scr_rank;
+    }
+    else if (!ctx->d_scr_rank_slot[slot]) HR_CUDA(ctx, cudaMalloc(&ctx->d_scr_rank_slot[slot], 128 * 128 * 4));
+    HR_CUDA(ctx, cudaMemcpy(ctx->d_scr_rank_slot[slot], sr, 128 * 128 * 4, cudaMemcpyHostToDevice));
     return HR_OK;
 }
 
@@ -739,7 +766,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
     else if (spp > 1)
     { // spp rays per pixel into an 8-bit count image (allocated on first use)
         if (!p->count) { rc = pass_alloc(p, p->count, px); if (rc != HR_OK) return rc; }
-        launch_shadows_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->count, spp, rt0, rt1, st);
+        launch_shadows_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->bias, ctx->d_sobol, bn_table(ctx, spp), p->count, spp, rt0, rt1, st);
         ctx->launches++;
         timer_mark(p, "Ray Trace", st);
     }
@@ -942,7 +969,7 @@ int hr_ao_render(hr_pass* p, const hr_frame* f, const hr_ao_params* prm, void* s
     else if (spp > 1)
     {
         if (!p->count) { rc = pass_alloc(p, p->count, px); if (rc != HR_OK) return rc; }
-        launch_ao_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, ctx->d_scr_rank, p->count, spp, rt0, rt1, st);
+        launch_ao_ray_trace_count(cur, hr_bvh_view(ctx->scene), fc, prm->ray_length, prm->bias, ctx->d_sobol, bn_table(ctx, spp), p->count, spp, rt0, rt1, st);
         ctx->launches++;
         timer_mark(p, "Ray Trace", st);
     }

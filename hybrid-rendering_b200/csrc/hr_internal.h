@@ -83,6 +83,7 @@ struct hr_ctx {
     // blue noise (device)
     uint8_t*     d_sobol    = nullptr; // 256*4
     uint8_t*     d_scr_rank = nullptr; // 128*128*4
+    uint8_t*     d_scr_rank_slot[9] = {}; // per sample count (BlueNoiseSpp): [0] aliases d_scr_rank
     bool         bn_set     = false;
     // g-buffer
     int          gb_w = 0, gb_h = 0;

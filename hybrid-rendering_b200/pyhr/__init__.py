@@ -95,7 +95,7 @@ ABI_SYMBOLS = [
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
-    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render",
+    "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render", "hr_bluenoise_set_slot",
 ]
 
 _product = None
@@ -294,6 +294,10 @@ class Context:
         if self.h:
             self.lib.hr_shutdown(self.h)
             self.h = None
+
+    def set_bluenoise_slot(self, slot, sr):
+        """scrambling / ranking table of sample-count slot `slot` (log2 spp), src/blue_noise.cpp:9-19"""
+        self.check(self.lib.hr_bluenoise_set_slot(self.h, slot, _ptr(np.ascontiguousarray(sr))), "hr_bluenoise_set_slot")
 
     def set_brdf_lut(self, lut):
         lut = np.ascontiguousarray(lut, np.uint16)

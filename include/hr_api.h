@@ -95,6 +95,11 @@ HR_API int         hr_version(void);
 /* Blue-noise tables (src/blue_noise.cpp:5-33, sampled by src/shaders/bnd_sampler.glsl:4-24).
  * sobol: 256 x RGBA8 (sobol_256_4d.png); scrambling_ranking: 128 x 128 x RGBA8 (…_1spp.png). Host pointers. */
 HR_API int hr_bluenoise_set(hr_ctx* ctx, const uint8_t* sobol_256x4, const uint8_t* scrambling_ranking_128x128x4);
+/* The reference loads nine scrambling / ranking tables, one per sample count (BlueNoiseSpp, src/blue_noise.h:5-16;
+ * scrambling_ranking_128x128_2d_{1,2,4,...,256}spp.png, src/blue_noise.cpp:9-19) and binds the 1-spp one to every pass.  slot =
+ * log2(spp) in 0..8.  A pass rendered with spp = 2^slot > 1 samples the table of its slot when one was set, the 1-spp table
+ * (hr_bluenoise_set, = slot 0) otherwise. */
+HR_API int hr_bluenoise_set_slot(hr_ctx* ctx, int slot, const uint8_t* scrambling_ranking_128x128x4);
 
 /* Split-sum BRDF LUT (dw::BRDFIntegrateLUT: textures/brdf_lut.bin, 512 x 512 RG16F, extras/brdf_preintegrate_lut.cpp:8-31; bound
  * with the bilinear CLAMP_TO_EDGE sampler, src/common.cpp:814-816).  Host pointer to 512 * 512 * 2 halves.  Until it is set the IBL

@@ -143,3 +143,38 @@ def test_reflections_spp_matches_oracle(spp):
     assert s.rays_primary > W * H  # more than one ray per traced GGX pixel
     rf.destroy()
     ctx.close()
+
+
+def test_per_spp_scrambling_table_slot_is_used():
+    """hr_bluenoise_set_slot (BlueNoiseSpp, src/blue_noise.cpp:9-19): a 2-spp shadows pass reads the table of slot 1 once it is set —
+    its count image equals the oracle's run with that table (and differs from the run with the 1-spp table)."""
+    W, H = 128, 96
+    sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+    tri, _ = sc.world_triangles()
+    osc = O.Scene(tri, brute=False)
+    sobol, sr1 = pyhr.blue_noise(1234)
+    _, sr2 = pyhr.blue_noise(99)
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(sobol, sr1)
+    ctx.set_bluenoise_slot(1, sr2)
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    sh = pyhr.Pass(ctx, "shadows", W, H, 0)
+    sh.params.spp = 2
+    sh.params.denoise = 0
+    f = pyhr.make_frame((0.0, 14.0, 34.0), (0.0, 3.0, 0.0), W, H)
+    g = pyhr.write_gbuffer(sc, f, W, H)
+    ctx.gbuffer_upload(f.ping_pong, g)
+    sh.render(f)
+    got = sh.download(0)
+    cur = O.GBufMips(g)
+    want = {}
+    for name, sr in (("slot", sr2), ("base", sr1)):
+        o = O.ShadowsOracle(W, H, 0, spp=2)
+        o.params.denoise = 0
+        o.render(osc, cur, cur, f, (sobol, sr))
+        want[name] = o.count.copy()
+    assert np.array_equal(got, want["slot"])
+    assert not np.array_equal(want["slot"], want["base"])
+    sh.destroy()
+    ctx.close()
