@@ -182,6 +182,7 @@ struct hr_pass {
     // reflections (RGBA16F images as uint2)
     uint2*    refl_rt = nullptr;
     uint2*    refl_rt_pp[2] = { nullptr, nullptr };   // ray-trace output by frame parity when the ranks trace cooperatively (refl_rt_pp[0] == refl_rt)
+    unsigned int* work_counters = nullptr;             // tile / job counters of this pass's persistent kernels
     float4*   refl_hits = nullptr;                     // wavefront K12: one hit record (t, primitive, u, v) per pixel
     uint2*    refl_temporal[2] = { nullptr, nullptr }; // current_output[pp] (also the history of the next frame)
     uint2*    refl_moments[2] = { nullptr, nullptr };
@@ -244,7 +245,7 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
 void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& prev, const void* input, const HistPeers& hist, const FrameConsts& fc, float alpha,
                                  float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st);
 int  launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
-                               float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st);
+                               float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, unsigned int* counters, cudaStream_t st);
 void launch_upsample_vec4(const GBufLevelDev& g0, const GBufLevelDev& gm, const void* in, void* out, int row0, int row1, cudaStream_t st);
 
 // ---- row-band sharding (shard.cu) ---------------------------------------------------------------------

@@ -588,22 +588,20 @@ bool tensor_map_2d(const void* ptr, int W, int H, int bw, int bh, CUtensorMap* o
     return true;
 }
 
+// counters: three words owned by the calling pass (one per step instantiation): passes of different contexts may run
+// concurrently on one device (emulated ranks on streams), so the tile counter cannot be a per-device static
 template <int STEP>
-bool launch_r2_tma(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, cudaStream_t st)
+bool launch_r2_tma(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, const R2Params& P, uint2* out, unsigned int* counters, cudaStream_t st)
 {
+    if (!counters) return false;
     using G = TmaGeom<STEP>;
     if ((((size_t)g.W * 8) & 15) != 0 || ((uintptr_t)g.gb2 & 15) || ((uintptr_t)g.gb3 & 15) || ((uintptr_t)in & 15)) return false;
     CUtensorMap t2, t3, ti;
     if (!tensor_map_2d(g.gb2, g.W, g.H, G::RW, G::RH, &t2) || !tensor_map_2d(g.gb3, g.W, g.H, G::RW, G::RH, &t3) || !tensor_map_2d(in, g.W, g.H, G::RW, G::RH, &ti)) return false;
-    static unsigned int* counter[64] = {};
-    static int           ctas[64]    = {};
+    static int ctas[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (!counter[dev])
-    {
-        cudaMalloc(&counter[dev], 4 * sizeof(unsigned int));
-    }
     static bool configured[64] = {};
     if (hr_once_per_device(configured))
     {
@@ -614,8 +612,7 @@ bool launch_r2_tma(const GBufLevelDev& g, const uint2* in, const uint8_t* tf, co
         ctas[dev] = sms * (per_sm > 0 ? per_sm : 1);
     }
     const int tiles_x = (P.W + TWR - 1) / TWR, tiles_y = (P.row1 - P.row0 + THR - 1) / THR, n_tiles = tiles_x * tiles_y;
-    // one counter word per STEP instantiation (iterations of different steps never overlap on a stream, passes on different streams might)
-    unsigned int* ctr = counter[dev] + (STEP == 1 ? 0 : STEP == 2 ? 1 : 2);
+    unsigned int* ctr = counters + (STEP == 1 ? 0 : STEP == 2 ? 1 : 2);
     cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st);
     const int grid = ctas[dev] < n_tiles ? ctas[dev] : n_tiles;
     k_refl_atrous_tma<STEP><<<grid, 256, G::SMEM, st>>>(t2, t3, ti, g, in, tf, P, out, tiles_x, n_tiles, ctr);
@@ -633,7 +630,7 @@ int g_hr_refl_atrous_impl = 3;
 
 // returns false when this variant does not support the configuration (the caller falls back to the scalar kernel)
 bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
-                                  float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st)
+                                  float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, unsigned int* counters, cudaStream_t st)
 {
     if (g_hr_refl_atrous_impl == 0 || radius != 1 || phi_normal != 32.0f || (g.W & 1) || row0 % 8 != 0 || !(step == 1 || step == 2 || step == 4 || step == 8 || step == 16))
         return false;
@@ -643,9 +640,9 @@ bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const u
     const bool   il = g_hr_refl_atrous_impl >= 2, tma1 = g_hr_refl_atrous_impl >= 3, tma = g_hr_refl_atrous_impl == 4;
     switch (step)
     {
-        case 1: if (!(tma1 && launch_r2_tma<1>(g, i2, tile_flags, P, o2, st))) launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
-        case 2: if (!(tma && launch_r2_tma<2>(g, i2, tile_flags, P, o2, st))) launch_r2<2>(g, i2, tile_flags, P, o2, st); break;
-        case 4: if (!(tma && launch_r2_tma<4>(g, i2, tile_flags, P, o2, st))) launch_r2<4>(g, i2, tile_flags, P, o2, st); break;
+        case 1: if (!(tma1 && launch_r2_tma<1>(g, i2, tile_flags, P, o2, counters, st))) launch_r2<1>(g, i2, tile_flags, P, o2, st); break;
+        case 2: if (!(tma && launch_r2_tma<2>(g, i2, tile_flags, P, o2, counters, st))) launch_r2<2>(g, i2, tile_flags, P, o2, st); break;
+        case 4: if (!(tma && launch_r2_tma<4>(g, i2, tile_flags, P, o2, counters, st))) launch_r2<4>(g, i2, tile_flags, P, o2, st); break;
         case 8: if (il) launch_r2s<8>(g, i2, tile_flags, P, o2, st); else launch_r2<8>(g, i2, tile_flags, P, o2, st); break;
         default: launch_r2s<16>(g, i2, tile_flags, P, o2, st); break;
     }

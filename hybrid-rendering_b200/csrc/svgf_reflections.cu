@@ -419,13 +419,13 @@ void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& pr
 }
 
 bool launch_reflections_atrous_v2(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
-                                  float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st); // svgf_refl_atrous_v2.cu
+                                  float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, unsigned int* counters, cudaStream_t st); // svgf_refl_atrous_v2.cu
 
 int launch_reflections_atrous(const GBufLevelDev& g, const void* in, const uint8_t* tile_flags, int radius, int step, float phi_color, float phi_normal,
-                              float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, cudaStream_t st)
+                              float sigma_depth, int approximate_with_ddgi, void* out, int row0, int row1, unsigned int* counters, cudaStream_t st)
 {
     if (row1 <= row0) return 0;
-    if (launch_reflections_atrous_v2(g, in, tile_flags, radius, step, phi_color, phi_normal, sigma_depth, approximate_with_ddgi, out, row0, row1, st)) return 0; // packed fp32x2
+    if (launch_reflections_atrous_v2(g, in, tile_flags, radius, step, phi_color, phi_normal, sigma_depth, approximate_with_ddgi, out, row0, row1, counters, st)) return 0; // packed fp32x2
     if (radius != 1 || !(step == 1 || step == 2 || step == 4 || step == 8 || step == 16)) return -1;
     ReflAtrousParams P { g.W, g.H, step, radius, phi_color, phi_normal, sigma_depth, approximate_with_ddgi, row0, row1 };
     switch (step)
