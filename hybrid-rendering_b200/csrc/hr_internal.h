@@ -291,6 +291,10 @@ inline void hr_extend(int b0, int b1, int halo, int H, int* e0, int* e1)
 // Make every rank's copy of each image complete: rank r broadcasts its band of every item (one NCCL group).
 // Asynchronous: enqueued on ctx->comm_stream after everything already enqueued on `st`; completion is p->ev_done.
 int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t st);
+// Same, with explicit per-rank row ranges [row0[r], row1[r]) (rank r broadcasts its rows of every item): DDGI atlases split by
+// probe z-slices.  SYNCHRONOUS with respect to `st`: the exchange is enqueued on `st` itself.
+struct RowRangeItem { void* base; size_t row_bytes; };
+int hr_shard_exchange_rows(hr_pass* p, const RowRangeItem* items, int n, const int* row0, const int* row1, cudaStream_t st);
 // Make `st` wait for the pass's pending exchange (no-op when nothing is pending).
 void hr_wait_exchange(hr_pass* p, cudaStream_t st);
 

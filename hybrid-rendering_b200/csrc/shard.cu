@@ -122,6 +122,23 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
 }
 
 
+int hr_shard_exchange_rows(hr_pass* p, const RowRangeItem* items, int n, const int* row0, const int* row1, cudaStream_t st)
+{
+    hr_ctx* ctx = p->ctx;
+    if (ctx->world <= 1 || !ctx->nccl_comm) return HR_OK;
+    NcclApi& N = nccl();
+    HR_NCCL(ctx, N.GroupStart());
+    for (int i = 0; i < n; i++)
+        for (int r = 0; r < ctx->world; r++)
+        {
+            if (row1[r] <= row0[r]) continue;
+            char* ptr = static_cast<char*>(items[i].base) + (size_t)row0[r] * items[i].row_bytes;
+            HR_NCCL(ctx, N.Broadcast(ptr, ptr, (size_t)(row1[r] - row0[r]) * items[i].row_bytes, ncclUint8, r, (ncclComm_t)ctx->nccl_comm, st));
+        }
+    HR_NCCL(ctx, N.GroupEnd());
+    return HR_OK;
+}
+
 // ---- peer history -----------------------------------------------------------------------------------------------------
 static int rt_init_bounds(hr_pass* p);
 
