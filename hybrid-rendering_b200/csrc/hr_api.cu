@@ -19,6 +19,7 @@ extern int         g_hr_refl_atrous_impl;
 extern int         g_hr_refl_trace_impl;
 extern int         g_hr_refl_atrous_minb;
 extern int         g_hr_shadow_packet;
+extern int         g_hr_refl_trace_minb;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -174,6 +175,7 @@ int hr_debug_set(int key, int value)
     if (key == 7) { g_hr_refl_trace_impl = value; return HR_OK; }
     if (key == 8) { g_hr_refl_atrous_minb = value; return HR_OK; }
     if (key == 9) { g_hr_shadow_packet = value; return HR_OK; }
+    if (key == 10) { g_hr_refl_trace_minb = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 

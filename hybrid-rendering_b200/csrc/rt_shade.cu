@@ -260,8 +260,8 @@ struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi;
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
 // 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
 // MULTI = false: exactly the reference's one ray per pixel (straight-line code); true: the spp > 1 extension (sample loop)
-template <bool MULTI>
-__global__ void __launch_bounds__(64, MULTI ? 8 : 14) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
+template <bool MULTI, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
                                                                 ReflTraceParams P, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk,
                                                                 uint2* __restrict__ out)
 {
@@ -613,6 +613,8 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
 // both forms) is what costs, and the 56 KB queue / stack footprint per CTA takes L1 away from the BVH (hit rate 40 % vs 64 %).
 // hr_debug_set key 7.
 int g_hr_refl_trace_impl = 0;
+// hr_debug_set key 10: resident 2-warp CTAs per SM the fused kernel's registers are tuned for (14 = 72 registers = default; 16 = 64; 12 = 80)
+int g_hr_refl_trace_minb = 14;
 
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
@@ -651,6 +653,8 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
         return;
     }
     dim3 grid((g.W + 15) / 16, chunk_stride > 1 ? 2 * n_chunks_mine : (row1 - row0 + 3) / 4);
-    if (spp > 1) k_reflections_ray_trace<true><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else k_reflections_ray_trace<false><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    if (spp > 1) k_reflections_ray_trace<true, 8><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else if (g_hr_refl_trace_minb == 16) k_reflections_ray_trace<false, 16><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else if (g_hr_refl_trace_minb == 12) k_reflections_ray_trace<false, 12><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else k_reflections_ray_trace<false, 14><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
 }

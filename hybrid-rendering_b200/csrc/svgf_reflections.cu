@@ -50,21 +50,31 @@ __device__ __forceinline__ int owner_of(const HistPeers& hp, int row)
     for (int r = 0; r < HR_MAX_RANKS - 1; r++) o += (r < hp.world - 1 && row >= hp.band_end[r]) ? 1 : 0;
     return o;
 }
+// All history taps of a pixel lie in rows hcy-1 .. hcy+1: the owner is looked up once per pixel (two owner_of calls) and only
+// pixels whose taps straddle a band border fall back to a lookup per load.
+struct OwnerCache { int o; bool uniform; };
 template <bool PEER>
-__device__ __forceinline__ uint2 hist_ld64(const void* const* tab, const HistPeers& hp, int row, size_t index)
+__device__ __forceinline__ OwnerCache owner_cache(const HistPeers& hp, int row_lo, int row_hi)
+{
+    OwnerCache c { 0, true };
+    if (PEER) { c.o = owner_of(hp, row_lo); c.uniform = c.o == owner_of(hp, row_hi); }
+    return c;
+}
+template <bool PEER>
+__device__ __forceinline__ uint2 hist_ld64(const void* const* tab, const HistPeers& hp, const OwnerCache& oc, int row, size_t index)
 {
     if (hp.no_history) return make_uint2(0u, 0u);
     if (!PEER) return __ldg(reinterpret_cast<const uint2*>(tab[0]) + index);
-    const int    o = owner_of(hp, row);
+    const int    o = oc.uniform ? oc.o : owner_of(hp, row);
     const uint2* p = reinterpret_cast<const uint2*>(tab[o]) + index;
     return o == hp.self ? __ldg(p) : __ldcg(p);
 }
 template <bool PEER>
-__device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const HistPeers& hp, int row, size_t word_index)
+__device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const HistPeers& hp, const OwnerCache& oc, int row, size_t word_index)
 {
     if (hp.no_history) return 0u;
     if (!PEER) return __ldg(reinterpret_cast<const uint32_t*>(tab[0]) + word_index);
-    const int       o = owner_of(hp, row);
+    const int       o = oc.uniform ? oc.o : owner_of(hp, row);
     const uint32_t* p = reinterpret_cast<const uint32_t*>(tab[o]) + word_index;
     return o == hp.self ? __ldg(p) : __ldcg(p);
 }
@@ -166,6 +176,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
             const int   hcx = (int)hfx, hcy = (int)hfy; // ivec2(reprojected_coord) :171
             const float hu = tu + g2.z, hv = tv + g2.w;
             const bool  in_frame = inside(hcx, hcy, W, H);
+            const OwnerCache oc = owner_cache<PEER>(hp, max(hcy - 1, 0), min(hcy + 1, H - 1));
             float hc[3] = { 0, 0, 0 }, hm0 = 0.0f, hm1 = 0.0f;
             bool  valid = false;
             if (in_frame)
@@ -186,8 +197,8 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                         if (inside(px, py, W, H))
                         {
                             const size_t pi = (size_t)py * W + px;
-                            const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, py, pi));
-                            const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, py, 2 * pi));
+                            const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, oc, py, pi));
+                            const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, oc, py, 2 * pi));
                             hc[0] += w4[s] * hv4.x; hc[1] += w4[s] * hv4.y; hc[2] += w4[s] * hv4.z;
                             hm0 += w4[s] * mm.x; hm1 += w4[s] * mm.y;
                         }
@@ -213,8 +224,8 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                                 if (inside(px, py, W, H))
                                 {
                                     const size_t pi = (size_t)py * W + px;
-                                    const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, py, pi));
-                                    const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, py, 2 * pi));
+                                    const float4 hv4 = h4_to_f4(hist_ld64<PEER>(hp.img, hp, oc, py, pi));
+                                    const float2 mm  = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, oc, py, 2 * pi));
                                     hc[0] += hv4.x; hc[1] += hv4.y; hc[2] += hv4.z; hm0 += mm.x; hm1 += mm.y;
                                 }
                                 cnt += 1.0f;
@@ -224,7 +235,7 @@ __global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLev
                 }
             }
             float hist_len = 0.0f;
-            if (valid) hist_len = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, hcy, 2 * ((size_t)hcy * W + hcx) + 1)).x;
+            if (valid) hist_len = h2_to_f2(hist_ld32<PEER>(hp.aux, hp, oc, hcy, 2 * ((size_t)hcy * W + hcx) + 1)).x;
             else { hc[0] = hc[1] = hc[2] = 0.0f; hm0 = hm1 = 0.0f; }
             const float hlen = fminf(32.0f, valid ? hist_len + 1.0f : 1.0f);
             if (valid)
