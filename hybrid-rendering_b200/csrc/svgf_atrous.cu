@@ -173,158 +173,6 @@ __global__ void __launch_bounds__(256) k_atrous_tiled(GBufLevelDev g, const uint
 }
 
 
-// ---- chain kernel: sliding 3x3 register window ----------------------------------------------------------------------
-// One CTA filters a 64x32 tile (32 reference tiles -> one 32-bit flag word).  Each thread owns "chains" of J output
-// pixels spaced STEP rows apart in one column; the taps of consecutive chain pixels share two of their three rows, so a
-// 3x3 window of staged cells lives in registers and only one new row (3 cells) is read from shared memory per output
-// pixel (72 B/px instead of 216 B/px of LDS traffic — the tiled kernel above is shared-memory-bandwidth bound).
-// Out-of-image cells are staged with a zero normal: dot = 0 -> x^32 = 0 -> weight 0, i.e. the reference's `inside`
-// test (shadows_denoise_atrous.comp:133-136) without a branch per tap.
-constexpr int CH_W = 64, CH_H = 32;
-
-struct Cell { float4 nz; float2 iv; };
-
-template <bool PHI32>
-__device__ __forceinline__ void tap(const Cell& c, const Cell& s, float kern, float c_sigma, float c_phi, float phi_normal, float& sum_w, float& s0, float& s1)
-{
-    const float wZ = fast_exp2(fabsf(c.nz.w - s.nz.w) * c_sigma);                       // exp(-|dz| / sigma_z)
-    const float ea = fmaf(wZ, -1.44269504f, fabsf(c.iv.x - s.iv.x) * c_phi);             // -(wL + wZ) * log2(e)
-    const float nd = __saturatef(fmaf(c.nz.x, s.nz.x, fmaf(c.nz.y, s.nz.y, c.nz.z * s.nz.z)));
-    const float wn = PHI32 ? pow32(nd) : pow_pos(nd, phi_normal);
-    const float wk = fast_exp2(ea) * wn * kern;
-    sum_w += wk;
-    s0 = fmaf(wk, s.iv.x, s0);
-    s1 = fmaf(wk * wk, s.iv.y, s1);
-}
-
-template <int STEP, bool PHI32>
-__global__ void __launch_bounds__(256) k_atrous_chain(GBufLevelDev g, const uint32_t* __restrict__ in, const uint8_t* __restrict__ tile_flags,
-                                                       AtrousParams P, uint32_t* __restrict__ out)
-{
-    extern __shared__ float4 smem4[];
-    constexpr int RW = CH_W + 2 * STEP, RH = CH_H + 2 * STEP;
-    constexpr int J = (STEP == 8) ? 4 : 8, CHAINS = CH_H / J;
-    float4*       s_nz = smem4;
-    float2*       s_in = reinterpret_cast<float2*>(smem4 + RW * RH);
-    __shared__ uint32_t s_tf;
-
-    const int W = P.W, H = P.H;
-    const int x0 = blockIdx.x * CH_W, y0 = P.row0 + blockIdx.y * CH_H;
-    const int TW = (W + 7) >> 3, TH = (H + 7) >> 3;
-    if (threadIdx.x < 32)
-    {
-        const int tx = (x0 >> 3) + (threadIdx.x & 7), ty = (y0 >> 3) + (threadIdx.x >> 3);
-        const bool f = tx < TW && ty < TH && tile_flags[(size_t)ty * TW + tx] != 0;
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, f);
-        if (threadIdx.x == 0) s_tf = b;
-    }
-    __syncthreads();
-    const uint32_t tf = s_tf;
-
-    if (tf != 0)
-    {
-        const uint32_t* gb2w = reinterpret_cast<const uint32_t*>(g.gb2);
-        const uint32_t* gb3w = reinterpret_cast<const uint32_t*>(g.gb3);
-        for (int i = threadIdx.x; i < RW * RH; i += 256)
-        {
-            const int rx = i % RW, ry = i / RW;
-            const int px = x0 - STEP + rx, py = y0 - STEP + ry;
-            float4    nz = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            float2    iv = make_float2(0.0f, 0.0f);
-            if (px >= 0 && py >= 0 && px < W && py < H)
-            {
-                const size_t pi = (size_t)py * W + px;
-                const float2 e  = h2_to_f2(__ldg(gb2w + 2 * pi));         // oct normal
-                const float2 zz = h2_to_f2(__ldg(gb3w + 2 * pi + 1));     // (mesh id, linear z)
-                const float3 n  = octohedral_to_direction(e.x, e.y);
-                nz              = make_float4(n.x, n.y, n.z, zz.y);
-                iv              = h2_to_f2(__ldg(in + pi));
-            }
-            s_nz[i] = nz;
-            s_in[i] = iv;
-        }
-    }
-    __syncthreads();
-
-    const int   lx = threadIdx.x & 63, c4 = threadIdx.x >> 6;
-    const int   x  = x0 + lx;
-    const float c_sigma = -1.44269504f / P.sigma_depth;
-    const float k1 = 2.0f / 3.0f, k2 = (2.0f / 3.0f) * (2.0f / 3.0f);
-#pragma unroll
-    for (int ch = c4; ch < CHAINS; ch += 4)
-    {
-        const int r = ch % STEP, seg = ch / STEP;
-        const int ly0 = r + STEP * seg * J;
-        Cell A[3], B[3], C[3];
-        {
-            const int ia = (ly0 + STEP - STEP) * RW + lx; // region row of (ly0 - STEP), first of the three columns
-            const int ib = (ly0 + STEP) * RW + lx;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-            {
-                A[k].nz = s_nz[ia + k * STEP]; A[k].iv = s_in[ia + k * STEP];
-                B[k].nz = s_nz[ib + k * STEP]; B[k].iv = s_in[ib + k * STEP];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < J; j++)
-        {
-            const int ly = ly0 + STEP * j;
-            const int ic = (ly + 2 * STEP) * RW + lx;
-#pragma unroll
-            for (int k = 0; k < 3; k++) { C[k].nz = s_nz[ic + k * STEP]; C[k].iv = s_in[ic + k * STEP]; }
-            const int y = y0 + ly;
-            if (x < W && y < H && y < P.row1)
-            {
-                const size_t idx = (size_t)y * W + x;
-                const Cell&  c   = B[1];
-                if (!((tf >> ((ly >> 3) * 8 + (lx >> 3))) & 1u)) out[idx] = 0u;
-                else if (c.nz.w < 0.0f) out[idx] = f2_to_h2(c.iv.x, c.iv.y);
-                else
-                {
-                    float var;
-                    if (STEP == 1)
-                        var = 0.25f * c.iv.y + 0.125f * (B[0].iv.y + B[2].iv.y + A[1].iv.y + C[1].iv.y) +
-                              0.0625f * (A[0].iv.y + A[2].iv.y + C[0].iv.y + C[2].iv.y);
-                    else
-                    {
-                        const int ci = (ly + STEP) * RW + lx + STEP;
-                        var = 0.25f * c.iv.y + 0.125f * (s_in[ci - 1].y + s_in[ci + 1].y + s_in[ci - RW].y + s_in[ci + RW].y) +
-                              0.0625f * (s_in[ci - RW - 1].y + s_in[ci - RW + 1].y + s_in[ci + RW - 1].y + s_in[ci + RW + 1].y);
-                    }
-                    const float c_phi = -1.44269504f * rsqrtf(fmaxf(1e-10f + var, 1e-30f)) / P.phi_visibility; // -log2e / (phi * sqrt(var))
-                    float       sum_w = 1.0f, s0 = c.iv.x, s1 = c.iv.y;
-                    tap<PHI32>(c, A[0], k2, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, A[1], k1, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, A[2], k2, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, B[0], k1, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, B[2], k1, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, C[0], k2, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, C[1], k1, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    tap<PHI32>(c, C[2], k2, c_sigma, c_phi, P.phi_normal, sum_w, s0, s1);
-                    const float inv = fast_rcp(sum_w);
-                    float       o0 = s0 * inv, o1 = s1 * inv * inv;
-                    if (P.power != 0.0f) o0 = pow_pos(o0, P.power);
-                    out[idx] = f2_to_h2(o0, o1);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) { A[k] = B[k]; B[k] = C[k]; }
-        }
-    }
-}
-
-template <int STEP, bool PHI32>
-void launch_chain(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, const AtrousParams& P, uint32_t* out, cudaStream_t st)
-{
-    constexpr int RW = CH_W + 2 * STEP, RH = CH_H + 2 * STEP;
-    const size_t  smem = (size_t)RW * RH * (sizeof(float4) + sizeof(float2));
-    static bool   configured[64] = {};
-    if (hr_once_per_device(configured)) cudaFuncSetAttribute(k_atrous_chain<STEP, PHI32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dim3 grid((P.W + CH_W - 1) / CH_W, (P.row1 - P.row0 + CH_H - 1) / CH_H);
-    k_atrous_chain<STEP, PHI32><<<grid, 256, smem, st>>>(g, in, tf, P, out);
-}
-
 template <int STEP>
 void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, const AtrousParams& P, uint32_t* out, cudaStream_t st)
 {
@@ -338,8 +186,9 @@ void launch_tiled(const GBufLevelDev& g, const uint32_t* in, const uint8_t* tf, 
 
 } // namespace
 
-// 0 = naive, 1 = tiled (default: measured 64-105 us/iter at 4K), 2 = chain / sliding window (72-107 us: the extra registers
-// cost more occupancy than the saved shared-memory traffic buys; profiles/README.md).  hr_debug_set key 1.
+// 0 = naive, 1 = tiled scalar kernel (64-105 us/iter at 4K).  hr_debug_set key 1.  (A sliding-register-window "chain" variant was
+// measured slower in round 1 — 72-107 us: its extra registers cost more occupancy than the saved shared-memory traffic bought —
+// and has been removed; profiles/README.md keeps the numbers.)
 // 3 = packed fp32x2 pixel-pair kernel (svgf_atrous_v3.cu; default: 53-85 us/iter, 47 % of HBM peak); it falls back to the
 // scalar tiled kernel for odd widths / phi_normal != 32.
 int g_hr_atrous_impl = 3;
@@ -355,20 +204,7 @@ void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8
     uint32_t*       o32 = reinterpret_cast<uint32_t*>(out);
     const bool tiled_ok = g_hr_atrous_impl != 0 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8);
     if (g_hr_atrous_impl == 3 && launch_shadows_atrous_v3(g, i32, tile_flags, radius, step, phi_vis, phi_n, sigma_z, power, o32, row0, row1, st)) return;
-    const bool chain_ok = g_hr_atrous_impl == 2 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8) && row0 % 8 == 0;
-    if (chain_ok)
-    {
-        const bool p32 = phi_n == 32.0f;
-#define CHAIN(S) do { if (p32) launch_chain<S, true>(g, i32, tile_flags, P, o32, st); else launch_chain<S, false>(g, i32, tile_flags, P, o32, st); } while (0)
-        switch (step)
-        {
-            case 1: CHAIN(1); break;
-            case 2: CHAIN(2); break;
-            case 4: CHAIN(4); break;
-            default: CHAIN(8); break;
-        }
-#undef CHAIN
-    }
+    if (false) {}
     else if (tiled_ok)
     {
         switch (step)

@@ -428,7 +428,7 @@ HR_API int hr_pass_destroy(hr_pass* pass);
  * Enable with hr_ctx_set_profiling(ctx,1); names/ms arrays of capacity cap; returns count via *n. Synchronises. */
 HR_API int hr_ctx_set_profiling(hr_ctx* ctx, int enabled);
 HR_API int hr_pass_stage_times(hr_pass* pass, const char** names, float* ms, int cap, int* n);
-/* Test / A-B hook.  key 1 = a-trous implementation (0 naive global-memory kernel, 1 shared-memory tiled kernel, 2 chained,
+/* Test / A-B hook.  key 1 = a-trous implementation (0 naive global-memory kernel, 1 shared-memory tiled kernel,
  * 3 packed fp32x2 pixel-pair kernel = default); key 2 = traversal kernel (0 one warp per 8x4 block = default, 1 persistent
  * threads + ray compaction); key 3 = BVH topology used by the next hr_scene_build / hr_scene_rebuild (0 Karras radix tree,
  * 1 PLOC agglomerative clustering = default); key 4 = run the cooperative (multi-GPU) ray-trace kernel on a single GPU;
