@@ -355,7 +355,7 @@ def main():
         sc = gsc = pyhr.SynthScene(pyhr.SCENE_ARCADE, cfg["tris"])
         cam, tgt = CAM_POS, CAM_TGT
     ctx = pyhr.Context(local_rank)
-    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7), ("HR_REFL_ATROUS_MINB", 8), ("HR_SHADOW_PACKET", 9), ("HR_REFL_TRACE_MINB", 10)):
+    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7), ("HR_REFL_ATROUS_MINB", 8), ("HR_SHADOW_PACKET", 9), ("HR_REFL_TRACE_MINB", 10), ("HR_GATHER_IMPL", 11)):
         if os.environ.get(env):
             ctx.lib.hr_debug_set(key, int(os.environ[env]))
     ctx.set_bluenoise(*pyhr.blue_noise())

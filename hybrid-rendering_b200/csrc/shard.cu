@@ -36,6 +36,8 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)()                                                                                 = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)       = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t)            = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                   = nullptr; // optional
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                         = nullptr; // optional
     const char* (*GetErrorString)(ncclResult_t)                                                                = nullptr;
     bool ok = false;
 };
@@ -59,6 +61,8 @@ NcclApi& nccl()
     LOAD(GroupEnd, "ncclGroupEnd");
     LOAD(Broadcast, "ncclBroadcast");
     LOAD(AllGather, "ncclAllGather");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
     LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
     api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Broadcast && api.AllGather && api.GetErrorString;
@@ -75,6 +79,10 @@ NcclApi& nccl()
             return HR_ERR_NCCL;                                                                                 \
         }                                                                                                       \
     } while (0)
+
+// How the final-output gather moves the bands: 0 = one ncclBroadcast per band, 1 = point-to-point (every rank sends its band to
+// each peer and receives theirs: 7 independent NVSwitch transfers per rank instead of 8 serial broadcast rings).  hr_debug_set key 11.
+int g_hr_gather_impl = 1;
 
 void hr_band(const hr_ctx* ctx, int H, int* b0, int* b1)
 {
@@ -112,8 +120,16 @@ int hr_shard_exchange(hr_pass* p, const ExchangeItem* items, int n, cudaStream_t
             if (items[i].div > 1) { rb /= items[i].div; re = (re + items[i].div - 1) / items[i].div; }
             if (last_band || re > items[i].rows) re = items[i].rows;
             if (re <= rb) continue;
-            char* p = static_cast<char*>(items[i].base) + (size_t)rb * items[i].row_bytes;
-            HR_NCCL(ctx, N.Broadcast(p, p, (size_t)(re - rb) * items[i].row_bytes, ncclUint8, r, (ncclComm_t)ctx->nccl_comm, st));
+            char*        p     = static_cast<char*>(items[i].base) + (size_t)rb * items[i].row_bytes;
+            const size_t bytes = (size_t)(re - rb) * items[i].row_bytes;
+            if (g_hr_gather_impl == 1 && N.Send && N.Recv)
+            {
+                if (r != ctx->rank) HR_NCCL(ctx, N.Recv(p, bytes, ncclUint8, r, (ncclComm_t)ctx->nccl_comm, st));
+                else
+                    for (int q = 0; q < ctx->world; q++)
+                        if (q != ctx->rank) HR_NCCL(ctx, N.Send(p, bytes, ncclUint8, q, (ncclComm_t)ctx->nccl_comm, st));
+            }
+            else HR_NCCL(ctx, N.Broadcast(p, p, bytes, ncclUint8, r, (ncclComm_t)ctx->nccl_comm, st));
         }
     HR_NCCL(ctx, N.GroupEnd());
     HR_CUDA(ctx, cudaEventRecord(p->ev_done, st));

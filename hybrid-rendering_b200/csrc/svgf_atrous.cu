@@ -204,8 +204,7 @@ void launch_shadows_atrous(const GBufLevelDev& g, const __half2* in, const uint8
     uint32_t*       o32 = reinterpret_cast<uint32_t*>(out);
     const bool tiled_ok = g_hr_atrous_impl != 0 && radius == 1 && (step == 1 || step == 2 || step == 4 || step == 8);
     if (g_hr_atrous_impl == 3 && launch_shadows_atrous_v3(g, i32, tile_flags, radius, step, phi_vis, phi_n, sigma_z, power, o32, row0, row1, st)) return;
-    if (false) {}
-    else if (tiled_ok)
+    if (tiled_ok)
     {
         switch (step)
         {
