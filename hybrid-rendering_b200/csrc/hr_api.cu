@@ -272,6 +272,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     ALLOC(sc->d_node_aabb, ni * 6 * sizeof(float));
     ALLOC(sc->d_flags, ni * sizeof(int));
     ALLOC(sc->d_nodes, ni * 4 * sizeof(float4));
+    ALLOC(sc->d_wnodes, ni * 8 * sizeof(float4));
     ALLOC(sc->d_tris, n * 3 * sizeof(float4));
     if (n_materials && materials)
     {
@@ -329,7 +330,7 @@ int hr_scene_destroy(hr_scene* sc)
     if (!sc) return HR_ERR_INVALID_ARG;
     if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
     void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
-                     sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_tris,
+                     sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_wnodes, sc->d_tris,
                      sc->d_materials, sc->d_sort_tmp, sc->d_ploc };
     for (void* p : ptrs) cudaFree(p);
     delete sc;

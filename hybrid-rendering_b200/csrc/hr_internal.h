@@ -37,6 +37,7 @@ struct GBufLevelDev {          // one mip of one G-buffer slot
 struct BvhDev {                // traversal view of hr_scene
     const float4* nodes;       // 4 x float4 per node (see bvh_build.cu)
     const float4* tris;        // 3 x float4 per triangle in leaf order: (v0,prim) (e1,0) (e2,0)
+    const float4* wnodes;      // 4-wide nodes, 8 x float4 each, indexed like `nodes` (bvh_build.cu k_widen); per-lane traversal
     int           root_is_valid;
 };
 
@@ -135,6 +136,7 @@ struct hr_scene {
     size_t    ploc_bytes = 0;
     // outputs
     float4*   d_nodes = nullptr;     // n_nodes*4
+    float4*   d_wnodes = nullptr;    // n_nodes*8: 4-wide nodes (k_widen)
     float4*   d_tris  = nullptr;     // n*3
     // shading data (reflections / ddgi hit shading)
     float4*   d_vnormals = nullptr;  // n*3 world-space vertex normals in primitive order
