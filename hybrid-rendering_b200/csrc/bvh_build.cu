@@ -288,6 +288,18 @@ __global__ void k_widen(int n_nodes, const float4* __restrict__ nodes, float4* _
     w[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+// Height of the binary tree: every leaf counts the edges to the root (both builders keep parent[], leaves at n-1+k, root -1).
+// The traversal stacks are sized for HR_BVH_MAX_DEPTH; hr_scene_build / hr_scene_rebuild refuse a deeper tree.
+__global__ void k_depth(int n, const int* __restrict__ parent, int* __restrict__ depth)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int d = 0;
+    for (int cur = n - 1 + k; d < (1 << 20) && parent[cur] >= 0; cur = parent[cur]) d++;
+    d = __reduce_max_sync(__activemask(), d);
+    if ((threadIdx.x & 31) == __ffs(__activemask()) - 1) atomicMax(depth, d);
+}
+
 __global__ void k_pack_tris(const float* __restrict__ verts, const uint32_t* __restrict__ sorted_prim, uint32_t n, float4* __restrict__ out)
 {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -532,12 +544,15 @@ int hr_bvh_build(hr_scene* sc, cudaStream_t st)
             ctx->launches += 2;
         }
         k_pack_nodes<<<gi, T, 0, st>>>((int)n, sc->d_children, sc->d_ranges, sc->d_tri_aabb, prim_order, sc->d_node_aabb, sc->d_bounds_i, sc->d_nodes);
+        HR_CUDA(ctx, cudaMemsetAsync(sc->d_depth, 0, sizeof(int), st));
+        k_depth<<<gb, T, 0, st>>>((int)n, sc->d_parent, sc->d_depth);
         sc->n_nodes = n - 1;
-        ctx->launches += 1;
+        ctx->launches += 2;
     }
     else
     {
         k_pack_tiny<<<1, 1, 0, st>>>((int)n, sc->d_bounds_i, sc->d_nodes);
+        HR_CUDA(ctx, cudaMemsetAsync(sc->d_depth, 0, sizeof(int), st));
         sc->n_nodes = 1;
         ctx->launches += 1;
     }

@@ -212,6 +212,8 @@ int hr_bluenoise_set_slot(hr_ctx* ctx, int slot, const uint8_t* sr)
 // ---------------------------------------------------------------------------------------------------------------
 // Scene
 // ---------------------------------------------------------------------------------------------------------------
+static int scene_check_depth(hr_scene* sc);
+
 int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, const uint32_t* indices, size_t n_indices, const hr_instance* instances,
                    size_t n_instances, const hr_material* materials, size_t n_materials, hr_scene** out)
 {
@@ -273,6 +275,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     ALLOC(sc->d_flags, ni * sizeof(int));
     ALLOC(sc->d_nodes, ni * 4 * sizeof(float4));
     ALLOC(sc->d_wnodes, ni * 8 * sizeof(float4));
+    ALLOC(sc->d_depth, sizeof(int));
     ALLOC(sc->d_tris, n * 3 * sizeof(float4));
     if (n_materials && materials)
     {
@@ -288,6 +291,8 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     int rc = hr_scene_rebuild(sc, ctx->build_stream);
     if (rc != HR_OK) { hr_scene_destroy(sc); return rc; }
     HR_CUDA(ctx, cudaStreamSynchronize(ctx->build_stream));
+    rc = scene_check_depth(sc);
+    if (rc != HR_OK) { hr_scene_destroy(sc); return rc; }
     // bounds for info
     int bi[6];
     HR_CUDA(ctx, cudaMemcpy(bi, sc->d_bounds_i, sizeof(bi), cudaMemcpyDeviceToHost));
@@ -300,6 +305,19 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     }
     *out = sc;
     if (!ctx->scene) ctx->scene = sc;
+    return HR_OK;
+}
+
+// The binary walks push at most one pending sibling per level, so their stacks (STACK_SIZE = HR_BVH_MAX_DEPTH + 1 entries, one of
+// them the sentinel) cannot overflow on a tree of height <= HR_BVH_MAX_DEPTH.  A deeper tree is refused here instead of being
+// traversed with dropped pushes.  Blocking read of one int: called where the host waits anyway.
+static int scene_check_depth(hr_scene* sc)
+{
+    hr_ctx* ctx = sc->ctx;
+    int     d   = 0;
+    HR_CUDA(ctx, cudaMemcpy(&d, sc->d_depth, sizeof(int), cudaMemcpyDeviceToHost));
+    sc->info.depth = (uint32_t)d;
+    HR_REQUIRE(ctx, d <= HR_BVH_MAX_DEPTH, HR_ERR_UNSUPPORTED, "scene: the BVH is deeper than the traversal stack (HR_BVH_MAX_DEPTH)");
     return HR_OK;
 }
 
@@ -319,6 +337,8 @@ int hr_scene_rebuild(hr_scene* sc, void* stream)
         cudaEventElapsedTime(&sc->info.build_ms, e0, e1);
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+        rc = scene_check_depth(sc); // the host has just waited for the build anyway
+        if (rc != HR_OK) return rc;
     }
     sc->info.n_triangles = sc->n_tris;
     sc->info.n_nodes     = sc->n_nodes;
@@ -330,7 +350,7 @@ int hr_scene_destroy(hr_scene* sc)
     if (!sc) return HR_ERR_INVALID_ARG;
     if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
     void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
-                     sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_wnodes, sc->d_tris,
+                     sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_wnodes, sc->d_depth, sc->d_tris,
                      sc->d_materials, sc->d_sort_tmp, sc->d_ploc };
     for (void* p : ptrs) cudaFree(p);
     delete sc;

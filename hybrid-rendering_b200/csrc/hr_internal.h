@@ -137,6 +137,7 @@ struct hr_scene {
     // outputs
     float4*   d_nodes = nullptr;     // n_nodes*4
     float4*   d_wnodes = nullptr;    // n_nodes*8: 4-wide nodes (k_widen)
+    int*      d_depth = nullptr;     // height of the binary tree (k_depth)
     float4*   d_tris  = nullptr;     // n*3
     // shading data (reflections / ddgi hit shading)
     float4*   d_vnormals = nullptr;  // n*3 world-space vertex normals in primitive order

@@ -52,7 +52,7 @@ class hr_instance(C.Structure):
 
 class hr_scene_info(C.Structure):
     _fields_ = [("n_triangles", C.c_uint64), ("n_nodes", C.c_uint64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
-                ("build_ms", C.c_float)]
+                ("build_ms", C.c_float), ("depth", C.c_uint32)]
 
 
 class hr_gbuffer_desc(C.Structure):

@@ -156,7 +156,9 @@ typedef struct hr_scene_info {
     float    bounds_min[3];
     float    bounds_max[3];
     float    build_ms;
+    uint32_t depth;        /* height of the binary tree (edges root -> deepest triangle); the traversal stacks hold HR_BVH_MAX_DEPTH pending nodes */
 } hr_scene_info;
+#define HR_BVH_MAX_DEPTH 63 /* a deeper tree is refused by hr_scene_build / hr_scene_rebuild (HR_ERR_UNSUPPORTED), never traversed lossily */
 HR_API int hr_scene_get_info(hr_scene* scene, hr_scene_info* out);
 /* Re-run only the device build (the reference rebuilds its TLAS every frame, src/main.cpp:74). */
 HR_API int hr_scene_rebuild(hr_scene* scene, void* stream);

@@ -26,7 +26,10 @@ def test_variant_masks_bit_exact(scene_kind, tris, W, H, cam, dbg_key, dbg_val, 
     try:
         ctx.lib.hr_debug_set(dbg_key, dbg_val)
         ctx.set_bluenoise(*bn)
-        ctx.build_scene(sc)
+        scene = ctx.build_scene(sc)
+        info = ctx.scene_info(scene)
+        assert 1 <= info.depth <= 63, "tree height is reported and within the traversal stack (HR_BVH_MAX_DEPTH)"
+        assert info.depth >= int(np.ceil(np.log2(max(info.n_triangles, 2) / 4.0))) - 1
         ctx.gbuffer_create(W, H)
         sh, ao = pyhr.Pass(ctx, "shadows", W, H, 0), pyhr.Pass(ctx, "ao", W, H, 0)
         sh.params.denoise = ao.params.denoise = 0
