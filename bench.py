@@ -355,7 +355,7 @@ def main():
         sc = gsc = pyhr.SynthScene(pyhr.SCENE_ARCADE, cfg["tris"])
         cam, tgt = CAM_POS, CAM_TGT
     ctx = pyhr.Context(local_rank)
-    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7), ("HR_REFL_ATROUS_MINB", 8), ("HR_SHADOW_PACKET", 9), ("HR_REFL_TRACE_MINB", 10), ("HR_GATHER_IMPL", 11)):
+    for env, key in (("HR_ATROUS_IMPL", 1), ("HR_TRACE_IMPL", 2), ("HR_BVH_QUALITY", 3), ("HR_FORCE_SHARED_RT", 4), ("HR_ATROUS_ROWS", 5), ("HR_REFL_ATROUS_IMPL", 6), ("HR_REFL_TRACE_IMPL", 7), ("HR_REFL_ATROUS_MINB", 8), ("HR_SHADOW_PACKET", 9), ("HR_REFL_TRACE_MINB", 10), ("HR_GATHER_IMPL", 11), ("HR_FORCE_PEER_TEMPORAL", 12)):
         if os.environ.get(env):
             ctx.lib.hr_debug_set(key, int(os.environ[env]))
     ctx.set_bluenoise(*pyhr.blue_noise())
@@ -438,7 +438,7 @@ def main():
         gather(False)
         for _ in range(3):
             step_resident()
-        r_dist = timed(step_resident, args.steps)
+        r_dist = timed(step_resident, args.steps, profile=True)
         gather(True)
 
     # ---- outputs / staging for the host legs -----------------------------------------------------------------------------------------
@@ -628,9 +628,13 @@ def main():
     busy = torch.tensor([sum(stage_sum.values()), sum(v.get("Ray Trace", 0.0) for v in r_val["stages"].values()),
                          sum(sum(x for n, x in v.items() if "Wait" in n) for v in r_val["stages"].values())], dtype=torch.float64, device="cuda")
     busy_all = [busy.clone() for _ in range(world)]
+    rank_stages = None
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_gather(busy_all, busy)
+        # per-rank stage times of the gathered and of the distributed leg (which rank waits for whom)
+        rank_stages = [None] * world
+        dist.all_gather_object(rank_stages, {"gathered": r_val["stages"], "distributed": r_dist["stages"] if r_dist else None})
     ms_val, ms_e2e, ms_dist, ms_pan = [float(x) for x in t]
 
     if rank == 0:
@@ -672,6 +676,8 @@ def main():
         if world > 1:
             line["value_gathered"] = fps
             line["value_distributed"] = args.steps / (ms_dist / 1e3)
+            line["rank_stages_ms"] = [{leg: ({pn: {k: round(v, 4) for k, v in st.items()} for pn, st in d.items()} if d else None) for leg, d in rs.items()}
+                                      for rs in rank_stages]
             line["parity_crc_ok"] = bool(parity and parity["ranks_agree"] and parity["equals_single_gpu"])
             line["parity"] = parity
         if "pan" in extras:

@@ -21,6 +21,7 @@ extern int         g_hr_refl_atrous_minb;
 extern int         g_hr_shadow_packet;
 extern int         g_hr_refl_trace_minb;
 extern int         g_hr_gather_impl;
+extern int         g_hr_force_peer_temporal;
 
 void hr_set_error(hr_ctx* ctx, const char* fmt, ...)
 {
@@ -178,6 +179,7 @@ int hr_debug_set(int key, int value)
     if (key == 9) { g_hr_shadow_packet = value; return HR_OK; }
     if (key == 10) { g_hr_refl_trace_minb = value; return HR_OK; }
     if (key == 11) { g_hr_gather_impl = value; return HR_OK; }
+    if (key == 12) { g_hr_force_peer_temporal = value; return HR_OK; }
     return HR_ERR_INVALID_ARG;
 }
 

@@ -50,7 +50,7 @@ __device__ __forceinline__ void count_rays(unsigned long long* ctr, int kind, ui
 //   1  all three 128-bit loads of a triangle issued up front (volatile asm: not sunk, not reordered)
 //   2  mode 1 + the next triangle of the leaf is fetched while the current one is tested (one exposed round trip per leaf)
 #ifndef TRV_TRI_MODE
-#define TRV_TRI_MODE 2
+#define TRV_TRI_MODE 0
 #endif
 struct Tri { float4 A, B, C; };
 __device__ __forceinline__ Tri load_tri(const float4* __restrict__ tris, int idx)
