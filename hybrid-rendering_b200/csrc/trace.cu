@@ -430,8 +430,10 @@ static inline dim3 mask_grid(int W, int mrow0, int mrow1) { return dim3(((W + 7)
 // Measured at 4K (profiles/README.md): shadows 585 us vs 712 us, AO 223 us vs 333 us — on this workload the 8x4 blocks are
 // almost uniformly active (coherent surfaces), so compaction buys little and the queue / refill bookkeeping costs more.
 int g_hr_trace_impl = 0;
-// hr_debug_set key 9: 1 (default) = packet traversal for the shadow rays of K1 (single-GPU / band-local path), 0 = per-lane traversal
-int g_hr_shadow_packet = 1;
+// hr_debug_set key 9: 1 = packet traversal for the shadow rays of K1 (single-GPU / band-local path), 0 (default) = per-lane traversal.
+// Measured on config 2 (1080p, profiles/README.md r2j): per-lane 147 us vs packet 332 us — the cone of a soft-shadow ray bundle makes
+// the union of the lanes' paths much longer than any single path, and every lane tests every triangle of every visited leaf.
+int g_hr_shadow_packet = 0;
 
 static const size_t kPtSmem = sizeof(QRay) * PT_WARPS * PT_QUEUE + sizeof(int) * SM_STACK * PT_WARPS * 32 + sizeof(uint32_t) * PT_WARPS * 4;
 
