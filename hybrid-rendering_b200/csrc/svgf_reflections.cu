@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t hist_ld32(const void* const* tab, const Hist
 // pixel then reads its six window sums.  ncu (r2a) had this kernel at 1 733 instructions per pixel, 72 % issue-active.
 // hp.img = last frame's temporal output (or prev_image), hp.aux = last frame's moments, of the rank that owns the row (PEER)
 template <bool PEER>
-__global__ void __launch_bounds__(256) k_refl_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint2* __restrict__ input, const HistPeers hp, FrameConsts fc,
+__global__ void __launch_bounds__(256, 5) k_refl_temporal(GBufLevelDev cur, GBufLevelDev prev, const uint2* __restrict__ input, const HistPeers hp, FrameConsts fc,
                                                         ReflTemporalParams P, uint2* __restrict__ out, uint2* __restrict__ mom_out, uint8_t* __restrict__ tile_flags)
 {
     __shared__ float    s_c[3][24][49];  // row pitch 49: the 144 row walkers of a phase hit 32 different banks

@@ -437,7 +437,9 @@ HR_API int hr_pass_stage_times(hr_pass* pass, const char** names, float* ms, int
  * key 5 = a-trous row-interleaved tiles: 1 = step 8 only (default), 2 = steps 4 and 8, 0 = dense tiles for every step; key 6 = reflections
  * a-trous (0 scalar kernel, 1 packed fp32x2 dense tiles, 2 = packed + row-interleaved tiles for steps >= 8, 3 = 2 + TMA-staged
  * persistent kernel for step 1 = default, 4 = TMA for steps 1, 2, 4); key 7 = reflections ray trace (0 fused kernel = default, 1 wavefront:
- * persistent closest-hit traversal with ray refill + compacted hit shading); key 8 = reflections a-trous register tuning (CTAs / SM).  None of them changes a result bit
+ * persistent closest-hit traversal with ray refill + compacted hit shading); key 8 = reflections a-trous register tuning (CTAs / SM);
+ * key 9 = shadow rays of K1: 0 per-lane traversal = default, 1 packet traversal; key 10 = fused reflections ray trace register tuning (CTAs / SM);
+ * key 11 = final-output gather: 1 point-to-point = default, 0 per-band broadcasts; key 12 = run the peer-history K14 on one GPU (overhead A/B).  None of them changes a result bit
  * of the visibility masks; keys 1 and 5 select kernels whose outputs agree to the last fp16 bit on the test scenes. */
 HR_API int hr_debug_set(int key, int value);
 /* Number of kernels this library launched since the context was created (bench.py gpu_launches). */
