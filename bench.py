@@ -506,9 +506,14 @@ def main():
     extras = {}
     if not args.no_extras and not single_tri:
         # ---- pan: 40 frames of lateral motion, G-buffer produced on the device every frame --------------------------------------------
+        sharded_gbuf = world > 1 and cfg["passes"] == ["reflections"] and cfg.get("refl_scale", 1) == 0
+
         def step_pan():
             f = next_frame(PAN_STEP)
-            ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream)
+            if sharded_gbuf:  # as in the e2e leg: only the rows this rank's stages read (the pan is lateral: reprojection stays within the 64-row halo)
+                ctx.gbuffer_render_sharded(f.ping_pong, f, 64, stream)
+            else:
+                ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream)
             rig.render(f, stream)
 
         gather(True)
@@ -520,7 +525,10 @@ def main():
         barrier()
         ge0.record()
         for _ in range(10):
-            ctx.gbuffer_render(state["f"].ping_pong, state["f"], 0, 0, stream)
+            if sharded_gbuf:
+                ctx.gbuffer_render_sharded(state["f"].ping_pong, state["f"], 64, stream)
+            else:
+                ctx.gbuffer_render(state["f"].ping_pong, state["f"], 0, 0, stream)
         ge1.record()
         torch.cuda.synchronize()
         extras["pan"] = {"frames": 40, "step_world_units": PAN_STEP, "ms": r_pan["ms"], "gbuffer_ms_per_frame": ge0.elapsed_time(ge1) / 10.0, "stages": r_pan["stages"]}
@@ -683,7 +691,7 @@ def main():
         if "pan" in extras:
             line["pan"] = {"value": 40 / (ms_pan / 1e3), "unit": "frames/s", "frames": 40, "world_units_per_frame": PAN_STEP,
                            "gbuffer_ms_per_frame": extras["pan"]["gbuffer_ms_per_frame"], "stages_ms": extras["pan"]["stages"],
-                           "note": "includes hr_gbuffer_render every frame"}
+                           "note": "includes the G-buffer ray cast every frame (N > 1: hr_gbuffer_render_sharded, this rank's rows only)"}
         if k5_dense:
             line["k5_dense"] = k5_dense
         if not args.no_cpu_baseline and world == 1:
