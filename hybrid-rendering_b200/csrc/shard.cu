@@ -316,11 +316,13 @@ __global__ void k_peer_wait(const int* __restrict__ ticks, int world, int self, 
 
 // Reflections (interleaved cooperative ray trace): block b copies this rank's chunk c = self + b * world (8 image rows of RGBA16F
 // texels) to every rank whose denoise stages read those rows; the last block to finish publishes the ray-trace tick.
+#define PUSH_SPLIT 4
 struct RowPtrs { uint2* p[HR_MAX_RANKS]; };
 struct NeedRows { int r0[HR_MAX_RANKS], r1[HR_MAX_RANKS]; };
 __global__ void __launch_bounds__(256) k_rt_push_chunks(RowPtrs imgs, NeedRows need, TickPtrs ticks, int* __restrict__ ctl, int world, int self, int W, int H, int tick)
 {
-    const int c = self + (int)blockIdx.x * world, r0 = c * 8, r1 = min(r0 + 8, H);
+    // PUSH_SPLIT blocks share one chunk (a chunk is 8 rows x W texels = 245 KB at 4K: one block would walk it in 60 dependent round trips)
+    const int c = self + ((int)blockIdx.x / PUSH_SPLIT) * world, part = (int)blockIdx.x % PUSH_SPLIT, r0 = c * 8, r1 = min(r0 + 8, H);
     if (r0 < H)
         for (int q = 0; q < world; q++)
         {
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(256) k_rt_push_chunks(RowPtrs imgs, NeedRows n
             const size_t first = (size_t)a * W, n = (size_t)(b - a) * W; // W is even: 16-byte pairs
             const uint4* s4 = reinterpret_cast<const uint4*>(imgs.p[self] + first);
             uint4*       d4 = reinterpret_cast<uint4*>(imgs.p[q] + first);
-            for (size_t i = threadIdx.x; i < n / 2; i += blockDim.x) d4[i] = s4[i];
+            for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < n / 2; i += (size_t)PUSH_SPLIT * blockDim.x) d4[i] = s4[i];
         }
     __threadfence_system();
     __syncthreads();
@@ -502,7 +504,7 @@ int hr_refl_push_chunks(hr_pass* p, int parity, int tick, const int* need0, cons
         t.p[r]   = p->peer_ticks[r];
     }
     const int n_chunks = (p->H + 7) / 8, mine = (n_chunks - ctx->rank + ctx->world - 1) / ctx->world;
-    k_rt_push_chunks<<<mine > 0 ? mine : 1, 256, 0, st>>>(im, nd, t, p->rt_bounds, ctx->world, ctx->rank, p->W, p->H, tick);
+    k_rt_push_chunks<<<(mine > 0 ? mine : 1) * PUSH_SPLIT, 256, 0, st>>>(im, nd, t, p->rt_bounds, ctx->world, ctx->rank, p->W, p->H, tick);
     ctx->launches++;
     return HR_OK;
 }

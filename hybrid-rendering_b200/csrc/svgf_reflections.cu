@@ -40,7 +40,7 @@ __device__ __forceinline__ bool tap_valid(const Tap& t, float3 cur_pos, float3 c
     return nd * nd > 0.1f;
 }
 
-struct ReflTemporalParams { float alpha, moments_alpha; int approximate_with_ddgi; int row0, row1; };
+struct ReflTemporalParams { float alpha, moments_alpha; int approximate_with_ddgi; int row0, row1; int rot; }; // rot: the last `rot` tile rows are scheduled first
 
 // ---- history fetches through the owner table (HistPeers, hr_internal.h; see svgf_temporal.cu) ----
 __device__ __forceinline__ int owner_of(const HistPeers& hp, int row)
@@ -94,7 +94,10 @@ __global__ void __launch_bounds__(256, 5) k_refl_temporal(GBufLevelDev cur, GBuf
     __shared__ float    s_v[6][8][32];   // 17x17 window sums per pixel of the tile
     __shared__ uint32_t s_flags;
     const int W = cur.W, H = cur.H;
-    const int x0 = blockIdx.x * 32, y0 = P.row0 + blockIdx.y * 8;
+    // PEER: the bottom halo rows read their history across NVLink (slow taps); they are scheduled first so that the bulk of the band
+    // covers their latency instead of leaving it as the kernel's tail
+    const int by = (int)blockIdx.y < P.rot ? (int)gridDim.y - P.rot + (int)blockIdx.y : (int)blockIdx.y - P.rot;
+    const int x0 = blockIdx.x * 32, y0 = P.row0 + by * 8;
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_flags = 0;
     for (int i = threadIdx.x; i < 48 * 24; i += 256)
@@ -425,8 +428,11 @@ void launch_reflections_temporal(const GBufLevelDev& cur, const GBufLevelDev& pr
                                  float moments_alpha, int approximate_with_ddgi, void* out, void* mom_out, uint8_t* tile_flags, int row0, int row1, cudaStream_t st)
 {
     if (row1 <= row0) return;
-    ReflTemporalParams P { alpha, moments_alpha, approximate_with_ddgi, row0, row1 };
     dim3               grid((cur.W + 31) / 32, (row1 - row0 + 7) / 8);
+    int                rot = 0;
+    if (hist.world > 1 && hist.self < hist.world - 1) rot = (row1 - hist.band_end[hist.self] + 7) / 8; // tile rows below this rank's band
+    if (rot < 0 || rot >= (int)grid.y) rot = 0;
+    ReflTemporalParams P { alpha, moments_alpha, approximate_with_ddgi, row0, row1, rot };
     if (hist.world > 1 || g_hr_force_peer_temporal) k_refl_temporal<true><<<grid, 256, 0, st>>>(cur, prev, (const uint2*)input, hist, fc, P, (uint2*)out, (uint2*)mom_out, tile_flags);
     else k_refl_temporal<false><<<grid, 256, 0, st>>>(cur, prev, (const uint2*)input, hist, fc, P, (uint2*)out, (uint2*)mom_out, tile_flags);
 }
