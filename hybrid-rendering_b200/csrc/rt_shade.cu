@@ -613,9 +613,10 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
 // both forms) is what costs, and the 56 KB queue / stack footprint per CTA takes L1 away from the BVH (hit rate 40 % vs 64 %).
 // hr_debug_set key 7.
 int g_hr_refl_trace_impl = 0;
-// hr_debug_set key 10: resident 2-warp CTAs per SM the fused kernel's registers are tuned for (16 = 64 registers = default; 14 = 72; 12 = 80;
-// 18 = 56; 20 = 48).  Config 3 at 4K (profiles/README.md r2l): 16 -> 2.211 ms, 14 -> 2.366 ms, 12 -> 2.527 ms.
-int g_hr_refl_trace_minb = 16;
+// hr_debug_set key 10: resident 2-warp CTAs per SM the fused kernel's registers are tuned for (18 = 56 registers = default; 20 = 48;
+// 16 = 64; 14 = 72; 12 = 80).  Config 3 at 4K (profiles/README.md r2l / r2m): 12 -> 2.527 ms, 14 -> 2.366, 16 -> 2.208, 18 -> 2.133,
+// 20 -> 2.123 (172 bytes of spills): the kernel is latency-bound, resident warps buy more than registers.
+int g_hr_refl_trace_minb = 18;
 
 void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, const FrameConsts& fc, const hr_ddgi_uniforms* d, const void* irr, const void* depth,
                                   float bias, float trim, int sample_gi, int approximate_with_ddgi, float gi_intensity, float rough_ddgi_intensity, const float* sky3,
@@ -657,7 +658,7 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     if (spp > 1) k_reflections_ray_trace<true, 8><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
     else if (g_hr_refl_trace_minb == 14) k_reflections_ray_trace<false, 14><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
     else if (g_hr_refl_trace_minb == 12) k_reflections_ray_trace<false, 12><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else if (g_hr_refl_trace_minb == 18) k_reflections_ray_trace<false, 18><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else if (g_hr_refl_trace_minb == 16) k_reflections_ray_trace<false, 16><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
     else if (g_hr_refl_trace_minb == 20) k_reflections_ray_trace<false, 20><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else k_reflections_ray_trace<false, 16><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    else k_reflections_ray_trace<false, 18><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
 }
