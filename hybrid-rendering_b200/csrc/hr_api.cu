@@ -677,6 +677,26 @@ static int atrous_halo_rows(int radius, int iterations)
     return round_up8((int)(h > (1 << 20) ? (1 << 20) : h) + 1);
 }
 
+// The plan above as a pure query (no context, no GPU): which rows beyond its band a sharded rank computes.  Tests restate the plan on
+// the CPU oracle with these numbers (tests/test_sharding_cpu.py) and the render functions use the same two helpers.
+int hr_shard_halo_rows(int pass_kind, int radius, int filter_iterations, int blur_radius, int* denoise_halo, int* ray_trace_halo)
+{
+    if (!denoise_halo || !ray_trace_halo || radius < 0 || filter_iterations < 0 || blur_radius < 0) return HR_ERR_INVALID_ARG;
+    switch (pass_kind)
+    {
+        case HR_PASS_KIND_SHADOWS:
+        case HR_PASS_KIND_REFLECTIONS:
+            *denoise_halo   = atrous_halo_rows(radius, filter_iterations);
+            *ray_trace_halo = *denoise_halo + 8; // 17x17 statistics of the temporal stage
+            return HR_OK;
+        case HR_PASS_KIND_AO:
+            *denoise_halo   = 8 + round_up8(blur_radius); // temporal / horizontal blur rows; the vertical blur erodes blur_radius of them
+            *ray_trace_halo = *denoise_halo + 8;
+            return HR_OK;
+        default: return HR_ERR_INVALID_ARG;
+    }
+}
+
 static int check_render_ready(hr_pass* p, const hr_frame* f, const void* params, bool needs_scene)
 {
     hr_ctx* ctx = p ? p->ctx : nullptr;

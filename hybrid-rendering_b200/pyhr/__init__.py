@@ -93,7 +93,7 @@ ABI_SYMBOLS = [
     "hr_gbuffer_stage_upload", "hr_gbuffer_commit_staged", "hr_pass_download_async", "hr_pass_download_rows_async",
     "hr_gbuffer_copy_from_device", "hr_gbuffer_bind_device", "hr_gbuffer_download", "hr_shadows_default_params", "hr_shadows_create",
     "hr_shadows_render", "hr_ao_default_params", "hr_ao_create", "hr_ao_render", "hr_pass_output", "hr_pass_download", "hr_pass_reset_history",
-    "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_link_local",
+    "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_halo_rows", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
     "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render", "hr_bluenoise_set_slot",
 ]
@@ -151,6 +151,16 @@ def shard_unique_id() -> bytes:
     if rc != 0:
         raise HrError(f"hr_shard_unique_id failed ({rc}): {load_product().hr_last_error(None).decode()}")
     return buf.raw
+
+
+def shard_halo_rows(kind, radius=1, filter_iterations=4, blur_radius=5):
+    """(denoise_halo, ray_trace_halo) of a sharded rank for the given pass parameters (hr_shard_halo_rows; pure, no GPU)"""
+    k = {"shadows": 1, "ao": 2, "reflections": 3}[kind]
+    a, b = C.c_int(), C.c_int()
+    rc = load_product().hr_shard_halo_rows(k, int(radius), int(filter_iterations), int(blur_radius), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise ValueError(f"hr_shard_halo_rows: {rc}")
+    return a.value, b.value
 
 
 def shard_rows(H, rank, world):

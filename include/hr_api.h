@@ -481,6 +481,13 @@ HR_API int hr_shard_shutdown(hr_ctx* ctx);
  * valid on the rank's own band only.  The FINAL output (which = 100) of every pass is all-gathered after each render
  * unless this is switched off (gather_final_output = 0: every rank keeps just its band of the frame). */
 HR_API int hr_shard_set_gather(hr_ctx* ctx, int gather_final_output);
+/* Pure query (no context, no GPU): the rows beyond its band a sharded rank recomputes, derived from the pass parameters — the
+ * denoise stages (temporal + a-trous chain: sum(radius << i) + 1 rounded up to 8; AO: 8 + blur_radius rounded up to 8) and the
+ * ray-trace output the temporal stage's 17x17 statistics read (8 more).  pass_kind: 1 shadows, 2 AO, 3 reflections. */
+#define HR_PASS_KIND_SHADOWS 1
+#define HR_PASS_KIND_AO 2
+#define HR_PASS_KIND_REFLECTIONS 3
+HR_API int hr_shard_halo_rows(int pass_kind, int radius, int filter_iterations, int blur_radius, int* denoise_halo, int* ray_trace_halo);
 /* Same-process peers (N ranks emulated on one GPU with hr_shard_config, or several GPUs driven by one process): declare
  * that rank `rank`'s band of this pass's history lives in `peer`.  Link every pass with every other rank's pass before
  * the first render, give every rank its own stream (the ranks wait for each other's ray masks inside a frame, so their

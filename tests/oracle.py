@@ -412,6 +412,12 @@ class ReflectionsOracle:
         self.upsample = np.zeros((H0, W0, 4), np.uint16) if scale else None
         self.first = True
         self.final = None
+        # sharding emulation (tests/test_sharding_cpu.py): band = (b0, b1) rows this rank owns, halos = (denoise, ray trace)
+        # rows beyond it that it recomputes (hr_shard_halo_rows); rt_chunks = (rank, world): this rank traces only the 8-row chunks
+        # c % world == rank and rt_exchange(image) must return the complete ray-trace image (what k_rt_push_chunks + the ticks do)
+        self.band, self.halos, self.rt_chunks, self.rt_exchange = None, (0, 0), None, None
+
+    _poison = ShadowsOracle._poison
 
     def render(self, ss: ShadingScene, cur: GBufMips, prev: GBufMips, frame, bn, ddgi: DDGIOracle = None):
         L, P, pp = lib(), self.params, frame.ping_pong
@@ -437,6 +443,15 @@ class ReflectionsOracle:
         else:
             L.orc_reflections_ray_trace(ss.h, C.byref(gc), C.byref(frame), P.bias, P.trim, sample_gi, approx, P.gi_intensity, P.rough_ddgi_intensity, p(sky), p(sobol), p(sr),
                                         up, irr, dep, p(self.rt))
+        if self.rt_chunks is not None:
+            rank, world = self.rt_chunks
+            rng = np.random.default_rng(4242 + rank)
+            for c in range((self.H + 7) // 8):
+                if c % world != rank:  # not traced by this rank
+                    rows = self.rt[c * 8:c * 8 + 8]
+                    rows[:] = rng.integers(0, 0x3C00, size=rows.shape, dtype=np.uint32).astype(np.uint16)
+            self.rt[:] = self.rt_exchange(self.rt)
+        self._poison(self.rt, self.halos[1] if P.denoise else 0)
         self.final = self.rt
         self.first = False
         if not P.denoise:
@@ -445,10 +460,13 @@ class ReflectionsOracle:
         L.orc_reflections_temporal(C.byref(gc), C.byref(gp), p(self.rt), p(hist), p(self.moments[1 - pp]), C.byref(frame), P.alpha, P.moments_alpha, approx,
                                    p(self.temporal[pp]), p(self.moments[pp]), p(self.tile_flags))
         self.cur_temporal, self.cur_moments = self.temporal[pp], self.moments[pp]
+        for a in (self.temporal[pp], self.moments[pp], self.tile_flags):
+            self._poison(a, self.halos[0], div=8 if a is self.tile_flags else 1)
         src, toggle = self.temporal[pp], 1
         for i in range(P.filter_iterations):
             dst = self.atrous[toggle]
             L.orc_reflections_atrous(C.byref(gc), p(src), p(self.tile_flags), P.radius, 1 << i, P.phi_color, P.phi_normal, P.sigma_depth, approx, p(dst))
+            self._poison(dst, self.halos[0])
             if P.blur_as_input and i == P.feedback_iteration:
                 self.prev_image[:] = dst
             src, toggle = dst, 1 - toggle
@@ -457,6 +475,7 @@ class ReflectionsOracle:
         if self.scale:
             g0 = cur.c(0)
             L.orc_upsample_vec4(C.byref(g0), C.byref(gc), p(src), p(self.upsample))
+            self._poison(self.upsample, 0, shift=self.scale)
             self.final = self.upsample
 
 

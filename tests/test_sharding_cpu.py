@@ -11,6 +11,7 @@ ray trace is split into arbitrary, frame-varying shares of mask rows that are ex
 re-trace), the denoise stages keep their band +- halo, and each rank keeps the temporal history of its own band only and
 fetches the peers' rows before the reprojection.
 """
+import ctypes as C
 import os
 import sys
 
@@ -177,11 +178,73 @@ def _worker_coop(rank, world, port, q):
         dist.destroy_process_group()
 
 
+RW, RH = 96, 160  # reflections plan: 20 tiles of 8 rows
+
+
+def _worker_refl(rank, world, port, q):
+    """Reflections, the production plan (hr_reflections_render): rank r traces the 8-row chunks c % world == r of the
+    whole image and the chunks are exchanged; temporal + a-trous run on band +- the halo hr_shard_halo_rows derives from the
+    parameters (here 3 and 5 iterations: 8 and 32 rows — not the default); the history (temporal output + moments) of a rank is
+    valid on its own band only and the peers' rows are fetched before the reprojection."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
+        ss = O.ShadingScene(sc, brute=True)
+        bn = pyhr.blue_noise()
+
+        def chunk_exchange(img):
+            out = img.copy()
+            for c in range((RH + 7) // 8):
+                t = torch.from_numpy(np.ascontiguousarray(img[c * 8:c * 8 + 8]).view(np.uint8).copy())
+                dist.broadcast(t, src=c % world)
+                out[c * 8:c * 8 + 8] = t.numpy().view(np.uint16).reshape(out[c * 8:c * 8 + 8].shape)
+            return out
+
+        for iters in (3, 5):
+            prm = pyhr.hr_reflections_params()
+            pyhr.load_product().hr_reflections_default_params(C.byref(prm))
+            prm.filter_iterations = iters
+            prm.sky_color[0], prm.sky_color[1], prm.sky_color[2] = 0.3, 0.4, 0.6
+            ref, o = O.ReflectionsOracle(RW, RH, 0, prm), O.ReflectionsOracle(RW, RH, 0, prm)
+            o.band = shard_rows(RH, rank, world)
+            o.halos = pyhr.shard_halo_rows("reflections", prm.radius, iters)
+            o.rt_chunks, o.rt_exchange = (rank, world), chunk_exchange
+            f, prev = None, O.zero_gbuf_mips(RW, RH)
+            for i in range(4):
+                dy = 0.0 if i < 2 else 0.4 * (i - 1)  # vertical motion: history taps cross the band borders
+                f = pyhr.make_frame((0.0, 14 + dy, 34), (0.0, 3 - dy, 0), RW, RH, prev=f, num_frames=i)
+                cur = O.GBufMips(pyhr.write_gbuffer(sc, f, RW, RH))
+                pp = f.ping_pong
+                ref.render(ss, cur, prev, f, bn)
+                if i > 0:  # peer history: rows owned by the other ranks come from them
+                    o.temporal[1 - pp][:] = _gather_bands(dist, o.temporal[1 - pp], RH, rank, world)
+                    o.moments[1 - pp][:] = _gather_bands(dist, o.moments[1 - pp], RH, rank, world)
+                o.render(ss, cur, prev, f, bn)
+                prev = cur
+                final = _gather_bands(dist, o.final, RH, rank, world)
+                b0, b1 = o.band
+                checks = (("gathered final", final, ref.final), ("temporal (own band)", o.temporal[pp][b0:b1], ref.temporal[pp][b0:b1]),
+                          ("moments (own band)", o.moments[pp][b0:b1], ref.moments[pp][b0:b1]))
+                for name, a, b in checks:
+                    if not np.array_equal(a, b):
+                        q.put(f"rank {rank} iterations {iters} frame {i}: {name} differs from the unsharded result")
+                        return
+                o._poison(o.temporal[pp], 0)  # a rank keeps the history of its own band only
+                o._poison(o.moments[pp], 0)
+        q.put("ok")
+    finally:
+        dist.destroy_process_group()
+
+
 def _run_world(worker, world):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000 + world + (17 if worker is _worker_coop else 0)
+    port = 29500 + os.getpid() % 2000 + world + (17 if worker is _worker_coop else 0) + (41 if worker is _worker_refl else 0)
     procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
     for p_ in procs:
         p_.start()
@@ -209,3 +272,22 @@ def test_sharded_oracle_gloo(world):
     for p_ in procs:
         p_.join(60)
     assert res == ["ok"] * world, res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reflections_chunks_and_param_halos_gloo(world):
+    assert _run_world(_worker_refl, world) == ["ok"] * world
+
+
+def test_halo_plan_query():
+    """hr_shard_halo_rows (pure, no GPU): the recompute halos follow from the parameters"""
+    assert pyhr.shard_halo_rows("shadows", 1, 4) == (16, 24)          # 1 + 2 + 4 + 8 + 1 = 16
+    assert pyhr.shard_halo_rows("reflections", 1, 5) == (32, 40)      # 31 + 1
+    assert pyhr.shard_halo_rows("shadows", 2, 4) == (32, 40)          # 2 * 15 + 1 = 31 -> 32
+    assert pyhr.shard_halo_rows("shadows", 1, 0) == (8, 16)           # the upsample's extra coarse row, rounded to a tile
+    assert pyhr.shard_halo_rows("ao", blur_radius=5) == (16, 24)
+    assert pyhr.shard_halo_rows("ao", blur_radius=12) == (24, 32)
+    for it in range(0, 9):
+        for rad in (1, 2):
+            d, r = pyhr.shard_halo_rows("shadows", rad, it)
+            assert d % 8 == 0 and d >= sum(rad << i for i in range(it)) + 1 and r == d + 8
