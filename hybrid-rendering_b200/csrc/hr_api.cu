@@ -794,7 +794,7 @@ int hr_shadows_render(hr_pass* p, const hr_frame* f, const hr_shadows_params* pr
         p->first = false;
     }
     // ray_trace (:972-1011).  Linked to peers: this rank traces its cost-balanced share of the WHOLE image and stores the
-    // mask words into every rank's mask image (no halo re-trace); otherwise its band +- 32 rows into its own image.
+    // mask words into every rank's mask image (no halo re-trace); otherwise its band +- (denoise halo + 8) rows into its own image.
     RtShare    rts;
     const bool shared_rt = spp == 1 && hr_rt_share(p, epoch & 1, &rts);
     uint32_t*  mask      = shared_rt ? p->mask_pp[epoch & 1] : p->mask;

@@ -2,8 +2,9 @@
 temporal history after every frame) reproduces the unsharded result exactly.
 
 Each rank runs the CPU oracle but trashes, after every stage, the rows a sharded GPU rank would NOT have computed
-(oracle._poison with the same halos the CUDA host code uses: ray trace +-32, temporal / a-trous +-16, AO vertical blur
-+-8); the bands are then all-gathered with torch.distributed (gloo) exactly like hr_shard_exchange does with NCCL.
+(oracle._poison with the halos the CUDA host code derives for the default parameters: ray trace +-24, temporal / a-trous
++-16, AO vertical blur +-8; test_reflections_chunks_and_param_halos_gloo takes them from hr_shard_halo_rows for non-default
+iteration counts); the bands are then all-gathered with torch.distributed (gloo) exactly like hr_shard_exchange does with NCCL.
 If a halo were too small, garbage would leak into a band and the comparison with the unsharded oracle would fail.
 
 test_cooperative_trace_and_distributed_history_gloo restates the production multi-GPU plan the same way: the
