@@ -1,7 +1,8 @@
 // hr_headless.cpp — headless frame loop in C++ on the host classes (the analogue of HybridRendering::update,
 // src/main.cpp:49-129): update_uniforms -> build_tlas -> GBuffer -> Shadows -> AO -> DDGI -> Reflections -> DeferredShading ->
 // end_frame, no window / swapchain / Vulkan: the G-buffer is ray cast on the device, the host only sends the per-frame constants.
-// Usage: hr_headless [width height frames tris]
+// Usage: hr_headless [width height frames tris [mesh.gltf|mesh.glb|mesh.obj]]   (a mesh file replaces the procedural arcade; it is drawn once
+// with an identity transform, like the single-instance scenes of src/common.cpp:340-534)
 #include "hybrid_rendering.h"
 #include <chrono>
 #include <cmath>
@@ -24,8 +25,24 @@ int main(int argc, char** argv)
         std::vector<uint16_t> lut(512 * 512 * 2);
         hrs_brdf_lut(64, lut.data());
         hr::check(common.ctx, hr_brdf_lut_set(common.ctx, lut.data()), "hr_brdf_lut_set");
-        hrs_scene* scene = hrs_scene_create(HRS_SCENE_ARCADE, tris, 7);
-        common.load_scene(scene);
+        hrs_scene* scene = nullptr;
+        if (argc > 5)
+        {
+            hra_mesh* mesh = nullptr;
+            if (hra_mesh_load(argv[5], &mesh) != HRA_OK) throw std::runtime_error(hra_last_error());
+            hra_scene*  as = hra_scene_create();
+            const float ident[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+            hra_scene_add_instance(as, mesh, ident);
+            hra_scene_finalize(as);
+            common.load_scene(as);
+            hra_scene_destroy(as);
+            hra_mesh_destroy(mesh);
+        }
+        else
+        {
+            scene = hrs_scene_create(HRS_SCENE_ARCADE, tris, 7);
+            common.load_scene(scene);
+        }
         hr::GBuffer              g_buffer(&common);
         hr::RayTracedShadows     shadows(&common, &g_buffer, hr::RAY_TRACE_SCALE_FULL_RES);
         hr::RayTracedAO          ao(&common, &g_buffer, hr::RAY_TRACE_SCALE_HALF_RES);
@@ -70,7 +87,7 @@ int main(int argc, char** argv)
             for (int c = 0; c < 3; c++) { const float v = __half2float(px[k + c]); finite = finite && std::isfinite(v); sum += v; }
         printf("frames=%d last frame %.3f ms (g-buffer + shadows + ao + ddgi + reflections + deferred); output %dx%d fmt %d mean %.5f finite %d\n", frames, gpu_ms, o.width,
                o.height, o.format, sum / (3.0 * o.width * o.height), finite ? 1 : 0);
-        hrs_scene_destroy(scene);
+        if (scene) hrs_scene_destroy(scene);
         if (!finite || !(sum > 0.0)) return 2;
     }
     catch (const std::exception& e)

@@ -11,6 +11,7 @@
 // not fail observably in the reference — here a failed launch throws as well.
 #pragma once
 #include "../../include/hr_api.h"
+#include "assets.h"
 #include "synth.h"
 #include <stdexcept>
 #include <string>
@@ -54,6 +55,26 @@ struct CommonResources {
         check(ctx, hr_scene_build(ctx, hrs_scene_vertices(s), nv, hrs_scene_indices(s), ni, hrs_scene_instances(s), nin, hrs_scene_materials(s), nm, &scene),
               "hr_scene_build");
         check(ctx, hr_scene_set_current(ctx, scene), "hr_scene_set_current");
+    }
+    // the same with meshes read from disk: dw::Mesh::load + RayTracedScene::create (common.cpp:340-534) = hra_mesh_load + hra_scene_* (assets.h)
+    void load_scene(const hra_scene* s)
+    {
+        uint64_t nv, ni, nin, nm;
+        hra_scene_counts(s, &nv, &ni, &nin, &nm);
+        if (scene) { hr_scene_destroy(scene); scene = nullptr; }
+        check(ctx, hr_scene_build(ctx, hra_scene_vertices(s), nv, hra_scene_indices(s), ni, hra_scene_instances(s), nin, hra_scene_materials(s), nm, &scene),
+              "hr_scene_build");
+        check(ctx, hr_scene_set_current(ctx, scene), "hr_scene_set_current");
+    }
+    // BlueNoise::BlueNoise (blue_noise.cpp:21-33): the Sobol' table and every scrambling / ranking table found in `dir`
+    void load_blue_noise(const char* dir)
+    {
+        std::string sobol(256 * 4, '\0'), sr(9ull * 128 * 128 * 4, '\0');
+        uint32_t    slots = 0;
+        if (hra_bluenoise_load(dir, (uint8_t*)&sobol[0], (uint8_t*)&sr[0], &slots) != HRA_OK) throw std::runtime_error(std::string("hra_bluenoise_load: ") + hra_last_error());
+        set_blue_noise((const uint8_t*)sobol.data(), (const uint8_t*)sr.data());
+        for (int s = 1; s < 9; s++)
+            if (slots & (1u << s)) check(ctx, hr_bluenoise_set_slot(ctx, s, (const uint8_t*)sr.data() + (size_t)s * 128 * 128 * 4), "hr_bluenoise_set_slot");
     }
     hr_scene* current_scene() { return scene; }
     // HybridRendering::update_uniforms (main.cpp:937-972) for a look-at camera
