@@ -610,6 +610,7 @@ static int texel_size(int fmt)
         case HR_FMT_RG16F: return 4;
         case HR_FMT_RGBA16F: return 8;
         case HR_FMT_R8_UINT: return 1;
+        case HR_FMT_RGBA8: return 4;
     }
     return 0;
 }
@@ -1308,3 +1309,4 @@ int hr_shard_config(hr_ctx* ctx, int rank, int world)
 } // extern "C"
 
 #include "hr_api_gi.inc"
+#include "hr_api_post.inc"

@@ -147,7 +147,7 @@ struct hr_scene {
     hr_scene_info info {};
 };
 
-enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4, PASS_DEFERRED = 5 };
+enum PassKind { PASS_SHADOWS = 1, PASS_AO = 2, PASS_REFLECTIONS = 3, PASS_DDGI = 4, PASS_DEFERRED = 5, PASS_TAA = 6, PASS_TONEMAP = 7, PASS_PATH_TRACER = 8 };
 
 struct StageTimer { // one Rec per profiled render; hr_pass_stage_times averages and recycles them
     struct Rec { std::vector<std::string> names; std::vector<cudaEvent_t> ev; };
@@ -205,6 +205,9 @@ struct hr_pass {
     uint32_t* ddgi_depth[2] = { nullptr, nullptr };
     uint2*    ddgi_sample = nullptr;
     uint2*    deferred_out = nullptr;                  // deferred shading combine: RGBA16F (Lo, 1)
+    uint2*    post_img[2] = { nullptr, nullptr };      // TAA: m_image[2] (temporal_aa.cpp:196-212); path tracer: images[2]; [0] = tone map RGBA8
+    uint32_t  pt_frame_idx = 0;                        // GroundTruthPathTracer::m_frame_idx
+    int       pt_ping_pong = 0;                        // GroundTruthPathTracer::m_ping_pong
     std::vector<void*> ddgi_grid_allocs;
     // asynchronous band exchange (shard.cu): ev_ready = pass kernels done on the caller's stream, ev_done = exchange done on
     // ctx->comm_stream.  Whoever next touches an exchanged image (next frame's temporal stage, hr_pass_output/download)
@@ -306,6 +309,11 @@ void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, 
                            float* depth, unsigned long long* ray_ctr, cudaStream_t st); // gbuffer.cu
 void launch_deferred(const GBufLevelDev& g, const FrameConsts& fc, const void* shadow, int shadow_channels, const void* ao, const void* reflections, const void* gi,
                      const float* env3, const void* brdf_lut, void* out, int row0, int row1, cudaStream_t st); // deferred.cu
+// post.cu
+void launch_taa(const GBufLevelDev& g, const void* current, int current_channels, const void* history, const float* jitter_xy, float feedback_min, float feedback_max,
+                int sharpen, void* out, cudaStream_t st);
+void launch_blit_rgba16f(const void* src, int channels, int W, int H, void* out, cudaStream_t st);
+void launch_tonemap(const void* src, int channels, int W, int H, float exposure, int single_channel, void* out_rgba8, cudaStream_t st);
 // stats.cu (measurement helpers, not on the frame path)
 void launch_tile_stats(const uint8_t* flags, int TW, int t0, int t1, unsigned long long* d_out, cudaStream_t st);
 void launch_drain_ray_counters(unsigned long long* ctr, unsigned long long* d_out, cudaStream_t st);

@@ -12,6 +12,7 @@
 #pragma once
 #include "../../include/hr_api.h"
 #include "assets.h"
+#include "hr_math.h"
 #include "synth.h"
 #include <stdexcept>
 #include <string>
@@ -208,6 +209,7 @@ public:
         check(m_common->ctx, hr_deferred_render(m_pass, &m_common->frame, &params, shadows, ao, reflections, ddgi, stream), "hr_deferred_render");
     }
     hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, 100, &img), "hr_pass_output"); return img; }
+    hr_pass* handle() { return m_pass; }
     hr_deferred_params params;
 private:
     CommonResources* m_common;
@@ -239,6 +241,78 @@ private:
     hr_pass*         m_pass = nullptr;
     RayTraceScale    m_scale;
     uint32_t         m_width = 0, m_height = 0;
+};
+
+// TemporalAA (src/temporal_aa.h:13-63): update() advances the Halton jitter, render() resolves the visualised pass's output.
+// update_uniforms (main.cpp:937-957) multiplies the projection by translate(current_jitter): apply_jitter() does that to an hr_frame
+// built without jitter (projection' = J * projection, so view_proj' = J * view_proj and the inverses gain J^-1 on the right).
+class TemporalAA {
+public:
+    TemporalAA(CommonResources* common, GBuffer* g_buffer) : m_common(common)
+    {
+        (void)g_buffer;
+        hr_taa_default_params(&params);
+        check(common->ctx, hr_taa_create(common->ctx, (int)common->width, (int)common->height, &m_pass), "hr_taa_create");
+    }
+    ~TemporalAA() { if (m_pass) hr_pass_destroy(m_pass); }
+    void update()
+    { // temporal_aa.cpp:66-81
+        if (m_enabled)
+        {
+            m_prev_jitter[0] = m_current_jitter[0]; m_prev_jitter[1] = m_current_jitter[1];
+            hr_taa_jitter((uint32_t)m_common->num_frames, (int)m_common->width, (int)m_common->height, m_current_jitter);
+        }
+        else m_prev_jitter[0] = m_prev_jitter[1] = m_current_jitter[0] = m_current_jitter[1] = 0.0f;
+    }
+    // what update_uniforms does with the jitter (main.cpp:941-957); call after CommonResources::update_uniforms
+    void apply_jitter()
+    {
+        hr_frame& f = m_common->frame;
+        f.ubo.current_prev_jitter[0] = m_current_jitter[0]; f.ubo.current_prev_jitter[1] = m_current_jitter[1];
+        f.ubo.current_prev_jitter[2] = m_prev_jitter[0];    f.ubo.current_prev_jitter[3] = m_prev_jitter[1];
+        if (!m_enabled) return;
+        const hrm::M4 J = hrm::translate({ m_current_jitter[0], m_current_jitter[1], 0.0f }), Ji = hrm::translate({ -m_current_jitter[0], -m_current_jitter[1], 0.0f });
+        auto left  = [&](float* m) { hrm::M4 a; std::memcpy(a.m, m, 64); a = hrm::mul(J, a); std::memcpy(m, a.m, 64); };
+        auto right = [&](float* m) { hrm::M4 a; std::memcpy(a.m, m, 64); a = hrm::mul(a, Ji); std::memcpy(m, a.m, 64); };
+        left(f.ubo.view_proj);
+        right(f.ubo.view_proj_inverse);
+        right(f.ubo.proj_inverse);
+        if (!m_common->first_frame) left(f.ubo.prev_view_proj); // main.cpp:955
+    }
+    void     render(void* stream, hr_pass* input) { if (m_enabled) check(m_common->ctx, hr_taa_render(m_pass, &m_common->frame, &params, input, stream), "hr_taa_render"); }
+    hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, 100, &img), "hr_pass_output"); return img; }
+    bool     enabled() const { return m_enabled; }
+    void     set_enabled(bool e) { if (e && !m_enabled) hr_pass_reset_history(m_pass); m_enabled = e; } // gui(): enabling sets m_reset (temporal_aa.cpp:181-185)
+    const float* current_jitter() const { return m_current_jitter; }
+    const float* prev_jitter() const { return m_prev_jitter; }
+    hr_pass* handle() { return m_pass; }
+    hr_taa_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+    bool             m_enabled = true;
+    float            m_current_jitter[2] = { 0.0f, 0.0f }, m_prev_jitter[2] = { 0.0f, 0.0f };
+};
+
+// ToneMap (src/tone_map.h): render(cmd_buf, temporal_aa, deferred, ...) picks the TAA output when TAA is enabled, else the visualised pass
+class ToneMap {
+public:
+    ToneMap(CommonResources* common) : m_common(common)
+    {
+        hr_tonemap_default_params(&params);
+        check(common->ctx, hr_tonemap_create(common->ctx, (int)common->width, (int)common->height, &m_pass), "hr_tonemap_create");
+    }
+    ~ToneMap() { if (m_pass) hr_pass_destroy(m_pass); }
+    void     render(void* stream, TemporalAA* temporal_aa, hr_pass* visualised)
+    { // tone_map.cpp:106-125
+        hr_pass* in = temporal_aa && temporal_aa->enabled() ? temporal_aa->handle() : visualised;
+        check(m_common->ctx, hr_tonemap_render(m_pass, &params, in, stream), "hr_tonemap_render");
+    }
+    hr_image output() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, 100, &img), "hr_pass_output"); return img; }
+    hr_tonemap_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
 };
 
 } // namespace hr

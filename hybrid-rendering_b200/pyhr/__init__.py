@@ -84,7 +84,7 @@ class hrs_light_desc(C.Structure):
                 ("intensity", C.c_float), ("color", C.c_float * 3), ("cone_inner_deg", C.c_float), ("cone_outer_deg", C.c_float)]
 
 
-HR_FMT = {1: ("<u4", 1), 2: ("<f2", 1), 3: ("<f2", 2), 4: ("<f2", 4), 5: ("u1", 1)}  # hr_format -> (dtype, channels)
+HR_FMT = {1: ("<u4", 1), 2: ("<f2", 1), 3: ("<f2", 2), 4: ("<f2", 4), 5: ("u1", 1), 6: ("u1", 4)}  # hr_format -> (dtype, channels)
 
 # every symbol include/hr_api.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_halo_rows", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
     "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render", "hr_bluenoise_set_slot",
+    "hr_taa_default_params", "hr_taa_jitter", "hr_taa_create", "hr_taa_render", "hr_tonemap_default_params", "hr_tonemap_create", "hr_tonemap_render",
 ]
 
 _product = None
@@ -566,3 +567,51 @@ class DeferredPass(Pass):
     def render(self, frame: hr_frame, shadows=None, ao=None, reflections=None, ddgi=None, stream=0):
         hs = [x.h if x is not None else None for x in (shadows, ao, reflections, ddgi)]
         self.ctx.check(self.lib.hr_deferred_render(self.h, C.byref(frame), C.byref(self.params), hs[0], hs[1], hs[2], hs[3], C.c_void_p(stream)), "hr_deferred_render")
+
+
+class hr_taa_params(C.Structure):
+    _fields_ = [("feedback_min", C.c_float), ("feedback_max", C.c_float), ("sharpen", C.c_int32), ("reset_every_frame", C.c_int32)]
+
+
+class hr_tonemap_params(C.Structure):
+    _fields_ = [("exposure", C.c_float), ("single_channel", C.c_int32)]
+
+
+def taa_jitter(num_frames, W, H):
+    """TemporalAA::update (hr_taa_jitter): (x, y) jitter of frame num_frames; pure host function"""
+    out = (C.c_float * 2)()
+    L = load_product()
+    L.hr_taa_jitter.restype = None
+    L.hr_taa_jitter.argtypes = [C.c_uint32, C.c_int, C.c_int, C.POINTER(C.c_float)]
+    L.hr_taa_jitter(num_frames, W, H, out)
+    return np.array(out[:], np.float32)
+
+
+class TAAPass(Pass):
+    """temporal anti-aliasing (hr_taa_*): resolves another pass's final output against its own previous output"""
+
+    def __init__(self, ctx: Context, W, H):
+        self.ctx, self.kind, self.lib = ctx, "taa", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_taa_create(ctx.h, W, H, C.byref(h)), "hr_taa_create")
+        self.h = h
+        self.params = hr_taa_params()
+        self.lib.hr_taa_default_params(C.byref(self.params))
+
+    def render(self, frame: hr_frame, input_pass, stream=0):
+        self.ctx.check(self.lib.hr_taa_render(self.h, C.byref(frame), C.byref(self.params), input_pass.h, C.c_void_p(stream)), "hr_taa_render")
+
+
+class TonemapPass(Pass):
+    """tone map (hr_tonemap_*): exposure + ACES + gamma -> RGBA8"""
+
+    def __init__(self, ctx: Context, W, H):
+        self.ctx, self.kind, self.lib = ctx, "tonemap", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_tonemap_create(ctx.h, W, H, C.byref(h)), "hr_tonemap_create")
+        self.h = h
+        self.params = hr_tonemap_params()
+        self.lib.hr_tonemap_default_params(C.byref(self.params))
+
+    def render(self, input_pass, stream=0):
+        self.ctx.check(self.lib.hr_tonemap_render(self.h, C.byref(self.params), input_pass.h, C.c_void_p(stream)), "hr_tonemap_render")

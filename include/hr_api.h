@@ -226,7 +226,7 @@ HR_API int hr_gbuffer_download(hr_ctx* ctx, int slot, int mip, int which, void* 
 /* ------------------------------------------------------------------------------------------------
  * Pass outputs
  * ---------------------------------------------------------------------------------------------- */
-typedef enum hr_format { HR_FMT_R32_UINT = 1, HR_FMT_R16F = 2, HR_FMT_RG16F = 3, HR_FMT_RGBA16F = 4, HR_FMT_R8_UINT = 5 } hr_format;
+typedef enum hr_format { HR_FMT_R32_UINT = 1, HR_FMT_R16F = 2, HR_FMT_RG16F = 3, HR_FMT_RGBA16F = 4, HR_FMT_R8_UINT = 5, HR_FMT_RGBA8 = 6 } hr_format;
 
 typedef struct hr_image {
     void*   data; /* device pointer, dense rows (pitch = width * texel size) */
@@ -408,6 +408,43 @@ typedef struct hr_deferred_params {
 HR_API int hr_deferred_create(hr_ctx* ctx, int width, int height, hr_pass** out);
 HR_API int hr_deferred_render(hr_pass* pass, const hr_frame* frame, const hr_deferred_params* params, hr_pass* shadows, hr_pass* ao, hr_pass* reflections, hr_pass* ddgi,
                               void* stream); /* output: hr_pass_output(pass, HR_..._OUT_FINAL = 100) */
+
+/* ------------------------------------------------------------------------------------------------
+ * Post-processing  (src/temporal_aa.{h,cpp} + shaders/taa.comp; src/tone_map.{h,cpp} + shaders/tone_map.frag)
+ * Both passes read the FINAL output (which = 100) of any other pass at full resolution — the reference binds the deferred,
+ * shadows, AO, reflections or DDGI output by visualisation type (temporal_aa.cpp:136-147, tone_map.cpp:106-125); R16F / RG16F
+ * inputs are read as (r, 0, 0, 1) / (r, g, 0, 1) like a sampler does.  Not sharded: with world > 1 run them on a rank that holds
+ * the gathered outputs (hr_shard_set_gather) and a complete G-buffer.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_taa_params { /* defaults: src/temporal_aa.h:54-59 */
+    float   feedback_min;      /* 0.88 */
+    float   feedback_max;      /* 0.97 */
+    int32_t sharpen;           /* 1    */
+    int32_t reset_every_frame; /* 1 = the reference as written: m_reset is initialised true and never cleared (temporal_aa.cpp:112,
+                                * temporal_aa.h:57), so every frame first overwrites the history image with the current input and the
+                                * resolve blends the frame with itself.  0 = what the code evidently intends: the blit happens on the
+                                * first render (and after hr_pass_reset_history) only and the history accumulates */
+} hr_taa_params;
+HR_API void hr_taa_default_params(hr_taa_params* p);
+/* TemporalAA::update (temporal_aa.cpp:66-81): the sub-pixel jitter of frame `num_frames` — Halton(2, 3) sample
+ * (num_frames % 16) + 1 mapped to [-1, 1), divided by (width, height).  The caller multiplies its projection by
+ * translate(jitter.xy, 0) and stores (current, previous) in hr_frame.ubo.current_prev_jitter (main.cpp:941-957).  Pure function. */
+HR_API void hr_taa_jitter(uint32_t num_frames, int width, int height, float out_xy[2]);
+HR_API int  hr_taa_create(hr_ctx* ctx, int width, int height, hr_pass** out); /* temporal_aa.cpp:44-56: two RGBA16F images */
+/* TemporalAA::render (temporal_aa.cpp:83-172): resolves `input`'s final output against this pass's previous output using the
+ * current G-buffer slot's depth and motion vectors and frame->ubo.current_prev_jitter.xy; writes image[frame->ping_pong] (RGBA16F,
+ * rgb clamped to [0, 1], a = 1), which = 100.  Bit-specified (oracle/orc_post.cpp). */
+HR_API int hr_taa_render(hr_pass* pass, const hr_frame* frame, const hr_taa_params* params, hr_pass* input, void* stream);
+
+typedef struct hr_tonemap_params { /* tone_map.h:41, push constants tone_map.frag:24-29 */
+    float   exposure;       /* 1.0 */
+    int32_t single_channel; /* 0; 1 = grey-scale visualisation of a one-channel pass (.rrr), no curve */
+} hr_tonemap_params;
+HR_API void hr_tonemap_default_params(hr_tonemap_params* p);
+HR_API int  hr_tonemap_create(hr_ctx* ctx, int width, int height, hr_pass** out);
+/* ToneMap::render (tone_map.cpp:44-150): exposure, ACES film curve, gamma 1 / 2.2 -> RGBA8 UNORM image of the input's size
+ * (the reference renders into the swap chain; row y of the output is row y of the input), which = 100. */
+HR_API int hr_tonemap_render(hr_pass* pass, const hr_tonemap_params* params, hr_pass* input, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Common pass functions

@@ -149,6 +149,67 @@ def main():
     defaults["ddgi"] = {k: member_default(t, k, rel) for k in ("infinite_bounces", "infinite_bounce_intensity", "rays_per_probe", "visibility_test", "probe_distance",
                                                                "recursive_energy_preservation", "irradiance_oct_size", "depth_oct_size", "hysteresis", "depth_sharpness",
                                                                "normal_bias", "gi_intensity")}
+    # ---- post-processing: taa.comp, temporal_aa.{h,cpp}, tone_map.{frag,h} ---------------------------------
+    rel = "src/shaders/taa.comp"
+    t = read(os.path.join(SH, "taa.comp"))
+    taa = {}
+    m = re.search(r"const\s+float\s+FLT_EPS\s*=\s*([^;]+);", t)
+    taa["FLT_EPS"] = {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start())}"}
+    # the feature switches that select which branches of the shader exist (only un-commented, top-level #define lines)
+    defs = [(mm.group(1), line_of(t, mm.start())) for mm in re.finditer(r"^#define\s+(\w+)\s*(?:\d+)?\s*$", t, re.M)]
+    taa["defines"] = {"value": [d for d, _ in defs], "src": f"{rel}:{defs[0][1]}-{defs[-1][1]}"}
+    m = re.search(r"max\(lum0,\s*max\(lum1,\s*([0-9.]+)\)\)", t)
+    taa["luminance_floor"] = {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start())}"}
+    m = re.search(r"sum \+= ([-0-9.]+) \* cml;\s*sum \+= ([-0-9.]+) \* ctc;\s*sum \+= ([-0-9.]+) \* texel0;\s*sum \+= ([-0-9.]+) \* cbc;\s*sum \+= ([-0-9.]+) \* cmr;", t)
+    taa["sharpen_weights"] = {"value": [num(m.group(i)) for i in range(1, 6)], "src": f"{rel}:{line_of(t, m.start())}-{line_of(t, m.end())}", "meaning": "cml, ctc, texel0, cbc, cmr"}
+    rel = "src/temporal_aa.cpp"
+    t = read(os.path.join(SRC, "temporal_aa.cpp"))
+    taa["HALTON_SAMPLES"] = define(t, "HALTON_SAMPLES", rel)
+    out["taa"] = taa
+    rel = "src/temporal_aa.h"
+    t = read(os.path.join(SRC, "temporal_aa.h"))
+    defaults["taa"] = {k: member_default(t, k, rel) for k in ("m_enabled", "m_sharpen", "m_reset", "m_feedback_min", "m_feedback_max")}
+    rel = "src/shaders/tone_map.frag"
+    t = read(os.path.join(SH, "tone_map.frag"))
+    aces = {}
+    for k in "abcde":
+        m = re.search(rf"float\s+{k}\s*=\s*([^;]+);", t)
+        aces[k] = num(m.group(1))
+    m0 = re.search(r"vec3\s+aces_film", t)
+    m = re.search(r"pow\(color,\s*vec3\(([^)]+)\)\)", t)
+    out["tone_map"] = {"aces": {"value": aces, "src": f"{rel}:{line_of(t, m0.start())}"}, "gamma_exponent": {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start())}"}}
+    rel = "src/tone_map.h"
+    t = read(os.path.join(SRC, "tone_map.h"))
+    defaults["tone_map"] = {"m_exposure": member_default(t, "m_exposure", rel)}
+
+    # ---- ground-truth path tracer: ground_truth_path_trace.{rgen,rchit}, ground_truth_path_tracer.h, common.glsl, lighting.glsl -------
+    pt = {}
+    rel = "src/shaders/ground_truth/ground_truth_path_trace.rgen"
+    t = read(os.path.join(SH, "ground_truth", "ground_truth_path_trace.rgen"))
+    m = re.search(r"float\s+tmin\s*=\s*([^;]+);\s*float\s+tmax\s*=\s*([^;]+);", t)
+    pt["primary_tmin_tmax"] = {"value": [num(m.group(1)), num(m.group(2))], "src": f"{rel}:{line_of(t, m.start())}"}
+    rel = "src/shaders/common.glsl"
+    t = read(os.path.join(SH, "common.glsl"))
+    m = re.search(r"#define\s+RADIANCE_CLAMP_COLOR\s+vec3\(([^)]+)\)", t)
+    pt["RADIANCE_CLAMP_COLOR"] = {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start())}"}
+    rel = "src/shaders/lighting.glsl"
+    t = read(os.path.join(SH, "lighting.glsl"))
+    m = re.search(r"vec3\s+ray_origin\s*=\s*P\s*\+\s*N\s*\*\s*([^;]+);", t)
+    pt["shadow_ray_origin_offset"] = {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start())}"}
+    rel = "src/shaders/ray_query.glsl"
+    t = read(os.path.join(SH, "ray_query.glsl"))
+    m = re.search(r"float\s+query_distance\(.*?float\s+t_min\s*=\s*([^;]+);", t, re.S)
+    pt["query_distance_t_min"] = {"value": num(m.group(1)), "src": f"{rel}:{line_of(t, m.start(1))}"}
+    rel = "src/shaders/ground_truth/ground_truth_path_trace.rchit"
+    t = read(os.path.join(SH, "ground_truth", "ground_truth_path_trace.rchit"))
+    m = re.search(r"^\s*//\s*traceRayEXT\(u_TopLevelAS", t, re.M)
+    pt["indirect_trace_is_commented_out"] = {"value": bool(m) and not re.search(r"^\s*traceRayEXT\(", t, re.M), "src": f"{rel}:{line_of(t, m.start()) if m else 0}"}
+    pt["rchit_defines"] = {"value": re.findall(r"^#define\s+(\w+)\s*$", t, re.M), "src": rel}
+    rel = "src/ground_truth_path_tracer.h"
+    t = read(os.path.join(SRC, "ground_truth_path_tracer.h"))
+    defaults["path_tracer"] = {"max_ray_bounces": member_default(t, "max_ray_bounces", rel)}
+    out["path_tracer"] = pt
+
     out["defaults"] = defaults
 
     # ---- struct sizes the ABI mirrors (counted from the member lists) ---------------------------------------------------

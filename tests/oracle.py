@@ -73,6 +73,10 @@ def lib():
         L.orc_rng_sequence.restype = U
         L.orc_rng_sequence.argtypes = [U, U, U, P, I]
         L.orc_gbuffer_render.argtypes = [P, P, P, I, I, P, P, P, P]
+        L.orc_taa.argtypes = [I, I, P, I, P, P, P, P, F, F, I, P]
+        L.orc_blit_rgba16f.argtypes = [I, I, P, I, P]
+        L.orc_taa_jitter.argtypes = [U, I, I, P]
+        L.orc_tonemap.argtypes = [I, I, P, I, F, I, P]
         _lib = L
     return _lib
 
@@ -494,3 +498,61 @@ def deferred(g: "pyhr.GBufferHost", frame, shadow=None, ao=None, reflections=Non
                        p(arrs[2]) if arrs[2] is not None else None, p(arrs[3]) if arrs[3] is not None else None, p(envv),
                        p(brdf_lut) if brdf_lut is not None else None, p(out))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- post-processing (oracle/orc_post.cpp)
+def _channels(img):
+    return 1 if img.ndim == 2 else img.shape[2]
+
+
+def taa_jitter(num_frames, W, H):
+    """TemporalAA::update (temporal_aa.cpp:66-81): jitter of frame num_frames"""
+    out = np.zeros(2, np.float32)
+    lib().orc_taa_jitter(num_frames, W, H, p(out))
+    return out
+
+
+def blit_rgba16f(src):
+    """vkCmdBlitImage into an RGBA16F image: (H, W[, C]) uint16 halves -> (H, W, 4)"""
+    src = np.ascontiguousarray(src, np.uint16)
+    H, W = src.shape[:2]
+    out = np.empty((H, W, 4), np.uint16)
+    lib().orc_blit_rgba16f(W, H, p(src), _channels(src), p(out))
+    return out
+
+
+def taa(cur, prev, depth, gb2, jitter_xy, feedback_min=0.88, feedback_max=0.97, sharpen=1):
+    """taa.comp over the whole image: cur (H, W[, C]) halves, prev (H, W, 4) halves, depth (H, W) f32, gb2 (H, W, 4) halves"""
+    cur, prev, gb2 = (np.ascontiguousarray(a, np.uint16) for a in (cur, prev, gb2))
+    depth = np.ascontiguousarray(depth, np.float32)
+    H, W = cur.shape[:2]
+    j = np.ascontiguousarray(jitter_xy, np.float32)
+    out = np.empty((H, W, 4), np.uint16)
+    lib().orc_taa(W, H, p(cur), _channels(cur), p(prev), p(depth), p(gb2), p(j), feedback_min, feedback_max, int(sharpen), p(out))
+    return out
+
+
+def tonemap(src, exposure=1.0, single_channel=0):
+    src = np.ascontiguousarray(src, np.uint16)
+    H, W = src.shape[:2]
+    out = np.empty((H, W, 4), np.uint8)
+    lib().orc_tonemap(W, H, p(src), _channels(src), exposure, int(single_channel), p(out))
+    return out
+
+
+class TAAOracle:
+    """TemporalAA::render (temporal_aa.cpp:83-172) host sequencing on the oracle: two RGBA16F images indexed by ping_pong, the reset
+    blit (reset_every_frame = the reference as written, see hr_taa_params)"""
+
+    def __init__(self, W, H, feedback_min=0.88, feedback_max=0.97, sharpen=1, reset_every_frame=1):
+        self.img = [np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)]
+        self.first = True
+        self.fmin, self.fmax, self.sharpen, self.reset_every_frame = feedback_min, feedback_max, sharpen, reset_every_frame
+
+    def render(self, frame, cur, depth, gb2):
+        w, r = frame.ping_pong, 1 - frame.ping_pong
+        if self.first or self.reset_every_frame:
+            self.img[r] = blit_rgba16f(cur)
+            self.first = False
+        self.img[w] = taa(cur, self.img[r], depth, gb2, frame.ubo.current_prev_jitter[0:2], self.fmin, self.fmax, self.sharpen)
+        return self.img[w]
