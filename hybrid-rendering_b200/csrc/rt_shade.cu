@@ -579,6 +579,113 @@ __global__ void __launch_bounds__(256) k_refl_shade(GBufLevelDev g, BvhDev bvh, 
     out[idx] = pack_h4(fminf(color.x, 0.7f), fminf(color.y, 0.7f), fminf(color.z, 0.7f), 0.001f + h.x);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Ground-truth progressive path tracer: ground_truth/ground_truth_path_trace.{rgen,rchit,rmiss}, host
+// src/ground_truth_path_tracer.cpp:44-113.  One jittered primary ray per pixel and frame; closest hit -> direct_lighting with SOFT_SHADOWS +
+// RAY_THROUGHPUT + SAMPLE_SKY_LIGHT (rchit:13-16): the punctual light sampled on its disk with its shadow ray, one cosine-lobe sky sample
+// with its shadow ray; miss -> the sky colour; running average into an RGBA16F image.  As written in the reference the indirect bounce's
+// traceRayEXT is commented out (rchit:92-104) and indirect_lighting returns p_IndirectPayload.L = vec3(0): the image converges to direct +
+// sky lighting; max_ray_bounces only gates that dead branch.  The primary ray, the hit and the two shadow rays follow the deterministic chain
+// (det_math.cuh): hit primitive and binary visibilities equal the oracle's (oracle/orc_path_trace.cpp) exactly, colours within tolerance.
+struct PathTraceParams {
+    float    view_inverse[16], proj_inverse[16];
+    hr_light light;
+    uint32_t num_frames, max_ray_bounces;
+    float    roughness_multiplier;
+    float    sky[3];
+    int      W, H;
+    unsigned long long* ray_ctr;
+};
+
+__device__ __forceinline__ float4 mat_vec4(const float* M, float x, float y, float z, float w)
+{ // mat4 * vec4, row r = ((m0r*x + m1r*y) + m2r*z) + m3r*w (oracle/orc_math.h::mul)
+    return make_float4(((M[0] * x + M[4] * y) + M[8] * z) + M[12] * w, ((M[1] * x + M[5] * y) + M[9] * z) + M[13] * w,
+                       ((M[2] * x + M[6] * y) + M[10] * z) + M[14] * w, ((M[3] * x + M[7] * y) + M[11] * z) + M[15] * w);
+}
+
+// warp = 8x4 pixel block (coherent primary rays), 2-warp CTAs like K12
+__global__ void __launch_bounds__(64) k_path_trace(BvhDev bvh, ShadeDev sd, PathTraceParams P, const uint2* __restrict__ prev, uint2* __restrict__ out, uint32_t* __restrict__ out_prim)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 16 + warp * 8 + (lane & 7), y = blockIdx.y * 4 + (lane >> 3);
+    if (x >= P.W || y >= P.H) return;
+    const size_t idx = (size_t)y * P.W + x;
+    // rgen:56-75
+    gi::RNG     rng = gi::rng_init((uint32_t)x, (uint32_t)y, P.num_frames);
+    const float j0 = gi::next_float(rng), j1 = gi::next_float(rng);
+    const float jx = ((float)x + 0.5f) + j0, jy = ((float)y + 0.5f) + j1;    // pixel_coord + vec2(next_float, next_float)
+    const float tx = jx / (float)P.W, ty = jy / (float)P.H;                   // tex_coord
+    const float nx = tx * 2.0f - 1.0f, ny = ty * 2.0f - 1.0f;                 // tex_coord_neg_to_pos
+    const float4 origin = mat_vec4(P.view_inverse, 0.0f, 0.0f, 0.0f, 1.0f);
+    const float4 target = mat_vec4(P.proj_inverse, nx, ny, 1.0f, 1.0f);
+    const V3     tn     = det::normalize(det::mk(target.x, target.y, target.z));
+    const float4 dir    = mat_vec4(P.view_inverse, tn.x, tn.y, tn.z, 0.0f);
+    Ray r;
+    r.o = det::mk(origin.x, origin.y, origin.z);
+    r.d = det::mk(dir.x, dir.y, dir.z);
+    r.tmin = 0.001f;
+    r.tmax = 10000.0f;
+    const float3 sky = make_float3(P.sky[0], P.sky[1], P.sky[2]);
+    float3   L = sky; // rmiss:29-32 at depth 0
+    float    t, hu, hv;
+    uint32_t prim = 0xFFFFFFFFu;
+    count_rays(P.ray_ctr, 0, 1u);
+    if (trace_closest(bvh, r, t, prim, hu, hv))
+    { // rchit:112-141
+        using namespace gi;
+        const Surface s  = fetch_surface(sd, prim, hu, hv);
+        const float   roughness = s.roughness * P.roughness_multiplier;
+        const V3      Wo = det::scale(r.d, -1.0f);
+        const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;
+        const float3  cd = (s.albedo * (f3(1, 1, 1) - F0)) * (1.0f - s.metallic) + f3(0, 0, 0) * s.metallic;
+        const float   r1x = next_float(rng), r1y = next_float(rng); // next_vec2: the light's disk sample
+        const float   r2x = next_float(rng), r2y = next_float(rng); // next_vec2: the sky sample
+        // direct_lighting, lighting.glsl:117-196 with SOFT_SHADOWS, RAY_THROUGHPUT (T = 1 at depth 0), SAMPLE_SKY_LIGHT
+        float3 Lo = f3(0, 0, 0);
+        Ray    sr;
+        sr.o    = det::add(s.P, det::scale(s.N, 0.1f));
+        sr.tmin = 0.01f;
+        {
+            const hr_light& light = P.light;
+            const float3    Li = make_float3(light.data2[0] * light.data0[3], light.data2[1] * light.data0[3], light.data2[2] * light.data0[3]);
+            V3    Wi;
+            float t_max, att;
+            det::fetch_light_properties_shadow(light, s.P, s.N, r1x, r1y, Wi, t_max, att);
+            const V3 Wh = det::normalize(det::add(Wo, Wi));
+            if (att > 0.0f)
+            {
+                sr.d    = Wi;
+                sr.tmax = t_max;
+                count_rays(P.ray_ctr, 1, 1u);
+                att *= trace_any(bvh, sr) ? 0.0f : 1.0f;
+            }
+            Lo = Lo + (evaluate_uber_brdf(cd, roughness, s.N, F0, Wo, Wh, Wi) * att) * Li;
+        }
+        {
+            const V3 Wi = det::sample_cosine_lobe(s.N, r2x, r2y);
+            const V3 Wh = det::normalize(det::add(Wo, Wi));
+            sr.d    = Wi;
+            sr.tmax = 10000.0f;
+            count_rays(P.ray_ctr, 1, 1u);
+            const float vis = trace_any(bvh, sr) ? 0.0f : 1.0f;
+            Lo = Lo + evaluate_uber_brdf(cd, roughness, s.N, F0, Wo, Wh, Wi) * (sky * vis);
+        }
+        L = Lo; // + indirect_lighting(...) = vec3(0): the bounce is commented out in the reference (rchit:92-106)
+    }
+    // rgen:94-111: clamp to RADIANCE_CLAMP_COLOR = 1, then the running average the reference writes (weight 1 / num_frames, not 1 / (n + 1))
+    const float3 c = make_float3(fminf(L.x, 1.0f), fminf(L.y, 1.0f), fminf(L.z, 1.0f));
+    float3 o = c;
+    if (P.num_frames != 0)
+    {
+        const uint2  pw = __ldg(prev + idx);
+        const float2 p01 = __half22float2(*reinterpret_cast<const __half2*>(&pw.x)), p2 = __half22float2(*reinterpret_cast<const __half2*>(&pw.y));
+        const float  n = (float)P.num_frames;
+        o = make_float3(p01.x + (c.x - p01.x) / n, p01.y + (c.y - p01.y) / n, p2.x + (c.z - p2.x) / n);
+    }
+    out[idx] = pack_h4(o.x, o.y, o.z, 1.0f);
+    out_prim[idx] = prim;
+}
+
 ShadeDev shade_view(const hr_scene* sc)
 {
     ShadeDev s;
@@ -661,4 +768,19 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     else if (g_hr_refl_trace_minb == 16) k_reflections_ray_trace<false, 16><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
     else if (g_hr_refl_trace_minb == 20) k_reflections_ray_trace<false, 20><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
     else k_reflections_ray_trace<false, 18><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+}
+
+void launch_path_trace(const hr_scene* sc, const hr_frame* f, int W, int H, uint32_t num_frames, uint32_t max_ray_bounces, float roughness_multiplier, const float* sky3,
+                       const void* prev, void* out, uint32_t* out_prim, unsigned long long* ray_ctr, cudaStream_t st)
+{
+    PathTraceParams P;
+    memcpy(P.view_inverse, f->ubo.view_inverse, 64);
+    memcpy(P.proj_inverse, f->ubo.proj_inverse, 64);
+    P.light = f->ubo.light;
+    P.num_frames = num_frames; P.max_ray_bounces = max_ray_bounces; P.roughness_multiplier = roughness_multiplier;
+    P.sky[0] = sky3[0]; P.sky[1] = sky3[1]; P.sky[2] = sky3[2];
+    P.W = W; P.H = H;
+    P.ray_ctr = ray_ctr;
+    dim3 grid((W + 15) / 16, (H + 3) / 4);
+    k_path_trace<<<grid, 64, 0, st>>>(hr_bvh_view(sc), shade_view(sc), P, (const uint2*)prev, (uint2*)out, out_prim);
 }

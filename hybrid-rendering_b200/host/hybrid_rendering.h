@@ -6,6 +6,7 @@
 //   RayTracedShadows(src/ray_traced_shadows.h)     hr::RayTracedShadows (ctor(common, gbuffer, scale); render(stream); output())
 //   RayTracedAO     (src/ray_traced_ao.h)          hr::RayTracedAO
 //   DDGI / RayTracedReflections / DeferredShading  hr::DDGI, hr::RayTracedReflections, hr::DeferredShading
+//   TemporalAA / ToneMap / GroundTruthPathTracer   hr::TemporalAA, hr::ToneMap, hr::GroundTruthPathTracer
 // Same method names and argument meaning; `dw::vk::CommandBuffer::Ptr` becomes a CUDA stream, descriptor sets become
 // hr_image views; construction errors throw std::runtime_error like the reference (common.cpp:350-353), render() does
 // not fail observably in the reference — here a failed launch throws as well.
@@ -310,6 +311,25 @@ public:
     }
     hr_image output() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, 100, &img), "hr_pass_output"); return img; }
     hr_tonemap_params params;
+private:
+    CommonResources* m_common;
+    hr_pass*         m_pass = nullptr;
+};
+
+// GroundTruthPathTracer (src/ground_truth_path_tracer.h:9-50): render(cmd_buf); restart_accumulation(); output_ds()
+class GroundTruthPathTracer {
+public:
+    GroundTruthPathTracer(CommonResources* common) : m_common(common)
+    {
+        hr_path_tracer_default_params(&params);
+        check(common->ctx, hr_path_tracer_create(common->ctx, (int)common->width, (int)common->height, &m_pass), "hr_path_tracer_create");
+    }
+    ~GroundTruthPathTracer() { if (m_pass) hr_pass_destroy(m_pass); }
+    void     render(void* stream) { check(m_common->ctx, hr_path_tracer_render(m_pass, &m_common->frame, &params, stream), "hr_path_tracer_render"); }
+    void     restart_accumulation() { hr_pass_reset_history(m_pass); } // ground_truth_path_tracer.h:17
+    hr_image output_ds() const { hr_image img {}; check(m_common->ctx, hr_pass_output(m_pass, HR_PATH_TRACER_OUT_FINAL, &img), "hr_pass_output"); return img; }
+    hr_pass* handle() { return m_pass; }
+    hr_path_tracer_params params;
 private:
     CommonResources* m_common;
     hr_pass*         m_pass = nullptr;

@@ -96,7 +96,7 @@ ABI_SYMBOLS = [
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_halo_rows", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
     "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render", "hr_bluenoise_set_slot",
-    "hr_taa_default_params", "hr_taa_jitter", "hr_taa_create", "hr_taa_render", "hr_tonemap_default_params", "hr_tonemap_create", "hr_tonemap_render",
+    "hr_taa_default_params", "hr_taa_jitter", "hr_taa_create", "hr_taa_render", "hr_tonemap_default_params", "hr_tonemap_create", "hr_tonemap_render", "hr_path_tracer_default_params", "hr_path_tracer_create", "hr_path_tracer_render",
 ]
 
 _product = None
@@ -615,3 +615,22 @@ class TonemapPass(Pass):
 
     def render(self, input_pass, stream=0):
         self.ctx.check(self.lib.hr_tonemap_render(self.h, C.byref(self.params), input_pass.h, C.c_void_p(stream)), "hr_tonemap_render")
+
+
+class hr_path_tracer_params(C.Structure):
+    _fields_ = [("max_ray_bounces", C.c_int32), ("roughness_multiplier", C.c_float), ("sky_color", C.c_float * 3)]
+
+
+class PathTracerPass(Pass):
+    """ground-truth progressive path tracer (hr_path_tracer_*); reset_history() = restart_accumulation()"""
+
+    def __init__(self, ctx: Context, W, H):
+        self.ctx, self.kind, self.lib = ctx, "path_tracer", ctx.lib
+        h = C.c_void_p()
+        ctx.check(self.lib.hr_path_tracer_create(ctx.h, W, H, C.byref(h)), "hr_path_tracer_create")
+        self.h = h
+        self.params = hr_path_tracer_params()
+        self.lib.hr_path_tracer_default_params(C.byref(self.params))
+
+    def render(self, frame: hr_frame, stream=0):
+        self.ctx.check(self.lib.hr_path_tracer_render(self.h, C.byref(frame), C.byref(self.params), C.c_void_p(stream)), "hr_path_tracer_render")

@@ -447,6 +447,29 @@ HR_API int  hr_tonemap_create(hr_ctx* ctx, int width, int height, hr_pass** out)
 HR_API int hr_tonemap_render(hr_pass* pass, const hr_tonemap_params* params, hr_pass* input, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Ground-truth progressive path tracer  (src/ground_truth_path_tracer.{h,cpp}; shaders/ground_truth/ *)
+ * One jittered primary ray per pixel per render; first hit shaded with the soft-shadowed punctual light and one cosine-lobe sky
+ * sample (each with its shadow ray); running average over renders.  As written in the reference the indirect bounce is disabled
+ * (its traceRayEXT is commented out, ground_truth_path_trace.rchit:92-104), so max_ray_bounces changes nothing.  Needs only the
+ * scene and frame->ubo.{view_inverse, proj_inverse, light}: no G-buffer.  Replicated (not sharded) when world > 1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hr_path_tracer_params {
+    int32_t max_ray_bounces;      /* 2 (ground_truth_path_tracer.h:28; the ctor overwrites it with the device's recursion limit) */
+    float   roughness_multiplier; /* 1.0 (CommonResources::roughness_multiplier, common.h:193) */
+    float   sky_color[3];         /* constant-colour environment replacing the sky cubemap */
+} hr_path_tracer_params;
+enum {
+    HR_PATH_TRACER_OUT_COLOR     = 0,  /* RGBA16F running average (rgb clamped to 1 per sample, a = 1) */
+    HR_PATH_TRACER_OUT_PRIMITIVE = 1,  /* R32_UINT primitive hit by the last render's primary ray, 0xFFFFFFFF = sky (tests) */
+    HR_PATH_TRACER_OUT_FINAL     = 100
+};
+HR_API void hr_path_tracer_default_params(hr_path_tracer_params* p);
+HR_API int  hr_path_tracer_create(hr_ctx* ctx, int width, int height, hr_pass** out);
+/* render(), ground_truth_path_tracer.cpp:44-113: the sample index is the pass's own counter (m_frame_idx, push constant num_frames),
+ * restarted by hr_pass_reset_history (restart_accumulation(), ground_truth_path_tracer.h:17). */
+HR_API int  hr_path_tracer_render(hr_pass* pass, const hr_frame* frame, const hr_path_tracer_params* params, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Common pass functions
  * ---------------------------------------------------------------------------------------------- */
 /* output_ds() equivalent: borrowed device image, valid until the next render/destroy of this pass. */

@@ -77,6 +77,7 @@ def lib():
         L.orc_blit_rgba16f.argtypes = [I, I, P, I, P]
         L.orc_taa_jitter.argtypes = [U, I, I, P]
         L.orc_tonemap.argtypes = [I, I, P, I, F, I, P]
+        L.orc_path_trace.argtypes = [P, P, I, I, U, U, F, P, P, P, P]
         _lib = L
     return _lib
 
@@ -556,3 +557,29 @@ class TAAOracle:
             self.first = False
         self.img[w] = taa(cur, self.img[r], depth, gb2, frame.ubo.current_prev_jitter[0:2], self.fmin, self.fmax, self.sharpen)
         return self.img[w]
+
+
+# ---------------------------------------------------------------------------------------------- ground-truth path tracer (oracle/orc_path_trace.cpp)
+class PathTracerOracle:
+    """GroundTruthPathTracer::render host sequencing (ground_truth_path_tracer.cpp:44-113): frame counter, two images, ping-pong"""
+
+    def __init__(self, W, H, max_ray_bounces=2, roughness_multiplier=1.0, sky=(0.0, 0.0, 0.0)):
+        self.W, self.H = W, H
+        self.img = [np.zeros((H, W, 4), np.uint16), np.zeros((H, W, 4), np.uint16)]
+        self.prim = np.full((H, W), 0xFFFFFFFF, np.uint32)
+        self.frame_idx, self.ping_pong = 0, 0
+        self.max_ray_bounces, self.roughness_multiplier, self.sky = max_ray_bounces, roughness_multiplier, np.asarray(sky, np.float32)
+
+    def restart_accumulation(self):
+        self.frame_idx = 0
+
+    def render(self, ss: "ShadingScene", frame):
+        if self.frame_idx == 0:
+            self.ping_pong = 0
+        r, w = self.ping_pong, 1 - self.ping_pong
+        lib().orc_path_trace(ss.h, C.byref(frame), self.W, self.H, self.frame_idx, self.max_ray_bounces, self.roughness_multiplier, p(self.sky), p(self.img[r]),
+                             p(self.img[w]), p(self.prim))
+        self.frame_idx += 1
+        self.ping_pong = 1 - self.ping_pong
+        self.final = self.img[w]
+        return self.final
