@@ -30,6 +30,8 @@ steps between barrier + synchronize, max over ranks):
             count fully, copy / zero-filled tiles count only their real bytes — / the average CUDA-event duration of a launch.
             frac_contract is the whole-frame 36 (24) B/px figure for comparison.  k5_dense: the shadows a-trous on a view
             where >= 95 % of the tiles are on the denoise list (no help from sparsity)
+  post_passes   (N = 1, informational, own process) deferred combine -> TAA -> tone map and the ground-truth path tracer at the bench
+            resolution: ms per launch, roofline fractions on their algorithmic bytes (36 / 12 B/px), Mrays/s of the path tracer
   cpu_baseline / --impl reference   the CPU oracle (a port: the reference has no CPU path and cannot be built here),
             OpenMP over all host threads (set explicitly), best of 5 frames on a 1/16-area render of the same workload
             (same scene and passes), stated as frames/s of that SAMPLE and extrapolated x16 in `value`
@@ -296,7 +298,83 @@ def texel_bytes(img):
     return {1: 4, 2: 2, 3: 4, 4: 8, 5: 1}[img.format]
 
 
+# ---------------------------------------------------------------------------------------------------------------- post-pass leg
+def post_leg(W, H, tris):
+    """Informational, run in its OWN process by the default single-GPU bench (crash isolation: these kernels had no GPU time before the
+    round-end run): deferred combine -> TAA -> tone map and the ground-truth path tracer at the bench resolution, CUDA-event timed.
+    Prints one JSON dict.  Algorithmic bytes per pixel: TAA 36, tone map 12."""
+    import torch
+    import pyhr
+    torch.cuda.set_device(0)
+    ctx = pyhr.Context(0)
+    ctx.set_bluenoise(*pyhr.blue_noise())
+    sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, tris)
+    ctx.build_scene(sc)
+    ctx.gbuffer_create(W, H)
+    light = pyhr.default_light(rot_x_deg=LIGHT_ROT_X)
+    stream = torch.cuda.current_stream().cuda_stream
+    f = pyhr.make_frame(CAM_POS, CAM_TGT, W, H, light=light)
+    f = pyhr.make_frame(CAM_POS, CAM_TGT, W, H, prev=f, num_frames=1, light=light)
+    ctx.gbuffer_render(0, f, 0, 0, stream)
+    ctx.gbuffer_render(1, f, 0, 0, stream)
+    de, taa, tm, pt = pyhr.DeferredPass(ctx, W, H), pyhr.TAAPass(ctx, W, H), pyhr.TonemapPass(ctx, W, H), pyhr.PathTracerPass(ctx, W, H)
+    for k in range(3):
+        de.params.env_color[k] = pt.params.sky_color[k] = SKY[k]
+    j = pyhr.taa_jitter(1, W, H)
+    f.ubo.current_prev_jitter[0], f.ubo.current_prev_jitter[1] = float(j[0]), float(j[1])
+
+    def timed(fn, n, warm=3):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    peak, peak_src = read_peaks()
+    px = float(W * H)
+    out = {"width": W, "height": H, "triangles": tris, "peak_source": peak_src}
+    out["deferred_ms"] = timed(lambda: de.render(f, None, None, None, None, stream), 20)
+    taa.params.reset_every_frame = 0
+    t = timed(lambda: taa.render(f, de, stream), 20)
+    out["taa"] = {"ms": t, "algorithmic_bytes": 36.0 * px, "achieved_gbs": 36.0 * px / 1e9 / (t / 1e3), "frac": 36.0 * px / 1e9 / (t / 1e3) / peak}
+    taa.params.reset_every_frame = 1
+    out["taa_with_reset_blit_ms"] = timed(lambda: taa.render(f, de, stream), 20)
+    t = timed(lambda: tm.render(taa, stream), 20)
+    out["tonemap"] = {"ms": t, "algorithmic_bytes": 12.0 * px, "achieved_gbs": 12.0 * px / 1e9 / (t / 1e3), "frac": 12.0 * px / 1e9 / (t / 1e3) / peak}
+    pt.stats(stream)
+    t = timed(lambda: pt.render(f, stream), 8, warm=2)
+    st = pt.stats(stream)
+    rays = (st.rays_primary + st.rays_secondary) / max(1, st.renders)
+    out["path_tracer"] = {"ms_per_sample": t, "rays_per_sample": rays, "mrays_per_s": rays / 1e6 / (t / 1e3)}
+    ldr = tm.download(100)
+    out["tonemapped_mean"] = float(ldr[..., :3].mean())
+    out["launches"] = ctx.launch_count()
+    for p in (de, taa, tm, pt):
+        p.destroy()
+    ctx.close()
+    print(json.dumps(out))
+
+
+def run_post_leg(W, H, tris):
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--post-leg", str(W), str(H), str(tris)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                           timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0]})
+        if r.returncode != 0:
+            return {"error": f"exit code {r.returncode}: {r.stderr.strip()[-400:]}"}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # informational leg: never takes the bench line down
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def main():
+    if len(sys.argv) == 5 and sys.argv[1] == "--post-leg":
+        return post_leg(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -694,6 +772,9 @@ def main():
                            "note": "includes the G-buffer ray cast every frame (N > 1: hr_gbuffer_render_sharded, this rank's rows only)"}
         if k5_dense:
             line["k5_dense"] = k5_dense
+        if not args.no_extras and world == 1 and not single_tri:
+            # deferred -> TAA -> tone map and the ground-truth path tracer, timed in a separate process
+            line["post_passes"] = run_post_leg(W, H, cfg["tris"])
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = oracle_fps(cfg)
         print(json.dumps(line))
