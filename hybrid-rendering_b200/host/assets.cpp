@@ -281,9 +281,23 @@ int png_decode(const uint8_t* d, size_t n, bool flip, int* W, int* H, int* C, ui
     if (ctype == 3 && plte.size() < 3) return fail(HRA_ERR_FORMAT, "PNG: palette image without PLTE");
     std::vector<uint8_t> raw;
     if (!zlib_inflate(idat.data(), idat.size(), raw)) return fail(HRA_ERR_FORMAT, "PNG: corrupt deflate stream");
+    const int bits_pp = depth * src_ch, bpp = std::max(1, bits_pp / 8);
+    { // a header may claim any size: the decompressed data must cover it before anything of that size is allocated
+        size_t need = 0;
+        if (!interlace) need = (((size_t)w * bits_pp + 7) / 8 + 1) * (size_t)h;
+        else
+        {
+            static const int xs[7] = { 0, 4, 0, 2, 0, 1, 0 }, ys[7] = { 0, 0, 4, 0, 2, 0, 1 }, dxs[7] = { 8, 8, 4, 4, 2, 2, 1 }, dys[7] = { 8, 8, 8, 4, 4, 2, 2 };
+            for (int p = 0; p < 7; p++)
+            {
+                const int pw = (w - xs[p] + dxs[p] - 1) / dxs[p], ph = (h - ys[p] + dys[p] - 1) / dys[p];
+                if (pw > 0 && ph > 0) need += (((size_t)pw * bits_pp + 7) / 8 + 1) * (size_t)ph;
+            }
+        }
+        if (raw.size() < need) return fail(HRA_ERR_FORMAT, "PNG: image data too short for %d x %d", w, h);
+    }
     // samples -> 16-bit values per channel, full image
     std::vector<uint16_t> samp((size_t)w * h * src_ch);
-    const int bits_pp = depth * src_ch, bpp = std::max(1, bits_pp / 8);
     auto unpack_pass = [&](const std::vector<uint8_t>& lines, int pw, int ph, int x0, int y0, int dx, int dy) {
         const size_t stride = ((size_t)pw * bits_pp + 7) / 8;
         for (int y = 0; y < ph; y++)

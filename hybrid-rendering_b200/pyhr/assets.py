@@ -54,7 +54,7 @@ def load_assets():
 
 def _check(rc, what):
     if rc != 0:
-        raise HrError(f"{what} failed ({rc}): {load_assets().hra_last_error().decode()}")
+        raise HrError(f"{what} failed ({rc}): {load_assets().hra_last_error().decode(errors='replace')}")
 
 
 def image_load(path=None, data=None, flip_vertical=False):
