@@ -1,4 +1,4 @@
-"""ctypes binding of libhr_assets.so (host/assets.h): scene / asset ingestion in the reference's formats.
+"""ctypes binding of libhr_assets.so (include/hr_assets.h): scene / asset ingestion in the reference's formats.
 Test / bench driver only, like the rest of pyhr."""
 import ctypes as C
 import os

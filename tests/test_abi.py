@@ -26,6 +26,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} is declared in hr_api.h but not exported"
 
 
+def test_asset_library_exports_every_declared_symbol():
+    """include/hr_assets.h is the boundary of libhr_assets.so (dw::Mesh::load / Image::create_from_file / BlueNoise / RayTracedScene tables)"""
+    from pyhr import assets
+    src = open(os.path.join(ROOT, "include", "hr_assets.h")).read()
+    names = sorted(set(re.findall(r"HR_API\s+[\w\s\*]+?\b(hra_\w+)\s*\(", src)))
+    assert len(names) >= 25, names
+    lib = assets.load_assets()
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in hr_assets.h but not exported"
+    assert C.sizeof(assets.hra_submesh) == 5 * 4 + 6 * 4
+
+
 def test_struct_layouts_match_the_reference():
     assert C.sizeof(pyhr.hr_ubo) == 416          # struct UBO, src/common.h:161-179 (5 mat4 + 2 vec4 + Light)
     assert C.sizeof(pyhr.hr_light) == 64         # src/common.h:106-111
