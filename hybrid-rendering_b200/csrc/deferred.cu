@@ -1,4 +1,5 @@
-// deferred.cu — deferred shading combine: src/shaders/deferred.frag:146-205, host src/deferred_shading.cpp:646-731.
+// deferred.cu — deferred shading combine + sky box: src/shaders/deferred.frag:146-205, skybox.{vert,frag}, host
+// src/deferred_shading.cpp:56-75 (render = render_shading + render_skybox), :646-731, :734-818.
 // Consumes the four pass outputs (shadows .r :187, AO :188, reflections rgb :166, DDGI irradiance :162) + the G-buffer and writes
 // Lo = direct_lighting(...) * visibility + indirect_lighting(...) as RGBA16F.  direct_lighting is the raster variant (no
 // RAY_TRACING / SOFT_SHADOWS defines in deferred.frag: the visibility is the shadows pass's output).  Environment = constant
@@ -54,8 +55,15 @@ __global__ void __launch_bounds__(256) k_deferred(GBufLevelDev g, FrameConsts fc
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = P.row0 + blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= g.W || y >= g.H || y >= P.row1) return;
     const size_t   pi  = (size_t)y * g.W + x;
+    const float    ndc_depth = __ldg(g.depth + pi);
+    if (ndc_depth == 1.0f)
+    { // render_skybox (deferred_shading.cpp:69, 734-818): the sky cube is drawn at depth 1 over the pixels the G-buffer left at its clear depth;
+      // skybox.frag:18-22 writes the environment cubemap's colour (a constant here), alpha 1
+        out[pi] = make_uint2(f2_to_h2(P.env[0], P.env[1]), f2_to_h2(P.env[2], 1.0f));
+        return;
+    }
     const float    tu = ((float)x + 0.5f) / (float)g.W, tv = ((float)y + 0.5f) / (float)g.H;
-    const float3   Pw = world_position_from_depth(tu, tv, __ldg(g.depth + pi), fc.view_proj_inverse);
+    const float3   Pw = world_position_from_depth(tu, tv, ndc_depth, fc.view_proj_inverse);
     const uint32_t a8 = g.gb1 ? __ldg(g.gb1 + pi) : 0u;
     const float3   albedo   = make_float3((float)(a8 & 255u) / 255.0f, (float)((a8 >> 8) & 255u) / 255.0f, (float)((a8 >> 16) & 255u) / 255.0f);
     const float    metallic = (float)(a8 >> 24) / 255.0f;

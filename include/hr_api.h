@@ -398,7 +398,8 @@ HR_API int hr_reflections_render(hr_pass* pass, const hr_frame* frame, const hr_
 
 /* ------------------------------------------------------------------------------------------------
  * Deferred shading combine  (src/deferred_shading.{h,cpp}; shaders/deferred.frag:146-205)
- * Lo = direct_lighting * shadows.r + indirect_lighting(DDGI irradiance, reflections, BRDF LUT) * AO  ->  RGBA16F (Lo, 1), full res.
+ * Lo = direct_lighting * shadows.r + indirect_lighting(DDGI irradiance, reflections, BRDF LUT) * AO  ->  RGBA16F (Lo, 1), full res;
+ * pixels at the G-buffer's clear depth (1.0) show the sky box = env_color (render_skybox, deferred_shading.cpp:69, skybox.frag).
  * Any of the four passes may be NULL (the reference's push constants shadow / ao / reflections / gi = 0: visibility 1, AO 1, the
  * environment colour as prefiltered reflection / irradiance).  Reads GB1 (albedo, metallic): bind or render it.
  * ---------------------------------------------------------------------------------------------- */

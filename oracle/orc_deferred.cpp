@@ -1,7 +1,8 @@
 // oracle/orc_deferred.cpp — TEST INFRASTRUCTURE ONLY (CPU oracle). Never linked into the product library.
 //
-// CPU restatement of the deferred shading combine: src/shaders/deferred.frag:146-205 (fresnel_schlick_roughness,
-// indirect_lighting, main) with direct_lighting of lighting.glsl:117-196 in its raster variant (deferred.frag defines neither
+// CPU restatement of the deferred shading combine and the sky box drawn over it (DeferredShading::render = render_shading +
+// render_skybox, src/deferred_shading.cpp:56-75): src/shaders/deferred.frag:146-205 (fresnel_schlick_roughness, indirect_lighting, main)
+// and skybox.frag:18-22, with direct_lighting of lighting.glsl:117-196 in its raster variant (deferred.frag defines neither
 // RAY_TRACING nor SOFT_SHADOWS: no shadow ray, the visibility comes from the shadows pass) and evaluate_uber_brdf (brdf.glsl:130-142).
 // It consumes exactly the four pass outputs (:162 GI, :166 reflections, :187 shadows .r, :188 AO) plus the G-buffer.
 // Environment: sky / prefiltered cubemaps and the irradiance SH are a constant colour c (assets absent), for which
@@ -43,6 +44,13 @@ extern "C" void orc_deferred(const orc_gbuf_full* g, const hr_frame* f, const ui
         for (int x = 0; x < W; x++)
         {
             const size_t pi = (size_t)y * W + x;
+            if (g->depth[pi] == 1.0f)
+            { // DeferredShading::render_skybox (deferred_shading.cpp:69, 734-818): the cube drawn at gl_Position = clipPos.xyww (skybox.vert:33, depth 1)
+              // covers exactly the pixels left at the G-buffer's clear depth; skybox.frag:18-22: vec4(texture(s_Cubemap, dir).rgb, 1) = the constant environment
+                uint16_t* o = out + 4 * pi;
+                o[0] = f2h(env.x); o[1] = f2h(env.y); o[2] = f2h(env.z); o[3] = f2h(1.0f);
+                continue;
+            }
             const vec2   tc = { ((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H };
             const vec3   P  = world_position_from_depth(tc, g->depth[pi], vpi);
             const vec3   albedo   = { g->gb1[4 * pi] / 255.0f, g->gb1[4 * pi + 1] / 255.0f, g->gb1[4 * pi + 2] / 255.0f };

@@ -43,7 +43,11 @@ def test_oracle_deferred_limits(lut):
     assert a[floor][:, :3].min() > 0.0                       # the floor faces the light
     b = f16(O.deferred(g, f, shadow=np.zeros((H, W), np.uint16)))  # visibility 0 everywhere: direct term gone, no environment => black
     assert np.abs(b[..., :3]).max() == 0.0
+    # render_skybox (deferred_shading.cpp:69): the pixels the G-buffer left at its clear depth show the environment, alpha 1
+    sky = g.depth == 1.0
+    assert sky.any() and np.abs(a[sky][:, :3]).max() == 0.0
     c = f16(O.deferred(g, f, env=SKY, brdf_lut=lut))
+    assert np.allclose(c[sky][:, :3], np.float16(SKY).astype(np.float32)) and (c[sky][:, 3] == 1.0).all()
     assert (c[floor][:, :3] >= a[floor][:, :3] - 1e-3).all() and c[floor][:, :3].mean() > a[floor][:, :3].mean()
 
 
