@@ -587,6 +587,30 @@ def taa_jitter(num_frames, W, H):
     return np.array(out[:], np.float32)
 
 
+def apply_jitter(frame, current, previous, first_frame=None):
+    """What HybridRendering::update_uniforms does with the TAA jitter (main.cpp:941-957) to an hr_frame built without it:
+    projection' = translate(current) * projection, hence view_proj' = J * view_proj, view_proj_inverse' = view_proj_inverse * J^-1,
+    proj_inverse' = proj_inverse * J^-1, prev_view_proj' = J * prev_view_proj (not on the first frame), current_prev_jitter = (current, previous).
+    Same arithmetic as hr::TemporalAA::apply_jitter (host/hybrid_rendering.h)."""
+    def mat(a):
+        return np.array(a[:], np.float32).reshape(4, 4).T  # column-major -> M[r, c]
+
+    def put(a, M):
+        a[:] = [float(v) for v in np.ascontiguousarray(M.T, np.float32).reshape(-1)]
+
+    J, Ji = np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)
+    J[0, 3], J[1, 3] = current[0], current[1]
+    Ji[0, 3], Ji[1, 3] = -current[0], -current[1]
+    u = frame.ubo
+    put(u.view_proj, J @ mat(u.view_proj))
+    put(u.view_proj_inverse, mat(u.view_proj_inverse) @ Ji)
+    put(u.proj_inverse, mat(u.proj_inverse) @ Ji)
+    if not (frame.first_frame if first_frame is None else first_frame):
+        put(u.prev_view_proj, J @ mat(u.prev_view_proj))
+    u.current_prev_jitter[0], u.current_prev_jitter[1], u.current_prev_jitter[2], u.current_prev_jitter[3] = [float(v) for v in (current[0], current[1], previous[0], previous[1])]
+    return frame
+
+
 class TAAPass(Pass):
     """temporal anti-aliasing (hr_taa_*): resolves another pass's final output against its own previous output"""
 

@@ -116,6 +116,37 @@ def test_taa_jitter_is_the_halton_2_3_sequence():
     assert O.taa_jitter(1, 256, 144)[0] == np.float32(-0.5) / np.float32(256)
 
 
+def test_apply_jitter_moves_the_image_by_the_jitter_in_ndc():
+    """update_uniforms (main.cpp:941-957): projection' = translate(jitter) * projection.  A world point's NDC position moves by exactly the
+    jitter; the inverse matrices stay inverses; the history matrix picks up the CURRENT jitter (not on the first frame)"""
+    W, H = 256, 144
+    f0 = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H)
+    f1 = pyhr.make_frame((0.1, 14, 34), (0, 3, 0), W, H, prev=f0, num_frames=1)
+    ref = pyhr.make_frame((0.1, 14, 34), (0, 3, 0), W, H, prev=f0, num_frames=1)
+    j1, j0 = pyhr.taa_jitter(1, W, H), pyhr.taa_jitter(0, W, H)
+    pyhr.apply_jitter(f1, j1, j0)
+
+    def M(a):
+        return np.array(a[:], np.float64).reshape(4, 4).T
+
+    P = np.array([1.0, 2.0, -3.0, 1.0])
+    a, b = M(ref.ubo.view_proj) @ P, M(f1.ubo.view_proj) @ P
+    assert np.allclose(b[:2] / b[3] - a[:2] / a[3], j1, atol=1e-6) and np.isclose(b[2] / b[3], a[2] / a[3], atol=1e-6)
+    assert np.allclose(M(f1.ubo.view_proj) @ M(f1.ubo.view_proj_inverse), np.eye(4), atol=2e-3)
+    a, b = M(ref.ubo.prev_view_proj) @ P, M(f1.ubo.prev_view_proj) @ P
+    assert np.allclose(b[:2] / b[3] - a[:2] / a[3], j1, atol=1e-6)
+    assert np.allclose(f1.ubo.current_prev_jitter[:], [j1[0], j1[1], j0[0], j0[1]])
+    # proj_inverse maps the jittered NDC back to the same view-space direction
+    nd = np.array([0.3, -0.2, 1.0, 1.0])
+    v0 = M(ref.ubo.proj_inverse) @ nd
+    v1 = M(f1.ubo.proj_inverse) @ (nd + np.array([j1[0], j1[1], 0, 0]))
+    assert np.allclose(v0[:3] / v0[3], v1[:3] / v1[3], rtol=1e-4, atol=1e-5)
+    first = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H)
+    keep = list(first.ubo.prev_view_proj[:])
+    pyhr.apply_jitter(first, j0, (0.0, 0.0))
+    assert list(first.ubo.prev_view_proj[:]) == keep  # main.cpp:955
+
+
 # ---------------------------------------------------------------------------------------------- TAA
 def test_taa_literals_equal_reference():
     t = REF["taa"]
