@@ -49,7 +49,7 @@ def test_taa_and_tonemap_match_the_oracle_over_a_jittered_pan():
         f = pyhr.make_frame((0.05 * max(0, i - 2), 14.0, 34.0), (0.0, 3.0, 0.0), W, H, prev=f, num_frames=i)
         j = pyhr.taa_jitter(i, W, H)
         assert np.array_equal(j, O.taa_jitter(i, W, H))
-        f.ubo.current_prev_jitter[0], f.ubo.current_prev_jitter[1], f.ubo.current_prev_jitter[2], f.ubo.current_prev_jitter[3] = j[0], j[1], prev_j[0], prev_j[1]
+        pyhr.apply_jitter(f, j, prev_j)  # update_uniforms: the projection carries the jitter, ubo.current_prev_jitter = (current, previous)
         prev_j = j
         ctx.gbuffer_render(f.ping_pong, f)
         sh.render(f)
