@@ -1,7 +1,8 @@
 // hr_headless.cpp — headless frame loop in C++ on the host classes (the analogue of HybridRendering::update,
 // src/main.cpp:49-129): update_uniforms -> build_tlas -> GBuffer -> Shadows -> AO -> DDGI -> Reflections -> DeferredShading ->
 // TemporalAA -> ToneMap -> end_frame, no window / swapchain / Vulkan: the G-buffer is ray cast on the device, the host only sends the per-frame constants.
-// Usage: hr_headless [width height frames tris [mesh.gltf|mesh.glb|mesh.obj]]   (a mesh file replaces the procedural arcade; it is drawn once
+// Usage: hr_headless [--post] [width height frames tris [mesh.gltf|mesh.glb|mesh.obj]]   --post: Halton-jittered camera + TemporalAA + ToneMap behind
+// the deferred combine;   (a mesh file replaces the procedural arcade; it is drawn once
 // with an identity transform, like the single-instance scenes of src/common.cpp:340-534)
 #include "hybrid_rendering.h"
 #include <chrono>
@@ -10,10 +11,21 @@
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <memory>
+#include <string>
 #include <vector>
 
 int main(int argc, char** argv)
 {
+    bool post = false;
+    for (int i = 1; i < argc; i++)
+        if (std::string(argv[i]) == "--post")
+        {
+            post = true;
+            for (int k = i; k + 1 < argc; k++) argv[k] = argv[k + 1];
+            argc--;
+            i--;
+        }
     const int W = argc > 1 ? atoi(argv[1]) : 1920, H = argc > 2 ? atoi(argv[2]) : 1080, frames = argc > 3 ? atoi(argv[3]) : 40;
     const int tris = argc > 4 ? atoi(argv[4]) : 262144;
     try
@@ -49,8 +61,8 @@ int main(int argc, char** argv)
         hr::DDGI                 ddgi(&common, &g_buffer, hr::RAY_TRACE_SCALE_FULL_RES);
         hr::RayTracedReflections reflections(&common, &g_buffer, hr::RAY_TRACE_SCALE_HALF_RES);
         hr::DeferredShading      deferred(&common, &g_buffer);
-        hr::TemporalAA           temporal_aa(&common, &g_buffer);
-        hr::ToneMap              tone_map(&common);
+        std::unique_ptr<hr::TemporalAA> temporal_aa_p(post ? new hr::TemporalAA(&common, &g_buffer) : nullptr); // only with --post
+        std::unique_ptr<hr::ToneMap>    tone_map_p(post ? new hr::ToneMap(&common) : nullptr);
         ddgi.set_probe_distance(8.0f);
         ddgi.set_normal_bias(0.5f);
         const float sky[3] = { 0.3f, 0.4f, 0.6f };
@@ -67,9 +79,9 @@ int main(int argc, char** argv)
         for (int i = 0; i < frames; i++)
         {
             const float pos[3] = { 0.02f * (float)i, 9.0f, -4.0f }; // slow lateral pan
-            temporal_aa.update(); // main.cpp:1025, before update_uniforms
+            if (post) temporal_aa_p->update(); // main.cpp:1025, before update_uniforms
             common.update_uniforms(pos, tgt, &light);
-            temporal_aa.apply_jitter();
+            if (post) temporal_aa_p->apply_jitter();
             hr_scene_rebuild(common.current_scene(), st); // build_tlas every frame (main.cpp:74)
             auto t0 = std::chrono::steady_clock::now();
             g_buffer.render(st);
@@ -78,8 +90,11 @@ int main(int argc, char** argv)
             ddgi.render(rot, st);
             reflections.render(st, &ddgi);
             deferred.render(st, shadows.handle(), ao.handle(), reflections.handle(), ddgi.handle());
-            temporal_aa.render(st, deferred.handle());
-            tone_map.render(st, &temporal_aa, deferred.handle());
+            if (post)
+            {
+                temporal_aa_p->render(st, deferred.handle());
+                tone_map_p->render(st, temporal_aa_p.get(), deferred.handle());
+            }
             cudaStreamSynchronize(st);
             gpu_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             common.end_frame();
@@ -93,17 +108,21 @@ int main(int argc, char** argv)
             for (int c = 0; c < 3; c++) { const float v = __half2float(px[k + c]); finite = finite && std::isfinite(v); sum += v; }
         printf("frames=%d last frame %.3f ms (g-buffer + shadows + ao + ddgi + reflections + deferred); output %dx%d fmt %d mean %.5f finite %d\n", frames, gpu_ms, o.width,
                o.height, o.format, sum / (3.0 * o.width * o.height), finite ? 1 : 0);
-        // the presented image: RGBA8 from the tone map over the TAA resolve
-        hr_image t = tone_map.output();
-        std::vector<uint8_t> ldr((size_t)t.width * t.height * 4);
-        cudaMemcpy(ldr.data(), t.data, ldr.size(), cudaMemcpyDeviceToHost);
-        double lsum = 0.0;
-        bool   opaque = true;
-        for (size_t k = 0; k < ldr.size(); k += 4) { lsum += ldr[k] + ldr[k + 1] + ldr[k + 2]; opaque = opaque && ldr[k + 3] == 255; }
-        printf("tone-mapped TAA output %dx%d fmt %d mean %.3f / 255, alpha opaque %d\n", t.width, t.height, t.format, lsum / (3.0 * t.width * t.height), opaque ? 1 : 0);
+        bool post_ok = true;
+        if (post)
+        { // the presented image: RGBA8 from the tone map over the TAA resolve
+            hr_image t = tone_map_p->output();
+            std::vector<uint8_t> ldr((size_t)t.width * t.height * 4);
+            cudaMemcpy(ldr.data(), t.data, ldr.size(), cudaMemcpyDeviceToHost);
+            double lsum = 0.0;
+            bool   opaque = true;
+            for (size_t k = 0; k < ldr.size(); k += 4) { lsum += ldr[k] + ldr[k + 1] + ldr[k + 2]; opaque = opaque && ldr[k + 3] == 255; }
+            printf("tone-mapped TAA output %dx%d fmt %d mean %.3f / 255, alpha opaque %d\n", t.width, t.height, t.format, lsum / (3.0 * t.width * t.height), opaque ? 1 : 0);
+            post_ok = opaque && lsum > 0.0 && t.format == HR_FMT_RGBA8;
+        }
         if (scene) hrs_scene_destroy(scene);
         if (!finite || !(sum > 0.0)) return 2;
-        if (!opaque || !(lsum > 0.0) || t.format != HR_FMT_RGBA8) return 3;
+        if (!post_ok) return 3;
     }
     catch (const std::exception& e)
     {

@@ -558,7 +558,7 @@ def test_procedural_scene_round_trip_is_bit_exact(tmp_path, fmt):
 
 
 def test_world_baked_export_reproduces_primitive_order_and_mesh_ids(tmp_path):
-    """the fixture of tests/test_gpu_scene_assets.py: one identity instance of the loaded file = the procedural scene"""
+    """the fixture of tests/widened/test_gpu_scene_assets.py: one identity instance of the loaded file = the procedural scene"""
     sc = pyhr.SynthScene(pyhr.SCENE_SHADOWS_TEST)
     mesh = A.Mesh(export_world_baked_glb(sc, tmp_path))
     asc = A.AssetScene([(mesh, np.eye(4, dtype=np.float32).reshape(-1))])

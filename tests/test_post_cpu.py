@@ -3,7 +3,7 @@
     parsed literals (tests/golden/ref_constants.json);
   * the PRODUCT's per-pixel device functions (hybrid-rendering_b200/csrc/post_px.cuh — the code k_taa / k_tonemap execute) compiled
     for the host (tests/hostemu) against the oracle: bit-exact for TAA, exact for the tone map (same libm), so the kernels'
-    arithmetic is checked without a GPU; tests/test_gpu_taa_tonemap.py repeats the comparison through the C ABI on the device;
+    arithmetic is checked without a GPU; tests/widened/test_gpu_taa_tonemap.py repeats the comparison through the C ABI on the device;
   * hr_taa_jitter (a pure host function of the product library) against the oracle and the Halton sequence's closed form."""
 import ctypes as C
 import json
