@@ -370,6 +370,35 @@ int png_decode(const uint8_t* d, size_t n, bool flip, int* W, int* H, int* C, ui
     return HRA_OK;
 }
 
+// ---- PNG writer (stored deflate blocks) -----------------------------------------------------------------------------------------
+uint32_t crc32_update(uint32_t c, const uint8_t* p, size_t n)
+{
+    static uint32_t table[256];
+    static bool     init = false;
+    if (!init)
+    {
+        for (uint32_t i = 0; i < 256; i++)
+        {
+            uint32_t v = i;
+            for (int k = 0; k < 8; k++) v = (v & 1u) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
+            table[i] = v;
+        }
+        init = true;
+    }
+    c = ~c;
+    for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+    return ~c;
+}
+void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+void png_chunk(std::vector<uint8_t>& out, const char* tag, const std::vector<uint8_t>& body)
+{
+    put_be32(out, (uint32_t)body.size());
+    const size_t start = out.size();
+    out.insert(out.end(), tag, tag + 4);
+    out.insert(out.end(), body.begin(), body.end());
+    put_be32(out, crc32_update(0, out.data() + start, out.size() - start));
+}
+
 // =====================================================================================================================
 // Radiance .hdr (RGBE)
 // =====================================================================================================================
@@ -1150,6 +1179,41 @@ int hra_image_loadf(const char* path, int flip_vertical, int* width, int* height
     return hdr_decode(file.data(), file.size(), flip_vertical != 0, width, height, rgba);
 }
 void hra_image_free(void* data) { free(data); }
+
+int hra_image_save_png(const char* path, int width, int height, int channels, const uint8_t* data)
+{
+    if (!path || !data || width <= 0 || height <= 0 || channels < 1 || channels > 4) return fail(HRA_ERR_INVALID_ARG, "hra_image_save_png: bad argument");
+    static const uint8_t ctype[5] = { 0, 0, 4, 2, 6 };
+    std::vector<uint8_t> out = { 137, 80, 78, 71, 13, 10, 26, 10 }, body;
+    put_be32(body, (uint32_t)width); put_be32(body, (uint32_t)height);
+    body.push_back(8); body.push_back(ctype[channels]); body.push_back(0); body.push_back(0); body.push_back(0);
+    png_chunk(out, "IHDR", body);
+    // scanlines with filter type 0, wrapped in a zlib stream of stored blocks (<= 65535 bytes each)
+    const size_t stride = (size_t)width * channels;
+    std::vector<uint8_t> raw;
+    raw.reserve((stride + 1) * (size_t)height);
+    for (int y = 0; y < height; y++) { raw.push_back(0); raw.insert(raw.end(), data + stride * (size_t)y, data + stride * (size_t)(y + 1)); }
+    body.clear();
+    body.push_back(0x78); body.push_back(0x01);
+    uint32_t a = 1, b = 0; // adler32
+    for (size_t pos = 0; pos < raw.size();)
+    {
+        const size_t n = std::min<size_t>(65535, raw.size() - pos);
+        body.push_back(pos + n == raw.size() ? 1 : 0);
+        body.push_back((uint8_t)(n & 255)); body.push_back((uint8_t)(n >> 8)); body.push_back((uint8_t)(~n & 255)); body.push_back((uint8_t)((~n >> 8) & 255));
+        body.insert(body.end(), raw.begin() + pos, raw.begin() + pos + n);
+        for (size_t i = 0; i < n; i++) { a = (a + raw[pos + i]) % 65521u; b = (b + a) % 65521u; }
+        pos += n;
+    }
+    put_be32(body, (b << 16) | a);
+    png_chunk(out, "IDAT", body);
+    png_chunk(out, "IEND", {});
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(HRA_ERR_IO, "cannot write %s", path);
+    const size_t w = fwrite(out.data(), 1, out.size(), f);
+    fclose(f);
+    return w == out.size() ? HRA_OK : fail(HRA_ERR_IO, "short write to %s", path);
+}
 
 int hra_bluenoise_load(const char* dir, uint8_t* sobol, uint8_t* sr, uint32_t* slots_loaded)
 {

@@ -1,7 +1,7 @@
 // hr_headless.cpp — headless frame loop in C++ on the host classes (the analogue of HybridRendering::update,
 // src/main.cpp:49-129): update_uniforms -> build_tlas -> GBuffer -> Shadows -> AO -> DDGI -> Reflections -> DeferredShading ->
 // TemporalAA -> ToneMap -> end_frame, no window / swapchain / Vulkan: the G-buffer is ray cast on the device, the host only sends the per-frame constants.
-// Usage: hr_headless [--post] [width height frames tris [mesh.gltf|mesh.glb|mesh.obj]]   --post: Halton-jittered camera + TemporalAA + ToneMap behind
+// Usage: hr_headless [--post [--png out.png]] [width height frames tris [mesh.gltf|mesh.glb|mesh.obj]]   --post: Halton-jittered camera + TemporalAA + ToneMap behind
 // the deferred combine;   (a mesh file replaces the procedural arcade; it is drawn once
 // with an identity transform, like the single-instance scenes of src/common.cpp:340-534)
 #include "hybrid_rendering.h"
@@ -17,15 +17,19 @@
 
 int main(int argc, char** argv)
 {
-    bool post = false;
+    bool        post = false;
+    std::string png_path; // --png FILE (with --post): write the tone-mapped frame as a PNG (hra_image_save_png)
     for (int i = 1; i < argc; i++)
-        if (std::string(argv[i]) == "--post")
-        {
-            post = true;
-            for (int k = i; k + 1 < argc; k++) argv[k] = argv[k + 1];
-            argc--;
-            i--;
-        }
+    {
+        const std::string a = argv[i];
+        const int drop = a == "--post" ? 1 : (a == "--png" && i + 1 < argc) ? 2 : 0;
+        if (!drop) continue;
+        if (drop == 1) post = true;
+        else png_path = argv[i + 1];
+        for (int k = i; k + drop < argc; k++) argv[k] = argv[k + drop];
+        argc -= drop;
+        i--;
+    }
     const int W = argc > 1 ? atoi(argv[1]) : 1920, H = argc > 2 ? atoi(argv[2]) : 1080, frames = argc > 3 ? atoi(argv[3]) : 40;
     const int tris = argc > 4 ? atoi(argv[4]) : 262144;
     try
@@ -119,6 +123,11 @@ int main(int argc, char** argv)
             for (size_t k = 0; k < ldr.size(); k += 4) { lsum += ldr[k] + ldr[k + 1] + ldr[k + 2]; opaque = opaque && ldr[k + 3] == 255; }
             printf("tone-mapped TAA output %dx%d fmt %d mean %.3f / 255, alpha opaque %d\n", t.width, t.height, t.format, lsum / (3.0 * t.width * t.height), opaque ? 1 : 0);
             post_ok = opaque && lsum > 0.0 && t.format == HR_FMT_RGBA8;
+            if (!png_path.empty())
+            {
+                if (hra_image_save_png(png_path.c_str(), t.width, t.height, 4, ldr.data()) != HRA_OK) throw std::runtime_error(hra_last_error());
+                printf("wrote %s\n", png_path.c_str());
+            }
         }
         if (scene) hrs_scene_destroy(scene);
         if (!finite || !(sum > 0.0)) return 2;

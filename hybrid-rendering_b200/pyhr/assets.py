@@ -30,6 +30,7 @@ def load_assets():
         L.hra_image_load_memory.argtypes = [C.c_void_p, C.c_size_t, C.c_int, ip, ip, ip, C.POINTER(C.c_void_p)]
         L.hra_image_loadf.argtypes = [C.c_char_p, C.c_int, ip, ip, C.POINTER(C.c_void_p)]
         L.hra_image_free.argtypes = [C.c_void_p]
+        L.hra_image_save_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.hra_bluenoise_load.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         L.hra_brdf_lut_load.argtypes = [C.c_char_p, C.c_void_p]
         L.hra_environment_constant.argtypes = [C.c_char_p, C.POINTER(C.c_float)]
@@ -70,6 +71,14 @@ def image_load(path=None, data=None, flip_vertical=False):
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), (h.value, w.value, c.value)).copy()
     finally:
         L.hra_image_free(p)
+
+
+def image_save_png(path, img):
+    """uint8 array (H, W) or (H, W, C), C in 1..4 -> PNG file (e.g. TonemapPass.download(100))"""
+    a = np.ascontiguousarray(img, np.uint8)
+    h, w = a.shape[:2]
+    c = 1 if a.ndim == 2 else a.shape[2]
+    _check(load_assets().hra_image_save_png(os.fsencode(path), w, h, c, a.ctypes.data), "hra_image_save_png")
 
 
 def image_loadf(path, flip_vertical=False):

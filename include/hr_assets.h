@@ -32,6 +32,10 @@ HR_API int  hra_image_load(const char* path, int flip_vertical, int* width, int*
 HR_API int  hra_image_load_memory(const uint8_t* bytes, size_t n, int flip_vertical, int* width, int* height, int* channels, uint8_t** data);
 HR_API int  hra_image_loadf(const char* path, int flip_vertical, int* width, int* height, float** rgba);
 HR_API void hra_image_free(void* data);
+/* Write an 8-bit image (1, 2, 3 or 4 channels: grey, grey + alpha, RGB, RGBA) as a PNG — e.g. the RGBA8 output of hr_tonemap_render read back
+ * with hr_pass_download (the reference has no screenshot function; its data/screenshot_*.jpg were taken by hand).  Filter type 0,
+ * deflate "stored" blocks: valid for every decoder, no compression. */
+HR_API int  hra_image_save_png(const char* path, int width, int height, int channels, const uint8_t* data);
 
 /* BlueNoise::BlueNoise (src/blue_noise.cpp:21-33): <dir>/sobol_256_4d.png and <dir>/scrambling_ranking_128x128_2d_{1..256}spp.png.
  * sobol: 256 x 1 RGBA8; scrambling_ranking[slot]: 128 x 128 RGBA8, slot = log2(spp).  slots_loaded: bit s set when table s was

@@ -280,6 +280,40 @@ def test_png_adam7_interlace(tmp_path):
     assert np.array_equal(A.image_load(tmp_path / "i1.png"), g1 * 255)
 
 
+def test_png_writer_round_trips_and_is_a_valid_zlib_stream(tmp_path):
+    """hra_image_save_png: read back by our decoder AND taken apart independently (chunk CRCs, Python's zlib on the IDAT stream)"""
+    rng = np.random.default_rng(8)
+    for shape in [(5, 7), (3, 4, 2), (300, 301, 3), (17, 9, 4)]:  # the RGB case spans several 65535-byte stored blocks
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        p = tmp_path / "w.png"
+        A.image_save_png(p, img)
+        got = A.image_load(p)
+        c = 1 if img.ndim == 2 else img.shape[2]
+        want = img.reshape(img.shape[0], img.shape[1], c)
+        if c == 3:
+            assert got.shape[2] == 4 and np.array_equal(got[..., :3], want) and np.all(got[..., 3] == 255)
+        else:
+            assert np.array_equal(got, want)
+        data = open(p, "rb").read()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat = 8, b""
+        while pos < len(data):
+            n = struct.unpack(">I", data[pos:pos + 4])[0]
+            tag, body = data[pos + 4:pos + 8], data[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + body) & 0xFFFFFFFF
+            if tag == b"IHDR":
+                assert struct.unpack(">IIBBBBB", body) == (img.shape[1], img.shape[0], 8, {1: 0, 2: 4, 3: 2, 4: 6}[c], 0, 0, 0)
+            if tag == b"IDAT":
+                idat += body
+            pos += 12 + n
+        raw = zlib.decompress(idat)  # checks the stored-block framing and the adler32
+        stride = img.shape[1] * c
+        assert len(raw) == (stride + 1) * img.shape[0] and all(raw[(stride + 1) * y] == 0 for y in range(img.shape[0]))
+        assert raw[1:stride + 1] == want[0].tobytes()
+    with pytest.raises(pyhr.HrError, match="cannot write"):
+        A.image_save_png(tmp_path / "no_such_dir" / "x.png", np.zeros((2, 2), np.uint8))
+
+
 def test_png_errors(tmp_path):
     img = np.zeros((4, 4, 4), np.uint8)
     write_png(tmp_path / "ok.png", img, 6, 8)
