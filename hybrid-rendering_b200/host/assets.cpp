@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <functional>
 #include <map>
 #include <string>
@@ -992,9 +993,13 @@ int gltf_accessor(Gltf& g, long ai, int want_comp, std::vector<float>* fout, std
     const long bv = a.integer("bufferView", -1);
     *count = n;
     const int out_comp = want_comp ? want_comp : ncomp;
-    if (fout) fout->assign(n * out_comp, 0.0f);
-    if (iout) iout->assign(n, 0u);
-    if (bv < 0) return HRA_OK; // all zeros
+    if (n > (1u << 28)) return fail(HRA_ERR_FORMAT, "%s: accessor %ld claims %zu elements", g.path.c_str(), ai, n);
+    if (bv < 0)
+    { // no bufferView: all zeros
+        if (fout) fout->assign(n * out_comp, 0.0f);
+        if (iout) iout->assign(n, 0u);
+        return HRA_OK;
+    }
     const JVal* views = g.root.array("bufferViews");
     if (!views || (size_t)bv >= views->arr.size()) return fail(HRA_ERR_FORMAT, "%s: bufferView %ld does not exist", g.path.c_str(), bv);
     const JVal& v = views->arr[bv];
@@ -1005,7 +1010,9 @@ int gltf_accessor(Gltf& g, long ai, int want_comp, std::vector<float>* fout, std
     size_t stride = (size_t)v.integer("byteStride", 0);
     if (!stride) stride = elem;
     const size_t off = (size_t)v.integer("byteOffset", 0) + (size_t)a.integer("byteOffset", 0);
-    if (n && off + stride * (n - 1) + elem > buf->size()) return fail(HRA_ERR_FORMAT, "%s: accessor %ld reads past the end of its buffer", g.path.c_str(), ai);
+    if (n && (off > buf->size() || stride > buf->size() || off + stride * (n - 1) + elem > buf->size())) return fail(HRA_ERR_FORMAT, "%s: accessor %ld reads past the end of its buffer", g.path.c_str(), ai);
+    if (fout) fout->assign(n * out_comp, 0.0f); // sized only after the data was seen to exist
+    if (iout) iout->assign(n, 0u);
     for (size_t i = 0; i < n; i++)
         for (int c = 0; c < (iout ? 1 : out_comp); c++)
         {
@@ -1159,10 +1166,15 @@ extern "C" {
 
 const char* hra_last_error(void) { return g_err.c_str(); }
 
+// no C++ exception may cross the C boundary (std::bad_alloc on absurd sizes, std::length_error ...)
+#define HRA_GUARDED(expr)                                                                       \
+    try { return (expr); }                                                                      \
+    catch (const std::exception& e) { return fail(HRA_ERR_IO, "out of memory or internal error: %s", e.what()); }
+
 int hra_image_load_memory(const uint8_t* bytes, size_t n, int flip_vertical, int* width, int* height, int* channels, uint8_t** data)
 {
     if (!bytes || !width || !height || !channels || !data) return fail(HRA_ERR_INVALID_ARG, "hra_image_load_memory: null argument");
-    return png_decode(bytes, n, flip_vertical != 0, width, height, channels, data);
+    HRA_GUARDED(png_decode(bytes, n, flip_vertical != 0, width, height, channels, data));
 }
 int hra_image_load(const char* path, int flip_vertical, int* width, int* height, int* channels, uint8_t** data)
 {
@@ -1176,7 +1188,7 @@ int hra_image_loadf(const char* path, int flip_vertical, int* width, int* height
     if (!path || !width || !height || !rgba) return fail(HRA_ERR_INVALID_ARG, "hra_image_loadf: null argument");
     std::vector<uint8_t> file;
     if (!read_file(path, file)) return fail(HRA_ERR_IO, "cannot read %s", path);
-    return hdr_decode(file.data(), file.size(), flip_vertical != 0, width, height, rgba);
+    HRA_GUARDED(hdr_decode(file.data(), file.size(), flip_vertical != 0, width, height, rgba));
 }
 void hra_image_free(void* data) { free(data); }
 
@@ -1285,9 +1297,13 @@ int hra_mesh_load(const char* path, hra_mesh** out)
     m->path = path;
     const std::string e = ext_of(path);
     int rc;
-    if (e == "obj") rc = load_obj(path, m);
-    else if (e == "gltf" || e == "glb") rc = load_gltf(path, m);
-    else rc = fail(HRA_ERR_UNSUPPORTED, "%s: unsupported mesh format '%s' (obj, gltf, glb)", path, e.c_str());
+    try
+    {
+        if (e == "obj") rc = load_obj(path, m);
+        else if (e == "gltf" || e == "glb") rc = load_gltf(path, m);
+        else rc = fail(HRA_ERR_UNSUPPORTED, "%s: unsupported mesh format '%s' (obj, gltf, glb)", path, e.c_str());
+    }
+    catch (const std::exception& ex) { rc = fail(HRA_ERR_IO, "%s: out of memory or internal error: %s", path, ex.what()); }
     if (rc) { delete m; *out = nullptr; return rc; }
     *out = m;
     return HRA_OK;
