@@ -2,7 +2,8 @@
  * hr_api.h — C ABI of the B200-native ray-trace + SVGF hot path.
  *
  * This is the drop-in boundary for the four render passes of diharaw/hybrid-rendering
- * (RayTracedShadows, RayTracedAO, RayTracedReflections, DDGI).  The reference has no
+ * (RayTracedShadows, RayTracedAO, RayTracedReflections, DDGI) and the stages either side of them
+ * (G-buffer producer; DeferredShading, TemporalAA, ToneMap, GroundTruthPathTracer).  The reference has no
  * FFI of its own; its seam is the C++ pass-class interface
  *     Pass(backend, CommonResources*, GBuffer*, RayTraceScale)   src/ray_traced_shadows.h:23
  *     void render(cmd_buf)                                       src/ray_traced_shadows.h:26
