@@ -1355,6 +1355,8 @@ int hra_scene_finalize(hra_scene* s)
         auto it = seen.find(in.mesh);
         if (it == seen.end())
         {
+            if (s->vertices.size() + in.mesh->vertices.size() > 0xFFFFFFFFull || s->indices.size() + in.mesh->indices.size() > 0xFFFFFFFFull)
+                return fail(HRA_ERR_UNSUPPORTED, "hra_scene_finalize: more than 2^32 vertices or indices (hr_instance offsets are 32-bit)");
             Off o { (uint32_t)s->vertices.size(), (uint32_t)s->indices.size(), (uint32_t)s->materials.size() };
             s->vertices.insert(s->vertices.end(), in.mesh->vertices.begin(), in.mesh->vertices.end());
             s->indices.insert(s->indices.end(), in.mesh->indices.begin(), in.mesh->indices.end());
