@@ -649,3 +649,32 @@ def test_loaders_reject_corrupted_files_without_crashing(tmp_path):
     big[16:24] = struct.pack(">II", 16000, 16000)
     with pytest.raises(pyhr.HrError, match="too short"):
         A.image_load(data=bytes(big))
+
+
+def test_png_encode_decode_property(tmp_path):
+    """hypothesis: any 8-bit image of 1-4 channels survives hra_image_save_png -> hra_image_load (RGB comes back with alpha 255), and
+    any image written by the independent test encoder with any filter cycle / deflate level / interlacing decodes to itself"""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+
+    @settings(max_examples=40, deadline=None)
+    @given(hnp.arrays(np.uint8, st.tuples(st.integers(1, 24), st.integers(1, 24), st.integers(1, 4))))
+    def ours(img):
+        p = tmp_path / "h.png"
+        A.image_save_png(p, img)
+        got = A.image_load(p)
+        if img.shape[2] == 3:
+            assert np.array_equal(got[..., :3], img) and np.all(got[..., 3] == 255)
+        else:
+            assert np.array_equal(got, img)
+
+    @settings(max_examples=40, deadline=None)
+    @given(hnp.arrays(np.uint8, st.tuples(st.integers(1, 20), st.integers(1, 20), st.just(4))), st.lists(st.integers(0, 4), min_size=1, max_size=5), st.integers(0, 9),
+           st.booleans(), st.integers(1, 4))
+    def theirs(img, cycle, level, interlace, split):
+        p = tmp_path / "t.png"
+        write_png(p, img, 6, 8, cycle=tuple(cycle), interlace=interlace, level=level, split_idat=split)
+        assert np.array_equal(A.image_load(p), img)
+
+    ours()
+    theirs()
