@@ -172,6 +172,33 @@ def test_taa_device_functions_equal_the_oracle_bit_for_bit(W, H, seed, channels,
     assert np.array_equal(a, emu_taa(cur, prev, depth, gb2, (0.0, 0.0), 0.5, 0.75, sharpen))
 
 
+def test_taa_device_functions_equal_the_oracle_on_arbitrary_finite_inputs():
+    """hypothesis: ANY finite binary16 images (negative values, subnormals, +-65504, zeros), any depths in [0, 1], motion vectors of up to +-4
+    texels, jitters of up to +-1.5 texels, any feedback pair in [0, 1]: the kernel's per-pixel function and the oracle agree on every bit"""
+    from hypothesis import given, settings, strategies as st
+    from hypothesis.extra import numpy as hnp
+    W, H = 12, 9
+    finite_half = st.integers(0, 0xFFFF).filter(lambda v: (v & 0x7C00) != 0x7C00)
+    halves = lambda shape: hnp.arrays(np.uint16, shape, elements=finite_half)
+
+    @settings(max_examples=60, deadline=None)
+    @given(halves((H, W, 4)), halves((H, W, 4)), hnp.arrays(np.float32, (H, W), elements=st.floats(0.0, 1.0, width=32)),
+           hnp.arrays(np.float32, (H, W, 2), elements=st.floats(-4.0, 4.0, width=32)), st.tuples(st.floats(-1.5, 1.5, width=32), st.floats(-1.5, 1.5, width=32)),
+           st.floats(0.0, 1.0, width=32), st.floats(0.0, 1.0, width=32), st.integers(0, 1), st.sampled_from([1, 2, 4]))
+    def check(cur, prev, depth, mv, jit, fmin, fmax, sharpen, channels):
+        gb2 = np.zeros((H, W, 4), np.float32)
+        gb2[..., 2], gb2[..., 3] = mv[..., 0] / W, mv[..., 1] / H
+        c = cur if channels == 4 else (cur[..., 0].copy() if channels == 1 else cur[..., :2].copy())
+        j = (np.float32(jit[0]) / np.float32(W), np.float32(jit[1]) / np.float32(H))
+        a = O.taa(c, prev, depth, h(gb2), j, fmin, fmax, sharpen)
+        b = emu_taa(c, prev, depth, h(gb2), j, fmin, fmax, sharpen)
+        assert np.array_equal(a, b)
+        out = a.view(np.float16).astype(np.float32)
+        assert np.all(out[..., 3] == 1.0) and np.all((out[..., :3] >= 0.0) & (out[..., :3] <= 1.0))  # NaNs are clamped away too
+
+    check()
+
+
 def test_taa_closed_form_properties():
     W, H = 32, 16
     gb2 = np.zeros((H, W, 4), np.uint16)
