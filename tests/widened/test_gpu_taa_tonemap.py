@@ -19,7 +19,7 @@ def u16(a):
 
 def same_halves(a, b):
     """equal as binary16 VALUES: bit-identical except that -0 == +0 (fmax(-0, +0) may return either zero, IEEE 754 leaves it open)"""
-    return np.array_equal(np.ascontiguousarray(a).view(np.float16), np.ascontiguousarray(b).view(np.float16))
+    return np.array_equal(np.ascontiguousarray(a).view(np.float16), np.ascontiguousarray(b).view(np.float16), equal_nan=True)
 
 
 def test_taa_and_tonemap_match_the_oracle_over_a_jittered_pan():
