@@ -45,8 +45,12 @@ __device__ __forceinline__ uint32_t unorm8(float v)
     return (uint32_t)(s < 0.0f ? 0.0f : (s > 255.0f ? 255.0f : s));
 }
 
+// TEX: material textures bound (hr_scene_set_textures): albedo / metallic / roughness of GB1 / GB3 come from fetch_albedo / fetch_metallic /
+// fetch_roughness at the hit (g_buffer.frag:90-105), sampled at mip 0 (a ray cast has no screen-space derivatives; the raster pass filters
+// trilinearly).  The untextured instantiation compiles exactly as before.
+template <bool TEX>
 __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc, GbufParams P, uint32_t* __restrict__ gb1, uint2* __restrict__ gb2, uint2* __restrict__ gb3,
-                                                        float* __restrict__ depth, unsigned long long* ray_ctr)
+                                                        float* __restrict__ depth, unsigned long long* ray_ctr, tex::TexDev T)
 {
     __shared__ int s_stack[2][STACK_SIZE]; // one packet-traversal stack per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,10 +109,20 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
                 fmid = (float)mid;
                 g2x  = pack_h2(ox, oy);
                 g2y  = pack_h2(pu - cu, pv - cv);
-                g3x  = pack_h2(m->roughness, 0.0f);
                 linz = c.z; // gl_FragCoord.z / gl_FragCoord.w = z_clip, g_buffer.frag:107
                 dz   = d;
-                g1   = unorm8(m->albedo[0]) | (unorm8(m->albedo[1]) << 8) | (unorm8(m->albedo[2]) << 16) | (unorm8(m->metallic) << 24);
+                if (TEX)
+                {
+                    float ar = m->albedo[0], ag = m->albedo[1], ab = m->albedo[2], rough = m->roughness, metal = m->metallic;
+                    tex::material_at_hit(T, __ldg(sc.prim_mat + prim), prim, b0, hu, hv, ar, ag, ab, rough, metal);
+                    g3x = pack_h2(rough, 0.0f);
+                    g1  = unorm8(ar) | (unorm8(ag) << 8) | (unorm8(ab) << 16) | (unorm8(metal) << 24);
+                }
+                else
+                {
+                    g3x = pack_h2(m->roughness, 0.0f);
+                    g1  = unorm8(m->albedo[0]) | (unorm8(m->albedo[1]) << 8) | (unorm8(m->albedo[2]) << 16) | (unorm8(m->metallic) << 24);
+                }
             }
         }
     }
@@ -158,5 +172,6 @@ void launch_gbuffer_render(const hr_scene* sc, const hr_frame* f, int W, int H, 
     P.W = W; P.H = H; P.row0 = row0; P.row1 = row1;
     P.chunk_first = chunk_first; P.chunk_stride = chunk_stride;
     dim3 grid((W + 15) / 16, chunk_stride > 1 ? 2 * n_chunks_mine : (row1 - row0 + 3) / 4);
-    k_gbuffer_render<<<grid, 64, 0, st>>>(hr_bvh_view(sc), gs, P, (uint32_t*)gb1, (uint2*)gb2, (uint2*)gb3, depth, ray_ctr);
+    if (sc->tex.n_textures > 0) k_gbuffer_render<true><<<grid, 64, 0, st>>>(hr_bvh_view(sc), gs, P, (uint32_t*)gb1, (uint2*)gb2, (uint2*)gb3, depth, ray_ctr, sc->tex);
+    else k_gbuffer_render<false><<<grid, 64, 0, st>>>(hr_bvh_view(sc), gs, P, (uint32_t*)gb1, (uint2*)gb2, (uint2*)gb3, depth, ray_ctr, sc->tex);
 }

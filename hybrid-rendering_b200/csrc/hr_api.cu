@@ -224,6 +224,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     // same arithmetic as transform_vertex (scene_descriptor_set.glsl:147-156): mat4 * vec4 position, normalize(mat3 * normal).
     std::vector<float>    soup;
     std::vector<float>    vnorm;
+    std::vector<float>    vuv; // texture coordinates per primitive corner (host copy; on the device only when textures are bound)
     std::vector<uint32_t> prim_inst, prim_mat;
     for (size_t ii = 0; ii < n_instances; ii++)
     {
@@ -246,6 +247,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
                 const float l = sqrtf((wx * wx + wy * wy) + wz * wz);
                 const float il = l > 0.0f ? 1.0f / l : 0.0f;
                 vnorm.push_back(wx * il); vnorm.push_back(wy * il); vnorm.push_back(wz * il); vnorm.push_back(0.0f);
+                vuv.push_back(v.tex_coord[0]); vuv.push_back(v.tex_coord[1]);
             }
             prim_inst.push_back((uint32_t)ii);
             prim_mat.push_back(in.material_idx);
@@ -258,6 +260,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     hr_scene* sc = new hr_scene();
     sc->ctx      = ctx;
     sc->n_tris   = (uint32_t)n;
+    sc->h_vuv    = std::move(vuv);
     const size_t ni = n > 1 ? n - 1 : 1;
 #define ALLOC(ptr, bytes) HR_CUDA(ctx, cudaMalloc((void**)&(ptr), (bytes)))
     ALLOC(sc->d_tri_verts, n * 9 * sizeof(float));
@@ -353,9 +356,89 @@ int hr_scene_destroy(hr_scene* sc)
     if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
     void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
                      sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_wnodes, sc->d_depth, sc->d_tris,
-                     sc->d_materials, sc->d_sort_tmp, sc->d_ploc };
+                     sc->d_materials, sc->d_sort_tmp, sc->d_ploc, sc->d_vuv, sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_srgb_lut };
     for (void* p : ptrs) cudaFree(p);
     delete sc;
+    return HR_OK;
+}
+
+// Material textures: Material::load uploads one VkImage per texture and RayTracedScene binds them as s_Textures[] (ray_traced_scene.cpp:345-420);
+// here every texture is expanded to RGBA8 and concatenated into one buffer (tex_px.cuh).
+int hr_scene_set_textures(hr_scene* sc, const hr_texture* textures, size_t n_textures, const hr_material_textures* bindings, size_t n_materials)
+{
+    if (!sc) return HR_ERR_INVALID_ARG;
+    hr_ctx* ctx = sc->ctx;
+    HR_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto drop = [&]() {
+        void* ptrs[] = { sc->d_texels, sc->d_tex_desc, sc->d_mat_tex };
+        for (void* p : ptrs) cudaFree(p);
+        sc->d_texels = nullptr; sc->d_tex_desc = nullptr; sc->d_mat_tex = nullptr;
+        sc->tex = tex::TexDev {};
+    };
+    if (n_textures == 0) { cudaDeviceSynchronize(); drop(); return HR_OK; }
+    HR_REQUIRE(ctx, textures && bindings, HR_ERR_INVALID_ARG, "hr_scene_set_textures: null argument");
+    HR_REQUIRE(ctx, n_materials == sc->n_materials && n_materials > 0, HR_ERR_INVALID_ARG, "hr_scene_set_textures: one binding per material of the scene is required");
+    HR_REQUIRE(ctx, n_textures < (1u << 20), HR_ERR_UNSUPPORTED, "hr_scene_set_textures: too many textures");
+    std::vector<tex::TexDesc> desc(n_textures);
+    size_t total = 0;
+    for (size_t i = 0; i < n_textures; i++)
+    {
+        const hr_texture& t = textures[i];
+        HR_REQUIRE(ctx, t.data && t.width > 0 && t.height > 0 && t.width <= 16384 && t.height <= 16384 && (t.channels == 1 || t.channels == 2 || t.channels == 4),
+                   HR_ERR_INVALID_ARG, "hr_scene_set_textures: a texture has no data, a bad size (1..16384) or a channel count other than 1, 2, 4");
+        desc[i].offset = (uint32_t)total; desc[i].width = t.width; desc[i].height = t.height; desc[i].srgb = t.srgb ? 1 : 0;
+        total += (size_t)t.width * t.height;
+        HR_REQUIRE(ctx, total < (1ull << 32), HR_ERR_UNSUPPORTED, "hr_scene_set_textures: more than 2^32 texels in total");
+    }
+    std::vector<tex::MatTex> mt(n_materials);
+    for (size_t m = 0; m < n_materials; m++)
+    {
+        const hr_material_textures& b = bindings[m];
+        const int32_t idx[5] = { b.albedo, b.normal, b.roughness, b.metallic, b.emissive };
+        for (int32_t i : idx) HR_REQUIRE(ctx, i >= -1 && i < (int32_t)n_textures, HR_ERR_INVALID_ARG, "hr_scene_set_textures: texture index out of range");
+        HR_REQUIRE(ctx, (b.roughness < 0 || (b.roughness_channel >= 0 && b.roughness_channel <= 3)) && (b.metallic < 0 || (b.metallic_channel >= 0 && b.metallic_channel <= 3)),
+                   HR_ERR_INVALID_ARG, "hr_scene_set_textures: roughness / metallic channel must be 0..3");
+        mt[m] = tex::MatTex { b.albedo, b.normal, b.roughness, b.roughness_channel, b.metallic, b.metallic_channel, b.emissive, 0 };
+    }
+    std::vector<uint32_t> texels(total);
+    for (size_t i = 0; i < n_textures; i++)
+    { // missing components read (0, 0, 1) like a sampler on an R8 / RG8 image
+        const hr_texture& t = textures[i];
+        uint32_t* dst = texels.data() + desc[i].offset;
+        const size_t px = (size_t)t.width * t.height;
+        for (size_t k = 0; k < px; k++)
+        {
+            const uint8_t* q = t.data + k * t.channels;
+            dst[k] = t.channels == 4 ? ((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24))
+                   : t.channels == 2 ? ((uint32_t)q[0] | ((uint32_t)q[1] << 8) | 0xFF000000u) : ((uint32_t)q[0] | 0xFF000000u);
+        }
+    }
+    float lut[256];
+    for (int i = 0; i < 256; i++)
+    { // sRGB EOTF in double, rounded once (the oracle builds the same table)
+        const double c = i / 255.0;
+        lut[i] = (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+    HR_REQUIRE(ctx, sc->h_vuv.size() == 6ull * sc->n_tris, HR_ERR_NOT_READY, "hr_scene_set_textures: the scene holds no texture coordinates");
+    cudaDeviceSynchronize();
+    drop();
+    if (!sc->d_vuv)
+    {
+        HR_CUDA(ctx, cudaMalloc((void**)&sc->d_vuv, sc->h_vuv.size() * sizeof(float)));
+        HR_CUDA(ctx, cudaMemcpy(sc->d_vuv, sc->h_vuv.data(), sc->h_vuv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (!sc->d_srgb_lut)
+    {
+        HR_CUDA(ctx, cudaMalloc((void**)&sc->d_srgb_lut, sizeof(lut)));
+        HR_CUDA(ctx, cudaMemcpy(sc->d_srgb_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    }
+    HR_CUDA(ctx, cudaMalloc((void**)&sc->d_texels, total * sizeof(uint32_t)));
+    HR_CUDA(ctx, cudaMalloc((void**)&sc->d_tex_desc, n_textures * sizeof(tex::TexDesc)));
+    HR_CUDA(ctx, cudaMalloc((void**)&sc->d_mat_tex, n_materials * sizeof(tex::MatTex)));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_texels, texels.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_tex_desc, desc.data(), n_textures * sizeof(tex::TexDesc), cudaMemcpyHostToDevice));
+    HR_CUDA(ctx, cudaMemcpy(sc->d_mat_tex, mt.data(), n_materials * sizeof(tex::MatTex), cudaMemcpyHostToDevice));
+    sc->tex = tex::TexDev { sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_vuv, sc->d_srgb_lut, (int32_t)n_textures };
     return HR_OK;
 }
 

@@ -1,6 +1,7 @@
 // hr_internal.h — internal types of libhr_b200 (not part of the ABI).
 #pragma once
 #include "../../include/hr_api.h"
+#include "tex_px.cuh"
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -144,6 +145,15 @@ struct hr_scene {
     uint32_t* d_prim_mat = nullptr;  // material index per primitive
     hr_material* d_materials = nullptr;
     uint32_t  n_materials = 0;
+    // material textures (hr_scene_set_textures): per-primitive texture coordinates are kept on the host by hr_scene_build and only uploaded when
+    // textures are bound; `tex` is what the TEX instantiations of the shading kernels receive (n_textures == 0: the untextured kernels run)
+    std::vector<float> h_vuv;        // 6 per primitive
+    float*         d_vuv = nullptr;
+    uint32_t*      d_texels = nullptr;
+    tex::TexDesc*  d_tex_desc = nullptr;
+    tex::MatTex*   d_mat_tex = nullptr;
+    float*         d_srgb_lut = nullptr;
+    tex::TexDev    tex {};
     hr_scene_info info {};
 };
 

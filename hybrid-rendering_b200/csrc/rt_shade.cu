@@ -178,6 +178,38 @@ __device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& s
     return Lo;
 }
 
+// Material textures (hr_scene_set_textures, tex_px.cuh): fetch_albedo / fetch_roughness / fetch_metallic at the hit point.  The TEX
+// instantiations of the kernels below call these; the untextured instantiations compile exactly as before (tools/sass_function_hashes.py).
+__device__ __forceinline__ Surface fetch_surface_tex(const ShadeDev& sd, const tex::TexDev& T, uint32_t prim, float u, float v)
+{
+    Surface s = fetch_surface(sd, prim, u, v);
+    tex::material_at_hit(T, __ldg(sd.prim_mat + prim), prim, 1.0f - u - v, u, v, s.albedo.x, s.albedo.y, s.albedo.z, s.roughness, s.metallic);
+    return s;
+}
+__device__ __forceinline__ float3 shade_hit_tex(const BvhDev& bvh, const ShadeDev& sd, const tex::TexDev& T, const hr_light& light, const Ray& r, uint32_t prim, float u, float v,
+                                                bool sky_light, float r0, float r1, float3 sky, bool gi_on, const hr_ddgi_uniforms& d, const gi::AtlasDev& at, float gi_intensity,
+                                                unsigned long long* ray_ctr, IblDev ibl = IblDev { nullptr, 0.0f })
+{ // shade_hit with the textured surface
+    using namespace gi;
+    const Surface s  = fetch_surface_tex(sd, T, prim, u, v);
+    const V3      Wo = det::scale(r.d, -1.0f);
+    const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;
+    const float3  cd = (s.albedo * (f3(1, 1, 1) - F0)) * (1.0f - s.metallic) + f3(0, 0, 0) * s.metallic;
+    float3        Lo = direct_lighting(bvh, light, Wo, s.N, s.P, F0, cd, s.roughness, sky_light, r0, r1, sky, ray_ctr);
+    if (gi_on)
+    {
+        Lo = Lo + indirect_diffuse(d, at, Wo, s.N, s.P, F0, cd, s.roughness, s.metallic, gi_intensity);
+        if (ibl.lut)
+        {
+            const float  ct = fmaxf(det::dot(s.N, Wo), 0.0f), p5 = powf(fmaxf(1.0f - ct, 0.0f), 5.0f), omr = 1.0f - s.roughness;
+            const float3 F  = F0 + (f3(fmaxf(omr, F0.x), fmaxf(omr, F0.y), fmaxf(omr, F0.z)) - F0) * p5;
+            const float2 b  = brdf_lut_fetch(ibl.lut, ct, s.roughness);
+            Lo = Lo + (sky * (F * b.x + f3(b.y, b.y, b.y))) * ibl.intensity;
+        }
+    }
+    return Lo;
+}
+
 __device__ __forceinline__ uint2 pack_h4(float a, float b, float c, float d)
 {
     const __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
@@ -200,8 +232,9 @@ __device__ __forceinline__ V3 spherical_fibonacci(float i, float n)
 struct GiTraceParams { float rot[16]; uint32_t num_frames, infinite_bounces; float gi_intensity; float sky[3]; int probe0, probe1; unsigned long long* ray_ctr; };
 
 // K18: one block per probe, one thread per ray (blockDim = rays_per_probe rounded up to 32, looped if > 256)
+template <bool TEX>
 __global__ void __launch_bounds__(256) k_ddgi_ray_trace(BvhDev bvh, ShadeDev sd, hr_ddgi_uniforms d, gi::AtlasDev at, hr_light light, GiTraceParams P,
-                                                         uint2* __restrict__ radiance, uint2* __restrict__ dirdepth)
+                                                         uint2* __restrict__ radiance, uint2* __restrict__ dirdepth, tex::TexDev T)
 {
     const int probe = P.probe0 + blockIdx.x;
     if (probe >= P.probe1) return;
@@ -226,7 +259,8 @@ __global__ void __launch_bounds__(256) k_ddgi_ray_trace(BvhDev bvh, ShadeDev sd,
         if (trace_closest(bvh, r, t, prim, u, v))
         {
             const float r0 = gi::next_float(rng), r1 = gi::next_float(rng);
-            L              = shade_hit(bvh, sd, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity, P.ray_ctr);
+            L              = TEX ? shade_hit_tex(bvh, sd, T, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity, P.ray_ctr)
+                                 : shade_hit(bvh, sd, light, r, prim, u, v, true, r0, r1, sky, P.infinite_bounces == 1, d, at, P.gi_intensity, P.ray_ctr);
             hit_distance   = 0.001f + t;
         }
         else L = sky;
@@ -260,10 +294,10 @@ struct ReflTraceParams { float bias, trim; int sample_gi, approximate_with_ddgi;
 // K12: warp = 8x4 pixel block (coherent reflection rays), 256 threads = 32x8 pixels
 // 2-warp CTAs (16x4 pixels): closest-hit rays + hit shading are heavy-tailed, small CTAs recycle their slots sooner (trace.cu)
 // MULTI = false: exactly the reference's one ray per pixel (straight-line code); true: the spp > 1 extension (sample loop)
-template <bool MULTI, int MINB>
+template <bool MULTI, int MINB, bool TEX>
 __global__ void __launch_bounds__(64, MINB) k_reflections_ray_trace(GBufLevelDev g, BvhDev bvh, ShadeDev sd, FrameConsts fc, hr_ddgi_uniforms d, gi::AtlasDev at,
                                                                 ReflTraceParams P, const uint8_t* __restrict__ sobol, const uint8_t* __restrict__ srk,
-                                                                uint2* __restrict__ out)
+                                                                uint2* __restrict__ out, tex::TexDev T)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // rows: [row0, row1) or, when the ranks trace cooperatively, the 8-row chunks c = chunk_first + i * chunk_stride of the whole image
@@ -319,7 +353,8 @@ __global__ void __launch_bounds__(64, MINB) k_reflections_ray_trace(GBufLevelDev
             count_rays(fc.ray_ctr, 0, 1u);
             if (trace_closest(bvh, r, t, prim, hu, hv))
             {
-                color = shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr, P.ibl);
+                color = TEX ? shade_hit_tex(bvh, sd, T, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr, P.ibl)
+                            : shade_hit(bvh, sd, fc.light, r, prim, hu, hv, false, 0.0f, 0.0f, sky, P.sample_gi == 1, d, at, P.gi_intensity, fc.ray_ctr, P.ibl);
                 if (s == 0) ray_length = 0.001f + t;
             }
             else color = sky;
@@ -604,7 +639,9 @@ __device__ __forceinline__ float4 mat_vec4(const float* M, float x, float y, flo
 }
 
 // warp = 8x4 pixel block (coherent primary rays), 2-warp CTAs like K12
-__global__ void __launch_bounds__(64) k_path_trace(BvhDev bvh, ShadeDev sd, PathTraceParams P, const uint2* __restrict__ prev, uint2* __restrict__ out, uint32_t* __restrict__ out_prim)
+template <bool TEX>
+__global__ void __launch_bounds__(64) k_path_trace(BvhDev bvh, ShadeDev sd, PathTraceParams P, const uint2* __restrict__ prev, uint2* __restrict__ out, uint32_t* __restrict__ out_prim,
+                                                   tex::TexDev T)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = blockIdx.x * 16 + warp * 8 + (lane & 7), y = blockIdx.y * 4 + (lane >> 3);
@@ -633,7 +670,7 @@ __global__ void __launch_bounds__(64) k_path_trace(BvhDev bvh, ShadeDev sd, Path
     if (trace_closest(bvh, r, t, prim, hu, hv))
     { // rchit:112-141
         using namespace gi;
-        const Surface s  = fetch_surface(sd, prim, hu, hv);
+        const Surface s  = TEX ? fetch_surface_tex(sd, T, prim, hu, hv) : fetch_surface(sd, prim, hu, hv);
         const float   roughness = s.roughness * P.roughness_multiplier;
         const V3      Wo = det::scale(r.d, -1.0f);
         const float3  F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - s.metallic) + s.albedo * s.metallic;
@@ -711,7 +748,8 @@ void launch_ddgi_ray_trace(const hr_scene* sc, const hr_ddgi_uniforms& d, const 
     P.ray_ctr = ray_ctr;
     gi::AtlasDev at { (const uint2*)irr_prev, (const uint32_t*)depth_prev };
     int threads = d.rays_per_probe < 256 ? ((d.rays_per_probe + 31) / 32) * 32 : 256;
-    k_ddgi_ray_trace<<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth);
+    if (sc->tex.n_textures > 0) k_ddgi_ray_trace<true><<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth, sc->tex);
+    else k_ddgi_ray_trace<false><<<probe1 - probe0, threads, 0, st>>>(hr_bvh_view(sc), shade_view(sc), d, at, light, P, (uint2*)radiance, (uint2*)dirdepth, sc->tex);
 }
 
 // 0 (default) = fused kernel (one warp per 8x4 block: ray generation, closest hit, hit shading incl. its shadow ray);
@@ -738,7 +776,8 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
     memset(&du, 0, sizeof(du));
     if (d) du = *d;
     gi::AtlasDev at { (const uint2*)irr, (const uint32_t*)depth };
-    if (g_hr_refl_trace_impl == 1 && hits && row0 % 4 == 0 && spp <= 1) // spp > 1 runs on the fused kernel
+    const bool textured = sc->tex.n_textures > 0; // material textures: the TEX instantiations of the fused kernel (the wavefront variant has none)
+    if (g_hr_refl_trace_impl == 1 && hits && row0 % 4 == 0 && spp <= 1 && !textured) // spp > 1 runs on the fused kernel
     {
         static unsigned int* counter[64] = {};
         static int           ctas[64]    = {};
@@ -762,12 +801,20 @@ void launch_reflections_ray_trace(const hr_scene* sc, const GBufLevelDev& g, con
         return;
     }
     dim3 grid((g.W + 15) / 16, chunk_stride > 1 ? 2 * n_chunks_mine : (row1 - row0 + 3) / 4);
-    if (spp > 1) k_reflections_ray_trace<true, 8><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else if (g_hr_refl_trace_minb == 14) k_reflections_ray_trace<false, 14><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else if (g_hr_refl_trace_minb == 12) k_reflections_ray_trace<false, 12><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else if (g_hr_refl_trace_minb == 16) k_reflections_ray_trace<false, 16><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else if (g_hr_refl_trace_minb == 20) k_reflections_ray_trace<false, 20><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
-    else k_reflections_ray_trace<false, 18><<<grid, 64, 0, st>>>(g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out);
+    const tex::TexDev& T = sc->tex;
+#define HR_K12_ARGS g, hr_bvh_view(sc), shade_view(sc), fc, du, at, P, sobol, srk, (uint2*)out, T
+    if (textured)
+    {
+        if (spp > 1) k_reflections_ray_trace<true, 8, true><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+        else k_reflections_ray_trace<false, 18, true><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    }
+    else if (spp > 1) k_reflections_ray_trace<true, 8, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    else if (g_hr_refl_trace_minb == 14) k_reflections_ray_trace<false, 14, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    else if (g_hr_refl_trace_minb == 12) k_reflections_ray_trace<false, 12, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    else if (g_hr_refl_trace_minb == 16) k_reflections_ray_trace<false, 16, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    else if (g_hr_refl_trace_minb == 20) k_reflections_ray_trace<false, 20, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+    else k_reflections_ray_trace<false, 18, false><<<grid, 64, 0, st>>>(HR_K12_ARGS);
+#undef HR_K12_ARGS
 }
 
 void launch_path_trace(const hr_scene* sc, const hr_frame* f, int W, int H, uint32_t num_frames, uint32_t max_ray_bounces, float roughness_multiplier, const float* sky3,
@@ -782,5 +829,6 @@ void launch_path_trace(const hr_scene* sc, const hr_frame* f, int W, int H, uint
     P.W = W; P.H = H;
     P.ray_ctr = ray_ctr;
     dim3 grid((W + 15) / 16, (H + 3) / 4);
-    k_path_trace<<<grid, 64, 0, st>>>(hr_bvh_view(sc), shade_view(sc), P, (const uint2*)prev, (uint2*)out, out_prim);
+    if (sc->tex.n_textures > 0) k_path_trace<true><<<grid, 64, 0, st>>>(hr_bvh_view(sc), shade_view(sc), P, (const uint2*)prev, (uint2*)out, out_prim, sc->tex);
+    else k_path_trace<false><<<grid, 64, 0, st>>>(hr_bvh_view(sc), shade_view(sc), P, (const uint2*)prev, (uint2*)out, out_prim, sc->tex);
 }

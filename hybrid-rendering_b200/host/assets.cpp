@@ -667,6 +667,11 @@ struct hra_scene {
     std::vector<uint32_t>    indices;
     std::vector<hr_instance> instances;
     std::vector<hr_material> materials;
+    // material textures (hra_scene_textures): decoded images, their hr_texture views, one binding per global material
+    std::vector<std::vector<uint8_t>>  tex_pixels;
+    std::vector<hr_texture>            textures;
+    std::vector<hr_material_textures>  bindings;
+    std::string                        tex_warnings;
     bool finalized = false;
 };
 
@@ -1348,6 +1353,30 @@ int hra_scene_finalize(hra_scene* s)
 {
     if (!s || s->insts.empty()) return fail(HRA_ERR_INVALID_ARG, "hra_scene_finalize: no instances");
     s->vertices.clear(); s->indices.clear(); s->instances.clear(); s->materials.clear();
+    s->tex_pixels.clear(); s->textures.clear(); s->bindings.clear(); s->tex_warnings.clear();
+    std::map<std::pair<std::string, int>, int32_t> tex_index; // (path, sRGB) -> texture index (-1: unusable)
+    auto use_texture = [&](const std::string& path, bool srgb) -> int32_t {
+        if (path.empty()) return -1;
+        auto key = std::make_pair(path, srgb ? 1 : 0);
+        auto it  = tex_index.find(key);
+        if (it != tex_index.end()) return it->second;
+        int32_t idx = -1;
+        int w = 0, h = 0, c = 0;
+        uint8_t* px = nullptr;
+        if (ext_of(path) != "png") s->tex_warnings += path + ": not a PNG (only PNG textures are decoded), constant used\n";
+        else if (hra_image_load(path.c_str(), 0, &w, &h, &c, &px) != HRA_OK) s->tex_warnings += path + ": " + g_err + ", constant used\n";
+        else
+        {
+            idx = (int32_t)s->tex_pixels.size();
+            s->tex_pixels.emplace_back(px, px + (size_t)w * h * c);
+            free(px);
+            hr_texture t;
+            t.width = w; t.height = h; t.channels = c; t.srgb = srgb ? 1 : 0; t.data = nullptr; // pointers are set once all images are in place
+            s->textures.push_back(t);
+        }
+        tex_index[key] = idx;
+        return idx;
+    };
     struct Off { uint32_t vertex, index, material; };
     std::map<const hra_mesh*, Off> seen; // m_local_to_global_mesh_idx, ray_traced_scene.cpp:283-297
     for (const auto& in : s->insts)
@@ -1361,6 +1390,19 @@ int hra_scene_finalize(hra_scene* s)
             s->vertices.insert(s->vertices.end(), in.mesh->vertices.begin(), in.mesh->vertices.end());
             s->indices.insert(s->indices.end(), in.mesh->indices.begin(), in.mesh->indices.end());
             s->materials.insert(s->materials.end(), in.mesh->material_consts.begin(), in.mesh->material_consts.end());
+            const bool gltf = ext_of(in.mesh->path) != "obj";
+            for (const auto& m : in.mesh->materials)
+            { // Material::load: albedo sRGB (material.cpp:114), the rest linear; packed glTF image: roughness .g, metallic .b (mesh.cpp:411,437)
+                hr_material_textures b;
+                b.albedo            = use_texture(m.tex[HRA_TEX_ALBEDO], true);
+                b.normal            = use_texture(m.tex[HRA_TEX_NORMAL], false);
+                b.roughness         = use_texture(m.tex[HRA_TEX_ROUGHNESS], false);
+                b.roughness_channel = gltf ? 1 : 0;
+                b.metallic          = use_texture(m.tex[HRA_TEX_METALLIC], false);
+                b.metallic_channel  = gltf ? 2 : 0;
+                b.emissive          = use_texture(m.tex[HRA_TEX_EMISSIVE], false);
+                s->bindings.push_back(b);
+            }
             it = seen.emplace(in.mesh, o).first;
         }
         for (const auto& sm : in.mesh->submeshes)
@@ -1374,9 +1416,18 @@ int hra_scene_finalize(hra_scene* s)
             s->instances.push_back(hi);
         }
     }
+    for (size_t i = 0; i < s->textures.size(); i++) s->textures[i].data = s->tex_pixels[i].data();
     s->finalized = true;
     return HRA_OK;
 }
+void hra_scene_texture_counts(const hra_scene* s, uint64_t* nt, uint64_t* nb)
+{
+    if (nt) *nt = s->textures.size();
+    if (nb) *nb = s->bindings.size();
+}
+const hr_texture*           hra_scene_textures(const hra_scene* s) { return s->textures.data(); }
+const hr_material_textures* hra_scene_material_textures(const hra_scene* s) { return s->bindings.data(); }
+const char*                 hra_scene_texture_warnings(const hra_scene* s) { return s->tex_warnings.c_str(); }
 void hra_scene_counts(const hra_scene* s, uint64_t* nv, uint64_t* ni, uint64_t* nin, uint64_t* nm)
 {
     if (nv) *nv = s->vertices.size();

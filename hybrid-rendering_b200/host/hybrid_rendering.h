@@ -67,6 +67,9 @@ struct CommonResources {
         check(ctx, hr_scene_build(ctx, hra_scene_vertices(s), nv, hra_scene_indices(s), ni, hra_scene_instances(s), nin, hra_scene_materials(s), nm, &scene),
               "hr_scene_build");
         check(ctx, hr_scene_set_current(ctx, scene), "hr_scene_set_current");
+        uint64_t nt = 0, nb = 0; // Material::load: the images the materials reference (PNG), bound like s_Textures[] (hr_scene_set_textures)
+        hra_scene_texture_counts(s, &nt, &nb);
+        if (nt > 0) check(ctx, hr_scene_set_textures(scene, hra_scene_textures(s), nt, hra_scene_material_textures(s), nb), "hr_scene_set_textures");
     }
     // BlueNoise::BlueNoise (blue_noise.cpp:21-33): the Sobol' table and every scrambling / ranking table found in `dir`
     void load_blue_noise(const char* dir)

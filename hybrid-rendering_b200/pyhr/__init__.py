@@ -50,6 +50,15 @@ class hr_instance(C.Structure):
                 ("material_idx", C.c_uint32)]
 
 
+class hr_texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("srgb", C.c_int32), ("data", C.c_void_p)]
+
+
+class hr_material_textures(C.Structure):
+    _fields_ = [("albedo", C.c_int32), ("normal", C.c_int32), ("roughness", C.c_int32), ("roughness_channel", C.c_int32), ("metallic", C.c_int32),
+                ("metallic_channel", C.c_int32), ("emissive", C.c_int32)]
+
+
 class hr_scene_info(C.Structure):
     _fields_ = [("n_triangles", C.c_uint64), ("n_nodes", C.c_uint64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3),
                 ("build_ms", C.c_float), ("depth", C.c_uint32)]
@@ -96,7 +105,7 @@ ABI_SYMBOLS = [
     "hr_pass_destroy", "hr_pass_upload", "hr_ctx_set_profiling", "hr_pass_stage_times", "hr_debug_set", "hr_ctx_launch_count", "hr_shard_config", "hr_shard_rows", "hr_shard_unique_id", "hr_shard_init", "hr_shard_shutdown", "hr_shard_set_gather", "hr_shard_halo_rows", "hr_shard_link_local",
     "hr_ddgi_default_params", "hr_ddgi_create", "hr_ddgi_render", "hr_ddgi_get_uniforms", "hr_reflections_default_params", "hr_reflections_create",
     "hr_reflections_render", "hr_pass_get_stats", "hr_pass_output_checksum", "hr_gbuffer_render", "hr_gbuffer_render_sharded", "hr_brdf_lut_set", "hr_deferred_create", "hr_deferred_render", "hr_gbuffer_stage_render", "hr_bluenoise_set_slot",
-    "hr_taa_default_params", "hr_taa_jitter", "hr_taa_create", "hr_taa_render", "hr_tonemap_default_params", "hr_tonemap_create", "hr_tonemap_render", "hr_path_tracer_default_params", "hr_path_tracer_create", "hr_path_tracer_render",
+    "hr_taa_default_params", "hr_taa_jitter", "hr_taa_create", "hr_taa_render", "hr_tonemap_default_params", "hr_tonemap_create", "hr_tonemap_render", "hr_path_tracer_default_params", "hr_path_tracer_create", "hr_path_tracer_render", "hr_scene_set_textures",
 ]
 
 _product = None
@@ -226,6 +235,30 @@ class SynthScene:
         return np.array(mn[:], np.float32), np.array(mx[:], np.float32)
 
 
+class ArrayScene:
+    """hr_scene_build arguments held as arrays (vertices (n, 20) float32 = dw::Vertex, uint32 indices, [hr_instance], [hr_material]): has the
+    attributes Context.build_scene reads.  Tests use it to change a procedural scene's texture coordinates."""
+
+    def __init__(self, vertices, indices, instances, materials):
+        self.V = np.ascontiguousarray(vertices, np.float32)
+        self.I = np.ascontiguousarray(indices, np.uint32)
+        self.inst = (hr_instance * len(instances))(*instances)
+        self.mats = (hr_material * len(materials))(*materials)
+        self.n_vertices, self.n_indices, self.n_instances, self.n_materials = len(self.V), len(self.I), len(instances), len(materials)
+        self.n_tris = self.n_indices // 3
+
+    def raw(self):
+        return (self.V.ctypes.data, self.I.ctypes.data, C.addressof(self.inst), C.addressof(self.mats))
+
+    def primitive_uvs(self):
+        """(n_tris, 6): texture coordinates of the three corners in hr_scene_build's primitive order (instances in order, triangles in index order)"""
+        out = []
+        for it in self.inst:
+            idx = self.I[it.first_index: it.first_index + it.index_count // 3 * 3].astype(np.int64) + it.base_vertex
+            out.append(self.V[idx, 4:6].reshape(-1, 6))
+        return np.ascontiguousarray(np.concatenate(out), np.float32)
+
+
 def default_light(**kw):
     l = hrs_light_desc()
     load_synth().hrs_default_light(C.byref(l))
@@ -325,6 +358,19 @@ class Context:
                                            C.c_size_t(s.n_instances), C.c_void_p(m), C.c_size_t(s.n_materials), C.byref(out)), "hr_scene_build")
         self.check(self.lib.hr_scene_set_current(self.h, out), "hr_scene_set_current")
         return out
+
+    def set_textures(self, scene, textures, bindings):
+        """hr_scene_set_textures: textures = [(uint8 array (H, W) / (H, W, C), srgb)], bindings = one dict per material with the keys of
+        hr_material_textures (missing keys: -1 / channel 0).  textures = [] removes them."""
+        keep = [np.ascontiguousarray(a, np.uint8) for a, _ in textures]
+        tx = (hr_texture * max(1, len(textures)))()
+        for i, (a, (_, srgb)) in enumerate(zip(keep, textures)):
+            tx[i] = hr_texture(a.shape[1], a.shape[0], 1 if a.ndim == 2 else a.shape[2], int(bool(srgb)), a.ctypes.data)
+        bd = (hr_material_textures * max(1, len(bindings)))()
+        for i, b in enumerate(bindings):
+            bd[i] = hr_material_textures(b.get("albedo", -1), b.get("normal", -1), b.get("roughness", -1), b.get("roughness_channel", 0), b.get("metallic", -1),
+                                         b.get("metallic_channel", 0), b.get("emissive", -1))
+        self.check(self.lib.hr_scene_set_textures(scene, tx, C.c_size_t(len(textures)), bd, C.c_size_t(len(bindings))), "hr_scene_set_textures")
 
     def scene_info(self, scene):
         info = hr_scene_info()

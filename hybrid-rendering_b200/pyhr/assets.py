@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-from . import BUILD_DIR, HrError, PKG_ROOT, hr_instance, hr_material, hr_vertex
+from . import BUILD_DIR, HrError, PKG_ROOT, hr_instance, hr_material, hr_material_textures, hr_texture, hr_vertex
 
 LIB_ASSETS = os.path.join(BUILD_DIR, "libhr_assets.so")
 _lib = None
@@ -49,6 +49,12 @@ def load_assets():
         L.hra_scene_add_instance.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.hra_scene_finalize.argtypes = [C.c_void_p]
         L.hra_scene_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 4
+        L.hra_scene_texture_counts.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 2
+        for n in ("hra_scene_textures", "hra_scene_material_textures"):
+            getattr(L, n).restype = C.c_void_p
+            getattr(L, n).argtypes = [C.c_void_p]
+        L.hra_scene_texture_warnings.restype = C.c_char_p
+        L.hra_scene_texture_warnings.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -192,6 +198,20 @@ class AssetScene:
     def raw(self):
         L = self.lib
         return (L.hra_scene_vertices(self.h), L.hra_scene_indices(self.h), L.hra_scene_instances(self.h), L.hra_scene_materials(self.h))
+
+    def textures(self):
+        """(textures, bindings, warnings) in the form pyhr.Context.set_textures / oracle.ShadingScene.set_textures take"""
+        nt, nb = C.c_uint64(), C.c_uint64()
+        self.lib.hra_scene_texture_counts(self.h, C.byref(nt), C.byref(nb))
+        tx = (hr_texture * nt.value).from_address(self.lib.hra_scene_textures(self.h)) if nt.value else []
+        bd = (hr_material_textures * nb.value).from_address(self.lib.hra_scene_material_textures(self.h)) if nb.value else []
+        textures = []
+        for t in tx:
+            a = np.ctypeslib.as_array(C.cast(t.data, C.POINTER(C.c_uint8)), (t.height, t.width, t.channels)).copy()
+            textures.append((a[..., 0] if t.channels == 1 else a, bool(t.srgb)))
+        keys = ("albedo", "normal", "roughness", "roughness_channel", "metallic", "metallic_channel", "emissive")
+        bindings = [{k: getattr(b, k) for k in keys} for b in bd]
+        return textures, bindings, self.lib.hra_scene_texture_warnings(self.h).decode(errors="replace")
 
     def instances(self):
         a = (hr_instance * self.n_instances).from_address(self.lib.hra_scene_instances(self.h))

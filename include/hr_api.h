@@ -164,6 +164,24 @@ HR_API int hr_scene_get_info(hr_scene* scene, hr_scene_info* out);
 /* Re-run only the device build (the reference rebuilds its TLAS every frame, src/main.cpp:74). */
 HR_API int hr_scene_rebuild(hr_scene* scene, void* stream);
 
+/* Material textures (Material::load + the bindless s_Textures array, extras/ray_traced_scene.cpp:345-420, scene_descriptor_set.glsl:84-93,180-218).
+ * textures: 8-bit images, 1, 2 or 4 channels (what Image::create_from_file produces: RGB files arrive as RGBA), host pointers, copied;
+ * srgb = 1 for albedo images (material.cpp:114).  bindings: one entry per material of the scene (n_materials must equal the scene's):
+ * texture index or -1 = use the hr_material constant; *_channel selects the component of the roughness / metallic image (glTF: 1 / 2).
+ * Sampled at every hit of the reflections / DDGI / path-tracer shading and by hr_gbuffer_render (albedo, metallic, roughness) at mip 0
+ * with bilinear filtering and REPEAT addressing.  Normal and emissive maps are accepted and ignored.
+ * n_textures = 0 removes them.  Not to be called while work that uses the scene is in flight. */
+typedef struct hr_texture {
+    int32_t        width, height;
+    int32_t        channels; /* 1, 2 or 4 */
+    int32_t        srgb;
+    const uint8_t* data;     /* width * height * channels bytes, rows top to bottom */
+} hr_texture;
+typedef struct hr_material_textures {
+    int32_t albedo, normal, roughness, roughness_channel, metallic, metallic_channel, emissive;
+} hr_material_textures;
+HR_API int hr_scene_set_textures(hr_scene* scene, const hr_texture* textures, size_t n_textures, const hr_material_textures* bindings, size_t n_materials);
+
 /* Generic ray query against the current scene, for tests of the traversal kernel.
  * rays: n x 8 floats {ox,oy,oz,tmin, dx,dy,dz,tmax} (device).  any-hit: out_hit[n] uint32 (1 = hit).
  * closest: out_t[n] float (tmax if miss), out_prim[n] uint32 (0xFFFFFFFF if miss), out_uv[n*2]. */

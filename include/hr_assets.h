@@ -91,6 +91,14 @@ HR_API const hr_vertex*   hra_scene_vertices(const hra_scene* s);
 HR_API const uint32_t*    hra_scene_indices(const hra_scene* s);
 HR_API const hr_instance* hra_scene_instances(const hra_scene* s);
 HR_API const hr_material* hra_scene_materials(const hra_scene* s);
+/* The scene's material textures for hr_scene_set_textures (Material::load, material.cpp:100-190: albedo sRGB, the others linear; roughness /
+ * metallic channel 1 / 2 for glTF's packed image, 0 otherwise, mesh.cpp:404-447).  hra_scene_finalize loads every referenced image once
+ * (PNG; a file that is missing or in another format leaves the material constant and is listed in hra_scene_texture_warnings).  The
+ * hr_texture::data pointers stay valid until the scene is finalized again or destroyed. */
+HR_API void hra_scene_texture_counts(const hra_scene* s, uint64_t* n_textures, uint64_t* n_material_bindings);
+HR_API const hr_texture*           hra_scene_textures(const hra_scene* s);
+HR_API const hr_material_textures* hra_scene_material_textures(const hra_scene* s);
+HR_API const char*                 hra_scene_texture_warnings(const hra_scene* s); /* one line per image that could not be used */
 
 #ifdef __cplusplus
 }

@@ -83,13 +83,16 @@ extern "C" void orc_gbuffer_render(void* shading_scene, const uint32_t* prim_ins
                     const float cu = (c.x / c.w) * 0.5f + 0.5f, cv = (c.y / c.w) * 0.5f + 0.5f;
                     const float pu = (pc.x / pc.w) * 0.5f + 0.5f, pv = (pc.y / pc.w) * 0.5f + 0.5f;
                     const hr_material& m = ss.materials[ss.prim_mat[h.prim]];
+                    vec3  albedo = { m.albedo[0], m.albedo[1], m.albedo[2] };
+                    float roughness = m.roughness, metallic = m.metallic;
+                    fetch_material(ss, h.prim, b0, b1, b2, albedo, roughness, metallic); // g_buffer.frag:90-105 (textures bound: fetch_* at the hit, mip 0)
                     g2[0] = f2h(oct[0]); g2[1] = f2h(oct[1]); g2[2] = f2h(pu - cu); g2[3] = f2h(pv - cv);
-                    g3[0] = f2h(m.roughness); g3[1] = 0; g3[2] = f2h((float)prim_inst[h.prim]); g3[3] = f2h(c.z);
+                    g3[0] = f2h(roughness); g3[1] = 0; g3[2] = f2h((float)prim_inst[h.prim]); g3[3] = f2h(c.z);
                     depth[pi] = dz;
                     if (gb1)
                     {
                         uint8_t* g1 = gb1 + 4 * pi;
-                        g1[0] = unorm8(m.albedo[0]); g1[1] = unorm8(m.albedo[1]); g1[2] = unorm8(m.albedo[2]); g1[3] = unorm8(m.metallic);
+                        g1[0] = unorm8(albedo.x); g1[1] = unorm8(albedo.y); g1[2] = unorm8(albedo.z); g1[3] = unorm8(metallic);
                     }
                     nrm[pi] = N;
                     mid[pi] = prim_inst[h.prim];

@@ -470,6 +470,47 @@ void* orc_shading_create(void* scene, const float* verts9, const float* vnormals
     return s;
 }
 void orc_shading_destroy(void* s) { delete (ShadingScene*)s; }
+// hr_scene_set_textures on the oracle's scene: n_textures images (w, h, channels, srgb, data), one MaterialTextures per material,
+// 6 texture coordinates per primitive; n_textures = 0 removes them
+struct orc_texture { int32_t width, height, channels, srgb; const uint8_t* data; };
+void orc_shading_set_textures(void* s, const orc_texture* textures, size_t n_textures, const MaterialTextures* bindings, size_t n_materials, const float* vuv6)
+{
+    ShadingScene& ss = *(ShadingScene*)s;
+    ss.textures.clear(); ss.bindings.clear(); ss.vuv.clear();
+    if (!n_textures) return;
+    for (size_t i = 0; i < n_textures; i++)
+    {
+        Texture2D t;
+        t.W = textures[i].width; t.H = textures[i].height; t.C = textures[i].channels; t.srgb = textures[i].srgb != 0;
+        t.px.assign(textures[i].data, textures[i].data + (size_t)t.W * t.H * t.C);
+        ss.textures.push_back(std::move(t));
+    }
+    ss.bindings.assign(bindings, bindings + n_materials);
+    ss.vuv.assign(vuv6, vuv6 + 6 * ss.prim_mat.size());
+}
+// fetch_surface's material part for n hits (primitive, barycentric u, v): out = albedo rgb, roughness, metallic (5 floats each)
+void orc_fetch_material(void* s, const uint32_t* prim, const float* bary_uv, size_t n, float* out5)
+{
+    const ShadingScene& ss = *(const ShadingScene*)s;
+    for (size_t i = 0; i < n; i++)
+    {
+        const Hit h { 0.0f, prim[i], bary_uv[2 * i], bary_uv[2 * i + 1] };
+        const Surface sf = fetch_surface(ss, h);
+        out5[5 * i] = sf.albedo.x; out5[5 * i + 1] = sf.albedo.y; out5[5 * i + 2] = sf.albedo.z; out5[5 * i + 3] = sf.roughness; out5[5 * i + 4] = sf.metallic;
+    }
+}
+// texture(s_Textures[..], uv) of one image, for unit tests: out = 4 floats per uv
+void orc_texture_sample(const orc_texture* t, const float* uv, size_t n, float* out4)
+{
+    Texture2D tx;
+    tx.W = t->width; tx.H = t->height; tx.C = t->channels; tx.srgb = t->srgb != 0;
+    tx.px.assign(t->data, t->data + (size_t)tx.W * tx.H * tx.C);
+    for (size_t i = 0; i < n; i++)
+    {
+        const vec4 c = tx.sample({ uv[2 * i], uv[2 * i + 1] });
+        out4[4 * i] = c.x; out4[4 * i + 1] = c.y; out4[4 * i + 2] = c.z; out4[4 * i + 3] = c.w;
+    }
+}
 
 static ImgH atlas_irr(const DDGIUniforms* d, const uint16_t* p) { return { d->irradiance_texture_width, d->irradiance_texture_height, 4, p }; }
 static ImgH atlas_dep(const DDGIUniforms* d, const uint16_t* p) { return { d->depth_texture_width, d->depth_texture_height, 2, p }; }

@@ -48,6 +48,42 @@ inline float next_float(RNG& r)
     return f - 1.0f;
 }
 
+// ---- material textures: the bindless s_Textures[] array + Material::texture_indices0 / 1 (scene_descriptor_set.glsl:84-93) -------------------
+// texture(s_Textures[i], uv) outside a fragment shader = textureLod(.., 0): base level, VK_FILTER_LINEAR, REPEAT (dw::Material::m_common_sampler,
+// material.cpp:210-228).  Albedo images are VK_FORMAT_*_SRGB (material.cpp:114): texels are decoded to linear before filtering.
+struct Texture2D {
+    int W = 0, H = 0, C = 4; // C = 1, 2 or 4 (stb_image's channel count; RGB files arrive as RGBA, vk.cpp:163-168)
+    bool srgb = false;
+    std::vector<uint8_t> px;
+    static float srgb_to_linear(uint8_t b)
+    {
+        const double c = b / 255.0;
+        return (float)(c <= 0.04045 ? c / 12.92 : pow((c + 0.055) / 1.055, 2.4));
+    }
+    vec4 texel(int x, int y) const
+    { // REPEAT
+        x %= W; if (x < 0) x += W;
+        y %= H; if (y < 0) y += H;
+        const uint8_t* t = px.data() + (size_t)C * ((size_t)y * W + x);
+        auto dec = [&](uint8_t b) { return srgb ? srgb_to_linear(b) : (float)b / 255.0f; };
+        vec4 r = { dec(t[0]), 0.0f, 0.0f, 1.0f };
+        if (C >= 2) r.y = dec(t[1]);
+        if (C == 4) { r.z = dec(t[2]); r.w = (float)t[3] / 255.0f; }
+        return r;
+    }
+    vec4 sample(vec2 uv) const
+    {
+        float x = uv.x * (float)W - 0.5f, y = uv.y * (float)H - 0.5f;
+        float i0 = floorf(x), j0 = floorf(y);
+        float a = x - i0, b = y - j0;
+        int   i = f2i(i0), j = f2i(j0);
+        vec4  t00 = texel(i, j), t10 = texel(i + 1, j), t01 = texel(i, j + 1), t11 = texel(i + 1, j + 1);
+        auto  lerp2 = [&](float p, float q, float r, float s) { return (p * (1.0f - a) + q * a) * (1.0f - b) + (r * (1.0f - a) + s * a) * b; };
+        return { lerp2(t00.x, t10.x, t01.x, t11.x), lerp2(t00.y, t10.y, t01.y, t11.y), lerp2(t00.z, t10.z, t01.z, t11.z), lerp2(t00.w, t10.w, t01.w, t11.w) };
+    }
+};
+struct MaterialTextures { int32_t albedo = -1, normal = -1, roughness = -1, roughness_channel = 0, metallic = -1, metallic_channel = 0, emissive = -1; }; // = hr_material_textures
+
 // ---- shading inputs (what RayTracedScene binds: vertices, materials) ------------------------------------------------
 struct ShadingScene {
     const Scene*       scene      = nullptr;
@@ -55,7 +91,26 @@ struct ShadingScene {
     std::vector<float> vnormals; // n*9 world-space unit vertex normals
     std::vector<uint32_t>    prim_mat;
     std::vector<hr_material> materials;
+    // optional: textures + per-material bindings + per-primitive texture coordinates (6 floats each)
+    std::vector<Texture2D>        textures;
+    std::vector<MaterialTextures> bindings;
+    std::vector<float>            vuv;
 };
+
+// fetch_albedo / fetch_roughness / fetch_metallic (scene_descriptor_set.glsl:180-218) at barycentrics (b0, b1, b2) of primitive prim;
+// the constants come in through the arguments (fetch_roughness's MIN_ROUGHNESS clamp applies to both paths)
+inline void fetch_material(const ShadingScene& ss, uint32_t prim, float b0, float b1, float b2, vec3& albedo, float& roughness, float& metallic)
+{
+    if (ss.textures.empty()) return;
+    const MaterialTextures& mt = ss.bindings[ss.prim_mat[prim]];
+    if (mt.albedo < 0 && mt.roughness < 0 && mt.metallic < 0) return;
+    const float* q = ss.vuv.data() + 6ull * prim;
+    const vec2 texcoord = { (q[0] * b0 + q[2] * b1) + q[4] * b2, (q[1] * b0 + q[3] * b1) + q[5] * b2 }; // interpolated_vertex :141
+    auto comp = [](vec4 v, int c) { return c == 0 ? v.x : (c == 1 ? v.y : (c == 2 ? v.z : v.w)); };
+    if (mt.albedo >= 0) { const vec4 c = ss.textures[mt.albedo].sample(texcoord); albedo = { c.x, c.y, c.z }; }
+    if (mt.roughness >= 0) roughness = fmaxf(comp(ss.textures[mt.roughness].sample(texcoord), mt.roughness_channel), orc_const::MIN_ROUGHNESS);
+    if (mt.metallic >= 0) metallic = comp(ss.textures[mt.metallic].sample(texcoord), mt.metallic_channel);
+}
 
 struct Surface { vec3 P, N, albedo; float roughness, metallic; };
 
@@ -73,6 +128,7 @@ inline Surface fetch_surface(const ShadingScene& ss, const Hit& h)
     s.albedo    = { m.albedo[0], m.albedo[1], m.albedo[2] };
     s.roughness = fmaxf(m.roughness, orc_const::MIN_ROUGHNESS); // MIN_ROUGHNESS, scene_descriptor_set.glsl:202
     s.metallic  = m.metallic;
+    fetch_material(ss, h.prim, b0, b1, b2, s.albedo, s.roughness, s.metallic);
     return s;
 }
 

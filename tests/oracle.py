@@ -78,6 +78,9 @@ def lib():
         L.orc_taa_jitter.argtypes = [U, I, I, P]
         L.orc_tonemap.argtypes = [I, I, P, I, F, I, P]
         L.orc_path_trace.argtypes = [P, P, I, I, U, U, F, P, P, P, P]
+        L.orc_shading_set_textures.argtypes = [P, P, C.c_size_t, P, C.c_size_t, P]
+        L.orc_texture_sample.argtypes = [P, P, C.c_size_t, P]
+        L.orc_fetch_material.argtypes = [P, P, P, C.c_size_t, P]
         _lib = L
     return _lib
 
@@ -328,11 +331,45 @@ class ShadingScene:
         mats = synth_scene.materials_array()
         self.h = lib().orc_shading_create(self.scene.h, p(tri), p(nrm), p(mat), tri.shape[0], C.cast(mats, C.c_void_p), synth_scene.n_materials)
 
+    def set_textures(self, textures, bindings, vuv):
+        """hr_scene_set_textures on the oracle's scene: textures = [(uint8 array, srgb)], bindings = [dict] per material (keys of
+        hr_material_textures), vuv = (n_tris, 6) texture coordinates per primitive corner"""
+        self._tex_keep = [np.ascontiguousarray(a, np.uint8) for a, _ in textures]
+        tx = (pyhr.hr_texture * max(1, len(textures)))()
+        for i, (a, (_, srgb)) in enumerate(zip(self._tex_keep, textures)):
+            tx[i] = pyhr.hr_texture(a.shape[1], a.shape[0], 1 if a.ndim == 2 else a.shape[2], int(bool(srgb)), a.ctypes.data)
+        bd = (pyhr.hr_material_textures * max(1, len(bindings)))()
+        for i, b in enumerate(bindings):
+            bd[i] = pyhr.hr_material_textures(b.get("albedo", -1), b.get("normal", -1), b.get("roughness", -1), b.get("roughness_channel", 0), b.get("metallic", -1),
+                                              b.get("metallic_channel", 0), b.get("emissive", -1))
+        vuv = np.ascontiguousarray(vuv, np.float32)
+        assert not textures or vuv.shape == (self.tri.shape[0], 6)
+        lib().orc_shading_set_textures(self.h, tx, len(textures), bd, len(bindings), p(vuv))
+
     def __del__(self):
         try:
             lib().orc_shading_destroy(self.h)
         except Exception:
             pass
+
+
+def fetch_material(ss: "ShadingScene", prim, bary_uv):
+    """fetch_surface's albedo rgb / roughness / metallic at hits (primitive, u, v): (n, 5) float32"""
+    prim = np.ascontiguousarray(prim, np.uint32)
+    uv = np.ascontiguousarray(bary_uv, np.float32).reshape(-1, 2)
+    out = np.empty((len(prim), 5), np.float32)
+    lib().orc_fetch_material(ss.h, p(prim), p(uv), len(prim), p(out))
+    return out
+
+
+def texture_sample(img, srgb, uv):
+    """texture(sampler2D over img (uint8 (H, W[, C])), uv) at mip 0, bilinear, REPEAT: (n, 4) float32"""
+    a = np.ascontiguousarray(img, np.uint8)
+    t = pyhr.hr_texture(a.shape[1], a.shape[0], 1 if a.ndim == 2 else a.shape[2], int(bool(srgb)), a.ctypes.data)
+    uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+    out = np.empty((len(uv), 4), np.float32)
+    lib().orc_texture_sample(C.byref(t), p(uv), len(uv), p(out))
+    return out
 
 
 def gbuffer_render(ss: "ShadingScene", frame, W, H, out=None):

@@ -566,6 +566,35 @@ def test_scene_tables_like_ray_traced_scene(tmp_path):
     assert np.array_equal(tri[7].reshape(3, 3), tri[0].reshape(3, 3) + (10, 20, 30))
 
 
+def test_scene_material_textures(tmp_path):
+    """hra_scene_finalize decodes every image the materials reference once and produces hr_scene_set_textures' arguments: albedo sRGB, glTF's
+    packed roughness (.g) / metallic (.b) image, OBJ maps on channel 0; files that cannot be decoded fall back to the constant with a warning"""
+    rng = np.random.default_rng(12)
+    (tmp_path / "textures").mkdir()
+    red = rng.integers(0, 256, (4, 6, 3), dtype=np.uint8)
+    write_png(tmp_path / "textures" / "red albedo.png", red, 2, 8)
+    (tmp_path / "cube.obj").write_text(OBJ_TEXT)
+    (tmp_path / "cube.mtl").write_text(MTL_TEXT + "map_Ns rough.png\nmap_Ka rough.png\nmap_Kd photo.jpg\n")
+    rough = rng.integers(0, 256, (8, 8, 1), dtype=np.uint8)
+    write_png(tmp_path / "rough.png", rough, 0, 8)
+    gl = _tiny_gltf(tmp_path, True)  # "gold" references tex/base%20color.png (missing)
+    a, b = A.Mesh(tmp_path / "cube.obj"), A.Mesh(gl)
+    ident = np.eye(4, dtype=np.float32).reshape(-1)
+    sc = A.AssetScene([(a, ident), (b, ident), (a, ident)])
+    textures, bindings, warnings = sc.textures()
+    assert len(bindings) == sc.n_materials == 4
+    # "red": albedo = the RGB file as RGBA, sRGB; bump.png (normal map) is missing -> -1 + warning
+    assert bindings[0]["albedo"] == 0 and textures[0][1] is True and np.array_equal(textures[0][0][..., :3], red) and np.all(textures[0][0][..., 3] == 255)
+    assert bindings[0]["normal"] == -1 and "bump.png" in warnings
+    # "shiny": roughness and metallic share one decoded grey image (channel 0 for OBJ), linear; its map_Kd is a JPEG -> constant + warning
+    assert bindings[1]["roughness"] == bindings[1]["metallic"] == 1 and bindings[1]["roughness_channel"] == bindings[1]["metallic_channel"] == 0
+    assert textures[1][1] is False and np.array_equal(textures[1][0], rough[..., 0]) and bindings[1]["albedo"] == -1 and "photo.jpg: not a PNG" in warnings
+    # glTF materials: channels 1 / 2; the missing base colour image falls back to the constant
+    assert bindings[2]["albedo"] == -1 and "base%20color.png" in warnings and bindings[2]["roughness_channel"] == 1 and bindings[2]["metallic_channel"] == 2
+    assert bindings[3] == dict(albedo=-1, normal=-1, roughness=-1, roughness_channel=1, metallic=-1, metallic_channel=2, emissive=-1)
+    assert len(textures) == 2  # every image decoded once although the mesh is instanced twice
+
+
 @pytest.mark.parametrize("fmt", ["obj", "gltf", "glb"])
 def test_procedural_scene_round_trip_is_bit_exact(tmp_path, fmt):
     """export the shadows-test scene, read it back through the loaders and the scene tables: the world-space triangle soup that
