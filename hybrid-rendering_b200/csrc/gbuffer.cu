@@ -94,10 +94,12 @@ __global__ void __launch_bounds__(64) k_gbuffer_render(BvhDev bvh, GbufScene sc,
                 const float4 n0 = __ldg(sc.vnormals + 3ull * prim), n1 = __ldg(sc.vnormals + 3ull * prim + 1), n2 = __ldg(sc.vnormals + 3ull * prim + 2);
                 const float  b0 = 1.0f - hu - hv;
                 N = det::normalize(det::add(det::add(det::scale(det::mk(n0.x, n0.y, n0.z), b0), det::scale(det::mk(n1.x, n1.y, n1.z), hu)), det::scale(det::mk(n2.x, n2.y, n2.z), hv)));
-                const float inv = 1.0f / ((fabsf(N.x) + fabsf(N.y)) + fabsf(N.z)); // direction_to_octohedral, g_buffer.frag:47-51
-                const float px = N.x * inv, py = N.y * inv;
+                V3 Ne = N; // the encoded normal: fetch_normal (g_buffer.frag:100); compute_curvature keeps using the interpolated normal (:73-74)
+                if (TEX) tex::normal_at_hit(T, __ldg(sc.prim_mat + prim), prim, b0, hu, hv, false, Ne.x, Ne.y, Ne.z);
+                const float inv = 1.0f / ((fabsf(Ne.x) + fabsf(Ne.y)) + fabsf(Ne.z)); // direction_to_octohedral, g_buffer.frag:47-51
+                const float px = Ne.x * inv, py = Ne.y * inv;
                 float       ox = px, oy = py;
-                if (!(N.z > 0.0f))
+                if (!(Ne.z > 0.0f))
                 {
                     ox = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
                     oy = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);

@@ -225,6 +225,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     std::vector<float>    soup;
     std::vector<float>    vnorm;
     std::vector<float>    vuv; // texture coordinates per primitive corner (host copy; on the device only when textures are bound)
+    std::vector<float>    vtb; // world-space unit tangents (3 corners) then bitangents (3 corners) per primitive, transform_vertex :155-156
     std::vector<uint32_t> prim_inst, prim_mat;
     for (size_t ii = 0; ii < n_instances; ii++)
     {
@@ -233,6 +234,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
         if ((size_t)in.first_index + in.index_count > n_indices) { hr_set_error(ctx, "hr_scene_build: instance %zu index range out of bounds", ii); return HR_ERR_INVALID_ARG; }
         for (uint32_t k = 0; k + 2 < in.index_count; k += 3)
         {
+            float tb[18];
             for (int j = 0; j < 3; j++)
             {
                 const size_t vi = (size_t)in.base_vertex + indices[in.first_index + k + j];
@@ -248,7 +250,15 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
                 const float il = l > 0.0f ? 1.0f / l : 0.0f;
                 vnorm.push_back(wx * il); vnorm.push_back(wy * il); vnorm.push_back(wz * il); vnorm.push_back(0.0f);
                 vuv.push_back(v.tex_coord[0]); vuv.push_back(v.tex_coord[1]);
+                for (int w = 0; w < 2; w++)
+                { // normalize(mat3(model) * tangent / bitangent), like the normal above
+                    const float* a = w ? v.bitangent : v.tangent;
+                    float tx = (M[0] * a[0] + M[4] * a[1]) + M[8] * a[2], ty = (M[1] * a[0] + M[5] * a[1]) + M[9] * a[2], tz = (M[2] * a[0] + M[6] * a[1]) + M[10] * a[2];
+                    const float tl = sqrtf((tx * tx + ty * ty) + tz * tz), til = tl > 0.0f ? 1.0f / tl : 0.0f;
+                    tb[9 * w + 3 * j] = tx * til; tb[9 * w + 3 * j + 1] = ty * til; tb[9 * w + 3 * j + 2] = tz * til;
+                }
             }
+            vtb.insert(vtb.end(), tb, tb + 18);
             prim_inst.push_back((uint32_t)ii);
             prim_mat.push_back(in.material_idx);
         }
@@ -261,6 +271,7 @@ int hr_scene_build(hr_ctx* ctx, const hr_vertex* vertices, size_t n_vertices, co
     sc->ctx      = ctx;
     sc->n_tris   = (uint32_t)n;
     sc->h_vuv    = std::move(vuv);
+    sc->h_vtb    = std::move(vtb);
     const size_t ni = n > 1 ? n - 1 : 1;
 #define ALLOC(ptr, bytes) HR_CUDA(ctx, cudaMalloc((void**)&(ptr), (bytes)))
     ALLOC(sc->d_tri_verts, n * 9 * sizeof(float));
@@ -356,7 +367,7 @@ int hr_scene_destroy(hr_scene* sc)
     if (sc->ctx && sc->ctx->scene == sc) sc->ctx->scene = nullptr;
     void* ptrs[] = { sc->d_tri_verts, sc->d_prim_inst, sc->d_prim_mat, sc->d_vnormals, sc->d_keys, sc->d_keys_sorted, sc->d_vals, sc->d_vals_sorted,
                      sc->d_tri_aabb, sc->d_bounds_i, sc->d_children, sc->d_ranges, sc->d_parent, sc->d_node_aabb, sc->d_flags, sc->d_nodes, sc->d_wnodes, sc->d_depth, sc->d_tris,
-                     sc->d_materials, sc->d_sort_tmp, sc->d_ploc, sc->d_vuv, sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_srgb_lut };
+                     sc->d_materials, sc->d_sort_tmp, sc->d_ploc, sc->d_vuv, sc->d_vtb, sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_srgb_lut };
     for (void* p : ptrs) cudaFree(p);
     delete sc;
     return HR_OK;
@@ -438,7 +449,15 @@ int hr_scene_set_textures(hr_scene* sc, const hr_texture* textures, size_t n_tex
     HR_CUDA(ctx, cudaMemcpy(sc->d_texels, texels.data(), total * sizeof(uint32_t), cudaMemcpyHostToDevice));
     HR_CUDA(ctx, cudaMemcpy(sc->d_tex_desc, desc.data(), n_textures * sizeof(tex::TexDesc), cudaMemcpyHostToDevice));
     HR_CUDA(ctx, cudaMemcpy(sc->d_mat_tex, mt.data(), n_materials * sizeof(tex::MatTex), cudaMemcpyHostToDevice));
-    sc->tex = tex::TexDev { sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_vuv, sc->d_srgb_lut, (int32_t)n_textures };
+    bool any_normal_map = false;
+    for (const auto& m : mt) any_normal_map = any_normal_map || m.normal >= 0;
+    if (any_normal_map && !sc->d_vtb)
+    {
+        HR_REQUIRE(ctx, sc->h_vtb.size() == 18ull * sc->n_tris, HR_ERR_NOT_READY, "hr_scene_set_textures: the scene holds no tangent frames");
+        HR_CUDA(ctx, cudaMalloc((void**)&sc->d_vtb, sc->h_vtb.size() * sizeof(float)));
+        HR_CUDA(ctx, cudaMemcpy(sc->d_vtb, sc->h_vtb.data(), sc->h_vtb.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    sc->tex = tex::TexDev { sc->d_texels, sc->d_tex_desc, sc->d_mat_tex, sc->d_vuv, sc->d_srgb_lut, (int32_t)n_textures, any_normal_map ? sc->d_vtb : nullptr };
     return HR_OK;
 }
 

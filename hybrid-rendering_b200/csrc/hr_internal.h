@@ -148,7 +148,9 @@ struct hr_scene {
     // material textures (hr_scene_set_textures): per-primitive texture coordinates are kept on the host by hr_scene_build and only uploaded when
     // textures are bound; `tex` is what the TEX instantiations of the shading kernels receive (n_textures == 0: the untextured kernels run)
     std::vector<float> h_vuv;        // 6 per primitive
+    std::vector<float> h_vtb;        // 18 per primitive: world-space unit tangents of the three corners, then bitangents (normal maps)
     float*         d_vuv = nullptr;
+    float*         d_vtb = nullptr;
     uint32_t*      d_texels = nullptr;
     tex::TexDesc*  d_tex_desc = nullptr;
     tex::MatTex*   d_mat_tex = nullptr;

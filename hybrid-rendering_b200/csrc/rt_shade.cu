@@ -183,7 +183,9 @@ __device__ __forceinline__ float3 shade_hit(const BvhDev& bvh, const ShadeDev& s
 __device__ __forceinline__ Surface fetch_surface_tex(const ShadeDev& sd, const tex::TexDev& T, uint32_t prim, float u, float v)
 {
     Surface s = fetch_surface(sd, prim, u, v);
-    tex::material_at_hit(T, __ldg(sd.prim_mat + prim), prim, 1.0f - u - v, u, v, s.albedo.x, s.albedo.y, s.albedo.z, s.roughness, s.metallic);
+    const uint32_t mat = __ldg(sd.prim_mat + prim);
+    tex::material_at_hit(T, mat, prim, 1.0f - u - v, u, v, s.albedo.x, s.albedo.y, s.albedo.z, s.roughness, s.metallic);
+    tex::normal_at_hit(T, mat, prim, 1.0f - u - v, u, v, true, s.N.x, s.N.y, s.N.z); // the hit shaders pass the tangent as bitangent (rchit:134)
     return s;
 }
 __device__ __forceinline__ float3 shade_hit_tex(const BvhDev& bvh, const ShadeDev& sd, const tex::TexDev& T, const hr_light& light, const Ray& r, uint32_t prim, float u, float v,

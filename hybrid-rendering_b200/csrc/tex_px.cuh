@@ -29,6 +29,8 @@ struct TexDev {                // device view of a scene's textures (hr_scene_se
     const float*    vuv;       // 6 floats per primitive (primitive order): uv of the three vertices
     const float*    srgb_lut;  // 256 floats: sRGB byte -> linear
     int32_t         n_textures;
+    const float*    vtb;       // 18 floats per primitive: world-space unit tangents of the three corners, then their bitangents; null when no
+                               // material binds a normal map
 };
 
 struct RGBA { float r, g, b, a; };
@@ -86,6 +88,46 @@ HR_TEX_HD void material_at_hit(const TexDev& T, uint32_t mat, uint32_t prim, flo
     if (m.albedo >= 0) { const RGBA c = sample(T, m.albedo, u, v); ar = c.r; ag = c.g; ab = c.b; }                               // fetch_albedo :180-186
     if (m.roughness >= 0) roughness = fmaxf(channel(sample(T, m.roughness, u, v), m.roughness_channel), 0.1f);                    // fetch_roughness :200-208 (MIN_ROUGHNESS)
     if (m.metallic >= 0) metallic = channel(sample(T, m.metallic, u, v), m.metallic_channel);                                     // fetch_metallic :212-218
+}
+
+// fetch_normal + get_normal_from_map (scene_descriptor_set.glsl:164-195): the interpolated unit normal (nx, ny, nz) is replaced by
+// normalize(TBN * normalize(texel.rgb * 2 - 1)), TBN = (normalize(T), normalize(B), normalize(N)).  The hit shaders pass the TANGENT as bitangent
+// (reflections_ray_trace.rchit:134, gi_ray_trace.rchit:112, ground_truth_path_trace.rchit:131: fetch_normal(material, vertex.tangent.xyz,
+// vertex.tangent.xyz, ...)) — tangent_as_bitangent = true reproduces that; the G-buffer pass passes the real bitangent (g_buffer.frag:100).
+// The result feeds shadow-ray origins and N.L tests: written in the deterministic chain's operation order (dot = (xx + yy) + zz,
+// normalize = v * (1 / sqrt(dot)), mat3 * vec3 = (c0 * x + c1 * y) + c2 * z); this header is only compiled without FMA contraction.
+HR_TEX_HD void normalize3(float& x, float& y, float& z)
+{
+    const float inv = 1.0f / sqrtf((x * x + y * y) + z * z);
+    x = x * inv; y = y * inv; z = z * inv;
+}
+HR_TEX_HD void normal_at_hit(const TexDev& T, uint32_t mat, uint32_t prim, float b0, float b1, float b2, bool tangent_as_bitangent, float& nx, float& ny, float& nz)
+{
+    const MatTex m = T.mat[mat];
+    if (m.normal < 0 || !T.vtb) return;
+    const float* q = T.vuv + 6ull * prim;
+    const float  u = (q[0] * b0 + q[2] * b1) + q[4] * b2, v = (q[1] * b0 + q[3] * b1) + q[5] * b2;
+    const RGBA   c = sample(T, m.normal, u, v);
+    float tx_ = c.r * 2.0f - 1.0f, ty_ = c.g * 2.0f - 1.0f, tz_ = c.b * 2.0f - 1.0f; // texel.rgb * 2.0 - 1.0
+    normalize3(tx_, ty_, tz_);
+    const float* t = T.vtb + 18ull * prim; // interpolated_vertex :143-144: normalize(t0 * b.x + t1 * b.y + t2 * b.z)
+    float Tx = (t[0] * b0 + t[3] * b1) + t[6] * b2, Ty = (t[1] * b0 + t[4] * b1) + t[7] * b2, Tz = (t[2] * b0 + t[5] * b1) + t[8] * b2;
+    normalize3(Tx, Ty, Tz);
+    float Bx = Tx, By = Ty, Bz = Tz;
+    if (!tangent_as_bitangent)
+    {
+        Bx = (t[9] * b0 + t[12] * b1) + t[15] * b2; By = (t[10] * b0 + t[13] * b1) + t[16] * b2; Bz = (t[11] * b0 + t[14] * b1) + t[17] * b2;
+        normalize3(Bx, By, Bz);
+    }
+    // mat3 TBN = mat3(normalize(tangent), normalize(bitangent), normalize(normal)): the arguments arrive normalised (interpolated_vertex /
+    // g_buffer.frag:100) and are normalised AGAIN here, as the shader does — a second normalisation can move the last bit
+    normalize3(Tx, Ty, Tz);
+    normalize3(Bx, By, Bz);
+    float Nx = nx, Ny = ny, Nz = nz;
+    normalize3(Nx, Ny, Nz);
+    float rx = (Tx * tx_ + Bx * ty_) + Nx * tz_, ry = (Ty * tx_ + By * ty_) + Ny * tz_, rz = (Tz * tx_ + Bz * ty_) + Nz * tz_;
+    normalize3(rx, ry, rz);
+    nx = rx; ny = ry; nz = rz;
 }
 
 } // namespace tex

@@ -250,6 +250,24 @@ class ArrayScene:
     def raw(self):
         return (self.V.ctypes.data, self.I.ctypes.data, C.addressof(self.inst), C.addressof(self.mats))
 
+    def primitive_tangent_frames(self):
+        """(n_tris, 18): world-space unit tangents of the three corners, then their bitangents, as hr_scene_build keeps them (normalize(mat3(model) * t))"""
+        out = []
+        for it in self.inst:
+            M = np.array(it.model[:], np.float32).reshape(4, 4).T
+            idx = self.I[it.first_index: it.first_index + it.index_count // 3 * 3].astype(np.int64) + it.base_vertex
+            rows = []
+            for col in (12, 16):  # tangent, bitangent of dw::Vertex
+                a = self.V[idx, col:col + 3]
+                w = np.empty_like(a)
+                for r in range(3):
+                    w[:, r] = (M[r, 0] * a[:, 0] + M[r, 1] * a[:, 1]) + M[r, 2] * a[:, 2]
+                ln = np.sqrt((w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1]) + w[:, 2] * w[:, 2]).astype(np.float32)
+                il = np.where(ln > 0, np.float32(1.0) / np.where(ln > 0, ln, 1).astype(np.float32), np.float32(0.0)).astype(np.float32)
+                rows.append((w * il[:, None]).astype(np.float32).reshape(-1, 9))
+            out.append(np.concatenate(rows, 1))
+        return np.ascontiguousarray(np.concatenate(out), np.float32)
+
     def primitive_uvs(self):
         """(n_tris, 6): texture coordinates of the three corners in hr_scene_build's primitive order (instances in order, triangles in index order)"""
         out = []

@@ -168,8 +168,8 @@ HR_API int hr_scene_rebuild(hr_scene* scene, void* stream);
  * textures: 8-bit images, 1, 2 or 4 channels (what Image::create_from_file produces: RGB files arrive as RGBA), host pointers, copied;
  * srgb = 1 for albedo images (material.cpp:114).  bindings: one entry per material of the scene (n_materials must equal the scene's):
  * texture index or -1 = use the hr_material constant; *_channel selects the component of the roughness / metallic image (glTF: 1 / 2).
- * Sampled at every hit of the reflections / DDGI / path-tracer shading and by hr_gbuffer_render (albedo, metallic, roughness) at mip 0
- * with bilinear filtering and REPEAT addressing.  Normal and emissive maps are accepted and ignored.
+ * Sampled at every hit of the reflections / DDGI / path-tracer shading and by hr_gbuffer_render (albedo, metallic, roughness, normal map)
+ * at mip 0 with bilinear filtering and REPEAT addressing.  Emissive maps are accepted and unused (no shader of the reference reads them).
  * n_textures = 0 removes them.  Not to be called while work that uses the scene is in flight. */
 typedef struct hr_texture {
     int32_t        width, height;

@@ -79,7 +79,7 @@ extern "C" void orc_gbuffer_render(void* shading_scene, const uint32_t* prim_ins
                     const float  b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
                     const vec3   N  = normalize((vec3{ n[0], n[1], n[2] } * b0 + vec3{ n[3], n[4], n[5] } * b1) + vec3{ n[6], n[7], n[8] } * b2);
                     float        oct[2];
-                    direction_to_octohedral(N, oct);
+                    direction_to_octohedral(fetch_normal(ss, h.prim, b0, b1, b2, false, N), oct); // g_buffer.frag:100; compute_curvature keeps the interpolated normal
                     const float cu = (c.x / c.w) * 0.5f + 0.5f, cv = (c.y / c.w) * 0.5f + 0.5f;
                     const float pu = (pc.x / pc.w) * 0.5f + 0.5f, pv = (pc.y / pc.w) * 0.5f + 0.5f;
                     const hr_material& m = ss.materials[ss.prim_mat[h.prim]];

@@ -473,10 +473,11 @@ void orc_shading_destroy(void* s) { delete (ShadingScene*)s; }
 // hr_scene_set_textures on the oracle's scene: n_textures images (w, h, channels, srgb, data), one MaterialTextures per material,
 // 6 texture coordinates per primitive; n_textures = 0 removes them
 struct orc_texture { int32_t width, height, channels, srgb; const uint8_t* data; };
-void orc_shading_set_textures(void* s, const orc_texture* textures, size_t n_textures, const MaterialTextures* bindings, size_t n_materials, const float* vuv6)
+void orc_shading_set_textures(void* s, const orc_texture* textures, size_t n_textures, const MaterialTextures* bindings, size_t n_materials, const float* vuv6,
+                              const float* vtb18)
 {
     ShadingScene& ss = *(ShadingScene*)s;
-    ss.textures.clear(); ss.bindings.clear(); ss.vuv.clear();
+    ss.textures.clear(); ss.bindings.clear(); ss.vuv.clear(); ss.vtb.clear();
     if (!n_textures) return;
     for (size_t i = 0; i < n_textures; i++)
     {
@@ -487,6 +488,20 @@ void orc_shading_set_textures(void* s, const orc_texture* textures, size_t n_tex
     }
     ss.bindings.assign(bindings, bindings + n_materials);
     ss.vuv.assign(vuv6, vuv6 + 6 * ss.prim_mat.size());
+    if (vtb18) ss.vtb.assign(vtb18, vtb18 + 18 * ss.prim_mat.size());
+}
+// fetch_surface's shading normal for n hits (unit tests): out = 3 floats each; hit_shader = the rchit call (tangent passed as bitangent)
+void orc_fetch_normal(void* s, const uint32_t* prim, const float* bary_uv, size_t n, int hit_shader, float* out3)
+{
+    const ShadingScene& ss = *(const ShadingScene*)s;
+    for (size_t i = 0; i < n; i++)
+    {
+        const float  u = bary_uv[2 * i], v = bary_uv[2 * i + 1], b0 = 1.0f - u - v;
+        const float* nn = ss.vnormals.data() + 9ull * prim[i];
+        const vec3   N = normalize((vec3{ nn[0], nn[1], nn[2] } * b0 + vec3{ nn[3], nn[4], nn[5] } * u) + vec3{ nn[6], nn[7], nn[8] } * v);
+        const vec3   r = fetch_normal(ss, prim[i], b0, u, v, hit_shader != 0, N);
+        out3[3 * i] = r.x; out3[3 * i + 1] = r.y; out3[3 * i + 2] = r.z;
+    }
 }
 // fetch_surface's material part for n hits (primitive, barycentric u, v): out = albedo rgb, roughness, metallic (5 floats each)
 void orc_fetch_material(void* s, const uint32_t* prim, const float* bary_uv, size_t n, float* out5)

@@ -95,6 +95,7 @@ struct ShadingScene {
     std::vector<Texture2D>        textures;
     std::vector<MaterialTextures> bindings;
     std::vector<float>            vuv;
+    std::vector<float>            vtb; // 18 per primitive: world-space unit tangents of the three corners, then bitangents (only with normal maps)
 };
 
 // fetch_albedo / fetch_roughness / fetch_metallic (scene_descriptor_set.glsl:180-218) at barycentrics (b0, b1, b2) of primitive prim;
@@ -110,6 +111,31 @@ inline void fetch_material(const ShadingScene& ss, uint32_t prim, float b0, floa
     if (mt.albedo >= 0) { const vec4 c = ss.textures[mt.albedo].sample(texcoord); albedo = { c.x, c.y, c.z }; }
     if (mt.roughness >= 0) roughness = fmaxf(comp(ss.textures[mt.roughness].sample(texcoord), mt.roughness_channel), orc_const::MIN_ROUGHNESS);
     if (mt.metallic >= 0) metallic = comp(ss.textures[mt.metallic].sample(texcoord), mt.metallic_channel);
+}
+
+// fetch_normal / get_normal_from_map (scene_descriptor_set.glsl:164-195).  `tangent`, `bitangent`, `normal` as the caller passes them: the hit
+// shaders pass vertex.tangent TWICE (reflections_ray_trace.rchit:134, gi_ray_trace.rchit:112, ground_truth_path_trace.rchit:131), the G-buffer
+// pass the real frame (g_buffer.frag:100).  Deterministic arithmetic (orc_math.h): the result decides shadow rays.
+inline vec3 get_normal_from_map(const Texture2D& normal_map, vec3 tangent, vec3 bitangent, vec3 normal, vec2 tex_coord)
+{
+    const vec3 T = normalize(tangent), B = normalize(bitangent), N = normalize(normal); // mat3 TBN
+    const vec4 t = normal_map.sample(tex_coord);
+    vec3 n = normalize(vec3{ t.x * 2.0f - 1.0f, t.y * 2.0f - 1.0f, t.z * 2.0f - 1.0f });
+    n = normalize((T * n.x + B * n.y) + N * n.z); // TBN * n
+    return n;
+}
+inline vec3 fetch_normal(const ShadingScene& ss, uint32_t prim, float b0, float b1, float b2, bool hit_shader, vec3 normal)
+{
+    if (ss.textures.empty() || ss.vtb.empty()) return normal;
+    const MaterialTextures& mt = ss.bindings[ss.prim_mat[prim]];
+    if (mt.normal < 0) return normal;
+    const float* q = ss.vuv.data() + 6ull * prim;
+    const vec2 texcoord = { (q[0] * b0 + q[2] * b1) + q[4] * b2, (q[1] * b0 + q[3] * b1) + q[5] * b2 };
+    const float* t = ss.vtb.data() + 18ull * prim;
+    // interpolated_vertex :143-144 (the per-vertex frames are already in world space, like the normals)
+    const vec3 tangent   = normalize((vec3{ t[0], t[1], t[2] } * b0 + vec3{ t[3], t[4], t[5] } * b1) + vec3{ t[6], t[7], t[8] } * b2);
+    const vec3 bitangent = normalize((vec3{ t[9], t[10], t[11] } * b0 + vec3{ t[12], t[13], t[14] } * b1) + vec3{ t[15], t[16], t[17] } * b2);
+    return get_normal_from_map(ss.textures[mt.normal], tangent, hit_shader ? tangent : bitangent, normal, texcoord);
 }
 
 struct Surface { vec3 P, N, albedo; float roughness, metallic; };
@@ -129,6 +155,7 @@ inline Surface fetch_surface(const ShadingScene& ss, const Hit& h)
     s.roughness = fmaxf(m.roughness, orc_const::MIN_ROUGHNESS); // MIN_ROUGHNESS, scene_descriptor_set.glsl:202
     s.metallic  = m.metallic;
     fetch_material(ss, h.prim, b0, b1, b2, s.albedo, s.roughness, s.metallic);
+    s.N = fetch_normal(ss, h.prim, b0, b1, b2, true, s.N); // rchit:134: N = fetch_normal(material, vertex.tangent.xyz, vertex.tangent.xyz, vertex.normal.xyz, uv)
     return s;
 }
 

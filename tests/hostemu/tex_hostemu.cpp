@@ -31,4 +31,17 @@ __attribute__((visibility("default"))) void emu_material_at_hit(const uint32_t* 
     }
 }
 
+// normal_at_hit for n hits: in/out arrays of the interpolated unit normal (3 floats each)
+__attribute__((visibility("default"))) void emu_normal_at_hit(const uint32_t* texels, const tex::TexDesc* desc, int n_textures, const float* srgb_lut, const tex::MatTex* mat,
+                                                              const float* vuv, const float* vtb, const uint32_t* prim_mat, const uint32_t* prim, const float* bary_uv, size_t n,
+                                                              int tangent_as_bitangent, float* normal3)
+{
+    tex::TexDev T { texels, desc, mat, vuv, srgb_lut, n_textures, vtb };
+    for (size_t i = 0; i < n; i++)
+    {
+        const float u = bary_uv[2 * i], v = bary_uv[2 * i + 1];
+        tex::normal_at_hit(T, prim_mat[prim[i]], prim[i], 1.0f - u - v, u, v, tangent_as_bitangent != 0, normal3[3 * i], normal3[3 * i + 1], normal3[3 * i + 2]);
+    }
+}
+
 } // extern "C"

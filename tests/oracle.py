@@ -78,7 +78,8 @@ def lib():
         L.orc_taa_jitter.argtypes = [U, I, I, P]
         L.orc_tonemap.argtypes = [I, I, P, I, F, I, P]
         L.orc_path_trace.argtypes = [P, P, I, I, U, U, F, P, P, P, P]
-        L.orc_shading_set_textures.argtypes = [P, P, C.c_size_t, P, C.c_size_t, P]
+        L.orc_shading_set_textures.argtypes = [P, P, C.c_size_t, P, C.c_size_t, P, P]
+        L.orc_fetch_normal.argtypes = [P, P, P, C.c_size_t, I, P]
         L.orc_texture_sample.argtypes = [P, P, C.c_size_t, P]
         L.orc_fetch_material.argtypes = [P, P, P, C.c_size_t, P]
         _lib = L
@@ -331,7 +332,7 @@ class ShadingScene:
         mats = synth_scene.materials_array()
         self.h = lib().orc_shading_create(self.scene.h, p(tri), p(nrm), p(mat), tri.shape[0], C.cast(mats, C.c_void_p), synth_scene.n_materials)
 
-    def set_textures(self, textures, bindings, vuv):
+    def set_textures(self, textures, bindings, vuv, vtb=None):
         """hr_scene_set_textures on the oracle's scene: textures = [(uint8 array, srgb)], bindings = [dict] per material (keys of
         hr_material_textures), vuv = (n_tris, 6) texture coordinates per primitive corner"""
         self._tex_keep = [np.ascontiguousarray(a, np.uint8) for a, _ in textures]
@@ -344,7 +345,10 @@ class ShadingScene:
                                               b.get("metallic_channel", 0), b.get("emissive", -1))
         vuv = np.ascontiguousarray(vuv, np.float32)
         assert not textures or vuv.shape == (self.tri.shape[0], 6)
-        lib().orc_shading_set_textures(self.h, tx, len(textures), bd, len(bindings), p(vuv))
+        if vtb is not None:
+            vtb = np.ascontiguousarray(vtb, np.float32)
+            assert vtb.shape == (self.tri.shape[0], 18)
+        lib().orc_shading_set_textures(self.h, tx, len(textures), bd, len(bindings), p(vuv), p(vtb) if vtb is not None else None)
 
     def __del__(self):
         try:
@@ -359,6 +363,15 @@ def fetch_material(ss: "ShadingScene", prim, bary_uv):
     uv = np.ascontiguousarray(bary_uv, np.float32).reshape(-1, 2)
     out = np.empty((len(prim), 5), np.float32)
     lib().orc_fetch_material(ss.h, p(prim), p(uv), len(prim), p(out))
+    return out
+
+
+def fetch_normal(ss: "ShadingScene", prim, bary_uv, hit_shader=True):
+    """the shading normal fetch_normal returns at hits (primitive, u, v): (n, 3) float32; hit_shader: the rchit call (tangent as bitangent)"""
+    prim = np.ascontiguousarray(prim, np.uint32)
+    uv = np.ascontiguousarray(bary_uv, np.float32).reshape(-1, 2)
+    out = np.empty((len(prim), 3), np.float32)
+    lib().orc_fetch_normal(ss.h, p(prim), p(uv), len(prim), int(hit_shader), p(out))
     return out
 
 

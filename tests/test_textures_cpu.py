@@ -33,6 +33,7 @@ def emu():
     P, I = C.c_void_p, C.c_int
     L.emu_tex_sample.argtypes = [P, P, I, P, I, P, C.c_size_t, P]
     L.emu_material_at_hit.argtypes = [P, P, I, P, P, P, P, P, P, C.c_size_t, P, P, P]
+    L.emu_normal_at_hit.argtypes = [P, P, I, P, P, P, P, P, P, P, C.c_size_t, I, P]
     return L
 
 
@@ -118,10 +119,17 @@ def textured_scene(seed=0):
     orm = rng.integers(0, 256, (16, 8, 4), dtype=np.uint8)
     orm[..., 1] = rng.integers(0, 256, (16, 8))          # roughness in .g: values below MIN_ROUGHNESS * 255 exercise the clamp
     grey = rng.integers(0, 256, (8, 8), dtype=np.uint8)
-    textures = [(checker, True), (orm, False), (grey, False), (rng.integers(0, 256, (4, 4, 4), dtype=np.uint8), True)]
+    bumps = np.zeros((16, 16, 4), np.uint8)  # tangent-space normals tilted up to ~35 degrees, blue (z) dominant like real normal maps
+    bumps[..., 0] = 128 + (60 * np.sin(xx[:16, :16] * 0.9)).astype(int)
+    bumps[..., 1] = 128 + (60 * np.cos(yy[:16, :16] * 0.7)).astype(int)
+    bumps[..., 2] = 230
+    bumps[..., 3] = 255
+    textures = [(checker, True), (orm, False), (grey, False), (rng.integers(0, 256, (4, 4, 4), dtype=np.uint8), True), (bumps, False)]
     bindings = []
     for k in range(sc.n_materials):
         b = {}
+        if k % 5 == 0 or k == 1:
+            b.update(normal=4)
         if k % 2 == 0:
             b.update(albedo=0 if k % 4 == 0 else 3)
         if k % 3 == 0:
@@ -136,7 +144,7 @@ def test_device_material_fetch_equals_the_oracle_bit_for_bit():
     sc, asc, textures, bindings = textured_scene()
     ss = O.ShadingScene(sc, brute=True)
     vuv = asc.primitive_uvs()
-    ss.set_textures(textures, bindings, vuv)
+    ss.set_textures(textures, bindings, vuv, asc.primitive_tangent_frames())
     rng = np.random.default_rng(3)
     n = 6000
     prim = rng.integers(0, sc.n_tris, n).astype(np.uint32)
@@ -154,7 +162,7 @@ def test_device_material_fetch_equals_the_oracle_bit_for_bit():
     texels, desc = pack(textures)
     mt = (MatTex * len(bindings))()
     for i, b in enumerate(bindings):
-        mt[i] = MatTex(b.get("albedo", -1), -1, b.get("roughness", -1), b.get("roughness_channel", 0), b.get("metallic", -1), b.get("metallic_channel", 0), -1, 0)
+        mt[i] = MatTex(b.get("albedo", -1), b.get("normal", -1), b.get("roughness", -1), b.get("roughness_channel", 0), b.get("metallic", -1), b.get("metallic_channel", 0), -1, 0)
     lut = srgb_lut()
     emu().emu_material_at_hit(O.p(texels), desc, len(textures), O.p(lut), mt, O.p(vuv), O.p(prim_mat), O.p(prim), O.p(bary), n, O.p(albedo), O.p(rough), O.p(metal))
     got = np.concatenate([albedo, rough[:, None], metal[:, None]], 1)
@@ -162,21 +170,71 @@ def test_device_material_fetch_equals_the_oracle_bit_for_bit():
     # something was actually textured, the roughness clamp fired, and unbound materials kept their constants
     ss0 = O.ShadingScene(sc, brute=True)
     base = O.fetch_material(ss0, prim, bary)
-    bound = np.array([bool(bindings[m]) for m in prim_mat[prim]])
+    bound = np.array([any(k in bindings[m] for k in ("albedo", "roughness", "metallic")) for m in prim_mat[prim]])
     assert np.array_equal(want[~bound], base[~bound]) and np.mean(np.any(want[bound] != base[bound], axis=1)) > 0.9
     assert want[:, 3].min() == np.float32(0.1) and want[:, 3].max() > 0.9
+
+
+def test_device_normal_map_fetch_equals_the_oracle_bit_for_bit():
+    """fetch_normal / get_normal_from_map: both call sites — the hit shaders' (tangent passed as bitangent, rchit:134) and the G-buffer pass's (real
+    frame, g_buffer.frag:100) — host build of csrc/tex_px.cuh::normal_at_hit vs the oracle, plus closed forms"""
+    sc, asc, textures, bindings = textured_scene()
+    ss = O.ShadingScene(sc, brute=True)
+    vuv, vtb = asc.primitive_uvs(), asc.primitive_tangent_frames()
+    ss.set_textures(textures, bindings, vuv, vtb)
+    rng = np.random.default_rng(5)
+    n = 5000
+    prim = rng.integers(0, sc.n_tris, n).astype(np.uint32)
+    bu = rng.random(n).astype(np.float32)
+    bary = np.stack([bu, (rng.random(n).astype(np.float32) * (1.0 - bu)).astype(np.float32)], -1)
+    _, prim_mat = sc.world_normals()
+    prim_mat = np.ascontiguousarray(prim_mat, np.uint32)
+    plain = O.ShadingScene(sc, brute=True)
+    n_interp = O.fetch_normal(plain, prim, bary)  # no textures: the interpolated unit normal
+    assert np.allclose(np.linalg.norm(n_interp, axis=1), 1.0, atol=1e-6)
+    texels, desc = pack(textures)
+    mt = (MatTex * len(bindings))()
+    for i, b in enumerate(bindings):
+        mt[i] = MatTex(b.get("albedo", -1), b.get("normal", -1), b.get("roughness", -1), b.get("roughness_channel", 0), b.get("metallic", -1), b.get("metallic_channel", 0), -1, 0)
+    lut = srgb_lut()
+    mapped = np.array(["normal" in bindings[m] for m in prim_mat[prim]])
+    assert mapped.any() and (~mapped).any()
+    for quirk in (1, 0):
+        want = O.fetch_normal(ss, prim, bary, hit_shader=bool(quirk))
+        got = n_interp.copy()
+        emu().emu_normal_at_hit(O.p(texels), desc, len(textures), O.p(lut), mt, O.p(vuv), O.p(vtb), O.p(prim_mat), O.p(prim), O.p(bary), n, quirk, O.p(got))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        assert np.array_equal(want[~mapped], n_interp[~mapped])                         # materials without a normal map keep the interpolated normal
+        assert np.allclose(np.linalg.norm(want, axis=1), 1.0, atol=1e-6)
+        tilt = np.degrees(np.arccos(np.clip(np.sum(want[mapped] * n_interp[mapped], axis=1), -1, 1)))
+        assert tilt.max() < 50.0 and tilt.mean() > 3.0                                 # the map tilts the normal, moderately (blue-dominant texels)
+    a, b = O.fetch_normal(ss, prim, bary, True), O.fetch_normal(ss, prim, bary, False)
+    assert not np.array_equal(a[mapped], b[mapped])                                     # the two call sites differ (the rchit quirk is real)
+    # a flat map (128, 128, 255) leaves the normal where it is up to the quantisation of 128 / 255 (0.3 degrees)
+    flat = np.zeros((2, 2, 4), np.uint8)
+    flat[...] = (128, 128, 255, 255)
+    ss.set_textures([(flat, False)], [dict(normal=0)] * sc.n_materials, vuv, vtb)
+    f = O.fetch_normal(ss, prim, bary, False)
+    assert np.degrees(np.arccos(np.clip(np.sum(f * n_interp, axis=1), -1, 1))).max() < 0.5
 
 
 def test_oracle_gbuffer_and_path_tracer_see_the_textures():
     W, H = 96, 54
     sc, asc, textures, bindings = textured_scene()
     plain, tex = O.ShadingScene(sc, brute=True), O.ShadingScene(sc, brute=True)
-    tex.set_textures(textures, bindings, asc.primitive_uvs())
+    tex.set_textures(textures, bindings, asc.primitive_uvs(), asc.primitive_tangent_frames())
     f = pyhr.make_frame((0, 14, 34), (0, 3, 0), W, H)
     g0, g1 = O.gbuffer_render(plain, f, W, H), O.gbuffer_render(tex, f, W, H)
-    # geometry channels identical, material channels differ: GB1 (albedo, metallic), GB3.x (roughness)
-    assert np.array_equal(g0.depth, g1.depth) and np.array_equal(g0.gb2, g1.gb2) and np.array_equal(g0.gb3[..., 1:], g1.gb3[..., 1:])
+    # geometry channels identical (depth, motion vectors, curvature — it uses the interpolated normal —, mesh id, linear z); material channels differ:
+    # GB1 (albedo, metallic), GB3.x (roughness), and the encoded normal where a normal map is bound
+    assert np.array_equal(g0.depth, g1.depth) and np.array_equal(g0.gb2[..., 2:], g1.gb2[..., 2:]) and np.array_equal(g0.gb3[..., 1:], g1.gb3[..., 1:])
     hit = g0.depth != 1.0
+    _, _, insts0, _ = synth_arrays(sc)
+    has_nmap = np.array(["normal" in bindings[it.material_idx] for it in insts0])
+    mid0 = np.clip(g1.gb3[..., 2].view(np.float16).astype(np.int64), 0, len(insts0) - 1)
+    nm_px = hit & has_nmap[mid0]
+    assert nm_px.any() and np.mean(np.any(g0.gb2[..., :2][nm_px] != g1.gb2[..., :2][nm_px], axis=-1)) > 0.9
+    assert np.array_equal(g0.gb2[..., :2][hit & ~nm_px], g1.gb2[..., :2][hit & ~nm_px])
     assert np.mean(np.any(g0.gb1[hit] != g1.gb1[hit], axis=-1)) > 0.3 and np.any(g0.gb3[..., 0] != g1.gb3[..., 0])
     # fetch_roughness clamps TEXTURED roughness to MIN_ROUGHNESS (fp16 of 0.1); pixels of materials without a roughness map keep their constant
     _, _, insts, _ = synth_arrays(sc)

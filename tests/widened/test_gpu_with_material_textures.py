@@ -1,5 +1,5 @@
 """GPU parity with material textures bound (hr_scene_set_textures; fetch_albedo / fetch_roughness / fetch_metallic of
-scene_descriptor_set.glsl:180-218) through the C ABI against the oracle: the TEX instantiations of the G-buffer producer (all four images bit
+scene_descriptor_set.glsl:164-218, normal maps included) through the C ABI against the oracle: the TEX instantiations of the G-buffer producer (all four images bit
 for bit), the reflections and DDGI ray-trace stages (ray lengths / probe distances exact, colours within the shading tolerance) and the
 ground-truth path tracer; removing the textures restores the untextured results.  The arithmetic of the texture functions themselves is
 checked on the CPU (tests/test_textures_cpu.py: host build of csrc/tex_px.cuh == oracle, bit for bit)."""
@@ -24,7 +24,7 @@ def f16(a):
 def test_textured_scene_matches_the_oracle():
     sc, asc, textures, bindings = textured_scene()
     ss = O.ShadingScene(sc, brute=sc.n_tris <= 4096)
-    ss.set_textures(textures, bindings, asc.primitive_uvs())
+    ss.set_textures(textures, bindings, asc.primitive_uvs(), asc.primitive_tangent_frames())
     bn = pyhr.blue_noise()
     ctx = pyhr.Context(0)
     ctx.set_bluenoise(*bn)
