@@ -309,7 +309,7 @@ def post_leg(W, H, tris):
     ctx = pyhr.Context(0)
     ctx.set_bluenoise(*pyhr.blue_noise())
     sc = pyhr.SynthScene(pyhr.SCENE_ARCADE, tris)
-    ctx.build_scene(sc)
+    ctx.current_scene_handle = ctx.build_scene(sc)
     ctx.gbuffer_create(W, H)
     light = pyhr.default_light(rot_x_deg=LIGHT_ROT_X)
     stream = torch.cuda.current_stream().cuda_stream
@@ -354,9 +354,51 @@ def post_leg(W, H, tris):
     ldr = tm.download(100)
     out["tonemapped_mean"] = float(ldr[..., :3].mean())
     out["launches"] = ctx.launch_count()
-    for p in (de, taa, tm, pt):
-        p.destroy()
-    ctx.close()
+    try:
+        # material textures (hr_scene_set_textures): cost of the TEX instantiations of the G-buffer producer and of the reflections ray trace
+        # against the untextured kernels, same frame; a 1024 x 1024 sRGB albedo, a packed roughness / metallic image and a normal map on every material
+        rng = np.random.default_rng(7)
+        yy, xx = np.mgrid[0:1024, 0:1024]
+        albedo = np.stack([np.where((xx // 64 + yy // 64) % 2, 220, 60), (xx // 4) % 256, (yy // 4) % 256, np.full_like(xx, 255)], -1).astype(np.uint8)
+        orm = rng.integers(0, 256, (512, 512, 4), dtype=np.uint8)
+        bump = np.stack([128 + (40 * np.sin(xx[:256, :256] * 0.2)).astype(int), 128 + (40 * np.cos(yy[:256, :256] * 0.2)).astype(int),
+                         np.full((256, 256), 235), np.full((256, 256), 255)], -1).astype(np.uint8)
+        rf = pyhr.ReflectionsPass(ctx, W, H, 0)
+        src = refl_params(CONFIGS[3])
+        for name, _ in src._fields_:
+            if name != "sky_color":
+                setattr(rf.params, name, getattr(src, name))
+        for k in range(3):
+            rf.params.sky_color[k] = SKY[k]
+        rf.params.denoise = 0
+
+        def frame_cost():
+            ctx.set_profiling(True)
+            g_ms = timed(lambda: ctx.gbuffer_render(f.ping_pong, f, 0, 0, stream), 10)
+            rf.stage_times()
+            for _ in range(6):
+                rf.render(f, None, stream)
+            torch.cuda.synchronize()
+            st = dict(rf.stage_times())
+            ctx.set_profiling(False)
+            return g_ms, st.get("Ray Trace")
+
+        plain = frame_cost()
+        scene_ptr = ctx.current_scene_handle
+        ctx.set_textures(scene_ptr, [(albedo, True), (orm, False), (bump, False)],
+                         [dict(albedo=0, roughness=1, roughness_channel=1, metallic=1, metallic_channel=2, normal=2)] * sc.n_materials)
+        textured = frame_cost()
+        out["textured"] = {"gbuffer_ms": {"constants": plain[0], "textures": textured[0]}, "reflections_ray_trace_ms": {"constants": plain[1], "textures": textured[1]},
+                           "textures": "1024x1024 sRGB albedo + 512x512 roughness/metallic + 256x256 normal map on every material"}
+        rf.destroy()
+    except Exception as e:  # informational: keep what was measured above
+        out["textured"] = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        for p in (de, taa, tm, pt):
+            p.destroy()
+        ctx.close()
+    except Exception:
+        pass
     print(json.dumps(out))
 
 
